@@ -1,0 +1,246 @@
+/*
+ * ssdk.h -- C-ABI of the B200-native SSD hot path (libssdk.so).
+ *
+ * The reference (pierluigiferrari/ssd_keras) is pure Python: it has no FFI / plugin
+ * interface of its own, so the drop-in boundary is its public Python surface (SURVEY.md
+ * section 8b).  Each entry point below names the reference interface it replaces
+ * (file:line relative to the reference root).  The Python package `ssd_keras_b200`
+ * re-creates those reference names on top of this library through ctypes; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success or a negative ssdk_status; it never throws.
+ *     ssdk_last_error() returns a thread-local, human readable message for the last failure.
+ *   - "dev" pointers are CUDA device pointers on the context's device; "host" pointers are
+ *     ordinary host memory.  Outputs are caller-allocated.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - a context (and the objects created from it) may be used by one host thread at a time.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     SSDK_ERR_CUDA.
+ */
+#ifndef SSDK_H_
+#define SSDK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSDK_VERSION 100
+
+typedef enum {
+  SSDK_OK = 0,
+  SSDK_ERR_INVALID = -1,     /* bad argument (the Python layer raises ValueError)          */
+  SSDK_ERR_CUDA = -2,        /* CUDA runtime/driver failure, message has the cuda error    */
+  SSDK_ERR_UNSUPPORTED = -3, /* valid in the reference but not implemented here            */
+  SSDK_ERR_NOMEM = -4,
+  SSDK_ERR_DEGENERATE = -5   /* degenerate ground-truth box (reference: DegenerateBoxError) */
+} ssdk_status;
+
+typedef enum { SSDK_COORDS_CENTROIDS = 0, SSDK_COORDS_CORNERS = 1, SSDK_COORDS_MINMAX = 2 } ssdk_coords;
+
+typedef struct ssdk_ctx ssdk_ctx;
+typedef struct ssdk_encoder ssdk_encoder;
+typedef struct ssdk_model ssdk_model;
+
+int ssdk_version(void);
+const char* ssdk_last_error(void);
+
+/* One context per (device, host thread).  Owns scratch workspaces. */
+int ssdk_ctx_create(int device, ssdk_ctx** out);
+int ssdk_ctx_destroy(ssdk_ctx* ctx);
+/* Number of kernels this library launched through `ctx` since creation (bench.py's gpu_launches). */
+int64_t ssdk_ctx_launch_count(const ssdk_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Anchor boxes.  Replaces SSDInputEncoder.generate_anchor_boxes_for_layer
+ * (ssd_encoder_decoder/ssd_input_encoder.py:420-548) and AnchorBoxes.call
+ * (keras_layers/keras_layer_AnchorBoxes.py:133-255).  Host-side float64 arithmetic, bit-exact
+ * with the reference; `out_f32` is the float32 cast the Keras layer emits (:252).
+ * steps_* / offsets_* entries that are NaN mean "None" (derive step from the feature map,
+ * offset 0.5).  Prior order: layers in order, ((y*W + x)*n_boxes + b) within a layer.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int img_height, img_width;
+  int n_layers;
+  const int* fm_height;          /* [n_layers] predictor feature-map sizes */
+  const int* fm_width;           /* [n_layers] */
+  const double* scales;          /* [n_layers + 1] */
+  const int* n_aspect_ratios;    /* [n_layers] */
+  const double* aspect_ratios;   /* concatenated, sum(n_aspect_ratios) entries */
+  int two_boxes_for_ar1;
+  const double* steps_h;         /* [n_layers] or NULL; NaN = None */
+  const double* steps_w;
+  const double* offsets_h;       /* [n_layers] or NULL; NaN = None */
+  const double* offsets_w;
+  int clip_boxes;
+  int coords;                    /* ssdk_coords */
+  int normalize_coords;
+} ssdk_anchor_cfg;
+
+int ssdk_anchors_count(const ssdk_anchor_cfg* cfg, int* out_P, int* out_n_boxes /* [n_layers] or NULL */);
+int ssdk_anchors_generate(const ssdk_anchor_cfg* cfg, double* out_f64 /* host [P*4] */, float* out_f32 /* host [P*4] or NULL */);
+
+/* ------------------------------------------------------------------------------------------
+ * Ground-truth encoder.  Replaces SSDInputEncoder.__call__
+ * (ssd_encoder_decoder/ssd_input_encoder.py:277-418) together with iou
+ * (bounding_box_utils/bounding_box_utils.py:283-383), match_bipartite_greedy and match_multi
+ * (ssd_encoder_decoder/matching_utils.py:22-116) and generate_encoding_template (:550-611).
+ * IoU and matching decisions are taken in float64 like the reference; the target tensor is
+ * written as float32 (what Keras feeds the loss).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int img_height, img_width;
+  int n_classes_total;       /* including background */
+  int P;                     /* number of anchors */
+  int background_id;
+  int coords;                /* ssdk_coords: format of `anchors` and of the encoded targets */
+  int matching_multi;        /* 1 = 'multi', 0 = 'bipartite' */
+  double pos_iou_threshold;
+  double neg_iou_limit;
+  int border_d;              /* 0 'half', 1 'include', -1 'exclude' */
+  int normalize_coords;
+  double variances[4];
+} ssdk_encode_cfg;
+
+int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, const double* anchors_host /* [P*4], in cfg->coords */,
+                        ssdk_encoder** out);
+int ssdk_encoder_destroy(ssdk_encoder* enc);
+/* gt_boxes_dev: [sum(G_i) * 5] float32 rows (class_id, xmin, ymin, xmax, ymax) in pixels, images concatenated;
+ * gt_offsets_host: [B+1] row offsets (host; the ragged shape is host knowledge in the reference too);
+ * out_y_dev: [B * P * (C+12)] float32;  out_match_dev (optional): [B * P] int32, matched gt index within the
+ * image, -1 = background, -2 = neutral.  status_dev (optional): one int32 that is set to the 1-based index of
+ * a batch item with a degenerate box (xmax<=xmin or ymax<=ymin), else left 0 (reference raises :333-336). */
+int ssdk_encode(ssdk_encoder* enc, const float* gt_boxes_dev, const int* gt_offsets_host, int B,
+                float* out_y_dev, int* out_match_dev, int* status_dev, void* stream);
+/* Standalone pieces, used by tests and the micro-benchmark: IoU matrix (G x P, float64, row-major). */
+int ssdk_iou_matrix(ssdk_encoder* enc, const float* gt_boxes_dev, int G, double* out_dev, void* stream);
+/* General IoU, replaces iou() (bounding_box_utils/bounding_box_utils.py:283-383): boxes1 [m*4], boxes2 [n*4] float64 in
+ * `coords` format; elementwise=0 -> out [m*n] ('outer_product'), elementwise=1 -> out [max(m,n)] with broadcasting of a
+ * single box ('element-wise').  Keeps the reference quirk: the intersection ignores border_d, the areas use it. */
+int ssdk_iou(ssdk_ctx* ctx, const double* boxes1_dev, int m, const double* boxes2_dev, int n, int coords, int border_d,
+             int elementwise, double* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoders.
+ *   mode PER_CLASS + layer_semantics=1: DecodeDetections.call   (keras_layers/keras_layer_DecodeDetections.py:109-265)
+ *   mode FAST      + layer_semantics=1: DecodeDetectionsFast.call (keras_layers/keras_layer_DecodeDetectionsFast.py:111-248)
+ *   mode PER_CLASS + layer_semantics=0: decode_detections        (ssd_encoder_decoder/ssd_output_decoder.py:111-226)
+ *   mode FAST      + layer_semantics=0: decode_detections_fast   (ssd_encoder_decoder/ssd_output_decoder.py:228-333)
+ * layer_semantics=1: float32 arithmetic, tf.image.non_max_suppression IoU rule, at most nms_max_output
+ *   survivors per class, output sorted by confidence (ties: lower row), zero padded to top_k rows.
+ * layer_semantics=0: float32 decode stored in float64 like NumPy, float64 IoU with the border_pixels
+ *   quirk, no per-class cap, strict '>' (per-class) / '>=' (fast) confidence test; out rows are the
+ *   top_k set (order: confidence desc, then class-major NMS order); out_counts gives the valid rows.
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { SSDK_DECODE_PER_CLASS = 0, SSDK_DECODE_FAST = 1 } ssdk_decode_mode;
+
+typedef struct {
+  int mode;                 /* ssdk_decode_mode */
+  int layer_semantics;
+  int n_classes_total;
+  int P;
+  double confidence_thresh; /* compared in float32 (layer) or float64 (NumPy API), like the reference */
+  double iou_threshold;     /* <= 0 with layer_semantics=0 and mode FAST: skip NMS (reference :326) */
+  int top_k;                /* <= 0: 'all' (NumPy API only; out must hold max_out rows) */
+  int nms_max_output;       /* layer only */
+  int coords;               /* input_coords */
+  int normalize_coords;
+  int img_height, img_width;
+  int border_d;
+  int max_out;              /* rows per image in `out`; layer: == top_k */
+} ssdk_decode_cfg;
+
+/* y_pred_dev [B*P*(C+12)] float32 -> out_dev [B*max_out*6] float32 rows (class, conf, xmin, ymin, xmax, ymax),
+ * out_counts_dev [B] int32 valid rows, out_index_dev (optional) [B*max_out] int32 prior index of each row (-1 pad). */
+int ssdk_decode(ssdk_ctx* ctx, const ssdk_decode_cfg* cfg, const float* y_pred_dev, int B,
+                float* out_dev, int* out_counts_dev, int* out_index_dev, void* stream);
+/* Single-class NMS micro-benchmark entry: boxes [B*n*4] corners, scores [B*n]. */
+int ssdk_nms(ssdk_ctx* ctx, const float* boxes_dev, const float* scores_dev, int B, int n,
+             double confidence_thresh, double iou_threshold, int nms_max_output, int top_k,
+             float* out_dev /* [B*top_k*6] */, int* out_counts_dev, int* out_index_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SSD loss.  Replaces SSDLoss.compute_loss (keras_loss_function/keras_ssd_loss.py:98-211).
+ * out_loss_dev [B] float32.  bwd writes d(sum_b upstream[b]*loss[b])/d y_pred with the hard-negative
+ * mask held constant (upstream_dev NULL = 1/B each, the Keras batch mean).
+ * ------------------------------------------------------------------------------------------ */
+int ssdk_ssd_loss_fwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pred_dev, int B, int P, int n_classes_total,
+                      int neg_pos_ratio, int n_neg_min, float alpha, float* out_loss_dev,
+                      int* out_stats_dev /* optional [4]: n_positive, n_neg_losses, k, ties_taken */, void* stream);
+int ssdk_ssd_loss_bwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pred_dev, int B, int P, int n_classes_total,
+                      int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream_dev,
+                      float* out_grad_dev /* [B*P*(C+12)] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model graph.  Replaces ssd_300 (models/keras_ssd300.py:31-457), ssd_512 (models/keras_ssd512.py:31-477)
+ * and build_model (models/keras_ssd7.py:30-430) + L2Normalization
+ * (keras_layers/keras_layer_L2Normalization.py:61-63): a static plan of tcgen05 implicit-GEMM
+ * convolutions, pooling, normalisation and the head epilogue producing (B,P,C+12).
+ * The graph is described layer by layer by the host (Python mirrors the reference builders).
+ * ------------------------------------------------------------------------------------------ */
+typedef enum {
+  SSDK_OP_INPUT = 0,      /* preprocessing: (x - mean)/std, channel swap; source = user images (B,H,W,3) f32 */
+  SSDK_OP_CONV = 1,       /* conv + bias + activation */
+  SSDK_OP_MAXPOOL = 2,
+  SSDK_OP_L2NORM = 3,     /* x * rsqrt(max(sum_c x^2, 1e-12)) * gamma_c */
+  SSDK_OP_HEAD = 4        /* fused conf+loc 3x3 predictor conv for one source layer -> rows of y_pred */
+} ssdk_op;
+
+typedef enum { SSDK_ACT_NONE = 0, SSDK_ACT_RELU = 1, SSDK_ACT_ELU = 2 } ssdk_act;
+
+typedef struct {
+  int op;                   /* ssdk_op */
+  int input;                /* index of the producing layer (-1 for SSDK_OP_INPUT) */
+  int cout;                 /* conv/head: output channels (head: n_boxes*(C+4) is derived; give n_boxes) */
+  int kh, kw, stride, dilation;
+  int pad_t, pad_l, pad_b, pad_r;   /* zero padding (conv) / -inf padding (pool) */
+  int act;                  /* ssdk_act */
+  int n_boxes;              /* head only */
+  /* Parameters, host pointers, copied at build time.  conv: kernel HWIO float32 [kh*kw*cin*cout], bias [cout];
+   * optional folded batch-norm scale/shift per output channel (applied after bias, before act);
+   * l2norm: gamma [c]; head: conf kernel/bias and loc kernel/bias; input: mean[3]/std[3]/swap[3]. */
+  const float* kernel; const float* bias;
+  const float* bn_scale; const float* bn_shift;
+  const float* kernel2; const float* bias2;      /* head: loc kernel/bias (kernel/bias = conf) */
+  const float* mean; const float* stddev; const int* swap;
+} ssdk_layer_desc;
+
+typedef struct {
+  int batch;                /* plan is built for this batch size */
+  int img_height, img_width, img_channels;
+  int n_classes_total;
+  int n_layers;
+  const ssdk_layer_desc* layers;
+  int precision;            /* 0 = bf16x3 split (fp32-faithful, default), 1 = single-pass bf16 */
+  const float* anchors_f32; /* host [P*4] */
+  float variances[4];
+} ssdk_model_desc;
+
+/* Stand-alone L2Normalization.call (keras_layers/keras_layer_L2Normalization.py:61-63) on a float32 tensor viewed as
+ * [rows, C] (rows = B*H*W, channels last): out = x * rsqrt(max(sum_c x^2, 1e-12)) * gamma_c. */
+int ssdk_l2_normalize(ssdk_ctx* ctx, const float* x_dev, long long rows, int C, const float* gamma_dev, float* out_dev, void* stream);
+
+int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssdk_model** out);
+int ssdk_model_destroy(ssdk_model* m);
+int ssdk_model_num_priors(const ssdk_model* m, int* out_P);
+/* Spatial size / channels of a layer's output (reference: model.get_layer(name).output_shape[1:3]). */
+int ssdk_model_layer_shape(const ssdk_model* m, int layer, int* out_h, int* out_w, int* out_c);
+/* images_dev (B,H,W,3) float32 NHWC -> y_pred_dev (B,P,C+12) float32. */
+int ssdk_model_forward(ssdk_model* m, const float* images_dev, float* y_pred_dev, void* stream);
+/* Copy a layer's activation (B,h,w,c) as float32 NHWC to out_dev (tests: per-layer parity). */
+int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, void* stream);
+/* FLOPs of one forward pass (2*MACs of every conv) and MMA flops actually issued. */
+int ssdk_model_flops(const ssdk_model* m, double* out_algorithmic, double* out_issued);
+/* Time of the conv kernels of the last forward in ms (CUDA events on `stream`), when enabled. */
+int ssdk_model_set_timing(ssdk_model* m, int enable);
+int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSDK_H_ */

@@ -1,0 +1,33 @@
+"""ssd_keras_b200 -- the SSD detection hot path of pierluigiferrari/ssd_keras on NVIDIA B200 (sm_100a).
+
+The sub-packages mirror the reference's module layout, so ``from ssd_keras_b200.models.keras_ssd300 import ssd_300``
+replaces ``from models.keras_ssd300 import ssd_300`` and so on.  All compute happens in hand-written CUDA kernels
+inside ``_lib/libssdk.so`` (C-ABI in ``include/ssdk.h``); there is no CPU or PyTorch fallback.
+"""
+__version__ = '0.1.0'
+
+
+def _exports():
+    from .models.keras_ssd300 import ssd_300
+    from .models.keras_ssd512 import ssd_512
+    from .models.keras_ssd7 import build_model, ssd_7
+    from .keras_layers.keras_layer_AnchorBoxes import AnchorBoxes
+    from .keras_layers.keras_layer_L2Normalization import L2Normalization
+    from .keras_layers.keras_layer_DecodeDetections import DecodeDetections
+    from .keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast
+    from .keras_loss_function.keras_ssd_loss import SSDLoss
+    from .ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder, DegenerateBoxError
+    from .ssd_encoder_decoder.ssd_output_decoder import decode_detections, decode_detections_fast
+    from .bounding_box_utils.bounding_box_utils import iou, convert_coordinates
+    return locals()
+
+
+_NAMES = ('ssd_300', 'ssd_512', 'build_model', 'ssd_7', 'AnchorBoxes', 'L2Normalization', 'DecodeDetections',
+          'DecodeDetectionsFast', 'SSDLoss', 'SSDInputEncoder', 'DegenerateBoxError', 'decode_detections',
+          'decode_detections_fast', 'iou', 'convert_coordinates')
+
+
+def __getattr__(name):
+    if name in _NAMES:
+        return _exports()[name]
+    raise AttributeError(name)

@@ -1,0 +1,60 @@
+"""``convert_coordinates`` and ``iou`` with the reference signatures (``bounding_box_utils/bounding_box_utils.py:24-87,
+283-383``).  ``iou`` runs on the GPU (``ssdk_iou``, float64, same operation order as NumPy, including the quirk that
+the intersection ignores ``border_pixels``); ``convert_coordinates`` is host-side index shuffling, as in the reference."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _ffi
+
+_CONV = ('minmax2centroids', 'centroids2minmax', 'corners2centroids', 'centroids2corners', 'minmax2corners', 'corners2minmax')
+
+
+def convert_coordinates(tensor, start_index, conversion, border_pixels='half'):
+    if conversion not in _CONV:
+        raise ValueError("Unexpected conversion value. Supported values are 'minmax2centroids', 'centroids2minmax', "
+                         "'corners2centroids', 'centroids2corners', 'minmax2corners', and 'corners2minmax'.")
+    d = _ffi.BORDER_D[border_pixels]
+    t = np.asarray(tensor)
+    out = np.array(t, dtype=np.float64, copy=True)
+    i = start_index
+    s0, s1, s2, s3 = t[..., i], t[..., i + 1], t[..., i + 2], t[..., i + 3]
+    if conversion == 'minmax2centroids':
+        out[..., i], out[..., i + 1], out[..., i + 2], out[..., i + 3] = (s0 + s1) / 2.0, (s2 + s3) / 2.0, s1 - s0 + d, s3 - s2 + d
+    elif conversion == 'centroids2minmax':
+        out[..., i], out[..., i + 1], out[..., i + 2], out[..., i + 3] = s0 - s2 / 2.0, s0 + s2 / 2.0, s1 - s3 / 2.0, s1 + s3 / 2.0
+    elif conversion == 'corners2centroids':
+        out[..., i], out[..., i + 1], out[..., i + 2], out[..., i + 3] = (s0 + s2) / 2.0, (s1 + s3) / 2.0, s2 - s0 + d, s3 - s1 + d
+    elif conversion == 'centroids2corners':
+        out[..., i], out[..., i + 1], out[..., i + 2], out[..., i + 3] = s0 - s2 / 2.0, s1 - s3 / 2.0, s0 + s2 / 2.0, s1 + s3 / 2.0
+    else:
+        out[..., i + 1], out[..., i + 2] = s2, s1
+    return out
+
+
+def iou(boxes1, boxes2, coords='centroids', mode='outer_product', border_pixels='half'):
+    import torch
+    b1, b2 = np.asarray(boxes1, dtype=np.float64), np.asarray(boxes2, dtype=np.float64)
+    if b1.ndim > 2:
+        raise ValueError("boxes1 must have rank either 1 or 2, but has rank {}.".format(b1.ndim))
+    if b2.ndim > 2:
+        raise ValueError("boxes2 must have rank either 1 or 2, but has rank {}.".format(b2.ndim))
+    if b1.ndim == 1:
+        b1 = b1[None]
+    if b2.ndim == 1:
+        b2 = b2[None]
+    if not (b1.shape[1] == b2.shape[1] == 4):
+        raise ValueError("All boxes must consist of 4 coordinates, but the boxes in `boxes1` and `boxes2` have {} and {} "
+                         "coordinates, respectively.".format(b1.shape[1], b2.shape[1]))
+    if mode not in ('outer_product', 'element-wise'):
+        raise ValueError("`mode` must be one of 'outer_product' and 'element-wise', but got '{}'.".format(mode))
+    if coords not in _ffi.COORDS:
+        raise ValueError("Unexpected value for `coords`. Supported values are 'minmax', 'corners' and 'centroids'.")
+    m, n = b1.shape[0], b2.shape[0]
+    d1 = torch.from_numpy(np.ascontiguousarray(b1)).cuda()
+    d2 = torch.from_numpy(np.ascontiguousarray(b2)).cuda()
+    elem = mode == 'element-wise'
+    out = torch.empty((max(m, n),) if elem else (m, n), dtype=torch.float64, device='cuda')
+    _ffi.check(_ffi.lib().ssdk_iou(_ffi.context(), _ffi.dptr(d1), m, _ffi.dptr(d2), n, _ffi.COORDS[coords],
+                                   _ffi.BORDER_D[border_pixels], 1 if elem else 0, _ffi.dptr(out), _ffi.stream_ptr()))
+    return out.cpu().numpy()

@@ -1,0 +1,599 @@
+// tcgen05 implicit-GEMM convolution for sm_100a plus the small data-movement kernels around it.
+// Reference ops: Conv2D / MaxPooling2D / Lambda preprocessing / L2Normalization / Reshape+softmax+Concat in
+// models/keras_ssd300.py:263-419, keras_layers/keras_layer_L2Normalization.py:61-63.
+//
+// conv_tcgen05_kernel -- persistent, warp-specialised (DESIGN.md section "conv"):
+//   GEMM view   D[M = output pixels, N = Cout] = sum over (tap, cin-block) A_tap[M, 64] * W_tap[N, 64]^T.
+//   "im2col in the TMA descriptor": the activation tensor is a zero-bordered NHWC buffer viewed as a 2-D
+//   matrix [B*Hp*Wp, C]; the A tile of filter tap (kh, kw) for output rows [m0, m0+128) is simply rows
+//   [m0 + shift(kh,kw), ...) of that matrix, so each tap is ONE 2-D TMA box load with a row offset, and
+//   padding / dilation come for free (the border is zero, rows past the end are TMA zero-filled).
+//   Outputs are computed for every position of the padded grid ("virtual rows"); the epilogue stores the
+//   valid ones, and m-tiles without any valid row are not scheduled.
+//   warp 0: TMA producer (one elected lane)      warp 1: tcgen05.mma issuer (one lane)
+//   warp 2: TMEM allocator                        warps 4-7: epilogue (tcgen05.ld -> bias/BN/act -> store)
+//   smem ring of `stages` {A_hi, A_lo, W_hi, W_lo} 128B-swizzled K-major tiles, full/empty mbarriers;
+//   two TMEM accumulators (2*BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   Precision: operands are bf16 "hi + lo" pairs; three MMAs per k-step (hi*hi, hi*lo, lo*hi) accumulate
+//   in fp32 TMEM, which reproduces an fp32 convolution to ~1e-5 relative (split=0 issues hi*hi only).
+#include "conv.cuh"
+#include <cudaTypedefs.h>
+#include <cmath>
+
+namespace ssdk {
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor creation (driver entry point resolved at run time)
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int tma_init() {
+  if (g_encode) return SSDK_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  SSDK_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return SSDK_ERR_CUDA; }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return SSDK_OK;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows) {
+  int rc = tma_init();
+  if (rc) return rc;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu box=%ux%u base=%p", (int)r,
+              (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner, box_rows, base);
+    return SSDK_ERR_CUDA;
+  }
+  return SSDK_OK;
+}
+
+static constexpr int kBM = 128;          // UMMA M (rows per tile)
+static constexpr int kBK = 64;           // channels per k-block = one 128-byte swizzle atom of bf16
+static constexpr int kATile = kBM * kBK * 2;   // 16 KB
+
+static size_t stage_bytes(int BN, int split) { return (size_t)(kATile + BN * kBK * 2) * (split ? 2 : 1); }
+size_t conv_smem_bytes(int BN, int split, int stages) { return 1024 + stage_bytes(BN, split) * stages + 256; }
+int conv_pick_stages(int BN, int split) {
+  int s = (int)((220 * 1024 - 1280) / stage_bytes(BN, split));
+  return s > 6 ? 6 : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spin on the phase parity; a barrier that never completes traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (spins & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("ssdk conv: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate), issued by one thread
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, 128B-swizzled operand tile: start address, SBO = 1024 B (8 rows x 128 B), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);            // [0,14)  start address >> 4
+  d |= (uint64_t)0 << 16;                            // [16,30) leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;     // [32,46) stride byte offset
+  d |= (uint64_t)1 << 46;                            // [46,48) version = 1
+  d |= (uint64_t)2 << 61;                            // [61,64) layout = SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == SSDK_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == SSDK_ACT_ELU) return x > 0.f ? x : expm1f(x);
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The convolution kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                    const __grid_constant__ ConvArgs args) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = args.stages, BN = args.BN, split = args.split;
+  const uint32_t b_tile = (uint32_t)BN * kBK * 2;
+  const uint32_t stage_sz = (uint32_t)(kATile + b_tile) * (split ? 2 : 1);
+  const uint32_t bar_base = smem_base + stage_sz * S;
+  // barrier slots (8 B each): full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b_hi)) : "memory");
+    if (split) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b_lo)) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = args.n_tiles_m * args.n_tiles_n;
+  const int k_iters = args.taps * args.kblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = stage_sz;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = args.tile_list[t / args.n_tiles_n] * kBM;
+        const int n0 = (t % args.n_tiles_n) * BN;
+        for (int tap = 0; tap < args.taps; ++tap) {
+          const int row0 = m0 + args.tap_shift[tap];
+          for (int kb = 0; kb < args.kblocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage_sz * stage;
+            mbar_expect_tx(full_bar(stage), tx);
+            const int kw = (tap * args.kblocks + kb) * kBK;
+            tma_load_2d(sa, &tm_a_hi, kb * kBK, row0, full_bar(stage));
+            if (split) {
+              tma_load_2d(sa + kATile, &tm_a_lo, kb * kBK, row0, full_bar(stage));
+              tma_load_2d(sa + 2 * kATile, &tm_b_hi, kw, n0, full_bar(stage));
+              tma_load_2d(sa + 2 * kATile + b_tile, &tm_b_lo, kw, n0, full_bar(stage));
+            } else {
+              tma_load_2d(sa + kATile, &tm_b_hi, kw, n0, full_bar(stage));
+            }
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int n0 = (t % args.n_tiles_n) * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      int n_eff = args.cout - n0;
+      n_eff = n_eff > BN ? BN : ((n_eff + 15) & ~15);
+      const uint32_t idesc = make_idesc(n_eff);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      uint32_t accumulate = 0;
+      for (int ki = 0; ki < k_iters; ++ki) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const int kb = ki % args.kblocks;
+          const int ksteps = (kb == args.kblocks - 1) ? args.last_ksteps : 4;
+          const uint32_t sa = smem_base + stage_sz * stage;
+          const uint32_t a_hi = sa, a_lo = sa + kATile;
+          const uint32_t b_hi = split ? sa + 2 * kATile : sa + kATile;
+          const uint32_t b_lo = b_hi + b_tile;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t ko = (uint32_t)k * 32u;       // 16 bf16 = 32 bytes along K inside the swizzle atom
+            const uint64_t da = make_smem_desc(a_hi + ko), db = make_smem_desc(b_hi + ko);
+            tc_mma(d_tmem, da, db, idesc, accumulate);
+            accumulate = 1;
+            if (split) {
+              tc_mma(d_tmem, da, make_smem_desc(b_lo + ko), idesc, 1);
+              tc_mma(d_tmem, make_smem_desc(a_lo + ko), db, idesc, 1);
+            }
+          }
+          tc_commit(empty_bar(stage));                    // smem slot is free once these MMAs retire
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1u; }
+      }
+      if (lane == 0) tc_commit(tfull_bar(acc));
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                                // TMEM lane quarter of this warp (== warp % 4)
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int m0 = args.tile_list[t / args.n_tiles_n] * kBM;
+      const int n0 = (t % args.n_tiles_n) * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int v = m0 + q * 32 + lane;                    // virtual row of this thread
+      bool valid = v < args.M_total;
+      int n = 0, y = 0, x = 0;
+      if (valid) {
+        n = v / args.rows_per_img;
+        const int r = v - n * args.rows_per_img;
+        y = r / args.in_Wp;
+        x = r - y * args.in_Wp;
+        valid = (y < args.Ho) && (x < args.Wo);
+      }
+      int ncols = args.cout - n0;
+      ncols = ncols > BN ? BN : ncols;
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      if (args.epi == EPI_SPLIT) {
+        const size_t o = (((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad)) * args.out_Cs + n0;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t vr[32];
+          tmem_ld32(t_row + (uint32_t)c0, vr);
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (c0 + g * 8 < ncols) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float f[2];
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const int col = n0 + c0 + g * 8 + j * 2 + e;
+                    float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + __ldg(args.bias + col);
+                    if (args.bn_scale) xv = xv * __ldg(args.bn_scale + col) + __ldg(args.bn_shift + col);
+                    f[e] = apply_act(xv, args.act);
+                  }
+                  __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
+                  __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0));
+                  __nv_bfloat16 l1 = __float2bfloat16_rn(f[1] - __bfloat162float(h1));
+                  ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint4*>(args.out_hi + o + c0 + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                if (args.out_lo) *reinterpret_cast<uint4*>(args.out_lo + o + c0 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              }
+            }
+          }
+        }
+      } else {
+        const size_t o = (((size_t)n * args.Ho + y) * args.Wo + x) * (size_t)args.cout + n0;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t vr[32];
+          tmem_ld32(t_row + (uint32_t)c0, vr);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < ncols) {
+                const int col = n0 + c0 + j;
+                float xv = __uint_as_float(vr[j]) + __ldg(args.bias + col);
+                args.out_f32[o + c0 + j] = apply_act(xv, args.act);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSDK_CHECK_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tcgen05_kernel<<<L.grid, 256, L.smem, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, L.args);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers: split store
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_store(const ActBuf& o, size_t idx, float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  o.hi[idx] = h;
+  if (o.lo) o.lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ float split_load(const ActBuf& a, size_t idx) {
+  float v = __bfloat162float(a.hi[idx]);
+  if (a.lo) v += __bfloat162float(a.lo[idx]);
+  return v;
+}
+__device__ __forceinline__ size_t act_index(const ActBuf& a, int n, int y, int x) {
+  return (((size_t)n * a.Hp() + (y + a.pad)) * a.Wp() + (x + a.pad)) * a.Cs;
+}
+
+// (x - mean) / std, channel swap (models/keras_ssd300.py:247-272) -> split bf16 planes
+__global__ void preprocess_kernel(const float* __restrict__ img, int B, int H, int W, int Cimg, float3 mean, float3 inv_std,
+                                  int has_std, int3 swap, ActBuf out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * H * W;
+  if (i >= total) return;
+  const int x = (int)(i % W); const int y = (int)((i / W) % H); const int n = (int)(i / ((size_t)W * H));
+  const float* p = img + i * Cimg;
+  float v[3];
+  const float m[3] = {mean.x, mean.y, mean.z};
+  const float s[3] = {inv_std.x, inv_std.y, inv_std.z};
+  for (int c = 0; c < Cimg && c < 3; ++c) {
+    float t = p[c] - m[c];
+    if (has_std) t = t / s[c];          // inv_std holds the divisor itself when has_std
+    v[c] = t;
+  }
+  const int sw[3] = {swap.x, swap.y, swap.z};
+  const size_t o = act_index(out, n, y, x);
+  for (int c = 0; c < Cimg && c < 3; ++c) split_store(out, o + c, v[sw[c]]);
+}
+
+int launch_preprocess(ssdk_ctx* ctx, const float* images, int B, int H, int W, int Cimg, const float* mean, const float* stddev,
+                      const int* swap, const ActBuf& out, cudaStream_t stream) {
+  SSDK_REQUIRE(Cimg == 3, "only 3-channel images are supported (got %d)", Cimg);
+  float3 m = mean ? make_float3(mean[0], mean[1], mean[2]) : make_float3(0, 0, 0);
+  float3 s = stddev ? make_float3(stddev[0], stddev[1], stddev[2]) : make_float3(1, 1, 1);
+  int3 sw = swap ? make_int3(swap[0], swap[1], swap[2]) : make_int3(0, 1, 2);
+  const size_t total = (size_t)B * H * W;
+  preprocess_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(images, B, H, W, Cimg, m, s, stddev ? 1 : 0, sw, out);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// Explicit im2col for the few layers the descriptor trick does not cover (3-channel input, strided convs):
+// out[row = (n, yo, xo)][k = (kh*KW + kw)*Cin + c], zero padded to Kpad columns.
+__global__ void im2col_kernel(ActBuf in, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int Ho, int Wo,
+                              int KH, int KW, int stride, int dil, int pad_t, int pad_l, int Kpad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)in.B * Ho * Wo * Kpad;
+  if (i >= total) return;
+  const int k = (int)(i % Kpad);
+  const size_t row = i / Kpad;
+  const int xo = (int)(row % Wo); const int yo = (int)((row / Wo) % Ho); const int n = (int)(row / ((size_t)Wo * Ho));
+  __nv_bfloat16 h = __float2bfloat16_rn(0.f), l = h;
+  if (k < KH * KW * in.C) {
+    const int c = k % in.C; const int tap = k / in.C; const int kw = tap % KW; const int kh = tap / KW;
+    const int y = yo * stride + kh * dil - pad_t, x = xo * stride + kw * dil - pad_l;
+    if (y >= 0 && y < in.H && x >= 0 && x < in.W) {
+      const size_t s = act_index(in, n, y, x) + c;
+      h = in.hi[s];
+      if (in.lo) l = in.lo[s];
+    }
+  }
+  out_hi[i] = h;
+  if (out_lo) out_lo[i] = l;
+}
+
+int launch_im2col(ssdk_ctx* ctx, const ActBuf& in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int Ho, int Wo, int kh, int kw,
+                  int stride, int dil, int pad_t, int pad_l, int Kpad, cudaStream_t stream) {
+  const size_t total = (size_t)in.B * Ho * Wo * Kpad;
+  im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out_hi, out_lo, Ho, Wo, kh, kw, stride, dil, pad_t, pad_l, Kpad);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// Max pooling; out-of-range window positions are ignored (TF 'same' pooling pads with -inf).
+// One thread per (pixel, group of 8 channels); the max is taken on the reconstructed value hi + lo.
+__global__ void maxpool_kernel(ActBuf in, ActBuf out, int KH, int KW, int stride, int pad_t, int pad_l) {
+  const int groups = in.Cs / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)out.B * out.H * out.W * groups;
+  if (i >= total) return;
+  const int g = (int)(i % groups);
+  const size_t pix = i / groups;
+  const int xo = (int)(pix % out.W); const int yo = (int)((pix / out.W) % out.H); const int n = (int)(pix / ((size_t)out.W * out.H));
+  float best[8];
+  uint32_t bh[8], bl[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bh[e] = 0; bl[e] = 0; }
+  for (int ky = 0; ky < KH; ++ky) {
+    const int y = yo * stride + ky - pad_t;
+    if (y < 0 || y >= in.H) continue;
+    for (int kx = 0; kx < KW; ++kx) {
+      const int x = xo * stride + kx - pad_l;
+      if (x < 0 || x >= in.W) continue;
+      const size_t s = act_index(in, n, y, x) + (size_t)g * 8;
+      const uint4 h4 = *reinterpret_cast<const uint4*>(in.hi + s);
+      uint4 l4 = make_uint4(0, 0, 0, 0);
+      if (in.lo) l4 = *reinterpret_cast<const uint4*>(in.lo + s);
+      const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t hb = (hw[e >> 1] >> ((e & 1) * 16)) & 0xffffu, lb = (lw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+        if (v > best[e]) { best[e] = v; bh[e] = hb; bl[e] = lb; }
+      }
+    }
+  }
+  const size_t o = act_index(out, n, yo, xo) + (size_t)g * 8;
+  uint4 oh, ol;
+  oh.x = bh[0] | (bh[1] << 16); oh.y = bh[2] | (bh[3] << 16); oh.z = bh[4] | (bh[5] << 16); oh.w = bh[6] | (bh[7] << 16);
+  ol.x = bl[0] | (bl[1] << 16); ol.y = bl[2] | (bl[3] << 16); ol.z = bl[4] | (bl[5] << 16); ol.w = bl[6] | (bl[7] << 16);
+  *reinterpret_cast<uint4*>(out.hi + o) = oh;
+  if (out.lo) *reinterpret_cast<uint4*>(out.lo + o) = ol;
+}
+
+int launch_maxpool(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, int kh, int kw, int stride, int pad_t, int pad_l,
+                   cudaStream_t stream) {
+  const size_t total = (size_t)out.B * out.H * out.W * (in.Cs / 8);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, kh, kw, stride, pad_t, pad_l);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// L2Normalization (keras_layer_L2Normalization.py:61-63): x * rsqrt(max(sum_c x^2, 1e-12)) * gamma_c, one warp per pixel.
+__global__ void l2norm_kernel(ActBuf in, ActBuf out, const float* __restrict__ gamma) {
+  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)in.B * in.H * in.W;
+  if (pix >= total) return;
+  const int x = (int)(pix % in.W); const int y = (int)((pix / in.W) % in.H); const int n = (int)(pix / ((size_t)in.W * in.H));
+  const size_t s = act_index(in, n, y, x), o = act_index(out, n, y, x);
+  float ss = 0.f;
+  for (int c = lane; c < in.C; c += 32) { float v = split_load(in, s + c); ss += v * v; }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  for (int c = lane; c < in.C; c += 32) split_store(out, o + c, split_load(in, s + c) * inv * __ldg(gamma + c));
+}
+
+int launch_l2norm(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* gamma, cudaStream_t stream) {
+  const size_t total = (size_t)in.B * in.H * in.W;
+  l2norm_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(in, out, gamma);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// Reshape / softmax / Concat (models/keras_ssd300.py:363-419): one warp per prior.
+// head row layout per pixel: n_boxes x [C class logits | 4 box offsets].
+__global__ void head_finalize_kernel(const float* __restrict__ head, int B, int HW, int n_boxes, int C, int P, int prior_off,
+                                     const float* __restrict__ anchors, float4 var, float* __restrict__ y_pred) {
+  const size_t wid = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)B * HW * n_boxes;
+  if (wid >= total) return;
+  const int b = (int)(wid % n_boxes); const size_t pix = wid / n_boxes;
+  const int n = (int)(pix / HW); const int p_local = (int)(pix % HW) * n_boxes + b;
+  const float* src = head + pix * (size_t)n_boxes * (C + 4) + (size_t)b * (C + 4);
+  float* dst = y_pred + ((size_t)n * P + prior_off + p_local) * (C + 12);
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, src[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(src[c] - mx);
+  sum = warp_sum(sum);
+  for (int c = lane; c < C; c += 32) dst[c] = expf(src[c] - mx) / sum;
+  if (lane < 4) {
+    dst[C + lane] = src[C + lane];
+    dst[C + 4 + lane] = anchors[(size_t)(prior_off + p_local) * 4 + lane];
+    const float v[4] = {var.x, var.y, var.z, var.w};
+    dst[C + 8 + lane] = v[lane];
+  }
+}
+
+int launch_head_finalize(ssdk_ctx* ctx, const float* head, int B, int HW, int n_boxes, int C, int P, int prior_off,
+                         const float* anchors, const float* variances, float* y_pred, cudaStream_t stream) {
+  const size_t total = (size_t)B * HW * n_boxes;
+  head_finalize_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(head, B, HW, n_boxes, C, P, prior_off, anchors,
+                                                                        make_float4(variances[0], variances[1], variances[2], variances[3]), y_pred);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+__global__ void l2norm_f32_kernel(const float* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
+                                  float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* p = x + r * C;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) { float v = p[c]; ss += v * v; }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  for (int c = lane; c < C; c += 32) out[r * C + c] = p[c] * inv * __ldg(gamma + c);
+}
+
+__global__ void unpack_kernel(ActBuf in, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)in.B * in.H * in.W * in.C;
+  if (i >= total) return;
+  const int c = (int)(i % in.C); const size_t pix = i / in.C;
+  const int x = (int)(pix % in.W); const int y = (int)((pix / in.W) % in.H); const int n = (int)(pix / ((size_t)in.W * in.H));
+  out[i] = split_load(in, act_index(in, n, y, x) + c);
+}
+
+int launch_unpack(ssdk_ctx* ctx, const ActBuf& in, float* out, cudaStream_t stream) {
+  const size_t total = (size_t)in.B * in.H * in.W * in.C;
+  unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+}  // namespace ssdk
+
+extern "C" int ssdk_l2_normalize(ssdk_ctx* ctx, const float* x_dev, long long rows, int C, const float* gamma_dev, float* out_dev,
+                                 void* stream) {
+  using namespace ssdk;
+  SSDK_REQUIRE(ctx && x_dev && gamma_dev && out_dev && rows > 0 && C > 0, "ssdk_l2_normalize: bad argument");
+  l2norm_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x_dev, rows, C, gamma_dev, out_dev);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}

@@ -1,0 +1,80 @@
+// Internal interface between model.cu (plan building) and conv.cu (kernels).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace ssdk {
+
+// An activation tensor: NHWC, channel-padded to a multiple of 8, spatially padded with a zero border
+// of `pad` pixels, stored as TWO bf16 planes: value = hi + lo (lo is absent in single-pass bf16 mode).
+// hi + lo carries 16 significant bits, which keeps the tcgen05 path within ~1e-5 of an fp32 conv.
+struct ActBuf {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;   // logical shape
+  int Cs = 0;                        // stored channels (multiple of 8)
+  int pad = 0;
+  __host__ __device__ int Hp() const { return H + 2 * pad; }
+  __host__ __device__ int Wp() const { return W + 2 * pad; }
+  size_t rows() const { return (size_t)B * Hp() * Wp(); }
+  size_t elems() const { return rows() * Cs; }
+};
+
+enum { EPI_SPLIT = 0, EPI_F32 = 1 };
+
+constexpr int kMaxTaps = 25;
+
+struct ConvArgs {
+  // GEMM view
+  int M_total;          // virtual rows (B * rows_per_img)
+  int rows_per_img;     // rows of the virtual grid per image
+  int in_Wp;            // virtual row pitch
+  int Ho, Wo, B;        // valid extent: virtual (y, x) is a real output iff y < Ho && x < Wo
+  int taps, kblocks;    // K loop = taps * kblocks blocks of 64 channels
+  int last_ksteps;      // UMMA k-steps (of 16) in the last k-block of every tap (1..4)
+  int tap_shift[kMaxTaps];
+  int n_tiles_m;        // number of entries in tile_list
+  int n_tiles_n;
+  const int* tile_list; // m-tile indices that contain at least one valid row
+  int BN;               // accumulator tile width (64/128/256); TMA box rows of the weight tile
+  int cout;
+  int split;            // 1: bf16x3 (hi*hi + hi*lo + lo*hi), 0: single bf16 pass
+  int stages;
+  // epilogue
+  int epi;
+  const float* bias; const float* bn_scale; const float* bn_shift;
+  int act;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int out_Hp, out_Wp, out_pad, out_Cs;
+  float* out_f32;       // EPI_F32: compact [B*Ho*Wo][cout]
+};
+
+struct ConvLaunch {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  ConvArgs args;
+  int grid;
+  size_t smem;
+  double flops_algo, flops_issued;
+};
+
+int tma_init();   // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows);
+size_t conv_smem_bytes(int BN, int split, int stages);
+int conv_pick_stages(int BN, int split);
+int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream);
+
+// elementwise / data movement kernels
+int launch_preprocess(ssdk_ctx* ctx, const float* images, int B, int H, int W, int Cimg, const float* mean, const float* stddev,
+                      const int* swap, const ActBuf& out, cudaStream_t stream);
+int launch_im2col(ssdk_ctx* ctx, const ActBuf& in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int Ho, int Wo, int kh, int kw,
+                  int stride, int dil, int pad_t, int pad_l, int Kpad, cudaStream_t stream);
+int launch_maxpool(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, int kh, int kw, int stride, int pad_t, int pad_l,
+                   cudaStream_t stream);
+int launch_l2norm(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* gamma, cudaStream_t stream);
+int launch_head_finalize(ssdk_ctx* ctx, const float* head, int B, int HW, int n_boxes, int C, int P, int prior_off,
+                         const float* anchors, const float* variances, float* y_pred, cudaStream_t stream);
+int launch_unpack(ssdk_ctx* ctx, const ActBuf& in, float* out, cudaStream_t stream);
+
+}  // namespace ssdk

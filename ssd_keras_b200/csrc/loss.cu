@@ -1,0 +1,322 @@
+// SSDLoss on sm_100a.  Reference: keras_loss_function/keras_ssd_loss.py:53-211.
+//
+// HBM-bound: the two (B,P,C+12) tensors are read exactly once per pass by warp-per-row kernels
+// (coalesced row reads, shuffle reductions).  The batch-global hard-negative top-k (tf.nn.top_k over
+// B*P values, :179-183) is a 4-pass radix select on the float bits done by one CTA over the per-box
+// negative losses (B*P floats, L2 resident); ties at the threshold value are resolved by flat index
+// like tf.nn.top_k.  All cross-block sums go through per-block partials reduced in a fixed order, so
+// the result is deterministic.
+//   loss_box_kernel     per-box log-loss / smooth-L1, positives, negatives; per-block partial sums
+//   loss_select_kernel  n_positive, k, threshold key and tie index limit
+//   loss_negsum_kernel  masked negative sums per image
+//   loss_final_kernel   (pos + neg + alpha*loc) / max(1, n_pos) * B
+//   loss_grad_kernel    d loss / d y_pred (mask held constant)
+#include "common.cuh"
+#include <cmath>
+
+using namespace ssdk;
+
+namespace {
+
+constexpr int kRowsPerBlock = 256;     // 8 warps x 32 rows
+constexpr int kSelThreads = 1024;
+
+struct SelResult {
+  uint32_t T;        // orderable key of the k-th largest negative loss
+  int limit;         // ties (key == T) are taken iff flat index <= limit
+  int none;          // 1: no negatives are kept (k == 0 or no non-zero negative loss)
+  int k, n_pos, nnz, ties_taken;
+  float inv_norm;    // 1 / max(1, n_positive)
+};
+
+__device__ __forceinline__ uint32_t okey(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// partial layout per (b, blk): [0] sum cls*pos, [1] sum loc*pos, [2] sum pos, [3] count nonzero(cls*neg)
+__global__ void __launch_bounds__(256) loss_box_kernel(const float* __restrict__ y_true, const float* __restrict__ y_pred,
+                                                       int P, int C, float* __restrict__ cls_out, float* __restrict__ negl_out,
+                                                       double* __restrict__ partial) {
+  __shared__ double s_acc[8][4];
+  const int W = C + 12;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double a_pc = 0, a_loc = 0, a_pos = 0, a_nnz = 0;
+  for (int r = 0; r < 32; ++r) {
+    const int p = blk * kRowsPerBlock + warp * 32 + r;
+    if (p >= P) break;
+    const float* yt = y_true + ((size_t)b * P + p) * W;
+    const float* yp = y_pred + ((size_t)b * P + p) * W;
+    float acc = 0.f, pmax = -INFINITY;
+    for (int c = lane; c < C; c += 32) {
+      float t = yt[c];
+      if (t != 0.f) acc += t * logf(fmaxf(yp[c], 1e-15f));          // :93-95
+      if (c >= 1) pmax = fmaxf(pmax, t);                             // :140
+    }
+    float l = 0.f;
+    if (lane < 4) {
+      float d = yt[C + lane] - yp[C + lane];
+      float ad = fabsf(d);
+      l = (ad < 1.0f) ? 0.5f * d * d : ad - 0.5f;                    // :72-74
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    acc = warp_sum(acc);
+    pmax = warp_max(pmax);
+    if (lane == 0) {
+      float cls = -acc;
+      float neg = yt[0];                                             // :139
+      float nl = cls * neg;                                          // :151
+      cls_out[(size_t)b * P + p] = cls;
+      negl_out[(size_t)b * P + p] = nl;
+      a_pc += (double)(cls * pmax);
+      a_loc += (double)(l * pmax);
+      a_pos += (double)pmax;
+      a_nnz += (nl != 0.f) ? 1.0 : 0.0;
+    }
+  }
+  if (lane == 0) { s_acc[warp][0] = a_pc; s_acc[warp][1] = a_loc; s_acc[warp][2] = a_pos; s_acc[warp][3] = a_nnz; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
+    partial[((size_t)b * gridDim.x + blk) * 4 + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) loss_select_kernel(const float* __restrict__ negl, int N, int B, int nblk,
+                                                                  const double* __restrict__ partial, int neg_pos_ratio,
+                                                                  int n_neg_min, SelResult* __restrict__ res) {
+  __shared__ int s_hist[256];
+  __shared__ int s_misc[4];
+  __shared__ double s_red[2];
+  __shared__ int s_w[kSelThreads / 32];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    double np = 0, nnz = 0;
+    for (int i = 0; i < B * nblk; ++i) { np += partial[(size_t)i * 4 + 2]; nnz += partial[(size_t)i * 4 + 3]; }
+    s_red[0] = np; s_red[1] = nnz;
+  }
+  __syncthreads();
+  const float n_pos_f = (float)s_red[0];
+  const int n_pos = (int)n_pos_f;                                       // tf.to_int32(n_positive)
+  const int nnz = (int)s_red[1];
+  int k = neg_pos_ratio * n_pos;
+  k = k > n_neg_min ? k : n_neg_min;
+  k = k < nnz ? k : nnz;                                                // :166
+  if (tid == 0) {
+    res->k = k; res->n_pos = n_pos; res->nnz = nnz; res->ties_taken = 0;
+    res->inv_norm = 1.0f / fmaxf(1.0f, n_pos_f);
+    res->none = (k <= 0 || nnz == 0) ? 1 : 0;
+    res->T = 0; res->limit = 0x7fffffff;
+  }
+  if (k <= 0 || nnz == 0) return;
+  uint32_t prefix = 0, mask = 0;
+  int want = k, ties_total = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += kSelThreads) {
+      uint32_t key = okey(negl[i]);
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, bsel = 0;
+      for (int bb = 255; bb >= 0; --bb) {
+        if (acc + s_hist[bb] >= want) { bsel = bb; break; }
+        acc += s_hist[bb];
+      }
+      s_misc[0] = bsel; s_misc[1] = want - acc; s_misc[2] = s_hist[bsel];
+    }
+    __syncthreads();
+    prefix |= ((uint32_t)s_misc[0]) << shift;
+    mask |= 0xFFu << shift;
+    want = s_misc[1];
+    ties_total = s_misc[2];
+    __syncthreads();
+  }
+  const uint32_t T = prefix;
+  int limit = 0x7fffffff;
+  if (want < ties_total) {
+    // ordered scan: flat index of the `want`-th element with key == T (tf.nn.top_k: lower index first)
+    int base_cnt = 0;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int base = 0; base < N; base += kSelThreads) {
+      int i = base + tid;
+      bool tie = (i < N) && (okey(negl[i]) == T);
+      unsigned bal = __ballot_sync(0xffffffffu, tie);
+      if (lane == 0) s_w[warp] = __popc(bal);
+      __syncthreads();
+      int wbase = 0, total = 0;
+      for (int w = 0; w < kSelThreads / 32; ++w) { int c = s_w[w]; if (w < warp) wbase += c; total += c; }
+      int rank = base_cnt + wbase + __popc(bal & ((1u << lane) - 1));   // 0-based rank among ties
+      if (tie && rank == want - 1) s_misc[3] = i;
+      __syncthreads();
+      base_cnt += total;
+      if (base_cnt >= want) break;                                       // uniform
+    }
+    __syncthreads();
+    limit = s_misc[3];
+  }
+  if (tid == 0) { res->T = T; res->limit = limit; res->ties_taken = want; }
+}
+
+__device__ __forceinline__ bool neg_taken(const SelResult& r, float nl, int flat) {
+  if (r.none) return false;
+  uint32_t key = okey(nl);
+  return key > r.T || (key == r.T && flat <= r.limit);
+}
+
+__global__ void __launch_bounds__(256) loss_negsum_kernel(const float* __restrict__ cls, const float* __restrict__ negl, int P,
+                                                          const SelResult* __restrict__ res, double* __restrict__ partial2) {
+  __shared__ double s_acc[8];
+  const SelResult r = *res;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int p = blk * 256 + threadIdx.x;
+  double v = 0;
+  if (p < P) {
+    const int flat = b * P + p;
+    if (neg_taken(r, negl[flat], flat)) v = (double)cls[flat];
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += s_acc[w];
+    partial2[(size_t)b * gridDim.x + blk] = t;
+  }
+}
+
+__global__ void loss_final_kernel(const double* __restrict__ partial, const double* __restrict__ partial2, int B, int nblk,
+                                  int nblk2, float alpha, const SelResult* __restrict__ res, float* __restrict__ out,
+                                  int* __restrict__ stats) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && stats) { stats[0] = res->n_pos; stats[1] = res->nnz; stats[2] = res->none ? 0 : res->k; stats[3] = res->ties_taken; }
+  if (b >= B) return;
+  double pc = 0, loc = 0, ng = 0;
+  for (int i = 0; i < nblk; ++i) { pc += partial[((size_t)b * nblk + i) * 4 + 0]; loc += partial[((size_t)b * nblk + i) * 4 + 1]; }
+  for (int i = 0; i < nblk2; ++i) ng += partial2[(size_t)b * nblk2 + i];
+  double total = (pc + ng + (double)alpha * loc) * (double)res->inv_norm;   // :204
+  out[b] = (float)(total * (double)B);                                       // :209
+}
+
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ y_true, const float* __restrict__ y_pred,
+                                                        int B, int P, int C, const float* __restrict__ negl,
+                                                        const SelResult* __restrict__ res, const float* __restrict__ upstream,
+                                                        float alpha, float* __restrict__ grad) {
+  const SelResult r = *res;
+  const int W = C + 12;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float up = upstream ? upstream[b] : (1.0f / (float)B);
+  const float scale = up * (float)B * r.inv_norm;
+  for (int rr = 0; rr < 32; ++rr) {
+    const int p = blk * kRowsPerBlock + warp * 32 + rr;
+    if (p >= P) break;
+    const size_t ro = ((size_t)b * P + p) * W;
+    const float* yt = y_true + ro;
+    const float* yp = y_pred + ro;
+    float pmax = -INFINITY;
+    for (int c = lane; c < C; c += 32)
+      if (c >= 1) pmax = fmaxf(pmax, yt[c]);                               // classes 1..C-1
+    pmax = warp_max(pmax);
+    const int flat = b * P + p;
+    float take = neg_taken(r, negl[flat], flat) ? 1.f : 0.f;
+    const float w_cls = (pmax + take) * scale;
+    const float w_loc = pmax * scale * alpha;
+    for (int c = lane; c < W; c += 32) {
+      float g = 0.f;
+      if (c < C) {
+        float t = yt[c];
+        if (t != 0.f) { float q = yp[c]; g = (q >= 1e-15f) ? (-t / q) * w_cls : 0.f; }
+      } else if (c < C + 4) {
+        float d = yp[c] - yt[c];
+        g = ((fabsf(d) < 1.0f) ? d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * w_loc;
+      }
+      grad[ro + c] = g;
+    }
+  }
+}
+
+struct LossWs {
+  float* cls; float* negl; double* partial; double* partial2; SelResult* res;
+  int nblk;
+};
+
+int loss_prepare(ssdk_ctx* ctx, int B, int P, LossWs& w) {
+  const size_t N = (size_t)B * P;
+  w.nblk = ceil_div(P, kRowsPerBlock);
+  size_t o_cls = 0, o_negl = (N * 4 + 255) / 256 * 256;
+  size_t o_part = o_negl + (N * 4 + 255) / 256 * 256;
+  size_t o_part2 = o_part + ((size_t)B * w.nblk * 4 * 8 + 255) / 256 * 256;
+  size_t o_res = o_part2 + ((size_t)B * w.nblk * 8 + 255) / 256 * 256;
+  size_t total = o_res + 256;
+  int rc = ctx->ws[2].ensure(total);
+  if (rc) return rc;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ctx->ws[2].ptr);
+  w.cls = reinterpret_cast<float*>(base + o_cls); w.negl = reinterpret_cast<float*>(base + o_negl);
+  w.partial = reinterpret_cast<double*>(base + o_part); w.partial2 = reinterpret_cast<double*>(base + o_part2);
+  w.res = reinterpret_cast<SelResult*>(base + o_res);
+  return SSDK_OK;
+}
+
+int loss_common(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C, int ratio, int n_neg_min,
+                LossWs& w, cudaStream_t stream) {
+  int rc = loss_prepare(ctx, B, P, w);
+  if (rc) return rc;
+  dim3 grid(w.nblk, B);
+  loss_box_kernel<<<grid, 256, 0, stream>>>(y_true, y_pred, P, C, w.cls, w.negl, w.partial);
+  SSDK_COUNT_LAUNCH(ctx);
+  loss_select_kernel<<<1, kSelThreads, 0, stream>>>(w.negl, B * P, B, w.nblk, w.partial, ratio, n_neg_min, w.res);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+int check_args(ssdk_ctx* ctx, const float* yt, const float* yp, int B, int P, int C) {
+  SSDK_REQUIRE(ctx && yt && yp, "ssd_loss: NULL argument");
+  SSDK_REQUIRE(B > 0 && P > 0 && C > 1, "ssd_loss: bad shape");
+  SSDK_REQUIRE((long long)B * P < (1ll << 31), "ssd_loss: B*P too large");
+  return SSDK_OK;
+}
+
+}  // namespace
+
+extern "C" int ssdk_ssd_loss_fwd(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C,
+                                 int neg_pos_ratio, int n_neg_min, float alpha, float* out_loss, int* out_stats, void* stream_) {
+  int rc = check_args(ctx, y_true, y_pred, B, P, C);
+  if (rc) return rc;
+  SSDK_REQUIRE(out_loss != nullptr, "ssd_loss: out_loss is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LossWs w;
+  rc = loss_common(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, w, stream);
+  if (rc) return rc;
+  const int nblk2 = ceil_div(P, 256);
+  dim3 grid(nblk2, B);
+  loss_negsum_kernel<<<grid, 256, 0, stream>>>(w.cls, w.negl, P, w.res, w.partial2);
+  SSDK_COUNT_LAUNCH(ctx);
+  loss_final_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(w.partial, w.partial2, B, w.nblk, nblk2, alpha, w.res, out_loss, out_stats);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_ssd_loss_bwd(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C,
+                                 int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream, float* out_grad,
+                                 void* stream_) {
+  int rc = check_args(ctx, y_true, y_pred, B, P, C);
+  if (rc) return rc;
+  SSDK_REQUIRE(out_grad != nullptr, "ssd_loss_bwd: out_grad is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  LossWs w;
+  rc = loss_common(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, w, stream);
+  if (rc) return rc;
+  dim3 grid(w.nblk, B);
+  loss_grad_kernel<<<grid, 256, 0, stream>>>(y_true, y_pred, B, P, C, w.negl, w.res, upstream, alpha, out_grad);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}

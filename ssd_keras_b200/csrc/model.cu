@@ -1,0 +1,418 @@
+// Static execution plan for the SSD graphs (models/keras_ssd300.py:263-419, keras_ssd512.py, keras_ssd7.py:266-393).
+// The host (Python, mirroring the reference builders) describes the graph layer by layer; this file sizes the
+// zero-bordered activation buffers, packs the weights into K-major bf16 hi/lo planes, builds the TMA descriptors
+// and tile lists once, and replays the kernel sequence on every forward call.
+#include "conv.cuh"
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+using namespace ssdk;
+
+namespace {
+
+inline uint16_t f2bf(float f) {                  // round-to-nearest-even float -> bf16
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+struct LayerPlan {
+  ssdk_layer_desc d{};
+  int H = 0, W = 0, C = 0;            // logical output shape
+  int in_H = 0, in_W = 0, in_C = 0;
+  ActBuf out;                         // INPUT / CONV / MAXPOOL / L2NORM
+  bool im2col = false;
+  int Kpad = 0;
+  __nv_bfloat16* col_hi = nullptr; __nv_bfloat16* col_lo = nullptr;
+  __nv_bfloat16* w_hi = nullptr; __nv_bfloat16* w_lo = nullptr;
+  float* bias = nullptr; float* bn_scale = nullptr; float* bn_shift = nullptr; float* gamma = nullptr;
+  int* tile_list = nullptr;
+  ConvLaunch launch{};
+  float* head_f32 = nullptr;
+  int prior_off = 0;
+  int need_pad = 0;                   // border required by the consumers of this layer's output
+  float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};
+  bool has_mean = false, has_std = false, has_swap = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace
+
+struct ssdk_model {
+  ssdk_ctx* ctx = nullptr;
+  int B = 0, H = 0, W = 0, Cimg = 0, Ctot = 0, P = 0, split = 1;
+  std::vector<LayerPlan> layers;
+  float* d_anchors = nullptr;
+  float var[4] = {0, 0, 0, 0};
+  double flops_algo = 0, flops_issued = 0;
+  int timing = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(ssdk_model* m, T** out, size_t count, bool zero) {
+  void* p = nullptr;
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return SSDK_ERR_NOMEM; }
+  if (zero) { e = cudaMemset(p, 0, bytes); if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return SSDK_ERR_CUDA; } }
+  m->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return SSDK_OK;
+}
+
+int upload_f32(ssdk_model* m, float** out, const float* host, size_t n) {
+  int rc = dev_alloc(m, out, n, false);
+  if (rc) return rc;
+  SSDK_CHECK_CUDA(cudaMemcpy(*out, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  return SSDK_OK;
+}
+
+int alloc_act(ssdk_model* m, ActBuf& a, int B, int H, int W, int C, int pad) {
+  a.B = B; a.H = H; a.W = W; a.C = C; a.Cs = (C + 7) / 8 * 8; a.pad = pad;
+  size_t n = a.elems() + 64 * 8;         // slack: TMA boxes may start on the last rows
+  int rc = dev_alloc(m, &a.hi, n, true);
+  if (rc) return rc;
+  if (m->split) { rc = dev_alloc(m, &a.lo, n, true); if (rc) return rc; }
+  return SSDK_OK;
+}
+
+// Pack an HWIO float32 kernel (optionally two kernels fused per box: conf + loc) into K-major bf16 hi/lo planes
+// [cout][taps][kblocks*64] (virtual path) or [cout][kblocks*64] with k = (kh*KW+kw)*cin + c (im2col path).
+void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, bool im2col, int Ctot,
+                  std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, std::vector<float>& bias) {
+  const ssdk_layer_desc& d = L.d;
+  const size_t Krow = im2col ? (size_t)kblocks * 64 : (size_t)taps * kblocks * 64;
+  hi.assign((size_t)cout * Krow, 0); lo.assign((size_t)cout * Krow, 0);
+  bias.assign(cout, 0.f);
+  const bool head = d.op == SSDK_OP_HEAD;
+  const int nb = d.n_boxes;
+  const int c_conf = head ? nb * Ctot : cout;       // channels of the first kernel
+  const int c_loc = head ? nb * 4 : 0;
+  for (int o = 0; o < cout; ++o) {
+    const float* ker; int oc, ocn;
+    if (!head) { ker = d.kernel; oc = o; ocn = c_conf; bias[o] = d.bias ? d.bias[o] : 0.f; }
+    else {
+      const int b = o / (Ctot + 4), r = o % (Ctot + 4);
+      if (r < Ctot) { ker = d.kernel; oc = b * Ctot + r; ocn = c_conf; bias[o] = d.bias ? d.bias[oc] : 0.f; }
+      else { ker = d.kernel2; oc = b * 4 + (r - Ctot); ocn = c_loc; bias[o] = d.bias2 ? d.bias2[oc] : 0.f; }
+    }
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < cin; ++c) {
+        const float w = ker[((size_t)t * cin + c) * ocn + oc];       // HWIO: ((kh*KW+kw)*cin + c)*cout + o
+        const size_t k = im2col ? (size_t)t * cin + c : (size_t)t * kblocks * 64 + c;
+        const uint16_t h = f2bf(w);
+        hi[(size_t)o * Krow + k] = h;
+        lo[(size_t)o * Krow + k] = f2bf(w - bf2f(h));
+      }
+  }
+}
+
+int build_conv(ssdk_model* m, int li) {
+  LayerPlan& L = m->layers[li];
+  const ssdk_layer_desc& d = L.d;
+  const LayerPlan& in = m->layers[d.input];
+  const ActBuf& ia = in.out;
+  const int cin = in.C;
+  const bool head = d.op == SSDK_OP_HEAD;
+  const int cout = head ? d.n_boxes * (m->Ctot + 4) : d.cout;
+  const int taps = d.kh * d.kw;
+  SSDK_REQUIRE(taps <= kMaxTaps, "conv kernel %dx%d is larger than the supported %d taps", d.kh, d.kw, kMaxTaps);
+  SSDK_REQUIRE(head || cout % 8 == 0, "conv output channels must be a multiple of 8 (got %d)", cout);
+  L.im2col = (d.stride != 1) || (cin < 8);
+  ConvLaunch& cl = L.launch;
+  ConvArgs& a = cl.args;
+  memset(&a, 0, sizeof(a));
+  const int Ho = L.H, Wo = L.W;
+  int kblocks, ktot;
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;
+  uint64_t a_inner, a_rows;
+  if (L.im2col) {
+    L.Kpad = (taps * cin + 7) / 8 * 8;
+    kblocks = (L.Kpad + 63) / 64;
+    ktot = L.Kpad;
+    size_t n = (size_t)m->B * Ho * Wo * L.Kpad + 64 * 8;
+    int rc = dev_alloc(m, &L.col_hi, n, true); if (rc) return rc;
+    if (m->split) { rc = dev_alloc(m, &L.col_lo, n, true); if (rc) return rc; }
+    a.M_total = m->B * Ho * Wo; a.rows_per_img = Ho * Wo; a.in_Wp = Wo;
+    a.taps = 1; a.tap_shift[0] = 0;
+    a_hi = L.col_hi; a_lo = L.col_lo; a_inner = L.Kpad; a_rows = (uint64_t)a.M_total;
+  } else {
+    SSDK_REQUIRE(ia.pad >= std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)), "internal: activation border too small");
+    kblocks = (ia.Cs + 63) / 64;
+    ktot = ia.Cs;
+    a.M_total = m->B * ia.Hp() * ia.Wp(); a.rows_per_img = ia.Hp() * ia.Wp(); a.in_Wp = ia.Wp();
+    a.taps = taps;
+    for (int kh = 0; kh < d.kh; ++kh)
+      for (int kw = 0; kw < d.kw; ++kw)
+        a.tap_shift[kh * d.kw + kw] = (kh * d.dilation - d.pad_t + ia.pad) * ia.Wp() + (kw * d.dilation - d.pad_l + ia.pad);
+    a_hi = ia.hi; a_lo = ia.lo; a_inner = ia.Cs; a_rows = (uint64_t)a.M_total;
+  }
+  a.kblocks = kblocks;
+  a.last_ksteps = (ktot - (kblocks - 1) * 64 + 15) / 16;
+  a.Ho = Ho; a.Wo = Wo; a.B = m->B;
+  a.cout = cout;
+  a.BN = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
+  a.n_tiles_n = (cout + a.BN - 1) / a.BN;
+  a.split = m->split;
+  a.stages = conv_pick_stages(a.BN, a.split);
+  SSDK_REQUIRE(a.stages >= 2, "internal: not enough shared memory for a 2-stage pipeline");
+  // m-tiles that hold at least one valid output row
+  std::vector<int> tiles;
+  const int n_m = (a.M_total + 127) / 128;
+  for (int t = 0; t < n_m; ++t) {
+    bool any = false;
+    for (int r = 0; r < 128 && !any; ++r) {
+      long long v = (long long)t * 128 + r;
+      if (v >= a.M_total) break;
+      int rr = (int)(v % a.rows_per_img);
+      any = (rr / a.in_Wp < Ho) && (rr % a.in_Wp < Wo);
+    }
+    if (any) tiles.push_back(t);
+  }
+  a.n_tiles_m = (int)tiles.size();
+  int rc = dev_alloc(m, &L.tile_list, tiles.size(), false); if (rc) return rc;
+  SSDK_CHECK_CUDA(cudaMemcpy(L.tile_list, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+  a.tile_list = L.tile_list;
+  // weights
+  std::vector<uint16_t> whi, wlo; std::vector<float> bias;
+  pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias);
+  const size_t Krow = whi.size() / cout;
+  rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
+  SSDK_CHECK_CUDA(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
+  if (m->split) {
+    rc = dev_alloc(m, &L.w_lo, wlo.size(), false); if (rc) return rc;
+    SSDK_CHECK_CUDA(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+  }
+  rc = upload_f32(m, &L.bias, bias.data(), bias.size()); if (rc) return rc;
+  a.bias = L.bias;
+  if (d.bn_scale && d.bn_shift && !head) {
+    rc = upload_f32(m, &L.bn_scale, d.bn_scale, cout); if (rc) return rc;
+    rc = upload_f32(m, &L.bn_shift, d.bn_shift, cout); if (rc) return rc;
+    a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
+  }
+  a.act = d.act;
+  if (head) {
+    a.epi = EPI_F32;
+    rc = dev_alloc(m, &L.head_f32, (size_t)m->B * Ho * Wo * cout, true); if (rc) return rc;
+    a.out_f32 = L.head_f32;
+  } else {
+    a.epi = EPI_SPLIT;
+    a.out_hi = L.out.hi; a.out_lo = L.out.lo; a.out_Hp = L.out.Hp(); a.out_Wp = L.out.Wp(); a.out_pad = L.out.pad; a.out_Cs = L.out.Cs;
+  }
+  // TMA descriptors
+  rc = make_tmap_2d(&cl.a_hi, a_hi, a_inner, a_rows, a_inner * 2, 64, 128); if (rc) return rc;
+  rc = make_tmap_2d(&cl.b_hi, L.w_hi, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
+  if (m->split) {
+    rc = make_tmap_2d(&cl.a_lo, a_lo, a_inner, a_rows, a_inner * 2, 64, 128); if (rc) return rc;
+    rc = make_tmap_2d(&cl.b_lo, L.w_lo, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
+  } else { cl.a_lo = cl.a_hi; cl.b_lo = cl.b_hi; }
+  const int total_tiles = a.n_tiles_m * a.n_tiles_n;
+  cl.grid = std::max(1, std::min(total_tiles, m->ctx->sm_count));
+  cl.smem = conv_smem_bytes(a.BN, a.split, a.stages);
+  cl.flops_algo = 2.0 * m->B * Ho * Wo * (double)taps * cin * cout;
+  double issued = 0;
+  for (int nt = 0; nt < a.n_tiles_n; ++nt) {
+    int ne = std::min(a.BN, ((cout - nt * a.BN) + 15) / 16 * 16);
+    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)a.taps * ((kblocks - 1) * 64 + a.last_ksteps * 16);
+  }
+  cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
+  m->flops_algo += cl.flops_algo; m->flops_issued += cl.flops_issued;
+  return SSDK_OK;
+}
+
+}  // namespace
+
+extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssdk_model** out) {
+  SSDK_REQUIRE(ctx && desc && out && desc->layers && desc->n_layers > 0, "ssdk_model_create: bad argument");
+  SSDK_REQUIRE(desc->batch > 0 && desc->img_height > 0 && desc->img_width > 0, "ssdk_model_create: bad input shape");
+  SSDK_REQUIRE(desc->precision == 0 || desc->precision == 1, "ssdk_model_create: precision must be 0 (bf16x3) or 1 (bf16)");
+  SSDK_REQUIRE(ctx->prop.major == 10, "libssdk's convolution kernels need an sm_100 (Blackwell) GPU, found sm_%d%d; there is no fallback",
+               ctx->prop.major, ctx->prop.minor);
+  SSDK_CHECK_CUDA(cudaSetDevice(ctx->device));
+  ssdk_model* m = new ssdk_model();
+  m->ctx = ctx; m->B = desc->batch; m->H = desc->img_height; m->W = desc->img_width; m->Cimg = desc->img_channels;
+  m->Ctot = desc->n_classes_total; m->split = desc->precision == 0 ? 1 : 0;
+  for (int i = 0; i < 4; ++i) m->var[i] = desc->variances[i];
+  const int n = desc->n_layers;
+  m->layers.resize(n);
+  int rc = SSDK_OK;
+  auto fail = [&](int code) { ssdk_model_destroy(m); return code; };
+  // pass 1: shapes
+  for (int i = 0; i < n; ++i) {
+    LayerPlan& L = m->layers[i];
+    L.d = desc->layers[i];
+    const ssdk_layer_desc& d = L.d;
+    if (d.op == SSDK_OP_INPUT) {
+      L.H = m->H; L.W = m->W; L.C = m->Cimg;
+      if (d.mean) { L.has_mean = true; for (int c = 0; c < 3; ++c) L.mean[c] = d.mean[c]; }
+      if (d.stddev) { L.has_std = true; for (int c = 0; c < 3; ++c) L.stddev[c] = d.stddev[c]; }
+      if (d.swap) { L.has_swap = true; for (int c = 0; c < 3; ++c) L.swap[c] = d.swap[c]; }
+      continue;
+    }
+    if (!(d.input >= 0 && d.input < i)) { set_error("layer %d: input %d must refer to an earlier layer", i, d.input); return fail(SSDK_ERR_INVALID); }
+    const LayerPlan& in = m->layers[d.input];
+    if (in.d.op == SSDK_OP_HEAD) { set_error("layer %d: a head cannot feed another layer", i); return fail(SSDK_ERR_INVALID); }
+    L.in_H = in.H; L.in_W = in.W; L.in_C = in.C;
+    if (d.op == SSDK_OP_CONV || d.op == SSDK_OP_HEAD) {
+      if (d.kh <= 0 || d.kw <= 0 || d.stride <= 0 || d.dilation <= 0) { set_error("layer %d: bad conv geometry", i); return fail(SSDK_ERR_INVALID); }
+      L.H = (in.H + d.pad_t + d.pad_b - d.dilation * (d.kh - 1) - 1) / d.stride + 1;
+      L.W = (in.W + d.pad_l + d.pad_r - d.dilation * (d.kw - 1) - 1) / d.stride + 1;
+      L.C = d.op == SSDK_OP_HEAD ? d.n_boxes * (m->Ctot + 4) : d.cout;
+      if (L.H <= 0 || L.W <= 0 || L.C <= 0) { set_error("layer %d: empty conv output", i); return fail(SSDK_ERR_INVALID); }
+    } else if (d.op == SSDK_OP_MAXPOOL) {
+      L.H = (in.H + d.pad_t + d.pad_b - d.kh) / d.stride + 1;
+      L.W = (in.W + d.pad_l + d.pad_r - d.kw) / d.stride + 1;
+      L.C = in.C;
+    } else if (d.op == SSDK_OP_L2NORM) {
+      L.H = in.H; L.W = in.W; L.C = in.C;
+    } else { set_error("layer %d: unknown op %d", i, d.op); return fail(SSDK_ERR_INVALID); }
+  }
+  // pass 2: border each producer must provide (max over its virtual-path conv consumers)
+  for (int i = 0; i < n; ++i) {
+    const ssdk_layer_desc& d = m->layers[i].d;
+    if (d.op != SSDK_OP_CONV && d.op != SSDK_OP_HEAD) continue;
+    LayerPlan& in = m->layers[d.input];
+    const bool im2col = (d.stride != 1) || (in.C < 8);
+    if (!im2col) in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)));
+  }
+  // pass 3: buffers, weights, launches
+  rc = tma_init(); if (rc) return fail(rc);
+  int prior_off = 0;
+  for (int i = 0; i < n; ++i) {
+    LayerPlan& L = m->layers[i];
+    const ssdk_layer_desc& d = L.d;
+    if (d.op != SSDK_OP_HEAD) { rc = alloc_act(m, L.out, m->B, L.H, L.W, L.C, L.need_pad); if (rc) return fail(rc); }
+    if (d.op == SSDK_OP_CONV || d.op == SSDK_OP_HEAD) {
+      if (!d.kernel || (d.op == SSDK_OP_HEAD && !d.kernel2)) { set_error("layer %d: missing kernel", i); return fail(SSDK_ERR_INVALID); }
+      rc = build_conv(m, i); if (rc) return fail(rc);
+      if (d.op == SSDK_OP_HEAD) { L.prior_off = prior_off; prior_off += L.H * L.W * d.n_boxes; }
+      cudaEventCreate(&L.ev0); cudaEventCreate(&L.ev1);
+    } else if (d.op == SSDK_OP_L2NORM) {
+      if (!d.kernel) { set_error("layer %d: L2Normalization needs gamma in `kernel`", i); return fail(SSDK_ERR_INVALID); }
+      rc = upload_f32(m, &L.gamma, d.kernel, L.C); if (rc) return fail(rc);
+    }
+  }
+  m->P = prior_off;
+  if (m->P > 0) {
+    if (!desc->anchors_f32) { set_error("ssdk_model_create: anchors_f32 is NULL"); return fail(SSDK_ERR_INVALID); }
+    rc = upload_f32(m, &m->d_anchors, desc->anchors_f32, (size_t)m->P * 4); if (rc) return fail(rc);
+  }
+  SSDK_CHECK_CUDA(cudaDeviceSynchronize());
+  *out = m;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_destroy(ssdk_model* m) {
+  if (!m) return SSDK_OK;
+  for (auto& L : m->layers) { if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_num_priors(const ssdk_model* m, int* out_P) {
+  SSDK_REQUIRE(m && out_P, "ssdk_model_num_priors: NULL argument");
+  *out_P = m->P;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_layer_shape(const ssdk_model* m, int layer, int* h, int* w, int* c) {
+  SSDK_REQUIRE(m && layer >= 0 && layer < (int)m->layers.size(), "ssdk_model_layer_shape: bad layer index");
+  if (h) *h = m->layers[layer].H;
+  if (w) *w = m->layers[layer].W;
+  if (c) *c = m->layers[layer].C;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_flops(const ssdk_model* m, double* algo, double* issued) {
+  SSDK_REQUIRE(m, "ssdk_model_flops: NULL model");
+  if (algo) *algo = m->flops_algo;
+  if (issued) *issued = m->flops_issued;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_set_timing(ssdk_model* m, int enable) {
+  SSDK_REQUIRE(m, "ssdk_model_set_timing: NULL model");
+  m->timing = enable ? 1 : 0;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms) {
+  SSDK_REQUIRE(m && out_ms, "ssdk_model_last_conv_ms: NULL argument");
+  float total = 0.f;
+  for (auto& L : m->layers) {
+    if (!L.ev0) continue;
+    SSDK_CHECK_CUDA(cudaEventSynchronize(L.ev1));
+    float ms = 0.f;
+    SSDK_CHECK_CUDA(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
+    total += ms;
+  }
+  *out_ms = total;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float* y_pred_dev, void* stream_) {
+  SSDK_REQUIRE(m && images_dev, "ssdk_model_forward: NULL argument");
+  SSDK_REQUIRE(m->P == 0 || y_pred_dev, "ssdk_model_forward: y_pred_dev is NULL");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ssdk_ctx* ctx = m->ctx;
+  int rc;
+  for (size_t i = 0; i < m->layers.size(); ++i) {
+    LayerPlan& L = m->layers[i];
+    const ssdk_layer_desc& d = L.d;
+    switch (d.op) {
+      case SSDK_OP_INPUT:
+        rc = launch_preprocess(ctx, images_dev, m->B, m->H, m->W, m->Cimg, L.has_mean ? L.mean : nullptr,
+                               L.has_std ? L.stddev : nullptr, L.has_swap ? L.swap : nullptr, L.out, stream);
+        if (rc) return rc;
+        break;
+      case SSDK_OP_CONV:
+      case SSDK_OP_HEAD: {
+        const LayerPlan& in = m->layers[d.input];
+        if (L.im2col) {
+          rc = launch_im2col(ctx, in.out, L.col_hi, L.col_lo, L.H, L.W, d.kh, d.kw, d.stride, d.dilation, d.pad_t, d.pad_l, L.Kpad, stream);
+          if (rc) return rc;
+        }
+        if (m->timing) cudaEventRecord(L.ev0, stream);
+        rc = launch_conv(ctx, L.launch, stream);
+        if (rc) return rc;
+        if (m->timing) cudaEventRecord(L.ev1, stream);
+        if (d.op == SSDK_OP_HEAD) {
+          rc = launch_head_finalize(ctx, L.head_f32, m->B, L.H * L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, m->d_anchors, m->var,
+                                    y_pred_dev, stream);
+          if (rc) return rc;
+        }
+        break;
+      }
+      case SSDK_OP_MAXPOOL:
+        rc = launch_maxpool(ctx, m->layers[d.input].out, L.out, d.kh, d.kw, d.stride, d.pad_t, d.pad_l, stream);
+        if (rc) return rc;
+        break;
+      case SSDK_OP_L2NORM:
+        rc = launch_l2norm(ctx, m->layers[d.input].out, L.out, L.gamma, stream);
+        if (rc) return rc;
+        break;
+      default:
+        break;
+    }
+  }
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, void* stream_) {
+  SSDK_REQUIRE(m && out_dev && layer >= 0 && layer < (int)m->layers.size(), "ssdk_model_read_layer: bad argument");
+  LayerPlan& L = m->layers[layer];
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (L.d.op == SSDK_OP_HEAD) {
+    SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev, L.head_f32, (size_t)m->B * L.H * L.W * L.C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    return SSDK_OK;
+  }
+  return launch_unpack(m->ctx, L.out, out_dev, stream);
+}

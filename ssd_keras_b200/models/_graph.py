@@ -1,0 +1,314 @@
+"""Host-side graph description shared by ``ssd_300`` / ``ssd_512`` / ``build_model``.
+
+The builders mirror the reference functions' arguments and produce an ``SSDModel`` whose forward pass
+is a static plan of hand-written sm_100a kernels inside libssdk.so (``ssdk_model_*``).  The object offers
+the part of the Keras ``Model`` surface that the reference's callers use: ``predict``, ``get_layer(name)
+.output_shape``, ``load_weights`` / ``set_weights`` / ``get_weights``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _ffi
+from ..keras_layers.keras_layer_DecodeDetections import DecodeDetections
+from ..keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast
+
+
+class _LayerInfo:
+    def __init__(self, name, output_shape):
+        self.name = name
+        self.output_shape = output_shape          # (None, H, W, C) like Keras
+
+
+class Spec:
+    """One node of the graph (see ssdk_layer_desc in include/ssdk.h)."""
+
+    def __init__(self, name, op, inp=None, cout=0, k=(1, 1), stride=1, dilation=1, pad=(0, 0, 0, 0), act=_ffi.ACT_NONE,
+                 n_boxes=0, bn=None, params=None):
+        self.name, self.op, self.inp, self.cout = name, op, inp, cout
+        self.kh, self.kw = k
+        self.stride, self.dilation, self.pad, self.act, self.n_boxes = stride, dilation, pad, act, n_boxes
+        self.bn = bn                               # name of the BatchNormalization layer folded into this conv
+        self.params = params or {}
+
+
+def same_pad(k, dilation=1):
+    p = dilation * (k - 1) // 2
+    return (p, p, p, p)
+
+
+def tf_same_pool_pad(size, k, s):
+    """TensorFlow 'same' pooling: total pad = max((ceil(n/s)-1)*s + k - n, 0), extra goes to the END."""
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return total // 2, total - total // 2
+
+
+class SSDModel:
+    def __init__(self, specs, img_height, img_width, img_channels, n_classes_total, anchor_cfg, variances, mode,
+                 decode_cfg, l2_reg=0.0, precision='bf16x3', seed=0):
+        self.specs = specs
+        self.index = {s.name: i for i, s in enumerate(specs)}
+        self.img_height, self.img_width, self.img_channels = img_height, img_width, img_channels
+        self.n_classes = n_classes_total
+        self.anchor_cfg = anchor_cfg
+        self.variances = np.asarray(variances, dtype=np.float32)
+        self.mode = mode
+        self.decode_cfg = decode_cfg
+        self.l2_regularization = l2_reg
+        self.precision = precision
+        self._plans = {}
+        self._shapes = self._infer_shapes()
+        self.predictor_sizes = np.array([self._shapes[self.index[s.name]][:2] for s in specs if s.op == _ffi.OP_HEAD])
+        a64, a32, nb = _ffi.generate_anchors(img_height, img_width, self.predictor_sizes, **anchor_cfg)
+        self.anchors, self.anchors_f32 = a64, a32
+        self.n_boxes_total = a64.shape[0]
+        self.weights = {}
+        self._init_weights(seed)
+        if mode == 'inference':
+            self.decoder = DecodeDetections(**decode_cfg)
+        elif mode == 'inference_fast':
+            self.decoder = DecodeDetectionsFast(**decode_cfg)
+        else:
+            self.decoder = None
+
+    # -- graph bookkeeping -------------------------------------------------------------------
+    def _infer_shapes(self):
+        shapes = []
+        for s in self.specs:
+            if s.op == _ffi.OP_INPUT:
+                shapes.append((self.img_height, self.img_width, self.img_channels))
+                continue
+            h, w, c = shapes[self.index[s.inp]]
+            pt, pl, pb, pr = s.pad
+            if s.op in (_ffi.OP_CONV, _ffi.OP_HEAD):
+                ho = (h + pt + pb - s.dilation * (s.kh - 1) - 1) // s.stride + 1
+                wo = (w + pl + pr - s.dilation * (s.kw - 1) - 1) // s.stride + 1
+                shapes.append((ho, wo, s.cout if s.op == _ffi.OP_CONV else s.n_boxes * (self.n_classes + 4)))
+            elif s.op == _ffi.OP_MAXPOOL:
+                shapes.append(((h + pt + pb - s.kh) // s.stride + 1, (w + pl + pr - s.kw) // s.stride + 1, c))
+            else:
+                shapes.append((h, w, c))
+        return shapes
+
+    def get_layer(self, name):
+        if name in self.index:
+            h, w, c = self._shapes[self.index[name]]
+            return _LayerInfo(name, (None, h, w, c))
+        # reference layer names for the fused predictor heads: '<src>_mbox_conf' / '<src>_mbox_loc', 'classesN' / 'boxesN'
+        for s in self.specs:
+            if s.op == _ffi.OP_HEAD and name in (s.params.get('conf_name'), s.params.get('loc_name')):
+                h, w, _ = self._shapes[self.index[s.name]]
+                c = s.n_boxes * (self.n_classes if name == s.params['conf_name'] else 4)
+                return _LayerInfo(name, (None, h, w, c))
+        raise ValueError('No such layer: ' + name)
+
+    @property
+    def layers(self):
+        return [self.get_layer(s.name) for s in self.specs]
+
+    # -- weights -----------------------------------------------------------------------------
+    def weight_shapes(self):
+        out = {}
+        for s in self.specs:
+            if s.op == _ffi.OP_CONV:
+                cin = self._shapes[self.index[s.inp]][2]
+                out[s.name + '/kernel'] = (s.kh, s.kw, cin, s.cout); out[s.name + '/bias'] = (s.cout,)
+                if s.bn:
+                    for p in ('gamma', 'beta', 'moving_mean', 'moving_variance'):
+                        out[s.bn + '/' + p] = (s.cout,)
+            elif s.op == _ffi.OP_HEAD:
+                cin = self._shapes[self.index[s.inp]][2]
+                out[s.params['conf_name'] + '/kernel'] = (3, 3, cin, s.n_boxes * self.n_classes)
+                out[s.params['conf_name'] + '/bias'] = (s.n_boxes * self.n_classes,)
+                out[s.params['loc_name'] + '/kernel'] = (3, 3, cin, s.n_boxes * 4)
+                out[s.params['loc_name'] + '/bias'] = (s.n_boxes * 4,)
+            elif s.op == _ffi.OP_L2NORM:
+                out[s.name + '/gamma'] = (self._shapes[self.index[s.name]][2],)
+        return out
+
+    def _init_weights(self, seed):
+        """kernel_initializer='he_normal' (truncation ignored), zero biases, gamma_init=20, BN identity."""
+        rng = np.random.default_rng(seed)
+        for name, shp in sorted(self.weight_shapes().items()):
+            if name.endswith('/kernel'):
+                fan_in = shp[0] * shp[1] * shp[2]
+                self.weights[name] = (rng.standard_normal(shp) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+            elif name.endswith('norm/gamma'):
+                self.weights[name] = np.full(shp, 20.0, np.float32)
+            elif name.endswith(('/gamma', '/moving_variance')):
+                self.weights[name] = np.ones(shp, np.float32)
+            else:
+                self.weights[name] = np.zeros(shp, np.float32)
+
+    def set_weights(self, weights):
+        """``weights``: dict name -> array using Keras' names ('conv1_1/kernel', 'conv4_3_norm/gamma', ...)."""
+        shapes = self.weight_shapes()
+        for k, v in weights.items():
+            if k not in shapes:
+                continue                                   # by_name semantics: unknown entries are skipped
+            v = np.asarray(v, dtype=np.float32)
+            if tuple(v.shape) != tuple(shapes[k]):
+                raise ValueError('Weight %s has shape %s, expected %s' % (k, v.shape, shapes[k]))
+            self.weights[k] = np.ascontiguousarray(v)
+        self._release()
+
+    def get_weights(self):
+        return dict(self.weights)
+
+    def load_weights(self, path, by_name=True):
+        """Loads an ``.npz`` with Keras layer names as keys (h5py is not available offline; see INTEGRATION.md
+        for the one-line HDF5 -> npz conversion)."""
+        if not str(path).endswith('.npz'):
+            raise NotImplementedError('Only .npz weight files are supported in this build (Keras HDF5 needs h5py).')
+        with np.load(path) as f:
+            self.set_weights({k: f[k] for k in f.files})
+
+    def save_weights(self, path):
+        np.savez(path, **self.weights)
+
+    # -- execution ---------------------------------------------------------------------------
+    def _release(self):
+        for h in self._plans.values():
+            _ffi.lib().ssdk_model_destroy(h['handle'])
+        self._plans = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _plan(self, batch):
+        if batch in self._plans:
+            return self._plans[batch]
+        n = len(self.specs)
+        descs = (_ffi.LayerDesc * n)()
+        keep = []
+
+        def fptr(a):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            keep.append(a)
+            return _ffi.np_ptr(a, C.c_float)
+
+        for i, s in enumerate(self.specs):
+            d = descs[i]
+            d.op = s.op
+            d.input = self.index[s.inp] if s.inp is not None else -1
+            d.cout, d.kh, d.kw, d.stride, d.dilation = s.cout, s.kh, s.kw, s.stride, s.dilation
+            d.pad_t, d.pad_l, d.pad_b, d.pad_r = s.pad
+            d.act, d.n_boxes = s.act, s.n_boxes
+            if s.op == _ffi.OP_INPUT:
+                if s.params.get('mean') is not None:
+                    d.mean = fptr(s.params['mean'])
+                if s.params.get('stddev') is not None:
+                    d.stddev = fptr(s.params['stddev'])
+                if s.params.get('swap'):
+                    sw = np.ascontiguousarray(s.params['swap'], dtype=np.int32); keep.append(sw)
+                    d.swap = _ffi.np_ptr(sw, C.c_int)
+            elif s.op == _ffi.OP_CONV:
+                d.kernel = fptr(self.weights[s.name + '/kernel']); d.bias = fptr(self.weights[s.name + '/bias'])
+                if s.bn:   # inference-mode BatchNormalization(eps=1e-3) folded to scale/shift
+                    g, b = self.weights[s.bn + '/gamma'], self.weights[s.bn + '/beta']
+                    mu, var = self.weights[s.bn + '/moving_mean'], self.weights[s.bn + '/moving_variance']
+                    scale = (g.astype(np.float64) / np.sqrt(var.astype(np.float64) + 1e-3))
+                    d.bn_scale = fptr(scale); d.bn_shift = fptr(b - mu * scale)
+            elif s.op == _ffi.OP_HEAD:
+                d.kernel = fptr(self.weights[s.params['conf_name'] + '/kernel']); d.bias = fptr(self.weights[s.params['conf_name'] + '/bias'])
+                d.kernel2 = fptr(self.weights[s.params['loc_name'] + '/kernel']); d.bias2 = fptr(self.weights[s.params['loc_name'] + '/bias'])
+            elif s.op == _ffi.OP_L2NORM:
+                d.kernel = fptr(self.weights[s.name + '/gamma'])
+        anc = np.ascontiguousarray(self.anchors_f32)
+        md = _ffi.ModelDesc(int(batch), self.img_height, self.img_width, self.img_channels, self.n_classes, n, descs,
+                            0 if self.precision == 'bf16x3' else 1, _ffi.np_ptr(anc, C.c_float),
+                            (C.c_float * 4)(*[float(v) for v in self.variances]))
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().ssdk_model_create(_ffi.context(), C.byref(md), C.byref(h)))
+        P = C.c_int()
+        _ffi.check(_ffi.lib().ssdk_model_num_priors(h, C.byref(P)))
+        assert P.value == self.n_boxes_total, (P.value, self.n_boxes_total)
+        self._plans[batch] = {'handle': h}
+        return self._plans[batch]
+
+    def forward_device(self, images):
+        """images: float32 CUDA tensor (B,H,W,3) -> y_pred float32 CUDA tensor (B,P,C+12) (raw predictions)."""
+        import torch
+        B = images.shape[0]
+        plan = self._plan(B)
+        images = images.to(dtype=torch.float32).contiguous()
+        y = torch.empty((B, self.n_boxes_total, self.n_classes + 12), dtype=torch.float32, device=images.device)
+        _ffi.check(_ffi.lib().ssdk_model_forward(plan['handle'], _ffi.dptr(images), _ffi.dptr(y), _ffi.stream_ptr()))
+        return y
+
+    def predict_device(self, images):
+        y = self.forward_device(images)
+        return y if self.decoder is None else self.decoder(y)
+
+    def predict(self, x, batch_size=None):
+        """Keras-style: ndarray (N,H,W,3) -> ndarray ((N,P,C+12) in 'training' mode, (N,top_k,6) otherwise)."""
+        import torch
+        x = np.asarray(x, dtype=np.float32)
+        bs = batch_size or x.shape[0]
+        outs = []
+        for i in range(0, x.shape[0], bs):
+            xb = torch.from_numpy(np.ascontiguousarray(x[i:i + bs])).pin_memory().cuda(non_blocking=True)
+            outs.append(self.predict_device(xb).cpu().numpy())
+        return np.concatenate(outs, axis=0)
+
+    def read_layer(self, name, batch):
+        """Activation of a layer after the last forward with this batch size, float32 ndarray (B,h,w,c)."""
+        import torch
+        i = self.index[name]
+        h, w, c = self._shapes[i]
+        out = torch.empty((batch, h, w, c), dtype=torch.float32, device='cuda')
+        _ffi.check(_ffi.lib().ssdk_model_read_layer(self._plan(batch)['handle'], i, _ffi.dptr(out), _ffi.stream_ptr()))
+        return out.cpu().numpy()
+
+    def flops(self, batch):
+        a, b = C.c_double(), C.c_double()
+        _ffi.check(_ffi.lib().ssdk_model_flops(self._plan(batch)['handle'], C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_timing(self, batch, enable=True):
+        _ffi.check(_ffi.lib().ssdk_model_set_timing(self._plan(batch)['handle'], 1 if enable else 0))
+
+    def last_conv_ms(self, batch):
+        v = C.c_float()
+        _ffi.check(_ffi.lib().ssdk_model_last_conv_ms(self._plan(batch)['handle'], C.byref(v)))
+        return v.value
+
+
+# ---------------------------------------------------------------------------------------------
+# argument handling shared by the three builders (reference: models/keras_ssd300.py:183-240)
+# ---------------------------------------------------------------------------------------------
+def resolve_box_args(n_predictor_layers, min_scale, max_scale, scales, aspect_ratios_global, aspect_ratios_per_layer,
+                     two_boxes_for_ar1, steps, offsets, variances):
+    if aspect_ratios_global is None and aspect_ratios_per_layer is None:
+        raise ValueError("`aspect_ratios_global` and `aspect_ratios_per_layer` cannot both be None. At least one needs to be specified.")
+    if aspect_ratios_per_layer:
+        if len(aspect_ratios_per_layer) != n_predictor_layers:
+            raise ValueError("It must be either aspect_ratios_per_layer is None or len(aspect_ratios_per_layer) == {}, but "
+                             "len(aspect_ratios_per_layer) == {}.".format(n_predictor_layers, len(aspect_ratios_per_layer)))
+    if (min_scale is None or max_scale is None) and scales is None:
+        raise ValueError("Either `min_scale` and `max_scale` or `scales` need to be specified.")
+    if scales:
+        if len(scales) != n_predictor_layers + 1:
+            raise ValueError("It must be either scales is None or len(scales) == {}, but len(scales) == {}."
+                             .format(n_predictor_layers + 1, len(scales)))
+    else:
+        scales = np.linspace(min_scale, max_scale, n_predictor_layers + 1)
+    if len(variances) != 4:
+        raise ValueError("4 variance values must be pased, but {} values were received.".format(len(variances)))
+    variances = np.array(variances)
+    if np.any(variances <= 0):
+        raise ValueError("All variances must be >0, but the variances given are {}".format(variances))
+    if (steps is not None) and (len(steps) != n_predictor_layers):
+        raise ValueError("You must provide at least one step value per predictor layer.")
+    if (offsets is not None) and (len(offsets) != n_predictor_layers):
+        raise ValueError("You must provide at least one offset value per predictor layer.")
+    if aspect_ratios_per_layer:
+        aspect_ratios = aspect_ratios_per_layer
+    else:
+        aspect_ratios = [aspect_ratios_global] * n_predictor_layers
+    n_boxes = [len(ar) + (1 if (1 in ar) and two_boxes_for_ar1 else 0) for ar in aspect_ratios]
+    return scales, aspect_ratios, n_boxes, variances

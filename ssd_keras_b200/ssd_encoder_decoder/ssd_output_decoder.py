@@ -1,0 +1,98 @@
+"""``decode_detections`` / ``decode_detections_fast`` on B200 (reference
+``ssd_encoder_decoder/ssd_output_decoder.py:111-333``), computed by ``csrc/decode.cu`` through ``ssdk_decode``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _ffi
+
+PER_CLASS, FAST = 0, 1
+
+
+def decode_device(y_pred, mode, layer_semantics, confidence_thresh, iou_threshold, top_k, nms_max_output_size,
+                  input_coords, normalize_coords, img_height, img_width, border_pixels='half', return_index=False):
+    """Device-to-device decode.  ``y_pred``: float32 CUDA tensor (B,P,C+12).
+    Returns (out (B,max_out,6) float32, counts (B,) int32[, prior index (B,max_out) int32])."""
+    import torch
+    if input_coords not in _ffi.COORDS:
+        raise ValueError("Unexpected value for `input_coords`. Supported input coordinate formats are 'minmax', 'corners' and 'centroids'.")
+    B, P, W = y_pred.shape
+    Ctot = W - 12
+    if layer_semantics:
+        max_out = int(top_k)
+        k = int(top_k)
+    elif top_k == 'all' or top_k is None:
+        k = 0
+        max_out = P * (Ctot - 1) if mode == PER_CLASS else P
+    else:
+        k = int(top_k)
+        max_out = k
+    cfg = _ffi.DecodeCfg(mode, 1 if layer_semantics else 0, Ctot, P, float(confidence_thresh),
+                         float(iou_threshold) if iou_threshold else 0.0, k, int(nms_max_output_size),
+                         _ffi.COORDS[input_coords], int(bool(normalize_coords)),
+                         int(img_height) if img_height is not None else 0, int(img_width) if img_width is not None else 0,
+                         _ffi.BORDER_D[border_pixels], max_out)
+    y_pred = y_pred.contiguous()
+    out = torch.empty((B, max_out, 6), dtype=torch.float32, device=y_pred.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=y_pred.device)
+    index = torch.empty((B, max_out), dtype=torch.int32, device=y_pred.device) if return_index else None
+    _ffi.check(_ffi.lib().ssdk_decode(_ffi.context(y_pred.device.index), C.byref(cfg), _ffi.dptr(y_pred), B, _ffi.dptr(out),
+                                      _ffi.dptr(counts), _ffi.dptr(index), _ffi.stream_ptr()))
+    return (out, counts, index) if return_index else (out, counts)
+
+
+def _to_device(y_pred):
+    import torch
+    if isinstance(y_pred, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(y_pred, dtype=np.float32))
+        return t.pin_memory().cuda(non_blocking=True)
+    return y_pred.to(dtype=torch.float32, device='cuda')
+
+
+def _check_norm(normalize_coords, img_height, img_width):
+    if normalize_coords and ((img_height is None) or (img_width is None)):
+        raise ValueError("If relative box coordinates are supposed to be converted to absolute coordinates, the decoder needs "
+                         "the image size in order to decode the predictions, but `img_height == {}` and `img_width == {}`"
+                         .format(img_height, img_width))
+
+
+def _ragged(out, counts):
+    out = out.cpu().numpy().astype(np.float64)
+    counts = counts.cpu().numpy()
+    return [out[i, :counts[i]] if counts[i] > 0 else np.array([]) for i in range(out.shape[0])]
+
+
+def decode_detections(y_pred, confidence_thresh=0.01, iou_threshold=0.45, top_k=200, input_coords='centroids',
+                      normalize_coords=True, img_height=None, img_width=None, border_pixels='half'):
+    """Reference :111-226.  Returns a list of ``(k_i, 6)`` float64 arrays ``[class, conf, xmin, ymin, xmax, ymax]``.
+    When more than ``top_k`` boxes survive, the reference keeps an unordered top-k set (``argpartition``);
+    here that set comes back sorted by confidence."""
+    _check_norm(normalize_coords, img_height, img_width)
+    out, counts = decode_device(_to_device(y_pred), PER_CLASS, False, confidence_thresh, iou_threshold, top_k, 0,
+                                input_coords, normalize_coords, img_height, img_width, border_pixels)
+    return _ragged(out, counts)
+
+
+def decode_detections_fast(y_pred, confidence_thresh=0.5, iou_threshold=0.45, top_k='all', input_coords='centroids',
+                           normalize_coords=True, img_height=None, img_width=None, border_pixels='half'):
+    """Reference :228-333 (class = argmax, one NMS over all classes, ``>=`` confidence test)."""
+    _check_norm(normalize_coords, img_height, img_width)
+    out, counts = decode_device(_to_device(y_pred), FAST, False, confidence_thresh, iou_threshold, top_k, 0,
+                                input_coords, normalize_coords, img_height, img_width, border_pixels)
+    res = _ragged(out, counts)
+    return [r if r.size else np.zeros((0, 6)) for r in res]
+
+
+def nms_device(boxes, scores, confidence_thresh=0.01, iou_threshold=0.45, nms_max_output_size=400, top_k=200,
+               return_index=False):
+    """Single-class greedy NMS + top-k on CUDA tensors: boxes (B,n,4) corners, scores (B,n)."""
+    import torch
+    B, n = scores.shape
+    out = torch.empty((B, top_k, 6), dtype=torch.float32, device=scores.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=scores.device)
+    index = torch.empty((B, top_k), dtype=torch.int32, device=scores.device) if return_index else None
+    _ffi.check(_ffi.lib().ssdk_nms(_ffi.context(scores.device.index), _ffi.dptr(boxes.contiguous()), _ffi.dptr(scores.contiguous()),
+                                   B, n, float(confidence_thresh), float(iou_threshold), int(nms_max_output_size), int(top_k),
+                                   _ffi.dptr(out), _ffi.dptr(counts), _ffi.dptr(index), _ffi.stream_ptr()))
+    return (out, counts, index) if return_index else (out, counts)
