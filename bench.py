@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- SSD300 images/sec (forward + DecodeDetections) on N B200s, plus the reference CPU arm.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3                   # this framework (one JSON line on stdout)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W                     # N ranks, NCCL, weak scaling (32 images / GPU)
+  python bench.py --impl reference --steps 3 --warmup 1             # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): SSD300, batch 32 synthetic 300x300x3 float32 images, 21 classes, 8732 priors,
+he_normal random weights, DecodeDetections(conf 0.01, iou 0.45, top_k 200, nms cap 400).
+A step = one forward + decode of one batch.  `value` = images/s with inputs resident in HBM (CUDA events, max over
+ranks); `e2e` = the same through SSDModel.predict with pinned host images copied H2D and the (B,200,6) result copied
+D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SC300 = [0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05]
+BATCH = 32
+N_CLASSES = 20
+METRIC = 'SSD300 images/sec (fwd+decode)'
+WORKLOAD = ('SSD300 inference, batch 32 per GPU, synthetic 300x300x3 float32, 21 classes, 8732 priors, he_normal random '
+            'weights, DecodeDetections(0.01/0.45/200/400)')
+
+
+def _peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+def _weights():
+    from oracle import synth
+    from oracle.model import vgg_weight_shapes
+    w = synth.synth_weights(1, vgg_weight_shapes(300, N_CLASSES), bias_scale=0.0)
+    w['conv4_3_norm/gamma'] = np.full((512,), 20.0, np.float32)
+    return w
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference CPU path, on the host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step(images, weights):
+    """One bounded sample of the workload on the CPU: torch-CPU restatement of the Keras graph (all host threads)
+    followed by the DecodeDetections restatement (NumPy).  Returns the (n,200,6) detections."""
+    from oracle.decoder import decode_layer
+    from oracle.model import ssd_vgg_forward
+    y = ssd_vgg_forward(images, weights, 300, N_CLASSES, scales=SC300)
+    return decode_layer(y, 0.01, 0.45, 200, 400, True, 300, 300)
+
+
+def time_cpu_reference(n_images, reps, warmup):
+    import torch
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = _weights()
+    x = synth.synth_images(0, n_images, 300, 300)
+    for _ in range(warmup):
+        cpu_reference_step(x, w)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_reference_step(x, w)
+    dt = (time.perf_counter() - t0) / max(reps, 1)
+    return n_images / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_img = 2
+    ips, dt, threads = time_cpu_reference(n_img, args.steps, args.warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'sample': '%d of 32 images per step' % n_img},
+            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d images per step: torch-CPU restatement of models/keras_ssd300.py (TF1/Keras2 not '
+                                       'installable offline) + NumPy restatement of DecodeDetections' % n_img},
+            'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# micro-benchmarks reported under "extra" (BASELINE metric part 2: IoU-match + NMS boxes/sec)
+# ------------------------------------------------------------------------------------------------------
+def _time_cuda(fn, iters=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+def micro_benchmarks(peaks):
+    """config 3 (encode + loss at SSD300 B=32) and config 5 (P=1e5 x G=128 encode, NMS) at a bounded batch."""
+    import torch
+    from oracle import synth
+    from ssd_keras_b200.keras_loss_function.keras_ssd_loss import SSDLoss
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_output_decoder import nms_device
+    hbm = peaks['hbm_gbs']
+    out = {}
+    # --- encode, SSD300/VOC B=32 G=8 (config 3)
+    ps = [(38, 38), (19, 19), (10, 10), (5, 5), (3, 3), (1, 1)]
+    from oracle.model import SSD300_AR
+    enc = SSDInputEncoder(300, 300, 20, ps, scales=SC300, aspect_ratios_per_layer=SSD300_AR, steps=[8, 16, 32, 64, 100, 300],
+                          offsets=[0.5] * 6, pos_iou_threshold=0.5, neg_iou_limit=0.5)
+    gt = synth.synth_gt(2, 32, 8, 300, 300, 20)
+    offs = np.cumsum([0] + [g.shape[0] for g in gt]).astype(np.int32)
+    gdev = torch.from_numpy(np.concatenate(gt)).cuda()
+    ms = _time_cuda(lambda: enc.encode_device(gdev, offs))
+    bytes_ = 32 * (8732 * 16 + 8 * 20 + 8732 * 4 * 33)
+    out['encode_ssd300_b32'] = {'ms': ms, 'images_per_s': 32e3 / ms, 'algorithmic_GB': bytes_ / 1e9, 'GBps': bytes_ / ms / 1e6,
+                                'frac_hbm': bytes_ / ms / 1e6 / hbm}
+    y_true = enc.encode_device(gdev, offs)
+    y_pred = torch.from_numpy(synth.synth_y_pred(3, 32, enc.anchors, 21, sharp=2.0)).cuda()
+    L = SSDLoss()
+    ms = _time_cuda(lambda: L.loss_and_stats(y_true, y_pred))
+    bytes_ = 2 * 8732 * 25 * 4 * 32
+    out['ssd_loss_fwd_b32'] = {'ms': ms, 'algorithmic_GB': bytes_ / 1e9, 'GBps': bytes_ / ms / 1e6, 'frac_hbm': bytes_ / ms / 1e6 / hbm}
+    # --- config 5: P = 100000, G = 128, B = 64 (of 256)
+    Bm = 64
+    encm = SSDInputEncoder(1000, 1600, 20, [(125, 200)], scales=[0.1, 0.2], aspect_ratios_global=[0.5, 1.0, 2.0],
+                           pos_iou_threshold=0.5, neg_iou_limit=0.5)
+    gtm = synth.synth_gt(4, Bm, 128, 1600, 1000, 20)
+    offm = np.cumsum([0] + [g.shape[0] for g in gtm]).astype(np.int32)
+    gm = torch.from_numpy(np.concatenate(gtm)).cuda()
+    ms = _time_cuda(lambda: encm.encode_device(gm, offm), iters=5, warm=2)
+    bytes_ = Bm * (100000 * 16 + 128 * 20 + 100000 * 4 * 33)
+    out['encode_micro_p1e5_g128'] = {'batch': Bm, 'ms': ms, 'priors_per_s': Bm * 1e5 / ms * 1e3, 'iou_pairs_per_s': Bm * 1.28e7 / ms * 1e3,
+                                     'algorithmic_GB': bytes_ / 1e9, 'GBps': bytes_ / ms / 1e6, 'frac_hbm': bytes_ / ms / 1e6 / hbm}
+    anc = torch.from_numpy(encm.anchors_f32.copy()).cuda()
+    boxes = torch.stack([anc[:, 0] - anc[:, 2] / 2, anc[:, 1] - anc[:, 3] / 2, anc[:, 0] + anc[:, 2] / 2, anc[:, 1] + anc[:, 3] / 2], 1)
+    boxes = (boxes * torch.tensor([1600., 1000., 1600., 1000.], device='cuda')).unsqueeze(0).expand(Bm, -1, -1).contiguous()
+    scores = torch.from_numpy(np.stack([np.random.default_rng(5 + i).uniform(0, 1, 100000) for i in range(Bm)]).astype(np.float32)).cuda()
+    ms = _time_cuda(lambda: nms_device(boxes, scores, 0.01, 0.45, 400, 200), iters=5, warm=2)
+    bytes_ = Bm * (100000 * 20 + 200 * 4)
+    out['nms_micro_p1e5'] = {'batch': Bm, 'ms': ms, 'boxes_per_s': Bm * 1e5 / ms * 1e3, 'algorithmic_GB': bytes_ / 1e9,
+                             'GBps': bytes_ / ms / 1e6, 'frac_hbm': bytes_ / ms / 1e6 / hbm}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from oracle import synth                     # synthetic input generator only (not measured, not shipped)
+    from ssd_keras_b200 import _ffi
+    from ssd_keras_b200.models.keras_ssd300 import ssd_300
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    peaks, peaks_src = _peaks()
+
+    precision = 'bf16' if args.fast else 'bf16x3'
+    model = ssd_300((300, 300, 3), N_CLASSES, mode='inference', scales=SC300, precision=precision)
+    model.set_weights(_weights())
+    # several distinct input batches so that a step never finds its images in L2 (4 x 34.6 MB > 126 MB L2)
+    n_in = 4
+    host = [torch.from_numpy(synth.synth_images(100 * rank + i, BATCH, 300, 300)).pin_memory() for i in range(n_in)]
+    dev = [h.cuda() for h in host]
+    gathered = [torch.empty((BATCH, 200, 6), dtype=torch.float32, device='cuda') for _ in range(world)] if world > 1 else None
+
+    def step_device(i):
+        out = model.predict_device(dev[i % n_in])
+        if world > 1:
+            dist.all_gather(gathered, out)              # decoded boxes of every rank
+        return out
+
+    def step_e2e(i):
+        x = host[i % n_in].cuda(non_blocking=True)       # pinned host -> device, inside the timed region
+        out = model.predict_device(x)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out.cpu()                                 # result back on the host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = _ffi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        launches = _ffi.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+            c = torch.tensor([launches], device='cuda', dtype=torch.int64); dist.all_reduce(c); launches = int(c.item())
+        return ms, clocks, launches
+
+    ms_dev, clocks, launches = timed(step_device, args.steps, max(args.warmup, 3))
+    ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    ips = world * BATCH * args.steps / (ms_dev * 1e-3)
+    ips_e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    # dominant kernel: the tcgen05 convolution.  Time of all conv launches of one step via CUDA events on the launch
+    # stream (instrumented passes outside the timed region).
+    model.set_timing(BATCH, True)
+    conv_ms = []
+    for i in range(3):
+        step_device(i)
+        torch.cuda.synchronize()
+        conv_ms.append(model.last_conv_ms(BATCH))
+    model.set_timing(BATCH, False)
+    conv_ms = float(np.median(conv_ms))
+    fl_algo, fl_issued = model.flops(BATCH)
+    peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    roofline = {'bound': 'tensor', 'kernel': 'conv_tcgen05_kernel (all conv launches of one step)',
+                'achieved': fl_algo / conv_ms / 1e9, 'peak': peak, 'unit': 'TFLOP/s', 'frac': fl_algo / conv_ms / 1e9 / peak,
+                'peak_source': peaks_src + ', bf16_tflops_sustained', 'traffic': None,
+                'algorithmic_tflop_per_step': fl_algo / 1e12, 'issued_mma_tflop_per_step': fl_issued / 1e12,
+                'issued_tflops': fl_issued / conv_ms / 1e9, 'issued_frac': fl_issued / conv_ms / 1e9 / peak,
+                'conv_ms_per_step': conv_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3 (bf16 hi+lo operands, 3 tcgen05 MMAs per product, fp32 accumulate)' if not args.fast else 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': 'dp%d' % world, 'precision': precision,
+                       'l2': 'no explicit flush: %d distinct 34.6 MB input batches are rotated and each step streams >4 GB of '
+                             'activations through the 126 MB L2' % n_in},
+            'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': BATCH * 300 * 300 * 3 * 4,
+                    'd2h_bytes_per_step': BATCH * 200 * 6 * 4, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline}
+    if world == 1:
+        if not args.no_cpu:
+            v, dt, threads = time_cpu_reference(2, 1, 1)
+            line['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                                    'sample': '2 of 32 images, 1 repetition after 1 warm-up (%.1f s): torch-CPU restatement of the '
+                                              'Keras graph + NumPy restatement of DecodeDetections' % dt}
+        if not args.no_micro:
+            try:
+                line['extra'] = micro_benchmarks(peaks)
+            except Exception as e:                    # the headline number must not depend on the extras
+                line['extra'] = {'error': repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--fast', action='store_true', help='single-pass bf16 convolutions instead of bf16x3')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-micro', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

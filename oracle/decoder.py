@@ -141,22 +141,32 @@ def decode_detections_fast(y_pred, confidence_thresh=0.5, iou_threshold=0.45, to
 # Keras-layer semantics (float32)
 # --------------------------------------------------------------------------------------
 
+def _smin(a, b):
+    """std::min<float>(a, b) == (b < a) ? b : a -- NaN handling depends on the argument order, as in the TF kernel."""
+    return np.where(b < a, b, a)
+
+
+def _smax(a, b):
+    """std::max<float>(a, b) == (a < b) ? b : a."""
+    return np.where(a < b, b, a)
+
+
 def _tf_iou(bi, bj):
-    """IoU as tf.image.non_max_suppression computes it (float32).  Boxes are (ymin,xmin,ymax,xmax)
-    in TF; for corner boxes with min<=max the value is order independent, so (x0,y0,x1,y1) is used."""
+    """IoU as tf.image.non_max_suppression computes it (float32), bi = candidate, bj = already selected box.
+    Boxes are (ymin,xmin,ymax,xmax) in TF; here (x0,y0,x1,y1) with the same per-axis argument order."""
     f = np.float32
-    x0i, x1i = min(bi[0], bi[2]), max(bi[0], bi[2])
-    y0i, y1i = min(bi[1], bi[3]), max(bi[1], bi[3])
-    x0j, x1j = min(bj[0], bj[2]), max(bj[0], bj[2])
-    y0j, y1j = min(bj[1], bj[3]), max(bj[1], bj[3])
-    ai = f(f(y1i - y0i) * f(x1i - x0i))
-    aj = f(f(y1j - y0j) * f(x1j - x0j))
-    if ai <= 0 or aj <= 0:
-        return f(0.0)
-    ih = max(f(min(y1i, y1j) - max(y0i, y0j)), f(0.0))
-    iw = max(f(min(x1i, x1j) - max(x0i, x0j)), f(0.0))
-    inter = f(ih * iw)
-    return f(inter / f(f(ai + aj) - inter))
+    with np.errstate(all='ignore'):
+        bi = np.asarray(bi, f); bj = np.asarray(bj, f)
+        x0i, x1i = _smin(bi[0], bi[2]), _smax(bi[0], bi[2]); y0i, y1i = _smin(bi[1], bi[3]), _smax(bi[1], bi[3])
+        x0j, x1j = _smin(bj[0], bj[2]), _smax(bj[0], bj[2]); y0j, y1j = _smin(bj[1], bj[3]), _smax(bj[1], bj[3])
+        ai = f(f(y1i - y0i) * f(x1i - x0i))
+        aj = f(f(y1j - y0j) * f(x1j - x0j))
+        if ai <= 0 or aj <= 0:
+            return f(0.0)
+        ih = _smax(f(_smin(y1i, y1j) - _smax(y0i, y0j)), f(0.0))
+        iw = _smax(f(_smin(x1i, x1j) - _smax(x0i, x0j)), f(0.0))
+        inter = f(ih * iw)
+        return f(inter / f(f(ai + aj) - inter))
 
 
 def tf_nms(boxes, scores, max_output_size, iou_threshold):
@@ -178,37 +188,35 @@ def tf_nms(boxes, scores, max_output_size, iou_threshold):
 
 
 def tf_nms_fast(boxes, scores, max_output_size, iou_threshold):
-    """Vectorised equivalent of ``tf_nms`` (same float32 formula) for larger inputs."""
+    """Vectorised equivalent of ``tf_nms`` (same float32 formula and min/max argument order) for larger inputs."""
     f = np.float32
     boxes = np.asarray(boxes, dtype=f)
     scores = np.asarray(scores, dtype=f)
     n = len(scores)
     order = np.lexsort((np.arange(n), -scores.astype(np.float64)))
-    x0 = np.minimum(boxes[:, 0], boxes[:, 2]); x1 = np.maximum(boxes[:, 0], boxes[:, 2])
-    y0 = np.minimum(boxes[:, 1], boxes[:, 3]); y1 = np.maximum(boxes[:, 1], boxes[:, 3])
-    area = ((y1 - y0).astype(f) * (x1 - x0).astype(f)).astype(f)
-    alive = np.ones(n, dtype=bool)
-    selected = []
-    thr = f(iou_threshold)
-    pos = {int(idx): r for r, idx in enumerate(order)}
-    for r, i in enumerate(order):
-        if not alive[i]:
-            continue
-        selected.append(int(i))
-        if len(selected) >= max_output_size:
-            break
-        rest = order[r + 1:]
-        rest = rest[alive[rest]]
-        if rest.size == 0:
-            continue
-        ih = np.maximum((np.minimum(y1[i], y1[rest]) - np.maximum(y0[i], y0[rest])).astype(f), f(0))
-        iw = np.maximum((np.minimum(x1[i], x1[rest]) - np.maximum(x0[i], x0[rest])).astype(f), f(0))
-        inter = (ih * iw).astype(f)
-        with np.errstate(divide='ignore', invalid='ignore'):
-            v = (inter / ((area[i] + area[rest]).astype(f) - inter).astype(f)).astype(f)
-        v = np.where((area[i] <= 0) | (area[rest] <= 0), f(0), v)
-        alive[rest[v > thr]] = False
-    del pos
+    with np.errstate(all='ignore'):
+        x0 = _smin(boxes[:, 0], boxes[:, 2]); x1 = _smax(boxes[:, 0], boxes[:, 2])
+        y0 = _smin(boxes[:, 1], boxes[:, 3]); y1 = _smax(boxes[:, 1], boxes[:, 3])
+        area = ((y1 - y0).astype(f) * (x1 - x0).astype(f)).astype(f)
+        alive = np.ones(n, dtype=bool)
+        selected = []
+        thr = f(iou_threshold)
+        for r, i in enumerate(order):          # i is the SELECTED box (j in TF); the remaining ones are candidates
+            if not alive[i]:
+                continue
+            selected.append(int(i))
+            if len(selected) >= max_output_size:
+                break
+            rest = order[r + 1:]
+            rest = rest[alive[rest]]
+            if rest.size == 0:
+                continue
+            ih = _smax((_smin(y1[rest], y1[i]) - _smax(y0[rest], y0[i])).astype(f), f(0))
+            iw = _smax((_smin(x1[rest], x1[i]) - _smax(x0[rest], x0[i])).astype(f), f(0))
+            inter = (ih * iw).astype(f)
+            v = (inter / ((area[rest] + area[i]).astype(f) - inter).astype(f)).astype(f)
+            v = np.where((area[rest] <= 0) | (area[i] <= 0), f(0), v)
+            alive[rest[v > thr]] = False
     return selected
 
 

@@ -55,7 +55,7 @@ def l2_normalize(x_nchw, gamma):
     return x_nchw * torch.rsqrt(torch.clamp(ss, min=1e-12)) * torch.as_tensor(gamma).view(1, -1, 1, 1)
 
 
-def _assemble(sources, weights, head_names, n_classes_total, anchors, variances):
+def _assemble(sources, weights, head_names, n_classes_total, anchors, variances, logits_out=None):
     """Reshape/Concat/softmax/Concat, models/keras_ssd300.py:363-419."""
     confs, locs = [], []
     for src, (cname, lname) in zip(sources, head_names):
@@ -64,7 +64,10 @@ def _assemble(sources, weights, head_names, n_classes_total, anchors, variances)
         B = c.shape[0]
         confs.append(c.permute(0, 2, 3, 1).reshape(B, -1, n_classes_total))
         locs.append(l.permute(0, 2, 3, 1).reshape(B, -1, 4))
-    conf = torch.softmax(torch.cat(confs, dim=1), dim=-1)
+    logits = torch.cat(confs, dim=1)
+    if logits_out is not None:
+        logits_out['logits'] = logits.numpy()
+    conf = torch.softmax(logits, dim=-1)
     loc = torch.cat(locs, dim=1)
     B, P = conf.shape[0], conf.shape[1]
     anc = torch.as_tensor(anchors.astype(np.float32)).unsqueeze(0).expand(B, P, 4)
@@ -122,9 +125,12 @@ def ssd_vgg_forward(x_nhwc, weights, variant=300, n_classes=20, scales=None, min
     anchors = all_anchors(img_h, img_w, sizes, sc, aspect_ratios_per_layer, two_boxes_for_ar1, steps, offsets,
                           clip_boxes, coords, normalize_coords)
     heads = [(n + '_mbox_conf', n + '_mbox_loc') for n in src_names]
-    y = _assemble(sources, weights, heads, C, anchors, variances)
+    extra_out = {}
+    y = _assemble(sources, weights, heads, C, anchors, variances, extra_out)
     if return_features:
-        return y, {k: v.permute(0, 2, 3, 1).contiguous().numpy() for k, v in feats.items()}
+        f = {k: v.permute(0, 2, 3, 1).contiguous().numpy() for k, v in feats.items()}
+        f.update(extra_out)
+        return y, f
     return y
 
 
@@ -155,9 +161,12 @@ def ssd7_forward(x_nhwc, weights, n_classes=5, min_scale=0.1, max_scale=0.9, sca
     anchors = all_anchors(img_h, img_w, sizes, sc, ar, two_boxes_for_ar1, steps, offsets, clip_boxes, coords,
                           normalize_coords)
     heads = [('classes%d' % i, 'boxes%d' % i) for i in (4, 5, 6, 7)]
-    y = _assemble(sources, weights, heads, C, anchors, variances)
+    extra_out = {}
+    y = _assemble(sources, weights, heads, C, anchors, variances, extra_out)
     if return_features:
-        return y, {k: v.permute(0, 2, 3, 1).contiguous().numpy() for k, v in feats.items()}
+        f = {k: v.permute(0, 2, 3, 1).contiguous().numpy() for k, v in feats.items()}
+        f.update(extra_out)
+        return y, f
     return y
 
 

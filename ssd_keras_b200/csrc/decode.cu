@@ -183,27 +183,30 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
 
-// tf.image.non_max_suppression: suppress iff IoU > thr; non-positive areas give IoU 0.
+// std::min / std::max exactly as the TF kernel uses them: NaN handling depends on the argument order.
+__device__ __forceinline__ float tf_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float tf_max(float a, float b) { return (a < b) ? b : a; }
+// tf.image.non_max_suppression (candidate c against selected m): suppress iff IoU > thr; non-positive areas give IoU 0.
 __device__ __forceinline__ bool suppress_tf(const Box4<float>& c, const Box4<float>& m, float thr) {
-  float cx0 = fminf(c.x0, c.x1), cx1 = fmaxf(c.x0, c.x1), cy0 = fminf(c.y0, c.y1), cy1 = fmaxf(c.y0, c.y1);
-  float mx0 = fminf(m.x0, m.x1), mx1 = fmaxf(m.x0, m.x1), my0 = fminf(m.y0, m.y1), my1 = fmaxf(m.y0, m.y1);
+  float cx0 = tf_min(c.x0, c.x1), cx1 = tf_max(c.x0, c.x1), cy0 = tf_min(c.y0, c.y1), cy1 = tf_max(c.y0, c.y1);
+  float mx0 = tf_min(m.x0, m.x1), mx1 = tf_max(m.x0, m.x1), my0 = tf_min(m.y0, m.y1), my1 = tf_max(m.y0, m.y1);
   float ac = mul_rn(sub_rn(cy1, cy0), sub_rn(cx1, cx0));
   float am = mul_rn(sub_rn(my1, my0), sub_rn(mx1, mx0));
   if (ac <= 0.f || am <= 0.f) return false;
-  float ih = fmaxf(sub_rn(fminf(cy1, my1), fmaxf(cy0, my0)), 0.f);
-  float iw = fmaxf(sub_rn(fminf(cx1, mx1), fmaxf(cx0, mx0)), 0.f);
+  float ih = tf_max(sub_rn(tf_min(cy1, my1), tf_max(cy0, my0)), 0.f);
+  float iw = tf_max(sub_rn(tf_min(cx1, mx1), tf_max(cx0, mx0)), 0.f);
   float inter = mul_rn(ih, iw);
   float iou = div_rn(inter, sub_rn(add_rn(ac, am), inter));
   return iou > thr;
 }
 // _greedy_nms (ssd_output_decoder.py:90-91): keep iff iou <= thr (NaN is dropped); areas use d, the
 // intersection does not (bounding_box_utils.py:345).
+template <typename T> __device__ __forceinline__ T np_min(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }   // NaN propagates
+template <typename T> __device__ __forceinline__ T np_max(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 template <typename T>
 __device__ __forceinline__ bool suppress_np(const Box4<T>& c, const Box4<T>& m, T thr, T d) {
-  T iw = sub_rn(c.x1 < m.x1 ? c.x1 : m.x1, c.x0 > m.x0 ? c.x0 : m.x0);
-  T ih = sub_rn(c.y1 < m.y1 ? c.y1 : m.y1, c.y0 > m.y0 ? c.y0 : m.y0);
-  iw = iw > (T)0 ? iw : (T)0;
-  ih = ih > (T)0 ? ih : (T)0;
+  T iw = np_max((T)0, sub_rn(np_min(c.x1, m.x1), np_max(c.x0, m.x0)));
+  T ih = np_max((T)0, sub_rn(np_min(c.y1, m.y1), np_max(c.y0, m.y0)));
   T inter = mul_rn(iw, ih);
   T ac = mul_rn(add_rn(sub_rn(c.x1, c.x0), d), add_rn(sub_rn(c.y1, c.y0), d));
   T am = mul_rn(add_rn(sub_rn(m.x1, m.x0), d), add_rn(sub_rn(m.y1, m.y0), d));
