@@ -231,19 +231,19 @@ def run_ours(args):
     n_in = 4
     host = [torch.from_numpy(synth.synth_images(100 * rank + i, BATCH, 300, 300)).pin_memory() for i in range(n_in)]
     dev = [h.cuda() for h in host]
-    gathered = [torch.empty((BATCH, 200, 6), dtype=torch.float32, device='cuda') for _ in range(world)] if world > 1 else None
+    from ssd_keras_b200.distributed import all_gather_detections
 
     def step_device(i):
         out = model.predict_device(dev[i % n_in])
         if world > 1:
-            dist.all_gather(gathered, out)              # decoded boxes of every rank
+            out = all_gather_detections(out)            # decoded boxes of every rank
         return out
 
     def step_e2e(i):
         x = host[i % n_in].cuda(non_blocking=True)       # pinned host -> device, inside the timed region
         out = model.predict_device(x)
         if world > 1:
-            dist.all_gather(gathered, out)
+            out = all_gather_detections(out)
         return out.cpu()                                 # result back on the host
 
     def barrier():

@@ -446,6 +446,105 @@ int launch_im2col(ssdk_ctx* ctx, const ActBuf& in, __nv_bfloat16* out_hi, __nv_b
   return SSDK_OK;
 }
 
+// Direct fp32 convolution for the image-facing layer (Cin < 8, e.g. conv1_1 3x3x3 or SSD7's conv1 5x5x3): K = kh*kw*cin is
+// far too thin for a tensor-core tile, so each thread computes FOUR horizontally adjacent output pixels x 16 output channels
+// with plain FMAs (one shared-memory weight fetch feeds 4 pixels); bias / BN / activation / hi-lo split are fused.
+// HWIO weights are used as they are ([K][Cout]).
+constexpr int kDirectPx = 4;
+__global__ void __launch_bounds__(256) conv_direct_kernel(ActBuf in, ActBuf out, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int act,
+                                                          int KH, int KW, int dil, int pad_t, int pad_l) {
+  extern __shared__ float s_w[];                 // [K][Cout]
+  const int K = KH * KW * in.C, Cout = out.C;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int groups = Cout / 16;
+  const int wq = (out.W + kDirectPx - 1) / kDirectPx;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)out.B * out.H * wq * groups;
+  if (gid >= total) return;
+  const int g = (int)(gid % groups);
+  const size_t q = gid / groups;
+  const int xo0 = (int)(q % wq) * kDirectPx; const int yo = (int)((q / wq) % out.H); const int n = (int)(q / ((size_t)wq * out.H));
+  float acc[kDirectPx][16];
+#pragma unroll
+  for (int p = 0; p < kDirectPx; ++p)
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[p][e] = 0.f;
+  for (int kh = 0; kh < KH; ++kh) {
+    const int y = yo + kh * dil - pad_t;
+    if (y < 0 || y >= in.H) continue;
+    for (int kw = 0; kw < KW; ++kw) {
+      float v[kDirectPx][4];
+#pragma unroll
+      for (int p = 0; p < kDirectPx; ++p) {
+        const int x = xo0 + p + kw * dil - pad_l;
+        uint2 h2 = make_uint2(0, 0), l2 = make_uint2(0, 0);
+        if (x >= 0 && x < in.W) {
+          const size_t s = act_index(in, n, y, x);
+          h2 = *reinterpret_cast<const uint2*>(in.hi + s);                    // channels 0..3 (Cin <= 4 used)
+          if (in.lo) l2 = *reinterpret_cast<const uint2*>(in.lo + s);
+        }
+        v[p][0] = __uint_as_float(h2.x << 16) + __uint_as_float(l2.x << 16);
+        v[p][1] = __uint_as_float(h2.x & 0xffff0000u) + __uint_as_float(l2.x & 0xffff0000u);
+        v[p][2] = __uint_as_float(h2.y << 16) + __uint_as_float(l2.y << 16);
+        v[p][3] = __uint_as_float(h2.y & 0xffff0000u) + __uint_as_float(l2.y & 0xffff0000u);
+      }
+      for (int c = 0; c < in.C; ++c) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + (size_t)((kh * KW + kw) * in.C + c) * Cout + g * 16);
+        const float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+        const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+        for (int p = 0; p < kDirectPx; ++p) {
+          const float vv = c == 0 ? v[p][0] : (c == 1 ? v[p][1] : (c == 2 ? v[p][2] : v[p][3]));
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[p][e] = fmaf(vv, wv[e], acc[p][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < kDirectPx; ++p) {
+    const int xo = xo0 + p;
+    if (xo >= out.W) break;
+    uint32_t ph[8], pl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = g * 16 + j * 2 + e;
+        float xv = acc[p][j * 2 + e] + __ldg(bias + col);
+        if (bn_scale) xv = xv * __ldg(bn_scale + col) + __ldg(bn_shift + col);
+        f[e] = apply_act(xv, act);
+      }
+      __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
+      __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(f[1] - __bfloat162float(h1));
+      ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t o = act_index(out, n, yo, xo) + (size_t)g * 16;
+    *reinterpret_cast<uint4*>(out.hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(out.hi + o + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+    if (out.lo) {
+      *reinterpret_cast<uint4*>(out.lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      *reinterpret_cast<uint4*>(out.lo + o + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+    }
+  }
+}
+
+int launch_conv_direct(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* w, const float* bias, const float* bn_scale,
+                       const float* bn_shift, int act, int kh, int kw, int dil, int pad_t, int pad_l, cudaStream_t stream) {
+  const size_t smem = (size_t)kh * kw * in.C * out.C * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) { SSDK_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
+  const size_t total = (size_t)out.B * out.H * ((out.W + kDirectPx - 1) / kDirectPx) * (out.C / 16);
+  conv_direct_kernel<<<(unsigned)((total + 255) / 256), 256, smem, stream>>>(in, out, w, bias, bn_scale, bn_shift, act, kh, kw, dil, pad_t, pad_l);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
 // Max pooling; out-of-range window positions are ignored (TF 'same' pooling pads with -inf).
 // One thread per (pixel, group of 8 channels); the max is taken on the reconstructed value hi + lo.
 __global__ void maxpool_kernel(ActBuf in, ActBuf out, int KH, int KW, int stride, int pad_t, int pad_l) {

@@ -70,6 +70,8 @@ int launch_preprocess(ssdk_ctx* ctx, const float* images, int B, int H, int W, i
                       const int* swap, const ActBuf& out, cudaStream_t stream);
 int launch_im2col(ssdk_ctx* ctx, const ActBuf& in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int Ho, int Wo, int kh, int kw,
                   int stride, int dil, int pad_t, int pad_l, int Kpad, cudaStream_t stream);
+int launch_conv_direct(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* w, const float* bias, const float* bn_scale,
+                       const float* bn_shift, int act, int kh, int kw, int dil, int pad_t, int pad_l, cudaStream_t stream);
 int launch_maxpool(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, int kh, int kw, int stride, int pad_t, int pad_l,
                    cudaStream_t stream);
 int launch_l2norm(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* gamma, cudaStream_t stream);

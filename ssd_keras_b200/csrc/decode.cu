@@ -6,7 +6,7 @@
 //   dec_prepare_kernel  rows of y_pred staged through shared memory -> decoded corner boxes and
 //                       class-major score planes (coalesced for the per-class NMS CTAs).
 //   nms_kernel          one CTA per (class, image) segment.  Candidates are consumed in descending
-//                       (score, then ascending index) order in BANDS of at most kCap entries: a
+//                       (score, then ascending index) order in BANDS of at most kNmsCap entries: a
 //                       4-pass radix select over the float bits finds the band boundary (ties at the
 //                       boundary are taken in index order), the band is compacted into shared memory,
 //                       bitonic-sorted there and run through the sequential greedy scan (each thread
@@ -22,20 +22,17 @@ using namespace ssdk;
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kCap = 16384;      // band capacity (64-bit keys in shared memory)
-constexpr int kKeptSm = 1024;    // kept boxes cached in shared memory
+constexpr int kNmsThreads = 128;  // NMS: small CTAs, many segments resident per SM (the scan is latency bound)
+constexpr int kNmsCap = 2048;     // NMS band capacity (64-bit keys in shared memory)
+constexpr int kKeptSm = 512;      // kept (prepared) boxes cached in shared memory
+constexpr int kTopThreads = 512;  // top-k stage
+constexpr int kTopCap = 16384;    // largest supported top_k
 
 typedef unsigned long long u64;
 
 __device__ __forceinline__ uint32_t okey(float f) {
   uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float okey_inv(uint32_t k) {
-  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-  return __uint_as_float(b);
 }
 
 struct SegView {
@@ -64,28 +61,30 @@ __device__ __forceinline__ bool remaining(const SegView& s, const BandState& st,
   return st.first || k < st.hi_key || (k == st.hi_key && i > st.hi_idx);
 }
 
+template <int NT>
 __device__ int block_sum_int(int v, int* s_w) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
   __syncthreads();
   int t = 0;
-  for (int w = 0; w < kWarps; ++w) t += s_w[w];
+  for (int w = 0; w < NT / 32; ++w) t += s_w[w];
   __syncthreads();
   return t;
 }
 
 // Fill keys[0..count) with the `cap` largest remaining (score desc, index asc) candidates of the segment
 // (unsorted).  key = (~okey(score)) << 32 | index, so an ascending sort gives the wanted order.
+template <int NT>
 __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* keys, int* s_hist, int* s_misc,
                            int* s_w, bool& more) {
   const int tid = threadIdx.x;
   int cnt = 0;
-  for (int i = tid; i < s.n; i += kThreads) {
+  for (int i = tid; i < s.n; i += NT) {
     uint32_t k;
     if (remaining(s, st, i, s.scores[i], k)) ++cnt;
   }
-  const int R = block_sum_int(cnt, s_w);
+  const int R = block_sum_int<NT>(cnt, s_w);
   if (R == 0) { more = false; return 0; }
   const bool take_all = (R <= cap);
   uint32_t T = 0;
@@ -94,20 +93,26 @@ __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* 
     uint32_t prefix = 0, mask = 0;
     int want = cap;
     for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = tid; i < 256; i += kThreads) s_hist[i] = 0;
+      for (int i = tid; i < 256; i += NT) s_hist[i] = 0;
       __syncthreads();
-      for (int i = tid; i < s.n; i += kThreads) {
+      for (int i = tid; i < s.n; i += NT) {
         uint32_t k;
         if (remaining(s, st, i, s.scores[i], k) && ((k & mask) == prefix)) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int acc = 0, bsel = 0;
-        for (int b = 255; b >= 0; --b) {
-          if (acc + s_hist[b] >= want) { bsel = b; break; }
-          acc += s_hist[b];
+      if (tid < 32) {                      // warp 0: suffix scan over the 256 bins, 8 bins per lane
+        int loc[8], sum = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { loc[e] = s_hist[255 - (tid * 8 + e)]; sum += loc[e]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+        int acc = incl - sum;              // candidates in bins above this lane's 8 bins
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (acc < want && acc + loc[e] >= want) { s_misc[0] = 255 - (tid * 8 + e); s_misc[1] = want - acc; }
+          acc += loc[e];
         }
-        s_misc[0] = bsel; s_misc[1] = want - acc;
       }
       __syncthreads();
       prefix |= ((uint32_t)s_misc[0]) << shift;
@@ -120,7 +125,7 @@ __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* 
   if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
-  for (int base = 0; base < s.n; base += kThreads) {
+  for (int base = 0; base < s.n; base += NT) {
     const int i = base + tid;
     bool take = false, tie = false;
     uint32_t k = 0;
@@ -134,7 +139,7 @@ __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* 
       if (lane == 0) s_w[warp] = __popc(bal);
       __syncthreads();
       int wbase = 0, total = 0;
-      for (int w = 0; w < kWarps; ++w) { int c = s_w[w]; if (w < warp) wbase += c; total += c; }
+      for (int w = 0; w < NT / 32; ++w) { int c = s_w[w]; if (w < warp) wbase += c; total += c; }
       int tie_rank = s_misc[3] + wbase + wrank;
       if (tie && tie_rank < m_ties) take = true;
       __syncthreads();
@@ -150,14 +155,15 @@ __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* 
   return s_misc[2];
 }
 
+template <int NT>
 __device__ void bitonic_sort(u64* keys, int count) {
   int n = 1;
   while (n < count) n <<= 1;
-  for (int i = count + threadIdx.x; i < n; i += kThreads) keys[i] = ~0ull;
+  for (int i = count + threadIdx.x; i < n; i += NT) keys[i] = ~0ull;
   __syncthreads();
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < (n >> 1); t += kThreads) {
+      for (int t = threadIdx.x; t < (n >> 1); t += NT) {
         int i = ((t / j) * (j << 1)) + (t % j);   // lower index of the pair
         int p = i + j;
         bool up = ((i & k) == 0);
@@ -170,9 +176,9 @@ __device__ void bitonic_sort(u64* keys, int count) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// IoU suppression rules
+// IoU suppression rules on "prepared" boxes (coordinates + area computed once per box)
 // ---------------------------------------------------------------------------------------------
-template <typename T> struct Box4 { T x0, y0, x1, y1; };
+template <typename T> struct PBox { T x0, y0, x1, y1, a; };
 
 __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
@@ -186,32 +192,44 @@ __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(
 // std::min / std::max exactly as the TF kernel uses them: NaN handling depends on the argument order.
 __device__ __forceinline__ float tf_min(float a, float b) { return (b < a) ? b : a; }
 __device__ __forceinline__ float tf_max(float a, float b) { return (a < b) ? b : a; }
-// tf.image.non_max_suppression (candidate c against selected m): suppress iff IoU > thr; non-positive areas give IoU 0.
-__device__ __forceinline__ bool suppress_tf(const Box4<float>& c, const Box4<float>& m, float thr) {
-  float cx0 = tf_min(c.x0, c.x1), cx1 = tf_max(c.x0, c.x1), cy0 = tf_min(c.y0, c.y1), cy1 = tf_max(c.y0, c.y1);
-  float mx0 = tf_min(m.x0, m.x1), mx1 = tf_max(m.x0, m.x1), my0 = tf_min(m.y0, m.y1), my1 = tf_max(m.y0, m.y1);
-  float ac = mul_rn(sub_rn(cy1, cy0), sub_rn(cx1, cx0));
-  float am = mul_rn(sub_rn(my1, my0), sub_rn(mx1, mx0));
-  if (ac <= 0.f || am <= 0.f) return false;
-  float ih = tf_max(sub_rn(tf_min(cy1, my1), tf_max(cy0, my0)), 0.f);
-  float iw = tf_max(sub_rn(tf_min(cx1, mx1), tf_max(cx0, mx0)), 0.f);
-  float inter = mul_rn(ih, iw);
-  float iou = div_rn(inter, sub_rn(add_rn(ac, am), inter));
-  return iou > thr;
-}
-// _greedy_nms (ssd_output_decoder.py:90-91): keep iff iou <= thr (NaN is dropped); areas use d, the
-// intersection does not (bounding_box_utils.py:345).
 template <typename T> __device__ __forceinline__ T np_min(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }   // NaN propagates
 template <typename T> __device__ __forceinline__ T np_max(T a, T b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
-template <typename T>
-__device__ __forceinline__ bool suppress_np(const Box4<T>& c, const Box4<T>& m, T thr, T d) {
-  T iw = np_max((T)0, sub_rn(np_min(c.x1, m.x1), np_max(c.x0, m.x0)));
-  T ih = np_max((T)0, sub_rn(np_min(c.y1, m.y1), np_max(c.y0, m.y0)));
-  T inter = mul_rn(iw, ih);
-  T ac = mul_rn(add_rn(sub_rn(c.x1, c.x0), d), add_rn(sub_rn(c.y1, c.y0), d));
-  T am = mul_rn(add_rn(sub_rn(m.x1, m.x0), d), add_rn(sub_rn(m.y1, m.y0), d));
-  T iou = div_rn(inter, sub_rn(add_rn(ac, am), inter));
-  return !(iou <= thr);
+
+template <typename T, bool LAYER>
+__device__ __forceinline__ PBox<T> prepare_box(const T* q, T d) {
+  PBox<T> b;
+  if constexpr (LAYER) {    // tf.image.non_max_suppression normalises each box with min/max first
+    b.x0 = tf_min((float)q[0], (float)q[2]); b.x1 = tf_max((float)q[0], (float)q[2]);
+    b.y0 = tf_min((float)q[1], (float)q[3]); b.y1 = tf_max((float)q[1], (float)q[3]);
+    b.a = mul_rn(sub_rn(b.y1, b.y0), sub_rn(b.x1, b.x0));
+  } else {        // iou(): areas use d, the intersection does not (bounding_box_utils.py:345,373-374)
+    b.x0 = q[0]; b.y0 = q[1]; b.x1 = q[2]; b.y1 = q[3];
+    b.a = mul_rn(add_rn(sub_rn(b.x1, b.x0), d), add_rn(sub_rn(b.y1, b.y0), d));
+  }
+  return b;
+}
+
+// candidate c against selected m.  LAYER: suppress iff IoU > thr, non-positive areas give IoU 0.
+// NumPy API (_greedy_nms, ssd_output_decoder.py:90-91): keep iff iou <= thr, i.e. NaN is dropped.
+template <typename T, bool LAYER>
+__device__ __forceinline__ bool suppressed(const PBox<T>& c, const PBox<T>& m, T thr) {
+  if constexpr (LAYER) {
+    if (c.a <= (T)0 || m.a <= (T)0) return false;
+    T ih = tf_max((float)sub_rn(tf_min((float)c.y1, (float)m.y1), tf_max((float)c.y0, (float)m.y0)), 0.f);
+    T iw = tf_max((float)sub_rn(tf_min((float)c.x1, (float)m.x1), tf_max((float)c.x0, (float)m.x0)), 0.f);
+    T inter = mul_rn(ih, iw);
+    if (inter == (T)0 && thr >= (T)0) return false;          // IoU is 0 (or NaN): never > thr
+    T iou = div_rn(inter, sub_rn(add_rn(c.a, m.a), inter));
+    return iou > thr;
+  } else {
+    T iw = np_max((T)0, sub_rn(np_min(c.x1, m.x1), np_max(c.x0, m.x0)));
+    T ih = np_max((T)0, sub_rn(np_min(c.y1, m.y1), np_max(c.y0, m.y0)));
+    T inter = mul_rn(iw, ih);
+    T uni = sub_rn(add_rn(c.a, m.a), inter);
+    if (inter == (T)0 && uni == uni && uni != (T)0) return !((T)0 <= thr);   // IoU is exactly +-0
+    T iou = div_rn(inter, uni);
+    return !(iou <= thr);
+  }
 }
 
 struct NmsParams {
@@ -227,13 +245,13 @@ struct NmsParams {
 };
 
 template <typename T, bool LAYER>
-__global__ void __launch_bounds__(kThreads) nms_kernel(NmsParams prm) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* keys = reinterpret_cast<u64*>(smem_raw);
-  T* kbox = reinterpret_cast<T*>(keys + kCap);                 // [kKeptSm*4]
+__global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
+  constexpr int NT = kNmsThreads, NW = NT / 32;
+  __shared__ __align__(16) u64 keys[kNmsCap];
+  __shared__ __align__(16) T kbox[kKeptSm * 5];
   __shared__ int s_hist[256];
   __shared__ int s_misc[8];
-  __shared__ int s_w[kWarps];
+  __shared__ int s_w[NW];
   __shared__ int s_K;
 
   const int sidx = blockIdx.x, b = blockIdx.y;
@@ -248,71 +266,62 @@ __global__ void __launch_bounds__(kThreads) nms_kernel(NmsParams prm) {
   const T dd = (T)prm.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  auto kept_box = [&](int t) {
+    PBox<T> m;
+    if (t < kKeptSm) { m.x0 = kbox[t * 5]; m.y0 = kbox[t * 5 + 1]; m.x1 = kbox[t * 5 + 2]; m.y1 = kbox[t * 5 + 3]; m.a = kbox[t * 5 + 4]; }
+    else m = prepare_box<T, LAYER>(boxes + (size_t)kept[t] * 4, dd);
+    return m;
+  };
+
   if (threadIdx.x == 0) s_K = 0;
   BandState st{0u, -1, 1};
   __syncthreads();
   bool done = false;
   while (!done) {
     bool more = false;
-    const int cnt = band_select(sv, st, kCap, keys, s_hist, s_misc, s_w, more);
+    const int cnt = band_select<NT>(sv, st, kNmsCap, keys, s_hist, s_misc, s_w, more);
     if (cnt == 0) break;
-    bitonic_sort(keys, cnt);
-    for (int c0 = 0; c0 < cnt && !done; c0 += kThreads) {
+    bitonic_sort<NT>(keys, cnt);
+    for (int c0 = 0; c0 < cnt && !done; c0 += NT) {
       const int j = c0 + threadIdx.x;
       bool alive = j < cnt;
       int idx = 0;
-      Box4<T> bx{};
+      PBox<T> bx{};
       if (alive) {
         idx = (int)(uint32_t)(keys[j] & 0xffffffffull);
-        const T* q = boxes + (size_t)idx * 4;
-        bx.x0 = q[0]; bx.y0 = q[1]; bx.x1 = q[2]; bx.y1 = q[3];
+        bx = prepare_box<T, LAYER>(boxes + (size_t)idx * 4, dd);
       }
       const int k_start = s_K;
-      for (int t = 0; t < k_start && alive; ++t) {
-        Box4<T> m;
-        if (t < kKeptSm) { m.x0 = kbox[t * 4]; m.y0 = kbox[t * 4 + 1]; m.x1 = kbox[t * 4 + 2]; m.y1 = kbox[t * 4 + 3]; }
-        else { const T* q = boxes + (size_t)kept[t] * 4; m.x0 = q[0]; m.y0 = q[1]; m.x1 = q[2]; m.y1 = q[3]; }
-        bool sup = LAYER ? suppress_tf(*reinterpret_cast<const Box4<float>*>(&bx), *reinterpret_cast<const Box4<float>*>(&m), (float)thr)
-                         : suppress_np<T>(bx, m, thr, dd);
-        if (sup) alive = false;
-      }
+      for (int t = 0; t < k_start && alive; ++t)
+        if (suppressed<T, LAYER>(bx, kept_box(t), thr)) alive = false;
       __syncthreads();
       // warps take turns (ascending candidate order) to settle intra-chunk suppression
-      for (int w = 0; w < kWarps; ++w) {
+      for (int w = 0; w < NW; ++w) {
         if (warp == w) {
-          int k_cur = *((volatile int*)&s_K);
-          for (int t = k_start; t < k_cur && alive; ++t) {     // survivors added by earlier warps of this chunk
-            Box4<T> m;
-            if (t < kKeptSm) { m.x0 = kbox[t * 4]; m.y0 = kbox[t * 4 + 1]; m.x1 = kbox[t * 4 + 2]; m.y1 = kbox[t * 4 + 3]; }
-            else { const T* q = boxes + (size_t)kept[t] * 4; m.x0 = q[0]; m.y0 = q[1]; m.x1 = q[2]; m.y1 = q[3]; }
-            bool sup = LAYER ? suppress_tf(*reinterpret_cast<const Box4<float>*>(&bx), *reinterpret_cast<const Box4<float>*>(&m), (float)thr)
-                             : suppress_np<T>(bx, m, thr, dd);
-            if (sup) alive = false;
-          }
+          const int k_cur = *((volatile int*)&s_K);
+          for (int t = k_start; t < k_cur && alive; ++t)          // survivors added by earlier warps of this chunk
+            if (suppressed<T, LAYER>(bx, kept_box(t), thr)) alive = false;
           unsigned am = __ballot_sync(0xffffffffu, alive);
           int nk = 0, my_rank = -1;
           while (am) {
-            int i = __ffs(am) - 1;
-            Box4<T> m;
+            const int i = __ffs(am) - 1;
+            PBox<T> m;
             m.x0 = __shfl_sync(0xffffffffu, bx.x0, i); m.y0 = __shfl_sync(0xffffffffu, bx.y0, i);
             m.x1 = __shfl_sync(0xffffffffu, bx.x1, i); m.y1 = __shfl_sync(0xffffffffu, bx.y1, i);
+            m.a = __shfl_sync(0xffffffffu, bx.a, i);
             if (lane == i) my_rank = nk;
             ++nk;
-            if (k_cur + nk >= prm.cap) break;                  // cap reached: later candidates are never looked at
-            if (alive && lane > i) {
-              bool sup = LAYER ? suppress_tf(*reinterpret_cast<const Box4<float>*>(&bx), *reinterpret_cast<const Box4<float>*>(&m), (float)thr)
-                               : suppress_np<T>(bx, m, thr, dd);
-              if (sup) alive = false;
-            }
+            if (k_cur + nk >= prm.cap) break;                      // cap reached: later candidates are never looked at
+            if (alive && lane > i && suppressed<T, LAYER>(bx, m, thr)) alive = false;
             am = __ballot_sync(0xffffffffu, alive && lane > i);
           }
           if (my_rank >= 0 && k_cur + my_rank < prm.cap) {
-            int pos = k_cur + my_rank;
+            const int pos = k_cur + my_rank;
             kept[pos] = idx;
-            if (pos < kKeptSm) { kbox[pos * 4] = bx.x0; kbox[pos * 4 + 1] = bx.y0; kbox[pos * 4 + 2] = bx.x1; kbox[pos * 4 + 3] = bx.y1; }
+            if (pos < kKeptSm) { kbox[pos * 5] = bx.x0; kbox[pos * 5 + 1] = bx.y0; kbox[pos * 5 + 2] = bx.x1; kbox[pos * 5 + 3] = bx.y1; kbox[pos * 5 + 4] = bx.a; }
           }
           __syncwarp();
-          if (lane == 0) { int nkk = k_cur + nk; s_K = nkk < prm.cap ? nkk : prm.cap; }
+          if (lane == 0) { const int nkk = k_cur + nk; s_K = nkk < prm.cap ? nkk : prm.cap; }
           __threadfence_block();
         }
         __syncthreads();
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) nms_kernel(NmsParams prm) {
     }
     if (!more) break;
     // next band starts strictly below the last (smallest) candidate of this band
-    u64 last = keys[cnt - 1];
+    const u64 last = keys[cnt - 1];
     st.hi_key = ~(uint32_t)(last >> 32);
     st.hi_idx = (int)(uint32_t)(last & 0xffffffffull);
     st.first = 0;
@@ -448,12 +457,13 @@ __device__ void emit_row(const TopkParams& p, int b, int row_out, int s, int idx
   if (p.out_index) p.out_index[(size_t)b * p.max_out + row_out] = idx;
 }
 
-__global__ void __launch_bounds__(kThreads) topk_kernel(TopkParams p) {
+__global__ void __launch_bounds__(kTopThreads) topk_kernel(TopkParams p) {
+  constexpr int kThreads = kTopThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* keys = reinterpret_cast<u64*>(smem_raw);
   __shared__ int s_hist[256];
   __shared__ int s_misc[8];
-  __shared__ int s_w[kWarps];
+  __shared__ int s_w[kTopThreads / 32];
   __shared__ int s_off[1025];
   const int b = blockIdx.x;
   const int S = p.S;
@@ -492,8 +502,8 @@ __global__ void __launch_bounds__(kThreads) topk_kernel(TopkParams p) {
     BandState st{0u, -1, 1};
     bool more;
     int want = p.top_k < M ? p.top_k : M;
-    int cnt = (M > 0) ? band_select(sv, st, want, keys, s_hist, s_misc, s_w, more) : 0;
-    if (cnt > 0) bitonic_sort(keys, cnt);
+    int cnt = (M > 0) ? band_select<kTopThreads>(sv, st, want, keys, s_hist, s_misc, s_w, more) : 0;
+    if (cnt > 0) bitonic_sort<kTopThreads>(keys, cnt);
     n_out = cnt < p.max_out ? cnt : p.max_out;
     for (int j = threadIdx.x; j < n_out; j += kThreads) {
       int r = (int)(uint32_t)(keys[j] & 0xffffffffull);
@@ -507,10 +517,8 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename T, bool LAYER>
 int launch_nms(ssdk_ctx* ctx, const NmsParams& np, int B, cudaStream_t stream) {
-  size_t sm = (size_t)kCap * sizeof(u64) + (size_t)kKeptSm * 4 * sizeof(T);
-  SSDK_CHECK_CUDA(cudaFuncSetAttribute(nms_kernel<T, LAYER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid(np.S, B);
-  nms_kernel<T, LAYER><<<grid, kThreads, sm, stream>>>(np);
+  nms_kernel<T, LAYER><<<grid, kNmsThreads, 0, stream>>>(np);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
@@ -539,9 +547,9 @@ int run_nms_topk(ssdk_ctx* ctx, int B, int n, int S, int layer, int box_f64, int
   tp.scores = scores; tp.labels = labels; tp.boxes = boxes; tp.box_f64 = box_f64; tp.kept_idx = kept_idx; tp.kept_cnt = kept_cnt;
   tp.n = n; tp.S = S; tp.kmax = kmax; tp.top_k = top_k; tp.max_out = max_out; tp.layer = layer;
   tp.cat_score = cat_score; tp.cat_src = cat_src; tp.out = out; tp.out_counts = out_counts; tp.out_index = out_index;
-  size_t sm = (size_t)kCap * sizeof(u64);
+  size_t sm = (size_t)kTopCap * sizeof(u64);
   SSDK_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  topk_kernel<<<B, kThreads, sm, stream>>>(tp);
+  topk_kernel<<<B, kTopThreads, sm, stream>>>(tp);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
@@ -563,7 +571,7 @@ extern "C" int ssdk_decode(ssdk_ctx* ctx, const ssdk_decode_cfg* cfg, const floa
   SSDK_REQUIRE(!cfg->normalize_coords || (cfg->img_height > 0 && cfg->img_width > 0),
                "If relative box coordinates are supposed to be converted to absolute coordinates, the decoder needs the image size");
   SSDK_REQUIRE(cfg->max_out > 0, "ssdk_decode: max_out must be > 0");
-  SSDK_REQUIRE(cfg->top_k <= kCap, "ssdk_decode: top_k > %d is not supported", kCap);
+  SSDK_REQUIRE(cfg->top_k <= kTopCap, "ssdk_decode: top_k > %d is not supported", kTopCap);
   SSDK_REQUIRE(cfg->n_classes_total - 1 <= 1024, "ssdk_decode: more than 1024 classes are not supported");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int P = cfg->P, C = cfg->n_classes_total, W = C + 12;
@@ -610,7 +618,7 @@ extern "C" int ssdk_nms(ssdk_ctx* ctx, const float* boxes_dev, const float* scor
                         double confidence_thresh, double iou_threshold, int nms_max_output, int top_k,
                         float* out_dev, int* out_counts_dev, int* out_index_dev, void* stream_) {
   SSDK_REQUIRE(ctx && boxes_dev && scores_dev && out_dev && out_counts_dev && B > 0 && n > 0, "ssdk_nms: bad argument");
-  SSDK_REQUIRE(nms_max_output > 0 && top_k > 0 && top_k <= kCap, "ssdk_nms: bad nms_max_output / top_k");
+  SSDK_REQUIRE(nms_max_output > 0 && top_k > 0 && top_k <= kTopCap, "ssdk_nms: bad nms_max_output / top_k");
   size_t total = nms_scratch_bytes(B, 1, nms_max_output);
   int rc = ctx->ws[1].ensure(total);
   if (rc) return rc;

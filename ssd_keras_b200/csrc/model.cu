@@ -25,6 +25,8 @@ struct LayerPlan {
   int in_H = 0, in_W = 0, in_C = 0;
   ActBuf out;                         // INPUT / CONV / MAXPOOL / L2NORM
   bool im2col = false;
+  bool direct = false;                // fp32 SIMT path for the image-facing conv (Cin < 8)
+  float* w_f32 = nullptr;
   int Kpad = 0;
   __nv_bfloat16* col_hi = nullptr; __nv_bfloat16* col_lo = nullptr;
   __nv_bfloat16* w_hi = nullptr; __nv_bfloat16* w_lo = nullptr;
@@ -125,6 +127,19 @@ int build_conv(ssdk_model* m, int li) {
   const int taps = d.kh * d.kw;
   SSDK_REQUIRE(taps <= kMaxTaps, "conv kernel %dx%d is larger than the supported %d taps", d.kh, d.kw, kMaxTaps);
   SSDK_REQUIRE(head || cout % 8 == 0, "conv output channels must be a multiple of 8 (got %d)", cout);
+  L.direct = !head && cin <= 4 && d.stride == 1 && cout % 16 == 0 && (size_t)taps * cin * cout * 4 <= 96 * 1024 && ia.Cs == 8;
+  if (L.direct) {
+    int rc = upload_f32(m, &L.w_f32, d.kernel, (size_t)taps * cin * cout); if (rc) return rc;
+    std::vector<float> b0(cout, 0.f);
+    rc = upload_f32(m, &L.bias, d.bias ? d.bias : b0.data(), cout); if (rc) return rc;
+    if (d.bn_scale && d.bn_shift) {
+      rc = upload_f32(m, &L.bn_scale, d.bn_scale, cout); if (rc) return rc;
+      rc = upload_f32(m, &L.bn_shift, d.bn_shift, cout); if (rc) return rc;
+    }
+    const double fl = 2.0 * m->B * L.H * L.W * (double)taps * cin * cout;
+    m->flops_algo += fl;                 // not tensor-core work: counted as algorithmic FLOPs only
+    return SSDK_OK;
+  }
   L.im2col = (d.stride != 1) || (cin < 8);
   ConvLaunch& cl = L.launch;
   ConvArgs& a = cl.args;
@@ -348,7 +363,7 @@ extern "C" int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms) {
   SSDK_REQUIRE(m && out_ms, "ssdk_model_last_conv_ms: NULL argument");
   float total = 0.f;
   for (auto& L : m->layers) {
-    if (!L.ev0) continue;
+    if (!L.ev0 || L.direct) continue;
     SSDK_CHECK_CUDA(cudaEventSynchronize(L.ev1));
     float ms = 0.f;
     SSDK_CHECK_CUDA(cudaEventElapsedTime(&ms, L.ev0, L.ev1));
@@ -376,6 +391,12 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
       case SSDK_OP_CONV:
       case SSDK_OP_HEAD: {
         const LayerPlan& in = m->layers[d.input];
+        if (L.direct) {
+          rc = launch_conv_direct(ctx, in.out, L.out, L.w_f32, L.bias, L.bn_scale, L.bn_shift, d.act, d.kh, d.kw, d.dilation, d.pad_t,
+                                  d.pad_l, stream);
+          if (rc) return rc;
+          break;
+        }
         if (L.im2col) {
           rc = launch_im2col(ctx, in.out, L.col_hi, L.col_lo, L.H, L.W, d.kh, d.kw, d.stride, d.dilation, d.pad_t, d.pad_l, L.Kpad, stream);
           if (rc) return rc;

@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests of the N>1 host logic (batch sharding + all-gather of decoded boxes), runnable without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ssd_keras_b200 import distributed as D
+
+
+def test_shard_bounds_cover_batch():
+    for n in (1, 2, 7, 16, 32, 33, 256):
+        for world in (1, 2, 3, 4, 8):
+            spans = [D.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_images, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        full = torch.from_numpy(rng.standard_normal((n_images, 5, 6)).astype(np.float32))   # "decoded boxes" of the whole batch
+        lo, hi = D.shard_bounds(n_images, rank, world)
+        local = full[lo:hi].clone()
+        if n_images % world == 0:
+            got = D.all_gather_detections(local)
+        else:
+            got = D.all_gather_ragged(local)
+        ok = bool(torch.equal(got, full))
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = ok and float(t.item()) == float(world)
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_images', [8, 7])
+def test_all_gather_two_ranks_gloo(n_images):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_images, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=90) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
