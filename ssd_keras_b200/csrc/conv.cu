@@ -19,6 +19,7 @@
 #include "conv.cuh"
 #include <cudaTypedefs.h>
 #include <cmath>
+#include <cstdlib>
 
 namespace ssdk {
 
@@ -60,11 +61,23 @@ static constexpr int kBM = 128;          // UMMA M (rows per tile)
 static constexpr int kBK = 64;           // channels per k-block = one 128-byte swizzle atom of bf16
 static constexpr int kATile = kBM * kBK * 2;   // 16 KB
 
-static size_t stage_bytes(int BN, int split) { return (size_t)(kATile + BN * kBK * 2) * (split ? 2 : 1); }
-size_t conv_smem_bytes(int BN, int split, int stages) { return 1024 + stage_bytes(BN, split) * stages + 256; }
-int conv_pick_stages(int BN, int split) {
-  int s = (int)((220 * 1024 - 1280) / stage_bytes(BN, split));
-  return s > 6 ? 6 : s;
+static size_t slot_a_bytes(const ConvArgs& a) { return (size_t)a.slab_rows * kBK * 2 * (a.split ? 2 : 1); }
+static size_t slot_b_bytes(const ConvArgs& a) { return (size_t)a.BN * kBK * 2 * (a.split ? 2 : 1); }
+static size_t epi_param_bytes(const ConvArgs& a) { return ((size_t)a.cout * 3 * sizeof(float) + 127) / 128 * 128; }   // bias | bn scale | bn shift
+size_t conv_smem_bytes(const ConvArgs& a) { return 1024 + slot_a_bytes(a) * a.stages_a + slot_b_bytes(a) * a.stages_b + 512 + epi_param_bytes(a); }
+// Two rings: A slabs (one per (kh, channel block), shared by the KW taps of that row) and weight tiles (one per tap).
+void conv_pick_stages(ConvArgs& a) {
+  const size_t budget = 218 * 1024 - 1536 - epi_param_bytes(a);
+  a.stages_a = 2; a.stages_b = 2;
+  int max_a = 4, max_b = 6;
+  if (const char* e = getenv("SSDK_SA_MAX")) max_a = atoi(e);
+  if (const char* e = getenv("SSDK_SB_MAX")) max_b = atoi(e);
+  bool grew = true;
+  while (grew) {
+    grew = false;
+    if (a.stages_b < max_b && slot_a_bytes(a) * a.stages_a + slot_b_bytes(a) * (a.stages_b + 1) <= budget) { ++a.stages_b; grew = true; }
+    if (a.stages_a < max_a && slot_a_bytes(a) * (a.stages_a + 1) + slot_b_bytes(a) * a.stages_b <= budget) { ++a.stages_a; grew = true; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -112,8 +125,11 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t desc_a, uint64_
                ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // K-major, 128B-swizzled operand tile: start address, SBO = 1024 B (8 rows x 128 B), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int bo_mode = 0) {
   uint64_t d = 0;
+  const uint32_t phase = (addr >> 7) & 0x7u;          // start row inside the 8-row (1024 B) swizzle atom
+  if (bo_mode == 1) d |= (uint64_t)phase << 49;       // [49,52) base offset
+  else if (bo_mode == 2) d |= (uint64_t)((8u - phase) & 7u) << 49;
   d |= (uint64_t)((addr >> 4) & 0x3FFFu);            // [0,14)  start address >> 4
   d |= (uint64_t)0 << 16;                            // [16,30) leading byte offset (unused for swizzled K-major)
   d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;     // [32,46) stride byte offset
@@ -154,17 +170,29 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = args.stages, BN = args.BN, split = args.split;
+  const int SA = args.stages_a, SB = args.stages_b, BN = args.BN, split = args.split;
+  const uint32_t a_plane = (uint32_t)args.slab_rows * kBK * 2;        // one A slab plane (hi or lo)
   const uint32_t b_tile = (uint32_t)BN * kBK * 2;
-  const uint32_t stage_sz = (uint32_t)(kATile + b_tile) * (split ? 2 : 1);
-  const uint32_t bar_base = smem_base + stage_sz * S;
-  // barrier slots (8 B each): full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+  const uint32_t slot_a = a_plane * (split ? 2 : 1), slot_b = b_tile * (split ? 2 : 1);
+  const uint32_t ring_b = smem_base + slot_a * SA;
+  const uint32_t bar_base = ring_b + slot_b * SB;
+  // barrier slots (8 B each): fullA[SA] | emptyA[SA] | fullB[SB] | emptyB[SB] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 2 * SB + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+  // epilogue parameters live in shared memory (L1 is almost entirely carved out for the rings, global loads would miss)
+  float* s_bias = reinterpret_cast<float*>(smem_dyn + (bar_base + 512u - smem_u32(smem_dyn)));
+  float* s_scale = s_bias + args.cout;
+  float* s_shift = s_scale + args.cout;
+  for (int i = threadIdx.x; i < args.cout; i += blockDim.x) {
+    s_bias[i] = args.bias[i];
+    if (args.bn_scale) { s_scale[i] = args.bn_scale[i]; s_shift[i] = args.bn_shift[i]; }
+  }
 
   int tmem_cols = 32;
   while (tmem_cols < 2 * BN) tmem_cols <<= 1;
@@ -178,7 +206,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,39 +221,39 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int total_tiles = args.n_tiles_m * args.n_tiles_n;
-  const int k_iters = args.taps * args.kblocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = stage_sz;
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = args.tile_list[t / args.n_tiles_n] * kBM;
         const int n0 = (t % args.n_tiles_n) * BN;
-        for (int tap = 0; tap < args.taps; ++tap) {
-          const int row0 = m0 + args.tap_shift[tap];
+        for (int kh = 0; kh < args.KH; ++kh) {
+          const int row0 = m0 + args.row_shift[kh];
           for (int kb = 0; kb < args.kblocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage_sz * stage;
-            mbar_expect_tx(full_bar(stage), tx);
-            const int kw = (tap * args.kblocks + kb) * kBK;
-            tma_load_2d(sa, &tm_a_hi, kb * kBK, row0, full_bar(stage));
-            if (split) {
-              tma_load_2d(sa + kATile, &tm_a_lo, kb * kBK, row0, full_bar(stage));
-              tma_load_2d(sa + 2 * kATile, &tm_b_hi, kw, n0, full_bar(stage));
-              tma_load_2d(sa + 2 * kATile + b_tile, &tm_b_lo, kw, n0, full_bar(stage));
-            } else {
-              tma_load_2d(sa + kATile, &tm_b_hi, kw, n0, full_bar(stage));
+            mbar_wait(emptyA(sa), pa ^ 1u);
+            const uint32_t da = smem_base + slot_a * sa;
+            mbar_expect_tx(fullA(sa), slot_a);
+            tma_load_2d(da, &tm_a_hi, kb * kBK, row0, fullA(sa));
+            if (split) tma_load_2d(da + a_plane, &tm_a_lo, kb * kBK, row0, fullA(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            for (int kw = 0; kw < args.KW; ++kw) {
+              mbar_wait(emptyB(sb), pb ^ 1u);
+              const uint32_t db = ring_b + slot_b * sb;
+              mbar_expect_tx(fullB(sb), slot_b);
+              const int kcol = ((kh * args.KW + kw) * args.kblocks + kb) * kBK;
+              tma_load_2d(db, &tm_b_hi, kcol, n0, fullB(sb));
+              if (split) tma_load_2d(db + b_tile, &tm_b_lo, kcol, n0, fullB(sb));
+              if (++sb == SB) { sb = 0; pb ^= 1u; }
             }
-            if (++stage == S) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    int stage = 0; uint32_t phase = 0;
+    int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int n0 = (t % args.n_tiles_n) * BN;
@@ -237,30 +266,35 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const uint32_t idesc = make_idesc(n_eff);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       uint32_t accumulate = 0;
-      for (int ki = 0; ki < k_iters; ++ki) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const int kb = ki % args.kblocks;
+      for (int kh = 0; kh < args.KH; ++kh) {
+        for (int kb = 0; kb < args.kblocks; ++kb) {
+          mbar_wait(fullA(sa), pa);
+          const uint32_t a_hi = smem_base + slot_a * sa, a_lo = a_hi + a_plane;
           const int ksteps = (kb == args.kblocks - 1) ? args.last_ksteps : 4;
-          const uint32_t sa = smem_base + stage_sz * stage;
-          const uint32_t a_hi = sa, a_lo = sa + kATile;
-          const uint32_t b_hi = split ? sa + 2 * kATile : sa + kATile;
-          const uint32_t b_lo = b_hi + b_tile;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint32_t ko = (uint32_t)k * 32u;       // 16 bf16 = 32 bytes along K inside the swizzle atom
-            const uint64_t da = make_smem_desc(a_hi + ko), db = make_smem_desc(b_hi + ko);
-            tc_mma(d_tmem, da, db, idesc, accumulate);
-            accumulate = 1;
-            if (split) {
-              tc_mma(d_tmem, da, make_smem_desc(b_lo + ko), idesc, 1);
-              tc_mma(d_tmem, make_smem_desc(a_lo + ko), db, idesc, 1);
+          for (int kw = 0; kw < args.KW; ++kw) {
+            mbar_wait(fullB(sb), pb);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t b_hi = ring_b + slot_b * sb, b_lo = b_hi + b_tile;
+              const uint32_t arow = (uint32_t)(kw * args.kw_rows) * 128u;     // tap kw = the same slab, kw*dil rows further down
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t ko = (uint32_t)k * 32u;       // 16 bf16 = 32 bytes along K inside the swizzle atom
+                const uint64_t da = make_smem_desc(a_hi + arow + ko, args.bo_mode), db = make_smem_desc(b_hi + ko);
+                tc_mma(d_tmem, da, db, idesc, accumulate);
+                accumulate = 1;
+                if (split) {
+                  tc_mma(d_tmem, da, make_smem_desc(b_lo + ko), idesc, 1);
+                  tc_mma(d_tmem, make_smem_desc(a_lo + arow + ko, args.bo_mode), db, idesc, 1);
+                }
+              }
+              tc_commit(emptyB(sb));                        // weight slot is free once these MMAs retire
+              if (kw == args.KW - 1) tc_commit(emptyA(sa));  // ... and the slab after its last tap
             }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
           }
-          tc_commit(empty_bar(stage));                    // smem slot is free once these MMAs retire
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1u; }
       }
       if (lane == 0) tc_commit(tfull_bar(acc));
       __syncwarp();
@@ -305,8 +339,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
                   for (int e = 0; e < 2; ++e) {
                     const int col = n0 + c0 + g * 8 + j * 2 + e;
-                    float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + __ldg(args.bias + col);
-                    if (args.bn_scale) xv = xv * __ldg(args.bn_scale + col) + __ldg(args.bn_shift + col);
+                    float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + s_bias[col];
+                    if (args.bn_scale) xv = xv * s_scale[col] + s_shift[col];
                     f[e] = apply_act(xv, args.act);
                   }
                   __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
@@ -331,7 +365,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             for (int j = 0; j < 32; ++j) {
               if (c0 + j < ncols) {
                 const int col = n0 + c0 + j;
-                float xv = __uint_as_float(vr[j]) + __ldg(args.bias + col);
+                float xv = __uint_as_float(vr[j]) + s_bias[col];
                 args.out_f32[o + c0 + j] = apply_act(xv, args.act);
               }
             }

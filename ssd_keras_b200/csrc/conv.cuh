@@ -31,16 +31,19 @@ struct ConvArgs {
   int rows_per_img;     // rows of the virtual grid per image
   int in_Wp;            // virtual row pitch
   int Ho, Wo, B;        // valid extent: virtual (y, x) is a real output iff y < Ho && x < Wo
-  int taps, kblocks;    // K loop = taps * kblocks blocks of 64 channels
+  int KH, KW, kblocks;  // K loop = KH * kblocks A-slabs, each feeding KW weight tiles (taps (kh, 0..KW-1))
   int last_ksteps;      // UMMA k-steps (of 16) in the last k-block of every tap (1..4)
-  int tap_shift[kMaxTaps];
+  int row_shift[8];     // row offset of tap (kh, kw=0)
+  int kw_rows;          // rows between consecutive kw taps (= dilation); tap kw reads slab rows [kw*kw_rows, +128)
+  int slab_rows;        // rows per A slab = round_up8(128 + (KW-1)*kw_rows) <= 256
+  int stages_a, stages_b;
+  int bo_mode;          // how the UMMA descriptor's base-offset field is filled for row-shifted A tiles (debug knob)
   int n_tiles_m;        // number of entries in tile_list
   int n_tiles_n;
   const int* tile_list; // m-tile indices that contain at least one valid row
   int BN;               // accumulator tile width (64/128/256); TMA box rows of the weight tile
   int cout;
   int split;            // 1: bf16x3 (hi*hi + hi*lo + lo*hi), 0: single bf16 pass
-  int stages;
   // epilogue
   int epi;
   const float* bias; const float* bn_scale; const float* bn_shift;
@@ -61,8 +64,8 @@ struct ConvLaunch {
 int tma_init();   // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows);
-size_t conv_smem_bytes(int BN, int split, int stages);
-int conv_pick_stages(int BN, int split);
+size_t conv_smem_bytes(const ConvArgs& a);
+void conv_pick_stages(ConvArgs& a);
 int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream);
 
 // elementwise / data movement kernels

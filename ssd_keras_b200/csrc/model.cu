@@ -6,6 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 using namespace ssdk;
 
@@ -156,17 +157,19 @@ int build_conv(ssdk_model* m, int li) {
     int rc = dev_alloc(m, &L.col_hi, n, true); if (rc) return rc;
     if (m->split) { rc = dev_alloc(m, &L.col_lo, n, true); if (rc) return rc; }
     a.M_total = m->B * Ho * Wo; a.rows_per_img = Ho * Wo; a.in_Wp = Wo;
-    a.taps = 1; a.tap_shift[0] = 0;
+    a.KH = 1; a.KW = 1; a.row_shift[0] = 0; a.kw_rows = 1; a.slab_rows = 128;
     a_hi = L.col_hi; a_lo = L.col_lo; a_inner = L.Kpad; a_rows = (uint64_t)a.M_total;
   } else {
     SSDK_REQUIRE(ia.pad >= std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)), "internal: activation border too small");
     kblocks = (ia.Cs + 63) / 64;
     ktot = ia.Cs;
     a.M_total = m->B * ia.Hp() * ia.Wp(); a.rows_per_img = ia.Hp() * ia.Wp(); a.in_Wp = ia.Wp();
-    a.taps = taps;
+    SSDK_REQUIRE(d.kh <= 8 && d.kw <= 8, "conv kernel %dx%d is larger than the supported 8x8", d.kh, d.kw);
+    a.KH = d.kh; a.KW = d.kw; a.kw_rows = d.dilation;
+    a.slab_rows = (128 + (d.kw - 1) * d.dilation + 7) / 8 * 8;
+    SSDK_REQUIRE(a.slab_rows <= 256, "conv kernel width x dilation too large for one TMA box");
     for (int kh = 0; kh < d.kh; ++kh)
-      for (int kw = 0; kw < d.kw; ++kw)
-        a.tap_shift[kh * d.kw + kw] = (kh * d.dilation - d.pad_t + ia.pad) * ia.Wp() + (kw * d.dilation - d.pad_l + ia.pad);
+      a.row_shift[kh] = (kh * d.dilation - d.pad_t + ia.pad) * ia.Wp() + (0 - d.pad_l + ia.pad);
     a_hi = ia.hi; a_lo = ia.lo; a_inner = ia.Cs; a_rows = (uint64_t)a.M_total;
   }
   a.kblocks = kblocks;
@@ -176,8 +179,8 @@ int build_conv(ssdk_model* m, int li) {
   a.BN = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
   a.n_tiles_n = (cout + a.BN - 1) / a.BN;
   a.split = m->split;
-  a.stages = conv_pick_stages(a.BN, a.split);
-  SSDK_REQUIRE(a.stages >= 2, "internal: not enough shared memory for a 2-stage pipeline");
+  conv_pick_stages(a);
+  { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
   // m-tiles that hold at least one valid output row
   std::vector<int> tiles;
   const int n_m = (a.M_total + 127) / 128;
@@ -222,20 +225,20 @@ int build_conv(ssdk_model* m, int li) {
     a.out_hi = L.out.hi; a.out_lo = L.out.lo; a.out_Hp = L.out.Hp(); a.out_Wp = L.out.Wp(); a.out_pad = L.out.pad; a.out_Cs = L.out.Cs;
   }
   // TMA descriptors
-  rc = make_tmap_2d(&cl.a_hi, a_hi, a_inner, a_rows, a_inner * 2, 64, 128); if (rc) return rc;
+  rc = make_tmap_2d(&cl.a_hi, a_hi, a_inner, a_rows, a_inner * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
   rc = make_tmap_2d(&cl.b_hi, L.w_hi, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
   if (m->split) {
-    rc = make_tmap_2d(&cl.a_lo, a_lo, a_inner, a_rows, a_inner * 2, 64, 128); if (rc) return rc;
+    rc = make_tmap_2d(&cl.a_lo, a_lo, a_inner, a_rows, a_inner * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
     rc = make_tmap_2d(&cl.b_lo, L.w_lo, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
   } else { cl.a_lo = cl.a_hi; cl.b_lo = cl.b_hi; }
   const int total_tiles = a.n_tiles_m * a.n_tiles_n;
   cl.grid = std::max(1, std::min(total_tiles, m->ctx->sm_count));
-  cl.smem = conv_smem_bytes(a.BN, a.split, a.stages);
+  cl.smem = conv_smem_bytes(a);
   cl.flops_algo = 2.0 * m->B * Ho * Wo * (double)taps * cin * cout;
   double issued = 0;
   for (int nt = 0; nt < a.n_tiles_n; ++nt) {
     int ne = std::min(a.BN, ((cout - nt * a.BN) + 15) / 16 * 16);
-    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)a.taps * ((kblocks - 1) * 64 + a.last_ksteps * 16);
+    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
   }
   cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
   m->flops_algo += cl.flops_algo; m->flops_issued += cl.flops_issued;
