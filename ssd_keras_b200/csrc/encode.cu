@@ -3,16 +3,17 @@
 // bounding_box_utils/bounding_box_utils.py:283-383, ssd_encoder_decoder/matching_utils.py:22-116.
 //
 // Kernels (all HBM/ALU-bound integer/float64 work, no tensor cores):
-//   enc_rowmax_kernel    one CTA per ground-truth box: row max / first argmax over all anchors
-//                        (tile bounding boxes prune anchors that cannot intersect).
-//   enc_bipartite_kernel one CTA per image: the G sequential greedy rounds, with the reference's
-//                        zeroed-row quirk; rows whose best anchor was taken are re-scanned.
-//   enc_main_kernel      one CTA per (anchor tile, image): per-anchor best gt over the pruned
-//                        candidate list, multi-match / neutral decision, offset encode, and a
-//                        coalesced write of the (C+12)-float target rows staged through shared memory.
-// Exactness: every decision-relevant value is computed with the reference's float64 operation
-// order using non-contracting intrinsics (__dmul_rn/__dadd_rn/...).  The running arg-max compares
-// IoUs by cross multiplication (inter1*union2 > inter2*union1) and divides once at the end.
+//   enc_fused_kernel   one CTA per (256-anchor tile, image), ONE pass over the IoU pairs: ground-truth boxes that
+//                      can touch the tile form an ordered candidate list; a float32 test on outward-rounded corners
+//                      rejects disjoint pairs before any float64 work; per anchor the best gt (multi-match /
+//                      neutral rule) and per (gt, tile) the best anchor are reduced; the (C+12)-float target rows
+//                      are staged in shared memory and written coalesced.
+//   enc_greedy_kernel  one CTA per image: reduces the per-tile bests to row maxima, then one warp runs the G
+//                      sequential greedy rounds of match_bipartite_greedy (zeroed-row quirk included).  When a
+//                      row loses its best anchor only that anchor's tile (256 IoUs) is re-evaluated.
+//   enc_fix_kernel     one warp per ground-truth box: rewrites the row of its bipartite anchor (last gt wins).
+// Exactness: every decision-relevant value is computed with the reference's float64 operation order using
+// non-contracting intrinsics (__dmul_rn/__dadd_rn/...); arg-max decisions compare the float64 quotients.
 #include "common.cuh"
 #include <climits>
 #include <cmath>
@@ -128,253 +129,381 @@ __global__ void iou_general_kernel(const double* __restrict__ b1, int m, const d
 }
 
 // ------------------------------------------------------------------------------------------
-// Block-wide (max value, min index) reduction, 256 threads.
+// shared helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_argmax(double& val, int& idx, double* s_val, int* s_idx) {
+__device__ __forceinline__ double iou_value(const Box& g, const Box& a, double inter) {
+  return __ddiv_rn(inter, union_area(g, a, inter));
+}
+
+struct RowDecision { int match_g; bool neutral; };
+
+// Write one target row: [one-hot class | 4 offsets | 4 anchor coords | 4 variances] (ssd_input_encoder.py:363,396-410).
+template <typename Store>
+__device__ __forceinline__ void emit_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec,
+                                         Store store) {
+  for (int c = 0; c < p.C; ++c) store(c, 0.f);
+  float o4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (dec.match_g >= 0) {
+    double gtc[4]; int cls;
+    gt_template(gt_rows + (size_t)(g0 + dec.match_g) * 5, p, gtc, cls);
+    if (cls >= 0 && cls < p.C) store(cls, 1.f);
+    if (p.coords == SSDK_COORDS_CENTROIDS) {                // :396-400
+      o4[0] = (float)__ddiv_rn(__dsub_rn(gtc[0], at[0]), __dmul_rn(at[2], p.var[0]));
+      o4[1] = (float)__ddiv_rn(__dsub_rn(gtc[1], at[1]), __dmul_rn(at[3], p.var[1]));
+      o4[2] = (float)__ddiv_rn(log(__ddiv_rn(gtc[2], at[2])), p.var[2]);
+      o4[3] = (float)__ddiv_rn(log(__ddiv_rn(gtc[3], at[3])), p.var[3]);
+    } else if (p.coords == SSDK_COORDS_CORNERS) {           // :401-405
+      double w = __dsub_rn(at[2], at[0]), h = __dsub_rn(at[3], at[1]);
+      o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
+      o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), h), p.var[1]);
+      o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), w), p.var[2]);
+      o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
+    } else {                                                // minmax :406-410
+      double w = __dsub_rn(at[1], at[0]), h = __dsub_rn(at[3], at[2]);
+      o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
+      o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), w), p.var[1]);
+      o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), h), p.var[2]);
+      o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
+    }
+    if (dec.neutral) store(p.bg, 0.f);                      // neg_iou_limit <= 0 corner case
+  } else {
+    store(p.bg, dec.neutral ? 0.f : 1.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    store(p.C + k, o4[k]);
+    store(p.C + 4 + k, (float)at[k]);
+    store(p.C + 8 + k, (float)p.var[k]);
+  }
+}
+
+// (value desc, index asc) warp reduction
+__device__ __forceinline__ void warp_argmax(double& val, int& idx) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double ov = __shfl_xor_sync(0xffffffffu, val, o);
     int oi = __shfl_xor_sync(0xffffffffu, idx, o);
     if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
   }
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) { s_val[w] = val; s_idx[w] = idx; }
-  __syncthreads();
-  if (w == 0) {
-    int nw = blockDim.x >> 5;
-    double v = l < nw ? s_val[l] : -1.0;
-    int i = l < nw ? s_idx[l] : INT_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      int oi = __shfl_xor_sync(0xffffffffu, i, o);
-      if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
-    if (l == 0) { s_val[0] = v; s_idx[0] = i; }
-  }
-  __syncthreads();
-  val = s_val[0]; idx = s_idx[0];
-  __syncthreads();
 }
 
-// Scan every anchor (tile-pruned) for ground-truth box `gb`; `removed` columns count as 0.
-// Returns the row maximum and its first index over the whole block (0 / 0 for an all-zero row).
-__device__ void row_scan(const EncParams& p, const Box& gb, const int* removed, int n_removed,
-                         double& out_val, int& out_idx, double* s_val, int* s_idx) {
-  double b_inter = 0.0, b_union = 1.0;
-  int b_idx = INT_MAX;
-  for (int t = 0; t < p.n_tiles; ++t) {
-    if (!bbox_hits(p.tile_bbox + (size_t)t * 4, gb)) continue;      // block-uniform
-    int a = t * kTile + threadIdx.x;
-    if (a >= p.P) continue;
-    Box ab = load_anchor(p, a);
-    double inter = inter_area(gb, ab);
-    if (inter > 0.0) {
-      double un = union_area(gb, ab, inter);
-      bool better = (p.d == 0) ? (__dmul_rn(inter, b_union) > __dmul_rn(b_inter, un))
-                               : (__ddiv_rn(inter, un) > __ddiv_rn(b_inter, b_union));
-      if (better) {
-        bool gone = false;
-        for (int r = 0; r < n_removed; ++r) gone |= (removed[r] == a);
-        if (!gone) { b_inter = inter; b_union = un; b_idx = a; }
-      }
-    }
-  }
-  double val = (b_idx != INT_MAX) ? __ddiv_rn(b_inter, b_union) : 0.0;
-  if (!(val > 0.0)) { val = 0.0; b_idx = INT_MAX; }
-  block_argmax(val, b_idx, s_val, s_idx);
-  out_val = val;
-  out_idx = (val > 0.0) ? b_idx : 0;       // argmax of an all-zero row is index 0
-}
-
-// One CTA per ground-truth box.
-__global__ void __launch_bounds__(kTile) enc_rowmax_kernel(EncParams p, const float* __restrict__ gt,
-                                                           const int* __restrict__ gt_offsets, int B,
-                                                           double* __restrict__ rowmax, int* __restrict__ rowarg,
-                                                           int* __restrict__ status) {
-  __shared__ double s_val[8];
-  __shared__ int s_idx[8];
-  int g = blockIdx.x;
-  double t[4]; int cls;
-  bool ok = gt_template(gt + (size_t)g * 5, p, t, cls);
-  if (!ok && threadIdx.x == 0 && status) {
-    int lo = 0, hi = B;                       // image of this gt row: largest b with offsets[b] <= g
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gt_offsets[mid] <= g) lo = mid; else hi = mid; }
-    atomicMax(status, lo + 1);
-  }
-  Box gb = corners_from_template(t, p.coords, p.d);
-  double val; int idx;
-  row_scan(p, gb, nullptr, 0, val, idx, s_val, s_idx);
-  if (threadIdx.x == 0) { rowmax[g] = val; rowarg[g] = idx; }
-}
-
-// One CTA per image: match_bipartite_greedy (matching_utils.py:63-77).
-__global__ void __launch_bounds__(kTile) enc_bipartite_kernel(EncParams p, const float* __restrict__ gt,
-                                                              const int* __restrict__ gt_offsets,
-                                                              const double* __restrict__ rowmax_g,
-                                                              const int* __restrict__ rowarg_g,
-                                                              int* __restrict__ matches) {
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ double s_val[8];
-  __shared__ int s_idx[8];
-  const int b = blockIdx.x;
-  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
-  if (G <= 0) return;
-  double* rv = reinterpret_cast<double*>(smem_raw);          // [G]
-  int* ra = reinterpret_cast<int*>(rv + G);                   // [G]
-  int* removed = ra + G;                                      // [G]
-  for (int g = threadIdx.x; g < G; g += blockDim.x) { rv[g] = rowmax_g[g0 + g]; ra[g] = rowarg_g[g0 + g]; matches[g0 + g] = 0; }
-  __syncthreads();
-  int n_removed = 0;
-  for (int round = 0; round < G; ++round) {
-    double v = -1.0; int gi = INT_MAX;
-    for (int g = threadIdx.x; g < G; g += blockDim.x)
-      if (rv[g] > v) { v = rv[g]; gi = g; }                   // ascending g per thread: first index kept
-    block_argmax(v, gi, s_val, s_idx);
-    const int a_star = ra[gi];
-    __syncthreads();
-    if (threadIdx.x == 0) { matches[g0 + gi] = a_star; rv[gi] = 0.0; ra[gi] = 0; removed[n_removed] = a_star; }
-    ++n_removed;
-    __syncthreads();
-    // rows whose recorded best anchor just disappeared must be re-scanned
-    for (int g = 0; g < G; ++g) {
-      if (rv[g] > 0.0 && ra[g] == a_star) {                   // block-uniform condition (shared memory)
-        double t[4]; int cls;
-        gt_template(gt + (size_t)(g0 + g) * 5, p, t, cls);
-        Box gb = corners_from_template(t, p.coords, p.d);
-        double nv; int ni;
-        row_scan(p, gb, removed, n_removed, nv, ni, s_val, s_idx);
-        if (threadIdx.x == 0) { rv[g] = nv; ra[g] = ni; }
-        __syncthreads();
-      }
-    }
-  }
-}
-
-// One CTA per (anchor tile, image).
-__global__ void __launch_bounds__(kTile) enc_main_kernel(EncParams p, const float* __restrict__ gt,
-                                                         const int* __restrict__ gt_offsets,
-                                                         const int* __restrict__ matches,
-                                                         float* __restrict__ out_y, int* __restrict__ out_match) {
-  extern __shared__ unsigned char smem_raw[];
+// ------------------------------------------------------------------------------------------
+// enc_fused_kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const float* __restrict__ gt,
+                                                          const int* __restrict__ gt_offsets,
+                                                          double* __restrict__ tb_val, int* __restrict__ tb_idx,
+                                                          float* __restrict__ out_y, int* __restrict__ out_match,
+                                                          int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tile = blockIdx.x, b = blockIdx.y;
   const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+  const int Gs = G > 0 ? G : 1;
   const int W = p.C + 12;
-  // shared layout: rows[kTile*W] floats | cand boxes [G] x (x0,y0,x1,y1,area) doubles | cand idx [G] | owner[kTile]
+  // shared layout: rows[kTile*W] f32 | cand f32 bounds 4*G (float4 aligned) | cand boxes 5*G f64 | per-warp tile bests 8*G f64 |
+  //                cand idx G | per-warp tile-best idx 8*G | cand slot of gt G
   float* rows = reinterpret_cast<float*>(smem_raw);
   size_t off = ((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15;
-  double* cb = reinterpret_cast<double*>(smem_raw + off);     // 5*G doubles
-  int* cidx = reinterpret_cast<int*>(cb + 5 * (size_t)(G > 0 ? G : 1));
-  int* owner = cidx + (G > 0 ? G : 1);
+  float* cf = reinterpret_cast<float*>(smem_raw + off); off += (size_t)4 * Gs * sizeof(float);
+  double* cb = reinterpret_cast<double*>(smem_raw + off); off += (size_t)5 * Gs * sizeof(double);
+  double* wv = reinterpret_cast<double*>(smem_raw + off); off += (size_t)8 * Gs * sizeof(double);
+  int* cidx = reinterpret_cast<int*>(smem_raw + off); off += (size_t)Gs * sizeof(int);
+  int* wi = reinterpret_cast<int*>(smem_raw + off); off += (size_t)8 * Gs * sizeof(int);
+  int* slot_of = reinterpret_cast<int*>(smem_raw + off); off += (size_t)Gs * sizeof(int);
+  int* s_wfirst = reinterpret_cast<int*>(smem_raw + off);   // [8*G] first anchor index attaining the per-warp best
   __shared__ int s_ncand;
+  __shared__ int s_wn[8];
 
   const int a0 = tile * kTile;
-  owner[threadIdx.x] = -1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) slot_of[g] = -1;
   if (threadIdx.x == 0) s_ncand = 0;
   __syncthreads();
-  // bipartite owners: the highest gt index wins on duplicates (NumPy fancy assignment, :363)
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    int m = matches[g0 + g] - a0;
-    if (m >= 0 && m < kTile) atomicMax(&owner[m], g);
-  }
   // ordered candidate list (ascending gt index) built by warp 0
-  if (threadIdx.x < 32) {
+  if (warp == 0) {
     const double* bb = p.tile_bbox + (size_t)tile * 4;
     int n = 0;
+    bool bad = false;
     for (int base = 0; base < G; base += 32) {
-      int g = base + threadIdx.x;
+      int g = base + lane;
       bool hit = false; Box gb{};
       if (g < G) {
         double t[4]; int cls;
-        gt_template(gt + (size_t)(g0 + g) * 5, p, t, cls);
+        bad |= !gt_template(gt + (size_t)(g0 + g) * 5, p, t, cls);
         gb = corners_from_template(t, p.coords, p.d);
         hit = bbox_hits(bb, gb);
       }
       unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
-        int pos = n + __popc(m & ((1u << threadIdx.x) - 1));
-        cb[pos * 5 + 0] = gb.x0; cb[pos * 5 + 1] = gb.y0; cb[pos * 5 + 2] = gb.x1; cb[pos * 5 + 3] = gb.y1;
-        cb[pos * 5 + 4] = gb.area; cidx[pos] = g;
+        int pos = n + __popc(m & ((1u << lane) - 1));
+        cb[pos * 5 + 0] = gb.x0; cb[pos * 5 + 1] = gb.y0; cb[pos * 5 + 2] = gb.x1; cb[pos * 5 + 3] = gb.y1; cb[pos * 5 + 4] = gb.area;
+        // outward-rounded float32 corners: disjoint here => disjoint in float64
+        cf[pos * 4 + 0] = __double2float_rd(gb.x0); cf[pos * 4 + 1] = __double2float_rd(gb.y0);
+        cf[pos * 4 + 2] = __double2float_ru(gb.x1); cf[pos * 4 + 3] = __double2float_ru(gb.y1);
+        cidx[pos] = g; slot_of[g] = pos;
       }
       n += __popc(m);
     }
-    if (threadIdx.x == 0) s_ncand = n;
+    if (lane == 0) s_ncand = n;
+    if (tile == 0 && status && __any_sync(0xffffffffu, bad) && lane == 0) atomicMax(status, b + 1);
   }
   __syncthreads();
   const int ncand = s_ncand;
   const int a = a0 + threadIdx.x;
+  const bool live = a < p.P;
   float* my = rows + (size_t)threadIdx.x * W;
-  if (a < p.P) {
+  double at[4] = {0, 0, 0, 0};
+  Box ab{};
+  float fx0 = 0, fy0 = 0, fx1 = 0, fy1 = 0;
+  if (live) {
     const double2* q = reinterpret_cast<const double2*>(p.anchors + (size_t)a * 4);
     double2 u = __ldg(q), v = __ldg(q + 1);
-    double at[4] = {u.x, u.y, v.x, v.y};
-    Box ab = corners_from_template(at, p.coords, p.d);
-    int match_g = owner[threadIdx.x];
-    bool neutral = false;
-    if (match_g < 0) {
-      double b_inter = 0.0, b_union = 1.0; int b_g = -1;
-      for (int c = 0; c < ncand; ++c) {
+    at[0] = u.x; at[1] = u.y; at[2] = v.x; at[3] = v.y;
+    ab = corners_from_template(at, p.coords, p.d);
+    fx0 = __double2float_rd(ab.x0); fy0 = __double2float_rd(ab.y0); fx1 = __double2float_ru(ab.x1); fy1 = __double2float_ru(ab.y1);
+  }
+  // per-warp candidate sub-list: only ground truth that can touch one of THIS warp's 32 anchors
+  int* wlist = wi;                                            // reuse: wi[warp*Gs + k] first holds the slot list, then the result idx
+  {
+    float bx0 = live ? fx0 : INFINITY, by0 = live ? fy0 : INFINITY, bx1 = live ? fx1 : -INFINITY, by1 = live ? fy1 : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+      bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    int n = 0;
+    for (int base = 0; base < ncand; base += 32) {
+      const int c = base + lane;
+      bool hit = false;
+      if (c < ncand) {
+        const float4 gf = *reinterpret_cast<const float4*>(cf + c * 4);
+        hit = (fminf(bx1, gf.z) > fmaxf(bx0, gf.x)) && (fminf(by1, gf.w) > fmaxf(by0, gf.y));
+        wv[warp * Gs + c] = 0.0;                               // default: this warp contributes nothing for candidate c
+      }
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) wlist[warp * Gs + n + __popc(m & ((1u << lane) - 1))] = c;
+      n += __popc(m);
+    }
+    __syncwarp();
+    s_wn[warp] = n;
+  }
+  const int wn = s_wn[warp];
+  double best = 0.0; int best_g = -1;
+  for (int k = 0; k < wn; ++k) {
+    const int c = wlist[warp * Gs + k];
+    double val = 0.0;
+    const float4 gf = *reinterpret_cast<const float4*>(cf + c * 4);
+    const bool maybe = live && (fminf(fx1, gf.z) > fmaxf(fx0, gf.x)) && (fminf(fy1, gf.w) > fmaxf(fy0, gf.y));
+    if (__any_sync(0xffffffffu, maybe)) {
+      if (maybe) {
         Box gb; gb.x0 = cb[c * 5]; gb.y0 = cb[c * 5 + 1]; gb.x1 = cb[c * 5 + 2]; gb.y1 = cb[c * 5 + 3]; gb.area = cb[c * 5 + 4];
         double inter = inter_area(gb, ab);
-        if (inter > 0.0) {
-          double un = union_area(gb, ab, inter);
-          bool better = (p.d == 0) ? (__dmul_rn(inter, b_union) > __dmul_rn(b_inter, un))
-                                   : (__ddiv_rn(inter, un) > __ddiv_rn(b_inter, b_union));
-          if (better) { b_inter = inter; b_union = un; b_g = cidx[c]; }
-        }
+        if (inter > 0.0) val = iou_value(gb, ab, inter);
       }
-      double val = (b_g >= 0) ? __ddiv_rn(b_inter, b_union) : 0.0;
-      int arg = (b_g >= 0 && val > 0.0) ? b_g : 0;           // np.argmax of an all-zero column is 0
-      if (!(val > 0.0)) val = 0.0;
-      if (p.multi && G > 0 && val >= p.pos_thr) { match_g = arg; val = 0.0; }     // column zeroed after matching (:381)
-      if (G > 0 && val >= p.neg_lim) neutral = true;                               // :388-390
-    } else {
-      if (0.0 >= p.neg_lim) neutral = true;                   // matched column is all zero
-    }
-    // ---- fill the row ----
-    for (int c = 0; c < p.C; ++c) my[c] = 0.f;
-    float o4[4] = {0.f, 0.f, 0.f, 0.f};
-    if (match_g >= 0) {
-      double gtc[4]; int cls;
-      gt_template(gt + (size_t)(g0 + match_g) * 5, p, gtc, cls);
-      if (cls >= 0 && cls < p.C) my[cls] = 1.f;
-      if (p.coords == SSDK_COORDS_CENTROIDS) {                // :396-400
-        o4[0] = (float)__ddiv_rn(__dsub_rn(gtc[0], at[0]), __dmul_rn(at[2], p.var[0]));
-        o4[1] = (float)__ddiv_rn(__dsub_rn(gtc[1], at[1]), __dmul_rn(at[3], p.var[1]));
-        o4[2] = (float)__ddiv_rn(log(__ddiv_rn(gtc[2], at[2])), p.var[2]);
-        o4[3] = (float)__ddiv_rn(log(__ddiv_rn(gtc[3], at[3])), p.var[3]);
-      } else if (p.coords == SSDK_COORDS_CORNERS) {           // :401-405
-        double w = __dsub_rn(at[2], at[0]), h = __dsub_rn(at[3], at[1]);
-        o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
-        o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), h), p.var[1]);
-        o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), w), p.var[2]);
-        o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
-      } else {                                                // minmax :406-410
-        double w = __dsub_rn(at[1], at[0]), h = __dsub_rn(at[3], at[2]);
-        o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
-        o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), w), p.var[1]);
-        o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), h), p.var[2]);
-        o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
-      }
-      if (neutral) my[p.bg] = 0.f;                            // neg_iou_limit <= 0 corner case
-    } else {
-      my[p.bg] = neutral ? 0.f : 1.f;
-    }
+      if (val > best) { best = val; best_g = cidx[c]; }        // strict '>' keeps the first gt on ties (np.argmax)
+      // best anchor of this gt among the warp's 32 anchors: max value, then the lowest lane holding it (= lowest index)
+      double mx = val;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      my[p.C + k] = o4[k];
-      my[p.C + 4 + k] = (float)at[k];
-      my[p.C + 8 + k] = (float)p.var[k];
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (mx > 0.0) {
+        const unsigned who = __ballot_sync(0xffffffffu, val == mx);
+        if (lane == 0) { wv[warp * Gs + c] = mx; s_wfirst[warp * Gs + c] = a0 + warp * 32 + (__ffs(who) - 1); }
+      }
     }
-    if (out_match) out_match[(size_t)b * p.P + a] = (match_g >= 0) ? match_g : (neutral ? -2 : -1);
+  }
+  __syncwarp();
+  if (live) {
+    RowDecision dec{-1, false};
+    double val = best;
+    if (G > 0) {
+      const int arg = best_g >= 0 ? best_g : 0;                // np.argmax of an all-zero column is 0
+      if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
+      if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
+    }
+    emit_row(p, gt, g0, at, dec, [&](int k, float v) { my[k] = v; });
+    if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
   }
   __syncthreads();
+  // per (gt, tile) best anchor -> global
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double v = 0.0; int i = INT_MAX;
+    const int c = slot_of[g];
+    if (c >= 0) {
+      for (int w = 0; w < 8; ++w) {                             // warps are in ascending anchor order: strict '>' keeps the first
+        double ov = wv[w * Gs + c];
+        if (ov > v) { v = ov; i = s_wfirst[w * Gs + c]; }
+      }
+    }
+    tb_val[(size_t)(g0 + g) * p.n_tiles + tile] = v;
+    tb_idx[(size_t)(g0 + g) * p.n_tiles + tile] = (v > 0.0) ? i : INT_MAX;
+  }
   // coalesced copy of the staged rows
   const int n_rows = min(kTile, p.P - a0);
   const size_t n_f = (size_t)n_rows * W;
   float* dst = out_y + ((size_t)b * p.P + a0) * W;
   for (size_t i = threadIdx.x; i < n_f; i += blockDim.x) dst[i] = rows[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_greedy_kernel: match_bipartite_greedy (matching_utils.py:63-77) for one image
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
+  bool r = false;
+  for (int i = 0; i < n; ++i) r |= (removed[i] == a);
+  return r;
+}
+
+// Row `g` keeps a COMPACT list of its non-zero per-tile bests (value, anchor index); the tile of an entry is idx / kTile.
+// Re-evaluate tile `t` for ground-truth `gb` ignoring removed anchors (one warp) and update the row's entry for that tile.
+__device__ void warp_fix_tile(const EncParams& p, const Box& gb, int t, const int* removed, int n_removed, double* tv, int* ti, int nnz) {
+  const int lane = threadIdx.x & 31;
+  double bv = 0.0; int bi = INT_MAX;
+  for (int k = 0; k < kTile / 32; ++k) {
+    const int a = t * kTile + k * 32 + lane;
+    if (a < p.P) {
+      Box ab = load_anchor(p, a);
+      double inter = inter_area(gb, ab);
+      if (inter > 0.0) {
+        double v = iou_value(gb, ab, inter);
+        if (v > bv && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
+      }
+    }
+  }
+  warp_argmax(bv, bi);
+  for (int e = lane; e < nnz; e += 32) {
+    if (__ldcg(ti + e) / kTile == t) {                       // exactly one entry per tile
+      tv[e] = bv;
+      if (bv > 0.0) ti[e] = bi;                              // keep the old index (tile id) when the tile is exhausted
+    }
+  }
+  __syncwarp();
+}
+
+__device__ void warp_row_reduce(const double* tv, const int* ti, int nnz, double& val, int& idx) {
+  const int lane = threadIdx.x & 31;
+  double bv = 0.0; int bi = INT_MAX;
+  for (int e = lane; e < nnz; e += 32) {
+    double v = __ldcg(tv + e); int i = __ldcg(ti + e);
+    if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
+  }
+  warp_argmax(bv, bi);
+  val = bv; idx = bi;
+}
+
+__global__ void __launch_bounds__(256) enc_greedy_kernel(EncParams p, const float* __restrict__ gt,
+                                                         const int* __restrict__ gt_offsets, double* tb_val, int* tb_idx,
+                                                         int* __restrict__ matches) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int b = blockIdx.x;
+  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
+  if (G <= 0) return;
+  double* rv = reinterpret_cast<double*>(smem_raw);          // [G] current row maximum
+  double* gbox = rv + G;                                      // [5*G] corner boxes of the ground truth
+  int* ra = reinterpret_cast<int*>(gbox + 5 * (size_t)G);     // [G] its (first) anchor index
+  int* removed = ra + G;                                      // [G] anchors taken so far
+  int* nnz = removed + G;                                     // [G] entries in the row's compact tile list
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // phase A (one warp per row): compact the non-zero per-tile bests in place, row maximum, cached gt box
+  for (int g = warp; g < G; g += (blockDim.x >> 5)) {
+    double* tv = tb_val + (size_t)(g0 + g) * p.n_tiles;
+    int* ti = tb_idx + (size_t)(g0 + g) * p.n_tiles;
+    int k = 0;
+    double bv = 0.0; int bi = INT_MAX;
+    for (int base = 0; base < p.n_tiles; base += 32) {
+      const int t = base + lane;
+      double v = 0.0; int i = INT_MAX;
+      if (t < p.n_tiles) { v = __ldcg(tv + t); i = __ldcg(ti + t); }
+      const bool nz = v > 0.0;
+      const unsigned m = __ballot_sync(0xffffffffu, nz);
+      __syncwarp();
+      if (nz) {
+        const int pos = k + __popc(m & ((1u << lane) - 1));
+        tv[pos] = v; ti[pos] = i;
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+      k += __popc(m);
+      __syncwarp();
+    }
+    warp_argmax(bv, bi);
+    double t4[4]; int cls;
+    gt_template(gt + (size_t)(g0 + g) * 5, p, t4, cls);
+    Box gb = corners_from_template(t4, p.coords, p.d);
+    if (lane == 0) {
+      rv[g] = bv; ra[g] = (bv > 0.0) ? bi : 0; nnz[g] = k; matches[g0 + g] = 0;    // argmax of an all-zero row is 0
+      gbox[g * 5] = gb.x0; gbox[g * 5 + 1] = gb.y0; gbox[g * 5 + 2] = gb.x1; gbox[g * 5 + 3] = gb.y1; gbox[g * 5 + 4] = gb.area;
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  if (warp != 0) return;
+  // phase B: the G sequential rounds, one warp
+  int n_removed = 0;
+  for (int round = 0; round < G; ++round) {
+    double v = -1.0; int gi = INT_MAX;
+    for (int g = lane; g < G; g += 32)
+      if (rv[g] > v) { v = rv[g]; gi = g; }                   // ascending g per lane: first index kept
+    warp_argmax(v, gi);
+    const int a_star = ra[gi];
+    __syncwarp();
+    if (lane == 0) { matches[g0 + gi] = a_star; rv[gi] = 0.0; ra[gi] = 0; removed[n_removed] = a_star; }
+    ++n_removed;
+    __syncwarp();
+    if (!(v > 0.0)) continue;                                  // nothing left to match: no row can point at a_star
+    // rows that pointed at the taken anchor: fix that tile, re-reduce, repeat while the new best is itself stale
+    for (int base = 0; base < G; base += 32) {
+      const int g = base + lane;
+      unsigned need = __ballot_sync(0xffffffffu, g < G && rv[g] > 0.0 && ra[g] == a_star);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int gg = base + src;
+        Box gb; gb.x0 = gbox[gg * 5]; gb.y0 = gbox[gg * 5 + 1]; gb.x1 = gbox[gg * 5 + 2]; gb.y1 = gbox[gg * 5 + 3]; gb.area = gbox[gg * 5 + 4];
+        double* tv = tb_val + (size_t)(g0 + gg) * p.n_tiles;
+        int* ti = tb_idx + (size_t)(g0 + gg) * p.n_tiles;
+        const int nz = nnz[gg];
+        int stale = a_star;
+        double nv; int ni;
+        while (true) {
+          warp_fix_tile(p, gb, stale / kTile, removed, n_removed, tv, ti, nz);
+          __threadfence_block();
+          warp_row_reduce(tv, ti, nz, nv, ni);
+          if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
+          stale = ni;                                          // a tile entry recorded before that anchor was taken
+        }
+        if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// enc_fix_kernel: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (:363), last writer wins
+// ------------------------------------------------------------------------------------------
+__global__ void enc_fix_kernel(EncParams p, const float* __restrict__ gt, const int* __restrict__ gt_offsets, int B,
+                               int total_g, const int* __restrict__ matches, float* __restrict__ out_y,
+                               int* __restrict__ out_match) {
+  const int gg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gg >= total_g) return;
+  int lo = 0, hi = B;                                         // image of this gt row
+  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gt_offsets[mid] <= gg) lo = mid; else hi = mid; }
+  const int b = lo, g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0, g = gg - g0;
+  const int a = matches[gg];
+  bool last = true;
+  for (int g2 = g + 1 + lane; g2 < G; g2 += 32) last &= (matches[g0 + g2] != a);
+  last = __all_sync(0xffffffffu, last);
+  if (!last) return;
+  const double2* q = reinterpret_cast<const double2*>(p.anchors + (size_t)a * 4);
+  double2 u = __ldg(q), v = __ldg(q + 1);
+  const double at[4] = {u.x, u.y, v.x, v.y};
+  RowDecision dec{g, 0.0 >= p.neg_lim};                       // the matched column is all zero
+  float* dst = out_y + ((size_t)b * p.P + a) * (p.C + 12);
+  if (lane == 0) {
+    emit_row(p, gt, g0, at, dec, [&](int k, float v2) { dst[k] = v2; });
+    if (out_match) out_match[(size_t)b * p.P + a] = g;
+  }
 }
 
 __global__ void anchor_tile_bbox_kernel(EncParams p, double* __restrict__ bbox) {
@@ -405,7 +534,7 @@ struct ssdk_encoder {
   EncParams p{};
   double* d_anchors = nullptr;
   double* d_bbox = nullptr;
-  Scratch rows;        // rowmax (double) + rowarg (int) + matches (int) + offsets (int)
+  Scratch rows;        // per-(gt, tile) bests + matches + offsets
   int* h_offsets = nullptr;   // pinned staging
   int h_offsets_cap = 0;
 };
@@ -482,14 +611,15 @@ extern "C" int ssdk_encode(ssdk_encoder* e, const float* gt_boxes_dev, const int
     max_g = g > max_g ? g : max_g;
   }
   SSDK_REQUIRE(total_g == 0 || gt_boxes_dev, "ssdk_encode: gt_boxes_dev is NULL");
-  // scratch: rowmax[total_g] f64 | rowarg[total_g] | matches[total_g] | offsets[B+1]
-  size_t n = (size_t)(total_g > 0 ? total_g : 1);
-  size_t bytes = n * 8 + n * 4 + n * 4 + (size_t)(B + 1) * 4 + 64;
+  // scratch: tile-best values [total_g * n_tiles] f64 | tile-best indices [total_g * n_tiles] | matches[total_g] | offsets[B+1]
+  const size_t n = (size_t)(total_g > 0 ? total_g : 1);
+  const size_t nt = n * (size_t)p.n_tiles;
+  const size_t bytes = nt * 8 + nt * 4 + n * 4 + (size_t)(B + 1) * 4 + 64;
   int rc = e->rows.ensure(bytes);
   if (rc) return rc;
-  double* rowmax = reinterpret_cast<double*>(e->rows.ptr);
-  int* rowarg = reinterpret_cast<int*>(rowmax + n);
-  int* matches = rowarg + n;
+  double* tb_val = reinterpret_cast<double*>(e->rows.ptr);
+  int* tb_idx = reinterpret_cast<int*>(tb_val + nt);
+  int* matches = tb_idx + nt;
   int* d_offsets = matches + n;
   if (e->h_offsets_cap < B + 1) {
     if (e->h_offsets) cudaFreeHost(e->h_offsets);
@@ -500,21 +630,22 @@ extern "C" int ssdk_encode(ssdk_encoder* e, const float* gt_boxes_dev, const int
   SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
   memcpy(e->h_offsets, gt_offsets_host, (size_t)(B + 1) * sizeof(int));
   SSDK_CHECK_CUDA(cudaMemcpyAsync(d_offsets, e->h_offsets, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  const int W = p.C + 12;
+  const size_t gs = (size_t)(max_g > 0 ? max_g : 1);
+  const size_t sm_m = (((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15) + gs * (5 * 8 + 8 * 8 + 4 * 4 + 4 + 8 * 4 + 4 + 8 * 4) + 64;
+  SSDK_REQUIRE(sm_m <= 227 * 1024, "ssdk_encode: n_classes (%d) / gt count (%d) need %zu bytes of shared memory", p.C, max_g, sm_m);
+  if (sm_m > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));
+  dim3 grid(p.n_tiles, B);
+  enc_fused_kernel<<<grid, kTile, sm_m, stream>>>(p, gt_boxes_dev, d_offsets, tb_val, tb_idx, out_y_dev, out_match_dev, status_dev);
+  SSDK_COUNT_LAUNCH(e->ctx);
   if (total_g > 0) {
-    enc_rowmax_kernel<<<total_g, kTile, 0, stream>>>(p, gt_boxes_dev, d_offsets, B, rowmax, rowarg, status_dev);
+    const size_t sm_b = (size_t)max_g * (8 + 40 + 4 + 4 + 4) + 16;
+    if (sm_b > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+    enc_greedy_kernel<<<B, 256, sm_b, stream>>>(p, gt_boxes_dev, d_offsets, tb_val, tb_idx, matches);
     SSDK_COUNT_LAUNCH(e->ctx);
-    size_t sm_b = (size_t)max_g * (8 + 4 + 4) + 16;
-    if (sm_b > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_bipartite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
-    enc_bipartite_kernel<<<B, kTile, sm_b, stream>>>(p, gt_boxes_dev, d_offsets, rowmax, rowarg, matches);
+    enc_fix_kernel<<<ceil_div(total_g, 8), 256, 0, stream>>>(p, gt_boxes_dev, d_offsets, B, total_g, matches, out_y_dev, out_match_dev);
     SSDK_COUNT_LAUNCH(e->ctx);
   }
-  const int W = p.C + 12;
-  size_t sm_m = (((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15) + (size_t)(max_g > 0 ? max_g : 1) * (5 * 8 + 4) + kTile * 4 + 16;
-  SSDK_REQUIRE(sm_m <= 227 * 1024, "ssdk_encode: n_classes (%d) / gt count (%d) need %zu bytes of shared memory", p.C, max_g, sm_m);
-  if (sm_m > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));
-  dim3 grid(p.n_tiles, B);
-  enc_main_kernel<<<grid, kTile, sm_m, stream>>>(p, gt_boxes_dev, d_offsets, matches, out_y_dev, out_match_dev);
-  SSDK_COUNT_LAUNCH(e->ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
 }
