@@ -239,12 +239,33 @@ def run_ours(args):
             out = all_gather_detections(out)            # decoded boxes of every rank
         return out
 
+    copy_stream = torch.cuda.Stream()
+    pinned_out = torch.empty((world * BATCH, 200, 6), dtype=torch.float32).pin_memory()
+    state = {}
+
+    def _upload(i):
+        """pinned host -> device on the copy stream (overlaps the previous step's kernels)."""
+        with torch.cuda.stream(copy_stream):
+            x = host[i % n_in].cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return x, ev
+
     def step_e2e(i):
-        x = host[i % n_in].cuda(non_blocking=True)       # pinned host -> device, inside the timed region
+        # every step uploads its own 34.6 MB batch and downloads its own result; the upload of step i+1 is issued
+        # before the kernels of step i so that PCIe and the SMs overlap (double buffering, all inside the timed region)
+        if 'next' not in state:
+            state['next'] = _upload(i)
+        x, ev = state.pop('next')
+        torch.cuda.current_stream().wait_event(ev)
+        x.record_stream(torch.cuda.current_stream())
+        state['next'] = _upload(i + 1)
         out = model.predict_device(x)
         if world > 1:
             out = all_gather_detections(out)
-        return out.cpu()                                 # result back on the host
+        pinned_out.copy_(out, non_blocking=True)          # result back on the host
+        torch.cuda.current_stream().synchronize()
+        return pinned_out
 
     def barrier():
         if world > 1:
@@ -274,6 +295,7 @@ def run_ours(args):
 
     ms_dev, clocks, launches = timed(step_device, args.steps, max(args.warmup, 3))
     ms_e2e, _, _ = timed(step_e2e, args.steps, 1)
+    state.clear()
     ips = world * BATCH * args.steps / (ms_dev * 1e-3)
     ips_e2e = world * BATCH * args.steps / (ms_e2e * 1e-3)
 
@@ -307,8 +329,10 @@ def run_ours(args):
             'config': {'workload': WORKLOAD, 'global_batch': world * BATCH, 'parallelism': 'dp%d' % world, 'precision': precision,
                        'l2': 'no explicit flush: %d distinct 34.6 MB input batches are rotated and each step streams >4 GB of '
                              'activations through the 126 MB L2' % n_in},
-            'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': BATCH * 300 * 300 * 3 * 4,
-                    'd2h_bytes_per_step': BATCH * 200 * 6 * 4, 'ms_per_step': ms_e2e / args.steps},
+            'e2e': {'value': ips_e2e, 'unit': 'images/s', 'h2d_bytes_per_step': world * BATCH * 300 * 300 * 3 * 4,
+                    'd2h_bytes_per_step': world * BATCH * 200 * 6 * 4, 'ms_per_step': ms_e2e / args.steps,
+                    'note': 'SSDModel.predict_device on pinned-host inputs; the H2D of step i+1 is issued on a copy stream before '
+                            'the kernels of step i (K uploads + K downloads inside the timed region)'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline}
     if world == 1:
         if not args.no_cpu:
