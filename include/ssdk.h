@@ -219,6 +219,7 @@ typedef struct {
   int precision;            /* 0 = bf16x3 split (fp32-faithful, default), 1 = single-pass bf16 */
   const float* anchors_f32; /* host [P*4] */
   float variances[4];
+  int training;             /* 1: size the activation borders for the backward pass too (needed by ssdk_trainer_create) */
 } ssdk_model_desc;
 
 /* Stand-alone L2Normalization.call (keras_layers/keras_layer_L2Normalization.py:61-63) on a float32 tensor viewed as
@@ -239,6 +240,29 @@ int ssdk_model_flops(const ssdk_model* m, double* out_algorithmic, double* out_i
 /* Time of the conv kernels of the last forward in ms (CUDA events on `stream`), when enabled. */
 int ssdk_model_set_timing(ssdk_model* m, int enable);
 int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 3).  Replaces what Keras/TensorFlow do for the reference in model.fit_generator:
+ * autodiff of the graph (models/keras_ssd300.py:263-419) and of SSDLoss (keras_ssd_loss.py:98-211), the kernel_regularizer
+ * l2(l2_reg) (models/keras_ssd300.py:274) and SGD(lr, momentum) (ssd300_training.ipynb:169).  ReLU / linear graphs only.
+ *   ssdk_train_backward  after ssdk_model_forward on the same images: loss + gradients of every kernel / bias / gamma into one
+ *                        flat float32 buffer (so that a single NCCL all-reduce covers it).
+ *   ssdk_train_apply     g = grad*grad_scale + 2*l2*w (kernels only); v = momentum*v - lr*g; w += v; re-pack the bf16 planes.
+ * Parameter order in the flat buffer: layers in graph order, for each conv [kernel as (cout, kh, kw, cin) | bias], for each
+ * head [fused kernel (n_boxes*(C+4), 3, 3, cin) | fused bias], for L2Normalization [gamma].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ssdk_trainer ssdk_trainer;
+int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev /* optional, else allocated */, ssdk_trainer** out);
+int ssdk_trainer_destroy(ssdk_trainer* t);
+int ssdk_trainer_num_params(const ssdk_trainer* t, long long* out_n);
+/* offset (in floats) and element count of a layer's kernel (which=0), bias (1) or gamma (2) inside the flat buffers */
+int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int which, long long* out_offset, long long* out_count);
+float* ssdk_trainer_grad_buffer(ssdk_trainer* t);
+int ssdk_train_backward(ssdk_trainer* t, const float* y_true_dev, const float* y_pred_dev, int neg_pos_ratio, int n_neg_min,
+                        float alpha, float* out_loss_dev /* [B] */, void* stream);
+int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float l2_reg, float grad_scale, void* stream);
+/* Copy the current float32 master parameters (same order / layout as the gradients) to out_dev. */
+int ssdk_trainer_read_params(ssdk_trainer* t, float* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

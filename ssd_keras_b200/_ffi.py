@@ -57,7 +57,7 @@ class LayerDesc(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [('batch', C.c_int), ('img_height', C.c_int), ('img_width', C.c_int), ('img_channels', C.c_int),
                 ('n_classes_total', C.c_int), ('n_layers', C.c_int), ('layers', C.POINTER(LayerDesc)),
-                ('precision', C.c_int), ('anchors_f32', c_float_p), ('variances', C.c_float * 4)]
+                ('precision', C.c_int), ('anchors_f32', c_float_p), ('variances', C.c_float * 4), ('training', C.c_int)]
 
 
 OP_INPUT, OP_CONV, OP_MAXPOOL, OP_L2NORM, OP_HEAD = range(5)
@@ -113,6 +113,19 @@ def lib():
             L.ssdk_model_flops.argtypes = [vp, c_double_p, c_double_p]
             L.ssdk_model_set_timing.argtypes = [vp, C.c_int]
             L.ssdk_model_last_conv_ms.argtypes = [vp, c_float_p]
+        if hasattr(L, 'ssdk_trainer_create'):
+            L.ssdk_trainer_create.argtypes = [vp, vp, C.POINTER(vp)]
+            L.ssdk_trainer_destroy.argtypes = [vp]
+            L.ssdk_trainer_num_params.argtypes = [vp, C.POINTER(C.c_longlong)]
+            L.ssdk_trainer_param_span.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+            L.ssdk_trainer_grad_buffer.argtypes = [vp]
+            L.ssdk_trainer_grad_buffer.restype = vp
+            L.ssdk_train_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]
+            L.ssdk_train_apply.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+            L.ssdk_trainer_read_params.argtypes = [vp, vp, vp]
+            for name in ('ssdk_trainer_create', 'ssdk_trainer_destroy', 'ssdk_trainer_num_params', 'ssdk_trainer_param_span',
+                         'ssdk_train_backward', 'ssdk_train_apply', 'ssdk_trainer_read_params'):
+                getattr(L, name).restype = C.c_int
         for name in ('ssdk_ctx_create', 'ssdk_ctx_destroy', 'ssdk_anchors_count', 'ssdk_anchors_generate',
                      'ssdk_encoder_create', 'ssdk_encoder_destroy', 'ssdk_encode', 'ssdk_iou_matrix', 'ssdk_iou', 'ssdk_decode',
                      'ssdk_nms', 'ssdk_ssd_loss_fwd', 'ssdk_ssd_loss_bwd'):

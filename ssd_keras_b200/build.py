@@ -26,6 +26,7 @@ SOURCES = {
     'loss.cu': ['--fmad=false'],
     'conv.cu': [],
     'model.cu': [],
+    'train.cu': [],
 }
 
 

@@ -190,7 +190,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   float* s_scale = s_bias + args.cout;
   float* s_shift = s_scale + args.cout;
   for (int i = threadIdx.x; i < args.cout; i += blockDim.x) {
-    s_bias[i] = args.bias[i];
+    s_bias[i] = args.bias ? args.bias[i] : 0.f;
     if (args.bn_scale) { s_scale[i] = args.bn_scale[i]; s_shift[i] = args.bn_shift[i]; }
   }
 
@@ -220,18 +220,22 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int total_tiles = args.n_tiles_m * args.n_tiles_n;
+  const int KS = args.k_split > 1 ? args.k_split : 1;
+  const int total_tiles = args.n_tiles_m * args.n_tiles_n * KS;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = args.tile_list[t / args.n_tiles_n] * kBM;
-        const int n0 = (t % args.n_tiles_n) * BN;
+        const int tt = t / KS, ks = t - tt * KS;
+        const int m0 = args.tile_list[tt / args.n_tiles_n] * kBM;
+        const int n0 = (tt % args.n_tiles_n) * BN;
+        const int kb0 = KS > 1 ? ks * args.kb_per : 0;
+        const int kb1 = KS > 1 ? min(args.kblocks, kb0 + args.kb_per) : args.kblocks;
         for (int kh = 0; kh < args.KH; ++kh) {
           const int row0 = m0 + args.row_shift[kh];
-          for (int kb = 0; kb < args.kblocks; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(emptyA(sa), pa ^ 1u);
             const uint32_t da = smem_base + slot_a * sa;
             mbar_expect_tx(fullA(sa), slot_a);
@@ -242,7 +246,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               mbar_wait(emptyB(sb), pb ^ 1u);
               const uint32_t db = ring_b + slot_b * sb;
               mbar_expect_tx(fullB(sb), slot_b);
-              const int kcol = ((kh * args.KW + kw) * args.kblocks + kb) * kBK;
+              const int kcol = ((kh * args.KW + kw) * args.kblocks + kb) * kBK + args.b_k_offset;
               tma_load_2d(db, &tm_b_hi, kcol, n0, fullB(sb));
               if (split) tma_load_2d(db + b_tile, &tm_b_lo, kcol, n0, fullB(sb));
               if (++sb == SB) { sb = 0; pb ^= 1u; }
@@ -256,7 +260,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int n0 = (t % args.n_tiles_n) * BN;
+      const int tt = t / KS, ks = t - tt * KS;
+      const int n0 = (tt % args.n_tiles_n) * BN;
+      const int kb0 = KS > 1 ? ks * args.kb_per : 0;
+      const int kb1 = KS > 1 ? min(args.kblocks, kb0 + args.kb_per) : args.kblocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -267,7 +274,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       uint32_t accumulate = 0;
       for (int kh = 0; kh < args.KH; ++kh) {
-        for (int kb = 0; kb < args.kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(fullA(sa), pa);
           const uint32_t a_hi = smem_base + slot_a * sa, a_lo = a_hi + a_plane;
           const int ksteps = (kb == args.kblocks - 1) ? args.last_ksteps : 4;
@@ -304,8 +311,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     const int q = warp - 4;                                // TMEM lane quarter of this warp (== warp % 4)
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int m0 = args.tile_list[t / args.n_tiles_n] * kBM;
-      const int n0 = (t % args.n_tiles_n) * BN;
+      const int tt = t / KS;
+      const int m0 = args.tile_list[tt / args.n_tiles_n] * kBM;
+      const int n0 = (tt % args.n_tiles_n) * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -333,6 +341,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             for (int g = 0; g < 4; ++g) {
               if (c0 + g * 8 < ncols) {
                 uint32_t ph[4], pl[4];
+                uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), oh = make_uint4(0, 0, 0, 0), ol = oh;
+                if (args.mask_hi) mk = *reinterpret_cast<const uint4*>(args.mask_hi + o + c0 + g * 8);
+                if (args.accumulate) {
+                  oh = *reinterpret_cast<const uint4*>(args.out_hi + o + c0 + g * 8);
+                  if (args.out_lo) ol = *reinterpret_cast<const uint4*>(args.out_lo + o + c0 + g * 8);
+                }
+                const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w}, ohw[4] = {oh.x, oh.y, oh.z, oh.w}, olw[4] = {ol.x, ol.y, ol.z, ol.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   float f[2];
@@ -341,7 +356,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                     const int col = n0 + c0 + g * 8 + j * 2 + e;
                     float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + s_bias[col];
                     if (args.bn_scale) xv = xv * s_scale[col] + s_shift[col];
-                    f[e] = apply_act(xv, args.act);
+                    xv = apply_act(xv, args.act);
+                    if (!(__uint_as_float(((mkw[j] >> (e * 16)) & 0xffffu) << 16) > 0.f)) xv = 0.f;       // ReLU'(forward value)
+                    xv += __uint_as_float(((ohw[j] >> (e * 16)) & 0xffffu) << 16) + __uint_as_float(((olw[j] >> (e * 16)) & 0xffffu) << 16);
+                    f[e] = xv;
                   }
                   __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
                   __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0));
@@ -353,6 +371,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                 if (args.out_lo) *reinterpret_cast<uint4*>(args.out_lo + o + c0 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
               }
             }
+          }
+        }
+      } else if (args.epi == EPI_ATOMIC) {
+        float* dstp = args.out_f32 + (size_t)v * args.out_ld + args.out_col_off + n0;
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t vr[32];
+          tmem_ld32(t_row + (uint32_t)c0, vr);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < ncols) atomicAdd(dstp + c0 + j, __uint_as_float(vr[j]));
           }
         }
       } else {

@@ -21,7 +21,7 @@ struct ActBuf {
   size_t elems() const { return rows() * Cs; }
 };
 
-enum { EPI_SPLIT = 0, EPI_F32 = 1 };
+enum { EPI_SPLIT = 0, EPI_F32 = 1, EPI_ATOMIC = 2 };
 
 constexpr int kMaxTaps = 25;
 
@@ -50,7 +50,14 @@ struct ConvArgs {
   int act;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int out_Hp, out_Wp, out_pad, out_Cs;
-  float* out_f32;       // EPI_F32: compact [B*Ho*Wo][cout]
+  float* out_f32;       // EPI_F32: compact [B*Ho*Wo][cout]; EPI_ATOMIC: atomicAdd into out_f32[row*out_ld + out_col_off + col]
+  // --- extensions used by the backward pass ---
+  int k_split;          // >1: the K loop (KH == KW == 1 only) is cut into k_split ranges, one work unit each (EPI_ATOMIC)
+  int kb_per;           // k-blocks per range
+  int b_k_offset;       // added to the K coordinate of the weight-side operand (row-shifted taps of a transposed tensor)
+  int out_ld, out_col_off;
+  const __nv_bfloat16* mask_hi;   // EPI_SPLIT: zero the result where this plane (same geometry as the output) is <= 0 (ReLU')
+  int accumulate;       // EPI_SPLIT: add to the value already stored in the output planes
 };
 
 struct ConvLaunch {

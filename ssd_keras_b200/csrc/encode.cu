@@ -212,7 +212,6 @@ __global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const flo
   int* slot_of = reinterpret_cast<int*>(smem_raw + off); off += (size_t)Gs * sizeof(int);
   int* s_wfirst = reinterpret_cast<int*>(smem_raw + off);   // [8*G] first anchor index attaining the per-warp best
   __shared__ int s_ncand;
-  __shared__ int s_wn[8];
 
   const int a0 = tile * kTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,56 +261,24 @@ __global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const flo
     ab = corners_from_template(at, p.coords, p.d);
     fx0 = __double2float_rd(ab.x0); fy0 = __double2float_rd(ab.y0); fx1 = __double2float_ru(ab.x1); fy1 = __double2float_ru(ab.y1);
   }
-  // per-warp candidate sub-list: only ground truth that can touch one of THIS warp's 32 anchors
-  int* wlist = wi;                                            // reuse: wi[warp*Gs + k] first holds the slot list, then the result idx
-  {
-    float bx0 = live ? fx0 : INFINITY, by0 = live ? fy0 : INFINITY, bx1 = live ? fx1 : -INFINITY, by1 = live ? fy1 : -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o));
-      bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
-    }
-    int n = 0;
-    for (int base = 0; base < ncand; base += 32) {
-      const int c = base + lane;
-      bool hit = false;
-      if (c < ncand) {
-        const float4 gf = *reinterpret_cast<const float4*>(cf + c * 4);
-        hit = (fminf(bx1, gf.z) > fmaxf(bx0, gf.x)) && (fminf(by1, gf.w) > fmaxf(by0, gf.y));
-        wv[warp * Gs + c] = 0.0;                               // default: this warp contributes nothing for candidate c
-      }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) wlist[warp * Gs + n + __popc(m & ((1u << lane) - 1))] = c;
-      n += __popc(m);
-    }
-    __syncwarp();
-    s_wn[warp] = n;
-  }
-  const int wn = s_wn[warp];
   double best = 0.0; int best_g = -1;
-  for (int k = 0; k < wn; ++k) {
-    const int c = wlist[warp * Gs + k];
+  for (int c = 0; c < ncand; ++c) {
     double val = 0.0;
     const float4 gf = *reinterpret_cast<const float4*>(cf + c * 4);
     const bool maybe = live && (fminf(fx1, gf.z) > fmaxf(fx0, gf.x)) && (fminf(fy1, gf.w) > fmaxf(fy0, gf.y));
-    if (__any_sync(0xffffffffu, maybe)) {
-      if (maybe) {
-        Box gb; gb.x0 = cb[c * 5]; gb.y0 = cb[c * 5 + 1]; gb.x1 = cb[c * 5 + 2]; gb.y1 = cb[c * 5 + 3]; gb.area = cb[c * 5 + 4];
-        double inter = inter_area(gb, ab);
-        if (inter > 0.0) val = iou_value(gb, ab, inter);
-      }
-      if (val > best) { best = val; best_g = cidx[c]; }        // strict '>' keeps the first gt on ties (np.argmax)
-      // best anchor of this gt among the warp's 32 anchors: max value, then the lowest lane holding it (= lowest index)
-      double mx = val;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (mx > 0.0) {
-        const unsigned who = __ballot_sync(0xffffffffu, val == mx);
-        if (lane == 0) { wv[warp * Gs + c] = mx; s_wfirst[warp * Gs + c] = a0 + warp * 32 + (__ffs(who) - 1); }
-      }
+    if (maybe) {
+      Box gb; gb.x0 = cb[c * 5]; gb.y0 = cb[c * 5 + 1]; gb.x1 = cb[c * 5 + 2]; gb.y1 = cb[c * 5 + 3]; gb.area = cb[c * 5 + 4];
+      double inter = inter_area(gb, ab);
+      if (inter > 0.0) val = iou_value(gb, ab, inter);
     }
+    if (val > best) { best = val; best_g = cidx[c]; }          // strict '>' keeps the first gt on ties (np.argmax)
+    // best anchor of this gt inside the warp's 32 anchors (first index on ties)
+    if (__any_sync(0xffffffffu, val > 0.0)) {
+      double rv = val; int ri = (val > 0.0) ? a : INT_MAX;
+      warp_argmax(rv, ri);
+      if (lane == 0) { wv[warp * Gs + c] = rv; s_wfirst[warp * Gs + c] = ri; }
+    } else if (lane == 0) { wv[warp * Gs + c] = 0.0; s_wfirst[warp * Gs + c] = INT_MAX; }
   }
-  __syncwarp();
   if (live) {
     RowDecision dec{-1, false};
     double val = best;

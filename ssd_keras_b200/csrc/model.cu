@@ -2,89 +2,11 @@
 // The host (Python, mirroring the reference builders) describes the graph layer by layer; this file sizes the
 // zero-bordered activation buffers, packs the weights into K-major bf16 hi/lo planes, builds the TMA descriptors
 // and tile lists once, and replays the kernel sequence on every forward call.
-#include "conv.cuh"
-#include <vector>
-#include <algorithm>
-#include <cmath>
-#include <cstdlib>
+#include "model.cuh"
 
 using namespace ssdk;
 
 namespace {
-
-inline uint16_t f2bf(float f) {                  // round-to-nearest-even float -> bf16
-  uint32_t u; memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-inline float bf2f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
-
-struct LayerPlan {
-  ssdk_layer_desc d{};
-  int H = 0, W = 0, C = 0;            // logical output shape
-  int in_H = 0, in_W = 0, in_C = 0;
-  ActBuf out;                         // INPUT / CONV / MAXPOOL / L2NORM
-  bool im2col = false;
-  bool direct = false;                // fp32 SIMT path for the image-facing conv (Cin < 8)
-  float* w_f32 = nullptr;
-  int Kpad = 0;
-  __nv_bfloat16* col_hi = nullptr; __nv_bfloat16* col_lo = nullptr;
-  __nv_bfloat16* w_hi = nullptr; __nv_bfloat16* w_lo = nullptr;
-  float* bias = nullptr; float* bn_scale = nullptr; float* bn_shift = nullptr; float* gamma = nullptr;
-  int* tile_list = nullptr;
-  ConvLaunch launch{};
-  float* head_f32 = nullptr;
-  int prior_off = 0;
-  int need_pad = 0;                   // border required by the consumers of this layer's output
-  float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};
-  bool has_mean = false, has_std = false, has_swap = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
-
-}  // namespace
-
-struct ssdk_model {
-  ssdk_ctx* ctx = nullptr;
-  int B = 0, H = 0, W = 0, Cimg = 0, Ctot = 0, P = 0, split = 1;
-  std::vector<LayerPlan> layers;
-  float* d_anchors = nullptr;
-  float var[4] = {0, 0, 0, 0};
-  double flops_algo = 0, flops_issued = 0;
-  int timing = 0;
-  std::vector<void*> allocs;
-};
-
-namespace {
-
-template <typename T>
-int dev_alloc(ssdk_model* m, T** out, size_t count, bool zero) {
-  void* p = nullptr;
-  size_t bytes = count * sizeof(T);
-  if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return SSDK_ERR_NOMEM; }
-  if (zero) { e = cudaMemset(p, 0, bytes); if (e != cudaSuccess) { set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return SSDK_ERR_CUDA; } }
-  m->allocs.push_back(p);
-  *out = reinterpret_cast<T*>(p);
-  return SSDK_OK;
-}
-
-int upload_f32(ssdk_model* m, float** out, const float* host, size_t n) {
-  int rc = dev_alloc(m, out, n, false);
-  if (rc) return rc;
-  SSDK_CHECK_CUDA(cudaMemcpy(*out, host, n * sizeof(float), cudaMemcpyHostToDevice));
-  return SSDK_OK;
-}
-
-int alloc_act(ssdk_model* m, ActBuf& a, int B, int H, int W, int C, int pad) {
-  a.B = B; a.H = H; a.W = W; a.C = C; a.Cs = (C + 7) / 8 * 8; a.pad = pad;
-  size_t n = a.elems() + 64 * 8;         // slack: TMA boxes may start on the last rows
-  int rc = dev_alloc(m, &a.hi, n, true);
-  if (rc) return rc;
-  if (m->split) { rc = dev_alloc(m, &a.lo, n, true); if (rc) return rc; }
-  return SSDK_OK;
-}
 
 // Pack an HWIO float32 kernel (optionally two kernels fused per box: conf + loc) into K-major bf16 hi/lo planes
 // [cout][taps][kblocks*64] (virtual path) or [cout][kblocks*64] with k = (kh*KW+kw)*cin + c (im2col path).
@@ -144,11 +66,10 @@ int build_conv(ssdk_model* m, int li) {
   L.im2col = (d.stride != 1) || (cin < 8);
   ConvLaunch& cl = L.launch;
   ConvArgs& a = cl.args;
-  memset(&a, 0, sizeof(a));
   const int Ho = L.H, Wo = L.W;
+  ConvGeom g;
+  g.Ho = Ho; g.Wo = Wo; g.B = m->B; g.cout = cout;
   int kblocks, ktot;
-  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;
-  uint64_t a_inner, a_rows;
   if (L.im2col) {
     L.Kpad = (taps * cin + 7) / 8 * 8;
     kblocks = (L.Kpad + 63) / 64;
@@ -156,57 +77,42 @@ int build_conv(ssdk_model* m, int li) {
     size_t n = (size_t)m->B * Ho * Wo * L.Kpad + 64 * 8;
     int rc = dev_alloc(m, &L.col_hi, n, true); if (rc) return rc;
     if (m->split) { rc = dev_alloc(m, &L.col_lo, n, true); if (rc) return rc; }
-    a.M_total = m->B * Ho * Wo; a.rows_per_img = Ho * Wo; a.in_Wp = Wo;
-    a.KH = 1; a.KW = 1; a.row_shift[0] = 0; a.kw_rows = 1; a.slab_rows = 128;
-    a_hi = L.col_hi; a_lo = L.col_lo; a_inner = L.Kpad; a_rows = (uint64_t)a.M_total;
+    g.a_hi = L.col_hi; g.a_lo = L.col_lo; g.a_inner = L.Kpad; g.a_rows = (uint64_t)m->B * Ho * Wo;
   } else {
-    SSDK_REQUIRE(ia.pad >= std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)), "internal: activation border too small");
     kblocks = (ia.Cs + 63) / 64;
     ktot = ia.Cs;
-    a.M_total = m->B * ia.Hp() * ia.Wp(); a.rows_per_img = ia.Hp() * ia.Wp(); a.in_Wp = ia.Wp();
-    SSDK_REQUIRE(d.kh <= 8 && d.kw <= 8, "conv kernel %dx%d is larger than the supported 8x8", d.kh, d.kw);
-    a.KH = d.kh; a.KW = d.kw; a.kw_rows = d.dilation;
-    a.slab_rows = (128 + (d.kw - 1) * d.dilation + 7) / 8 * 8;
-    SSDK_REQUIRE(a.slab_rows <= 256, "conv kernel width x dilation too large for one TMA box");
-    for (int kh = 0; kh < d.kh; ++kh)
-      a.row_shift[kh] = (kh * d.dilation - d.pad_t + ia.pad) * ia.Wp() + (0 - d.pad_l + ia.pad);
-    a_hi = ia.hi; a_lo = ia.lo; a_inner = ia.Cs; a_rows = (uint64_t)a.M_total;
+    g.in = &ia; g.kh = d.kh; g.kw = d.kw; g.dilation = d.dilation; g.pad_t = d.pad_t; g.pad_l = d.pad_l;
+    SSDK_REQUIRE(ia.pad >= std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)), "internal: activation border too small");
   }
-  a.kblocks = kblocks;
-  a.last_ksteps = (ktot - (kblocks - 1) * 64 + 15) / 16;
-  a.Ho = Ho; a.Wo = Wo; a.B = m->B;
-  a.cout = cout;
-  a.BN = cout <= 64 ? 64 : (cout <= 128 ? 128 : 256);
-  a.n_tiles_n = (cout + a.BN - 1) / a.BN;
-  a.split = m->split;
-  conv_pick_stages(a);
-  { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
-  // m-tiles that hold at least one valid output row
-  std::vector<int> tiles;
-  const int n_m = (a.M_total + 127) / 128;
-  for (int t = 0; t < n_m; ++t) {
-    bool any = false;
-    for (int r = 0; r < 128 && !any; ++r) {
-      long long v = (long long)t * 128 + r;
-      if (v >= a.M_total) break;
-      int rr = (int)(v % a.rows_per_img);
-      any = (rr / a.in_Wp < Ho) && (rr % a.in_Wp < Wo);
-    }
-    if (any) tiles.push_back(t);
-  }
-  a.n_tiles_m = (int)tiles.size();
-  int rc = dev_alloc(m, &L.tile_list, tiles.size(), false); if (rc) return rc;
-  SSDK_CHECK_CUDA(cudaMemcpy(L.tile_list, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
-  a.tile_list = L.tile_list;
+  L.kblocks = kblocks;
   // weights
   std::vector<uint16_t> whi, wlo; std::vector<float> bias;
   pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias);
   const size_t Krow = whi.size() / cout;
-  rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
+  L.w_krow = Krow;
+  int rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
   SSDK_CHECK_CUDA(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
   if (m->split) {
     rc = dev_alloc(m, &L.w_lo, wlo.size(), false); if (rc) return rc;
     SSDK_CHECK_CUDA(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+  }
+  rc = plan_conv_gemm(m, cl, g, L.w_hi, L.w_lo, Krow, kblocks, (ktot - (kblocks - 1) * 64 + 15) / 16, &L.tile_list);
+  if (rc) return rc;
+  if (m->training) {          // fp32 master kernel, HWIO, with the conf/loc kernels of a head fused per box like the packed planes
+    std::vector<float> master((size_t)taps * cin * cout);
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < cin; ++c)
+        for (int o = 0; o < cout; ++o) {
+          float w;
+          if (!head) w = d.kernel[((size_t)t * cin + c) * cout + o];
+          else {
+            const int b = o / (m->Ctot + 4), r = o % (m->Ctot + 4);
+            w = r < m->Ctot ? d.kernel[((size_t)t * cin + c) * (d.n_boxes * m->Ctot) + b * m->Ctot + r]
+                            : d.kernel2[((size_t)t * cin + c) * (d.n_boxes * 4) + b * 4 + (r - m->Ctot)];
+          }
+          master[((size_t)t * cin + c) * cout + o] = w;
+        }
+    rc = upload_f32(m, &L.w_f32, master.data(), master.size()); if (rc) return rc;
   }
   rc = upload_f32(m, &L.bias, bias.data(), bias.size()); if (rc) return rc;
   a.bias = L.bias;
@@ -224,28 +130,90 @@ int build_conv(ssdk_model* m, int li) {
     a.epi = EPI_SPLIT;
     a.out_hi = L.out.hi; a.out_lo = L.out.lo; a.out_Hp = L.out.Hp(); a.out_Wp = L.out.Wp(); a.out_pad = L.out.pad; a.out_Cs = L.out.Cs;
   }
-  // TMA descriptors
-  rc = make_tmap_2d(&cl.a_hi, a_hi, a_inner, a_rows, a_inner * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
-  rc = make_tmap_2d(&cl.b_hi, L.w_hi, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
-  if (m->split) {
-    rc = make_tmap_2d(&cl.a_lo, a_lo, a_inner, a_rows, a_inner * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
-    rc = make_tmap_2d(&cl.b_lo, L.w_lo, Krow, (uint64_t)cout, Krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
-  } else { cl.a_lo = cl.a_hi; cl.b_lo = cl.b_hi; }
-  const int total_tiles = a.n_tiles_m * a.n_tiles_n;
-  cl.grid = std::max(1, std::min(total_tiles, m->ctx->sm_count));
-  cl.smem = conv_smem_bytes(a);
   cl.flops_algo = 2.0 * m->B * Ho * Wo * (double)taps * cin * cout;
-  double issued = 0;
-  for (int nt = 0; nt < a.n_tiles_n; ++nt) {
-    int ne = std::min(a.BN, ((cout - nt * a.BN) + 15) / 16 * 16);
-    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
-  }
-  cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
   m->flops_algo += cl.flops_algo; m->flops_issued += cl.flops_issued;
   return SSDK_OK;
 }
 
 }  // namespace
+
+namespace ssdk {
+
+// Geometry, tile list, pipeline depths and TMA descriptors of one implicit-GEMM launch.  The caller fills the epilogue.
+int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                   size_t krow, int kblocks, int last_ksteps, int** tile_list_out) {
+  ConvArgs& a = cl.args;
+  memset(&a, 0, sizeof(a));
+  const __nv_bfloat16* a_hi; const __nv_bfloat16* a_lo;
+  uint64_t a_inner, a_rows;
+  if (!g.in) {
+    SSDK_REQUIRE(g.a_rows < (1ull << 31), "GEMM with too many rows");
+    a.M_total = (int)g.a_rows; a.rows_per_img = g.Ho * g.Wo; a.in_Wp = g.Wo;
+    a.KH = 1; a.KW = 1; a.row_shift[0] = 0; a.kw_rows = 1; a.slab_rows = 128;
+    a_hi = g.a_hi; a_lo = g.a_lo; a_inner = g.a_inner; a_rows = g.a_rows;
+  } else {
+    const ActBuf& ia = *g.in;
+    SSDK_REQUIRE((long long)g.B * ia.Hp() * ia.Wp() < (1ll << 31), "activation tensor with too many rows");
+    a.M_total = g.B * ia.Hp() * ia.Wp(); a.rows_per_img = ia.Hp() * ia.Wp(); a.in_Wp = ia.Wp();
+    SSDK_REQUIRE(g.kh <= 8 && g.kw <= 8, "conv kernel %dx%d is larger than the supported 8x8", g.kh, g.kw);
+    a.KH = g.kh; a.KW = g.kw; a.kw_rows = g.dilation;
+    a.slab_rows = (128 + (g.kw - 1) * g.dilation + 7) / 8 * 8;
+    SSDK_REQUIRE(a.slab_rows <= 256, "conv kernel width x dilation too large for one TMA box");
+    for (int kh = 0; kh < g.kh; ++kh) {
+      a.row_shift[kh] = (kh * g.dilation - g.pad_t + ia.pad) * ia.Wp() + (0 - g.pad_l + ia.pad);
+      SSDK_REQUIRE(a.row_shift[kh] >= 0, "internal: activation border too small for this convolution");
+    }
+    a_hi = ia.hi; a_lo = ia.lo; a_inner = ia.Cs; a_rows = (uint64_t)a.M_total;
+  }
+  a.kblocks = kblocks;
+  a.last_ksteps = last_ksteps;
+  a.Ho = g.Ho; a.Wo = g.Wo; a.B = g.B;
+  a.cout = g.cout;
+  a.BN = g.cout <= 64 ? 64 : (g.cout <= 128 ? 128 : 256);
+  a.n_tiles_n = (g.cout + a.BN - 1) / a.BN;
+  a.split = m->split;
+  a.k_split = 1;
+  conv_pick_stages(a);
+  { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
+  // m-tiles that hold at least one valid output row
+  std::vector<int> tiles;
+  const int n_m = (a.M_total + 127) / 128;
+  for (int t = 0; t < n_m; ++t) {
+    bool any = false;
+    for (int r = 0; r < 128 && !any; ++r) {
+      long long v = (long long)t * 128 + r;
+      if (v >= a.M_total) break;
+      int rr = (int)(v % a.rows_per_img);
+      any = (rr / a.in_Wp < g.Ho) && (rr % a.in_Wp < g.Wo);
+    }
+    if (any) tiles.push_back(t);
+  }
+  a.n_tiles_m = (int)tiles.size();
+  int* tl = nullptr;
+  int rc = dev_alloc(m, &tl, tiles.size(), false); if (rc) return rc;
+  SSDK_CHECK_CUDA(cudaMemcpy(tl, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+  a.tile_list = tl;
+  if (tile_list_out) *tile_list_out = tl;
+  const uint64_t a_ld = (!g.in && g.a_ld) ? g.a_ld : a_inner;
+  rc = make_tmap_2d(&cl.a_hi, a_hi, a_inner, a_rows, a_ld * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
+  rc = make_tmap_2d(&cl.b_hi, w_hi, krow, (uint64_t)g.cout, krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
+  if (m->split) {
+    rc = make_tmap_2d(&cl.a_lo, a_lo, a_inner, a_rows, a_ld * 2, 64, (uint32_t)a.slab_rows); if (rc) return rc;
+    rc = make_tmap_2d(&cl.b_lo, w_lo, krow, (uint64_t)g.cout, krow * 2, 64, (uint32_t)a.BN); if (rc) return rc;
+  } else { cl.a_lo = cl.a_hi; cl.b_lo = cl.b_hi; }
+  const int total_tiles = a.n_tiles_m * a.n_tiles_n;
+  cl.grid = std::max(1, std::min(total_tiles, m->ctx->sm_count));
+  cl.smem = conv_smem_bytes(a);
+  double issued = 0;
+  for (int nt = 0; nt < a.n_tiles_n; ++nt) {
+    int ne = std::min(a.BN, ((g.cout - nt * a.BN) + 15) / 16 * 16);
+    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
+  }
+  cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
+  return SSDK_OK;
+}
+
+}  // namespace ssdk
 
 extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssdk_model** out) {
   SSDK_REQUIRE(ctx && desc && out && desc->layers && desc->n_layers > 0, "ssdk_model_create: bad argument");
@@ -256,7 +224,7 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
   SSDK_CHECK_CUDA(cudaSetDevice(ctx->device));
   ssdk_model* m = new ssdk_model();
   m->ctx = ctx; m->B = desc->batch; m->H = desc->img_height; m->W = desc->img_width; m->Cimg = desc->img_channels;
-  m->Ctot = desc->n_classes_total; m->split = desc->precision == 0 ? 1 : 0;
+  m->Ctot = desc->n_classes_total; m->split = desc->precision == 0 ? 1 : 0; m->training = desc->training ? 1 : 0;
   for (int i = 0; i < 4; ++i) m->var[i] = desc->variances[i];
   const int n = desc->n_layers;
   m->layers.resize(n);
@@ -299,6 +267,14 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
     LayerPlan& in = m->layers[d.input];
     const bool im2col = (d.stride != 1) || (in.C < 8);
     if (!im2col) in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)));
+    if (desc->training && !im2col) {
+      // the gradient of this layer's output shares the geometry of the output itself and is the input of the
+      // data-gradient convolution, whose padding is dilation*(k-1) - pad
+      LayerPlan& self = m->layers[i];
+      const int pt = d.dilation * (d.kh - 1) - d.pad_t, pb = d.dilation * (d.kh - 1) - d.pad_b;
+      const int pl = d.dilation * (d.kw - 1) - d.pad_l, pr = d.dilation * (d.kw - 1) - d.pad_r;
+      self.need_pad = std::max(self.need_pad, std::max(std::max(pt, pb), std::max(pl, pr)));
+    }
   }
   // pass 3: buffers, weights, launches
   rc = tma_init(); if (rc) return fail(rc);

@@ -1,0 +1,761 @@
+// Training step for the SSD graphs on sm_100a: backward pass + SGD.  Replaces what TensorFlow/Keras do for the reference
+// in fit_generator (autodiff of models/keras_ssd300.py:263-419 and keras_loss_function/keras_ssd_loss.py:98-211, the
+// l2 kernel regulariser models/keras_ssd300.py:274 and SGD(lr, momentum) ssd300_training.ipynb:169).
+//
+// Every convolution gradient runs on the SAME tcgen05 implicit-GEMM kernel as the forward pass (conv.cu):
+//   data gradient    dX = conv(dZ, W rotated by 180 degrees with in/out channels swapped), padding dilation*(k-1)-pad;
+//                    the epilogue multiplies by ReLU'(forward value) and accumulates when a tensor has several consumers.
+//   weight gradient  dW[co][tap][ci] = sum_v dZT[co][v] * XT[ci][v + shift(tap)]: both operands are transposed once into
+//                    [channels][pixels] matrices (K = pixels contiguous), each tap is one GEMM whose weight-side operand
+//                    is read at a K offset, the pixel axis is split across CTAs (split-K) and reduced with fp32 atomics.
+// Operands stay bf16 hi+lo (three MMAs per product) like the forward pass.  Small pieces (max-pool routing, L2Normalization,
+// softmax/concat head, bias sums, image-facing 3-channel conv, SGD, re-packing of the bf16 planes) are plain CUDA kernels.
+#include "model.cuh"
+#include <climits>
+
+using namespace ssdk;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t aidx(const ActBuf& a, int n, int y, int x) {
+  return (((size_t)n * a.Hp() + (y + a.pad)) * a.Wp() + (x + a.pad)) * a.Cs;
+}
+__device__ __forceinline__ float ld2(const ActBuf& a, size_t i) {
+  float v = __bfloat162float(a.hi[i]);
+  if (a.lo) v += __bfloat162float(a.lo[i]);
+  return v;
+}
+__device__ __forceinline__ void st2(const ActBuf& a, size_t i, float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  a.hi[i] = h;
+  if (a.lo) a.lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// dst[c][v] = src[row(v)][c] (or 0), v in [0, Kv): K-major operands for the weight-gradient GEMMs.
+struct TMap {
+  int identity;             // row(v) = v
+  int rows_per_img, Wp;     // the X grid the GEMM iterates over
+  int Ho, Wo;               // valid extent on that grid
+  int src_Hp, src_Wp, src_pad;
+};
+__global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __restrict__ src_hi, const __nv_bfloat16* __restrict__ src_lo,
+                                                        int src_ld, long long src_rows, TMap mp, long long row_off, long long Kv, int C,
+                                                        __nv_bfloat16* __restrict__ dst_hi, __nv_bfloat16* __restrict__ dst_lo, long long ldT) {
+  __shared__ uint16_t th[64][72], tl[64][72];
+  const long long v0 = (long long)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {          // 64 rows x 8 chunks of 8 channels
+    const int r = i >> 3, ch = (i & 7) * 8;
+    const long long v = v0 + r;
+    long long row = -1;
+    if (v < Kv) {
+      if (mp.identity) row = v + row_off;
+      else {
+        const int n = (int)(v / mp.rows_per_img); const int rr = (int)(v - (long long)n * mp.rows_per_img);
+        const int y = rr / mp.Wp, x = rr - y * mp.Wp;
+        if (y < mp.Ho && x < mp.Wo) row = ((long long)n * mp.src_Hp + (y + mp.src_pad)) * mp.src_Wp + (x + mp.src_pad);
+      }
+    }
+    uint4 h = make_uint4(0, 0, 0, 0), l = h;
+    if (row >= 0 && row < src_rows && c0 + ch < src_ld) {
+      h = *reinterpret_cast<const uint4*>(src_hi + row * src_ld + c0 + ch);
+      if (src_lo) l = *reinterpret_cast<const uint4*>(src_lo + row * src_ld + c0 + ch);
+    }
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      th[ch + e][r] = (uint16_t)((hw[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+      tl[ch + e][r] = (uint16_t)((lw[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {          // 64 channels x 8 chunks of 8 pixels
+    const int c = i >> 3, vv = (i & 7) * 8;
+    if (c0 + c >= C) continue;
+    if (v0 + vv >= ldT) continue;
+    uint4 h, l;
+    h.x = th[c][vv] | ((uint32_t)th[c][vv + 1] << 16); h.y = th[c][vv + 2] | ((uint32_t)th[c][vv + 3] << 16);
+    h.z = th[c][vv + 4] | ((uint32_t)th[c][vv + 5] << 16); h.w = th[c][vv + 6] | ((uint32_t)th[c][vv + 7] << 16);
+    l.x = tl[c][vv] | ((uint32_t)tl[c][vv + 1] << 16); l.y = tl[c][vv + 2] | ((uint32_t)tl[c][vv + 3] << 16);
+    l.z = tl[c][vv + 4] | ((uint32_t)tl[c][vv + 5] << 16); l.w = tl[c][vv + 6] | ((uint32_t)tl[c][vv + 7] << 16);
+    *reinterpret_cast<uint4*>(dst_hi + (long long)(c0 + c) * ldT + v0 + vv) = h;
+    if (dst_lo) *reinterpret_cast<uint4*>(dst_lo + (long long)(c0 + c) * ldT + v0 + vv) = l;
+  }
+}
+
+// bias gradient: gb[c] += sum_v dZT[c][v]
+__global__ void __launch_bounds__(256) rowsum_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long ldT,
+                                                     long long Kv, float* __restrict__ gb) {
+  __shared__ float s[8];
+  const int c = blockIdx.y;
+  const long long chunk = (Kv + gridDim.x - 1) / gridDim.x;
+  const long long v0 = (long long)blockIdx.x * chunk, v1 = min(Kv, v0 + chunk);
+  float acc = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += 256) {
+    acc += __bfloat162float(hi[(long long)c * ldT + v]);
+    if (lo) acc += __bfloat162float(lo[(long long)c * ldT + v]);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s[w];
+    atomicAdd(gb + c, t);
+  }
+}
+
+// Backward of Reshape/softmax/Concat (models/keras_ssd300.py:363-419): dY_pred rows -> gradient of the fused head conv output.
+__global__ void head_bwd_kernel(const float* __restrict__ head, const float* __restrict__ dy, int B, int H, int W, int n_boxes, int C,
+                                int P, int prior_off, ActBuf g) {
+  const size_t wid = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)B * H * W * n_boxes;
+  if (wid >= total) return;
+  const int b = (int)(wid % n_boxes); const size_t pix = wid / n_boxes;
+  const int hw = H * W;
+  const int n = (int)(pix / hw); const int pl = (int)(pix % hw);
+  const int y = pl / W, x = pl % W;
+  const float* src = head + pix * (size_t)n_boxes * (C + 4) + (size_t)b * (C + 4);
+  const float* d = dy + ((size_t)n * P + prior_off + (size_t)pl * n_boxes + b) * (C + 12);
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, src[c]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane; c < C; c += 32) sum += expf(src[c] - mx);
+  sum = warp_sum(sum);
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot += (expf(src[c] - mx) / sum) * d[c];
+  dot = warp_sum(dot);
+  const size_t o = aidx(g, n, y, x) + (size_t)b * (C + 4);
+  for (int c = lane; c < C; c += 32) { const float p = expf(src[c] - mx) / sum; st2(g, o + c, p * (d[c] - dot)); }
+  if (lane < 4) st2(g, o + C + lane, d[C + lane]);
+}
+
+// Max-pool backward (gather form): gin(n,y,x,c) (+)= sum over windows whose FIRST maximum is (y,x) of gout; optional ReLU' mask.
+__global__ void pool_bwd_kernel(ActBuf in, ActBuf gout, ActBuf gin, int Hout, int Wout, int KH, int KW, int stride, int pad_t, int pad_l,
+                                int relu_mask, int accumulate) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)in.B * in.H * in.W * in.C;
+  if (i >= total) return;
+  const int c = (int)(i % in.C); const size_t pix = i / in.C;
+  const int x = (int)(pix % in.W); const int y = (int)((pix / in.W) % in.H); const int n = (int)(pix / ((size_t)in.W * in.H));
+  const size_t me = aidx(in, n, y, x) + c;
+  const float v = ld2(in, me);
+  float acc = 0.f;
+  const int yo_lo = max(0, (y + pad_t - KH + stride) / stride), yo_hi = min(Hout - 1, (y + pad_t) / stride);
+  const int xo_lo = max(0, (x + pad_l - KW + stride) / stride), xo_hi = min(Wout - 1, (x + pad_l) / stride);
+  for (int yo = yo_lo; yo <= yo_hi; ++yo) {
+    const int y0 = yo * stride - pad_t;
+    if (y < y0 || y >= y0 + KH) continue;
+    for (int xo = xo_lo; xo <= xo_hi; ++xo) {
+      const int x0 = xo * stride - pad_l;
+      if (x < x0 || x >= x0 + KW) continue;
+      // is (y, x) the first maximum of this window (row-major scan, strict '>')?
+      bool first = true;
+      for (int ky = 0; ky < KH && first; ++ky) {
+        const int yy = y0 + ky;
+        if (yy < 0 || yy >= in.H) continue;
+        for (int kx = 0; kx < KW; ++kx) {
+          const int xx = x0 + kx;
+          if (xx < 0 || xx >= in.W) continue;
+          const float u = ld2(in, aidx(in, n, yy, xx) + c);
+          const bool before = (yy < y) || (yy == y && xx < x);
+          if (u > v || (u == v && before)) { first = false; break; }
+        }
+      }
+      if (first) acc += ld2(gout, aidx(gout, n, yo, xo) + c);
+    }
+  }
+  if (relu_mask && !(v > 0.f)) acc = 0.f;
+  const size_t o = aidx(gin, n, y, x) + c;
+  if (accumulate) acc += ld2(gin, o);
+  st2(gin, o, acc);
+}
+
+// L2Normalization backward (y_c = gamma_c * x_c * s, s = rsqrt(max(sum x^2, 1e-12))): one warp per pixel.
+__global__ void l2norm_bwd_kernel(ActBuf x, ActBuf gy, ActBuf gx, const float* __restrict__ gamma, float* __restrict__ ggamma,
+                                  int relu_mask, int accumulate) {
+  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)x.B * x.H * x.W;
+  if (pix >= total) return;
+  const int xx = (int)(pix % x.W); const int yy = (int)((pix / x.W) % x.H); const int n = (int)(pix / ((size_t)x.W * x.H));
+  const size_t sx = aidx(x, n, yy, xx), sg = aidx(gy, n, yy, xx), so = aidx(gx, n, yy, xx);
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane; c < x.C; c += 32) {
+    const float v = ld2(x, sx + c);
+    ss += v * v;
+    dot += gamma[c] * ld2(gy, sg + c) * v;
+  }
+  ss = warp_sum(ss); dot = warp_sum(dot);
+  const bool clamped = !(ss > 1e-12f);
+  const float s = rsqrtf(fmaxf(ss, 1e-12f));
+  for (int c = lane; c < x.C; c += 32) {
+    const float v = ld2(x, sx + c), d = ld2(gy, sg + c);
+    float g = s * gamma[c] * d;
+    if (!clamped) g -= v * s * s * s * dot;
+    atomicAdd(ggamma + c, d * v * s);
+    if (relu_mask && !(v > 0.f)) g = 0.f;
+    if (accumulate) g += ld2(gx, so + c);
+    st2(gx, so + c, g);
+  }
+}
+
+// Data gradient of a strided convolution: dX = col2im(dCol), dCol = dZ * W^T computed by the GEMM kernel (one tap).
+__global__ void col2im_kernel(const float* __restrict__ dcol, int Ho, int Wo, int KH, int KW, int stride, int dil, int pad_t, int pad_l,
+                              int ld, ActBuf fwd, ActBuf gin, int relu_mask, int accumulate) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)gin.B * gin.H * gin.W * gin.C;
+  if (i >= total) return;
+  const int c = (int)(i % gin.C); const size_t pix = i / gin.C;
+  const int x = (int)(pix % gin.W); const int y = (int)((pix / gin.W) % gin.H); const int n = (int)(pix / ((size_t)gin.W * gin.H));
+  float acc = 0.f;
+  for (int kh = 0; kh < KH; ++kh) {
+    const int yy = y + pad_t - kh * dil;
+    if (yy < 0 || yy % stride) continue;
+    const int yo = yy / stride;
+    if (yo >= Ho) continue;
+    for (int kw = 0; kw < KW; ++kw) {
+      const int xx = x + pad_l - kw * dil;
+      if (xx < 0 || xx % stride) continue;
+      const int xo = xx / stride;
+      if (xo >= Wo) continue;
+      acc += dcol[(((size_t)n * Ho + yo) * Wo + xo) * ld + (size_t)(kh * KW + kw) * gin.C + c];
+    }
+  }
+  const size_t o = aidx(gin, n, y, x) + c;
+  if (relu_mask && !(ld2(fwd, aidx(fwd, n, y, x) + c) > 0.f)) acc = 0.f;
+  if (accumulate) acc += ld2(gin, o);
+  st2(gin, o, acc);
+}
+
+// Weight gradient of the image-facing conv (Cin <= 4): gw[co][tap][ci] += sum_pix dZ[pix][co] * X[pix + tap][ci].
+__global__ void __launch_bounds__(256) wgrad_direct_kernel(ActBuf in, ActBuf g, float* __restrict__ gw, int KH, int KW, int dil,
+                                                           int pad_t, int pad_l, int pix_per_block) {
+  extern __shared__ float s_acc[];               // [K][Cout]
+  const int K = KH * KW * in.C, Cout = g.C;
+  for (int i = threadIdx.x; i < K * Cout; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const size_t total = (size_t)g.B * g.H * g.W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  // thread -> (k, group of co); loops over the block's pixels
+  for (int idx = threadIdx.x; idx < K * (Cout / 8); idx += 256) {
+    const int k = idx / (Cout / 8), cg = (idx % (Cout / 8)) * 8;
+    const int c = k % in.C, tap = k / in.C, kw = tap % KW, kh = tap / KW;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t p = p0; p < min(total, p0 + (size_t)pix_per_block); ++p) {
+      const int xo = (int)(p % g.W); const int yo = (int)((p / g.W) % g.H); const int n = (int)(p / ((size_t)g.W * g.H));
+      const int y = yo + kh * dil - pad_t, x = xo + kw * dil - pad_l;
+      if (y < 0 || y >= in.H || x < 0 || x >= in.W) continue;
+      const float xv = ld2(in, aidx(in, n, y, x) + c);
+      const size_t go = aidx(g, n, yo, xo) + cg;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += xv * ld2(g, go + e);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[k * Cout + cg + e] += acc[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * Cout; i += 256) {
+    const int k = i / Cout, co = i % Cout;
+    atomicAdd(gw + (size_t)co * K + k, s_acc[i]);     // OHWI: [co][tap][ci], k = tap*cin + ci
+  }
+}
+
+// SGD with momentum (Keras: v = m*v - lr*g; w += v); kernels get the l2 regulariser's gradient 2*l2*w.
+// `w` is HWIO [taps][cin][cout]; the gradient is OHWI [cout][taps][cin].
+__global__ void sgd_kernel_w(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, int taps, int cin, int cout,
+                             float lr, float mom, float l2, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)taps * cin * cout;
+  if (i >= total) return;
+  const int co = (int)(i % cout); const size_t r = i / cout; const int ci = (int)(r % cin); const int t = (int)(r / cin);
+  const float grad = g[((size_t)co * taps + t) * cin + ci] * scale + 2.f * l2 * w[i];
+  const float nv = mom * v[i] - lr * grad;
+  v[i] = nv;
+  w[i] += nv;
+}
+__global__ void sgd_kernel_flat(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, size_t n, float lr, float mom,
+                                float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float nv = mom * v[i] - lr * g[i] * scale;
+  v[i] = nv;
+  w[i] += nv;
+}
+
+// master HWIO -> packed K-major bf16 hi/lo planes.  mode 0: forward virtual path [cout][tap][kblocks*64];
+// mode 1: forward im2col path [cout][k = tap*cin + c]; mode 2: data-gradient kernel [cin][taps-1-tap][kb2*64 over cout];
+// mode 3: [tap*cin + c][cout] (col-gradient GEMM of strided convolutions).
+__global__ void repack_kernel(const float* __restrict__ w, int taps, int cin, int cout, int mode, int kblocks, size_t krow, int rows,
+                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)rows * krow;
+  if (i >= total) return;
+  const int row = (int)(i / krow); const size_t k = i % krow;
+  float val = 0.f;
+  if (mode == 0) {
+    const int t = (int)(k / ((size_t)kblocks * 64)), c = (int)(k % ((size_t)kblocks * 64));
+    if (t < taps && c < cin) val = w[((size_t)t * cin + c) * cout + row];
+  } else if (mode == 1) {
+    if (k < (size_t)taps * cin) val = w[k * cout + row];
+  } else if (mode == 2) {
+    const int t2 = (int)(k / ((size_t)kblocks * 64)), co = (int)(k % ((size_t)kblocks * 64));
+    if (t2 < taps && co < cout) val = w[((size_t)(taps - 1 - t2) * cin + row) * cout + co];
+  } else {                      // mode 3: W^T for the col-gradient GEMM of strided convs: [k = tap*cin + c][cout]
+    if (k < (size_t)cout) val = w[(size_t)row * cout + k];
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(val);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(val - __bfloat162float(h));
+}
+
+__global__ void hwio_to_ohwi_kernel(const float* __restrict__ w, int taps, int cin, int cout, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)taps * cin * cout;
+  if (i >= total) return;
+  const int ci = (int)(i % cin); const size_t r = i / cin; const int t = (int)(r % taps); const int co = (int)(r / taps);
+  out[i] = w[((size_t)t * cin + ci) * cout + co];
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+struct TLayer {
+  int li = -1, op = -1;
+  // parameters (conv / head): master kernel HWIO in L.w_f32, bias in L.bias (shared with the forward plan)
+  int cin = 0, cout = 0, taps = 0;
+  float *vw = nullptr, *vb = nullptr;       // momentum
+  long long off_w = -1, off_b = -1, off_g = -1;
+  ActBuf g;                                 // gradient of this layer's output (pre-activation); same geometry as the output
+  bool has_g = false;
+  // data gradient
+  bool has_dgrad = false;
+  ConvLaunch dgrad{};
+  __nv_bfloat16 *w2_hi = nullptr, *w2_lo = nullptr; size_t w2_krow = 0; int w2_kblocks = 0;
+  int* dgrad_tiles = nullptr;
+  bool dgrad_strided = false;               // stride != 1: col-gradient GEMM (dZ * W^T) + col2im
+  float* dcol = nullptr; int dcol_ld = 0;
+  // weight gradient
+  std::vector<ConvLaunch> wgrad;            // one per tap (or one for the im2col path)
+  std::vector<int> wgrad_res;               // tap shift mod 8: TMA needs 16-byte aligned K offsets, so XT is built once per residue
+  long long Kv = 0, ldT = 0;
+  TMap dy_map{}, x_map{};
+  float* vgamma = nullptr;
+};
+
+}  // namespace
+
+struct ssdk_trainer {
+  ssdk_model* m = nullptr;
+  std::vector<TLayer> tl;
+  float* grad = nullptr; bool own_grad = false;
+  long long n_params = 0;
+  __nv_bfloat16 *xT_hi = nullptr, *xT_lo = nullptr, *dyT_hi = nullptr, *dyT_lo = nullptr;   // scratch, sized for the largest layer
+  long long xT_elems = 0, dyT_elems = 0;
+  float* dypred = nullptr;                  // [B*P*(C+12)]
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int t_alloc(ssdk_trainer* t, T** out, size_t count, bool zero) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return SSDK_ERR_NOMEM; }
+  if (zero) cudaMemset(p, 0, bytes);
+  t->allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return SSDK_OK;
+}
+
+int launch_repack(ssdk_ctx* ctx, const float* w, int taps, int cin, int cout, int mode, int kblocks, size_t krow, int rows,
+                  __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
+  const size_t total = (size_t)rows * krow;
+  repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, taps, cin, cout, mode, kblocks, krow, rows, hi, lo);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+bool is_conv(int op) { return op == SSDK_OP_CONV || op == SSDK_OP_HEAD; }
+
+}  // namespace
+
+extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_trainer** out) {
+  SSDK_REQUIRE(m && out, "ssdk_trainer_create: NULL argument");
+  SSDK_REQUIRE(m->training, "ssdk_trainer_create: the model plan was not created with training=1");
+  SSDK_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+  ssdk_trainer* t = new ssdk_trainer();
+  t->m = m;
+  const int n = (int)m->layers.size();
+  t->tl.resize(n);
+  int rc = SSDK_OK;
+  auto fail = [&](int code) { ssdk_trainer_destroy(t); return code; };
+  // parameter spans
+  long long off = 0;
+  for (int i = 0; i < n; ++i) {
+    LayerPlan& L = m->layers[i];
+    TLayer& T = t->tl[i];
+    T.li = i; T.op = L.d.op;
+    if (is_conv(L.d.op)) {
+      if (L.d.act == SSDK_ACT_ELU || L.bn_scale) { set_error("training supports ReLU / linear graphs without BatchNormalization only (layer %d)", i); return fail(SSDK_ERR_UNSUPPORTED); }
+      T.cin = m->layers[L.d.input].C; T.cout = L.C; T.taps = L.d.kh * L.d.kw;
+      T.off_w = off; off += (long long)T.cout * T.taps * T.cin;
+      T.off_b = off; off += T.cout;
+    } else if (L.d.op == SSDK_OP_L2NORM) {
+      T.off_g = off; off += L.C;
+    }
+  }
+  t->n_params = off;
+  if (flat_grad_dev) t->grad = flat_grad_dev;
+  else { rc = t_alloc(t, &t->grad, (size_t)off, true); if (rc) return fail(rc); t->own_grad = true; }
+  rc = t_alloc(t, &t->dypred, (size_t)m->B * m->P * (m->Ctot + 12), true); if (rc) return fail(rc);
+  // gradient buffers: same geometry as the forward outputs
+  for (int i = 0; i < n; ++i) {
+    LayerPlan& L = m->layers[i];
+    TLayer& T = t->tl[i];
+    if (L.d.op == SSDK_OP_INPUT) continue;
+    ActBuf& g = T.g;
+    if (L.d.op == SSDK_OP_HEAD) { g.B = m->B; g.H = L.H; g.W = L.W; g.C = L.C; g.Cs = (L.C + 7) / 8 * 8; g.pad = 1; }
+    else { g = L.out; g.hi = nullptr; g.lo = nullptr; }
+    const size_t ne = g.elems() + 64 * 8;
+    rc = t_alloc(t, &g.hi, ne, true); if (rc) return fail(rc);
+    if (m->split) { rc = t_alloc(t, &g.lo, ne, true); if (rc) return fail(rc); }
+    T.has_g = true;
+  }
+  // per conv: momentum, data-gradient plan, weight-gradient plans
+  std::vector<char> written(n, 0);            // does the producer's gradient buffer already hold a contribution?
+  long long max_xT = 0, max_dyT = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    LayerPlan& L = m->layers[i];
+    TLayer& T = t->tl[i];
+    const ssdk_layer_desc& d = L.d;
+    if (d.op == SSDK_OP_INPUT) continue;
+    const int pi = d.input;
+    LayerPlan& PL = m->layers[pi];
+    TLayer& PT = t->tl[pi];
+    const bool prod_needs_grad = PL.d.op != SSDK_OP_INPUT;
+    if (d.op == SSDK_OP_L2NORM) { rc = t_alloc(t, &T.vgamma, (size_t)L.C, true); if (rc) return fail(rc); }
+    if (!is_conv(d.op)) { if (prod_needs_grad) written[pi] = 1; continue; }
+    rc = t_alloc(t, &T.vw, (size_t)T.cout * T.taps * T.cin, true); if (rc) return fail(rc);
+    rc = t_alloc(t, &T.vb, (size_t)T.cout, true); if (rc) return fail(rc);
+    // ---- data gradient
+    if (prod_needs_grad) {
+      if (T.cin % 8 != 0) { set_error("training: input channels must be a multiple of 8 (layer %d)", i); return fail(SSDK_ERR_UNSUPPORTED); }
+      if (d.stride != 1) {
+        // dCol[M][taps*cin] = dZ[M][cout] * W^T, then col2im
+        T.has_dgrad = true; T.dgrad_strided = true;
+        const int kcol = T.taps * T.cin;
+        T.w2_kblocks = (T.g.Cs + 63) / 64;
+        T.w2_krow = (size_t)T.w2_kblocks * 64;
+        rc = t_alloc(t, &T.w2_hi, (size_t)kcol * T.w2_krow, true); if (rc) return fail(rc);
+        if (m->split) { rc = t_alloc(t, &T.w2_lo, (size_t)kcol * T.w2_krow, true); if (rc) return fail(rc); }
+        T.dcol_ld = kcol;
+        rc = t_alloc(t, &T.dcol, (size_t)m->B * L.H * L.W * kcol, true); if (rc) return fail(rc);
+        ConvGeom gg;
+        gg.in = &T.g; gg.kh = 1; gg.kw = 1; gg.dilation = 1; gg.pad_t = 0; gg.pad_l = 0;
+        gg.Ho = L.H; gg.Wo = L.W; gg.B = m->B; gg.cout = kcol;
+        rc = plan_conv_gemm(m, T.dgrad, gg, T.w2_hi, T.w2_lo, T.w2_krow, T.w2_kblocks, (T.g.Cs - (T.w2_kblocks - 1) * 64 + 15) / 16, &T.dgrad_tiles);
+        if (rc) return fail(rc);
+        ConvArgs& a = T.dgrad.args;
+        a.epi = EPI_F32; a.bias = nullptr; a.act = SSDK_ACT_NONE; a.out_f32 = T.dcol;
+        written[pi] = 1;
+        goto wgrad_plan;
+      }
+      T.has_dgrad = true;
+      T.w2_kblocks = (T.g.Cs + 63) / 64;
+      T.w2_krow = (size_t)T.taps * T.w2_kblocks * 64;
+      rc = t_alloc(t, &T.w2_hi, (size_t)T.cin * T.w2_krow, true); if (rc) return fail(rc);
+      if (m->split) { rc = t_alloc(t, &T.w2_lo, (size_t)T.cin * T.w2_krow, true); if (rc) return fail(rc); }
+      ConvGeom gg;
+      gg.in = &T.g; gg.kh = d.kh; gg.kw = d.kw; gg.dilation = d.dilation;
+      gg.pad_t = d.dilation * (d.kh - 1) - d.pad_t; gg.pad_l = d.dilation * (d.kw - 1) - d.pad_l;
+      gg.Ho = PL.H; gg.Wo = PL.W; gg.B = m->B; gg.cout = T.cin;
+      rc = plan_conv_gemm(m, T.dgrad, gg, T.w2_hi, T.w2_lo, T.w2_krow, T.w2_kblocks, (T.g.Cs - (T.w2_kblocks - 1) * 64 + 15) / 16, &T.dgrad_tiles);
+      if (rc) return fail(rc);
+      ConvArgs& a = T.dgrad.args;
+      a.epi = EPI_SPLIT; a.bias = nullptr; a.act = SSDK_ACT_NONE;
+      a.out_hi = PT.g.hi; a.out_lo = PT.g.lo; a.out_Hp = PT.g.Hp(); a.out_Wp = PT.g.Wp(); a.out_pad = PT.g.pad; a.out_Cs = PT.g.Cs;
+      a.mask_hi = (PL.d.op == SSDK_OP_CONV && PL.d.act == SSDK_ACT_RELU) ? PL.out.hi : nullptr;
+      a.accumulate = written[pi] ? 1 : 0;
+      written[pi] = 1;
+    }
+    // ---- weight gradient
+    wgrad_plan:
+    if (L.direct) continue;                     // handled by wgrad_direct_kernel
+    const ActBuf& X = PL.out;
+    long long Kv;
+    if (L.im2col) {
+      Kv = (long long)m->B * L.H * L.W;
+      T.dy_map = TMap{0, L.H * L.W, L.W, L.H, L.W, T.g.Hp(), T.g.Wp(), T.g.pad};
+      T.x_map = TMap{1, 0, 0, 0, 0, 0, 0, 0};
+      max_xT = std::max(max_xT, (long long)L.Kpad * ((Kv + 7) / 8 * 8 + 64));
+    } else {
+      Kv = (long long)m->B * X.Hp() * X.Wp();
+      T.dy_map = TMap{0, X.Hp() * X.Wp(), X.Wp(), L.H, L.W, T.g.Hp(), T.g.Wp(), T.g.pad};
+      T.x_map = TMap{1, 0, 0, 0, 0, 0, 0, 0};
+      max_xT = std::max(max_xT, (long long)X.Cs * ((Kv + 7) / 8 * 8 + 64));
+    }
+    T.Kv = Kv; T.ldT = (Kv + 7) / 8 * 8 + 64;
+    max_dyT = std::max(max_dyT, (long long)T.g.Cs * T.ldT);
+  }
+  t->xT_elems = max_xT; t->dyT_elems = max_dyT;
+  rc = t_alloc(t, &t->xT_hi, (size_t)max_xT + 4096, true); if (rc) return fail(rc);
+  rc = t_alloc(t, &t->dyT_hi, (size_t)max_dyT + 4096, true); if (rc) return fail(rc);
+  if (m->split) {
+    rc = t_alloc(t, &t->xT_lo, (size_t)max_xT + 4096, true); if (rc) return fail(rc);
+    rc = t_alloc(t, &t->dyT_lo, (size_t)max_dyT + 4096, true); if (rc) return fail(rc);
+  }
+  // weight-gradient GEMM plans (need the scratch addresses)
+  for (int i = 0; i < n; ++i) {
+    LayerPlan& L = m->layers[i];
+    TLayer& T = t->tl[i];
+    if (!is_conv(L.d.op) || L.direct) continue;
+    const ssdk_layer_desc& d = L.d;
+    const ActBuf& X = m->layers[d.input].out;
+    const int n_gemm = L.im2col ? 1 : T.taps;
+    const int ncols = L.im2col ? L.Kpad : T.cin;            // N of the GEMM
+    const int kblocks = (int)((T.Kv + 63) / 64);
+    const int last_ksteps = (int)((T.Kv - (long long)(kblocks - 1) * 64 + 15) / 16);
+    T.wgrad.resize(n_gemm); T.wgrad_res.assign(n_gemm, 0);
+    for (int tp = 0; tp < n_gemm; ++tp) {
+      ConvGeom wg;
+      wg.a_hi = t->dyT_hi; wg.a_lo = t->dyT_lo; wg.a_inner = (uint64_t)T.ldT; wg.a_ld = (uint64_t)T.ldT; wg.a_rows = (uint64_t)T.cout;
+      wg.Ho = T.cout; wg.Wo = 1; wg.B = 1; wg.cout = ncols;
+      ConvLaunch& cl = T.wgrad[tp];
+      // the transposed operands are [channels][ldT] with zeros in [Kv, ldT)
+      rc = plan_conv_gemm(m, cl, wg, t->xT_hi, t->xT_lo, (size_t)T.ldT, kblocks, last_ksteps, nullptr);
+      if (rc) return fail(rc);
+      ConvArgs& a = cl.args;
+      a.epi = EPI_ATOMIC; a.bias = nullptr; a.act = SSDK_ACT_NONE;
+      a.out_f32 = t->grad + T.off_w;
+      if (L.im2col) { a.out_ld = T.taps * T.cin; a.out_col_off = 0; a.b_k_offset = 0; a.cout = T.taps * T.cin; a.n_tiles_n = (a.cout + a.BN - 1) / a.BN; }
+      else {
+        const int kh = tp / d.kw, kw = tp % d.kw;
+        a.out_ld = T.taps * T.cin; a.out_col_off = tp * T.cin;
+        const int shift = (kh * d.dilation - d.pad_t + X.pad) * X.Wp() + (kw * d.dilation - d.pad_l + X.pad);
+        T.wgrad_res[tp] = shift & 7;                 // XT_r[c][v] = X[v + r][c], read at the aligned offset shift - r
+        a.b_k_offset = shift - (shift & 7);
+      }
+      const int units = a.n_tiles_m * a.n_tiles_n;
+      int ks = std::max(1, (4 * m->ctx->sm_count + units - 1) / units);
+      ks = std::min(ks, kblocks);
+      a.kb_per = (kblocks + ks - 1) / ks;
+      a.k_split = (kblocks + a.kb_per - 1) / a.kb_per;
+      cl.grid = std::max(1, std::min(units * a.k_split, m->ctx->sm_count));
+    }
+  }
+  // rotated kernels for the data gradients
+  for (int i = 0; i < n; ++i) {
+    TLayer& T = t->tl[i];
+    if (!T.has_dgrad) continue;
+    if (T.dgrad_strided) rc = launch_repack(m->ctx, m->layers[i].w_f32, T.taps, T.cin, T.cout, 3, T.w2_kblocks, T.w2_krow, T.taps * T.cin, T.w2_hi, T.w2_lo, 0);
+    else rc = launch_repack(m->ctx, m->layers[i].w_f32, T.taps, T.cin, T.cout, 2, T.w2_kblocks, T.w2_krow, T.cin, T.w2_hi, T.w2_lo, 0);
+    if (rc) return fail(rc);
+  }
+  SSDK_CHECK_CUDA(cudaDeviceSynchronize());
+  *out = t;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_trainer_destroy(ssdk_trainer* t) {
+  if (!t) return SSDK_OK;
+  for (void* p : t->allocs) cudaFree(p);
+  delete t;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_trainer_num_params(const ssdk_trainer* t, long long* out_n) {
+  SSDK_REQUIRE(t && out_n, "ssdk_trainer_num_params: NULL argument");
+  *out_n = t->n_params;
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int which, long long* out_offset, long long* out_count) {
+  SSDK_REQUIRE(t && out_offset && out_count && layer >= 0 && layer < (int)t->tl.size(), "ssdk_trainer_param_span: bad argument");
+  const TLayer& T = t->tl[layer];
+  *out_offset = -1; *out_count = 0;
+  if (which == 0 && T.off_w >= 0) { *out_offset = T.off_w; *out_count = (long long)T.cout * T.taps * T.cin; }
+  else if (which == 1 && T.off_b >= 0) { *out_offset = T.off_b; *out_count = T.cout; }
+  else if (which == 2 && T.off_g >= 0) { *out_offset = T.off_g; *out_count = t->m->layers[layer].C; }
+  return SSDK_OK;
+}
+
+extern "C" float* ssdk_trainer_grad_buffer(ssdk_trainer* t) { return t ? t->grad : nullptr; }
+
+namespace {
+
+int do_transpose(ssdk_trainer* t, const __nv_bfloat16* hi, const __nv_bfloat16* lo, int src_ld, long long src_rows, const TMap& mp,
+                 long long Kv, int C, __nv_bfloat16* dhi, __nv_bfloat16* dlo, long long ldT, cudaStream_t s, long long row_off = 0) {
+  dim3 grid((unsigned)((ldT + 63) / 64), (unsigned)((C + 63) / 64));
+  transpose_kernel<<<grid, 256, 0, s>>>(hi, lo, src_ld, src_rows, mp, row_off, Kv, C, dhi, dlo, ldT);
+  SSDK_COUNT_LAUNCH(t->m->ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+}  // namespace
+
+extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const float* y_pred, int neg_pos_ratio, int n_neg_min,
+                                   float alpha, float* out_loss, void* stream_) {
+  SSDK_REQUIRE(t && y_true && y_pred, "ssdk_train_backward: NULL argument");
+  ssdk_model* m = t->m;
+  ssdk_ctx* ctx = m->ctx;
+  cudaStream_t s = (cudaStream_t)stream_;
+  int rc;
+  SSDK_CHECK_CUDA(cudaMemsetAsync(t->grad, 0, (size_t)t->n_params * sizeof(float), s));
+  if (out_loss) {
+    rc = ssdk_ssd_loss_fwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, out_loss, nullptr, stream_);
+    if (rc) return rc;
+  }
+  rc = ssdk_ssd_loss_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, t->dypred, stream_);
+  if (rc) return rc;
+  const int n = (int)m->layers.size();
+  std::vector<char> written(n, 0);
+  for (int i = n - 1; i >= 0; --i) {
+    LayerPlan& L = m->layers[i];
+    TLayer& T = t->tl[i];
+    const ssdk_layer_desc& d = L.d;
+    if (d.op == SSDK_OP_INPUT) continue;
+    const int pi = d.input;
+    LayerPlan& PL = m->layers[pi];
+    TLayer& PT = t->tl[pi];
+    const bool prod_needs_grad = PL.d.op != SSDK_OP_INPUT;
+    const int relu_mask = (PL.d.op == SSDK_OP_CONV && PL.d.act == SSDK_ACT_RELU) ? 1 : 0;
+    if (d.op == SSDK_OP_HEAD) {
+      const size_t total = (size_t)m->B * L.H * L.W * d.n_boxes;
+      head_bwd_kernel<<<(unsigned)((total + 7) / 8), 256, 0, s>>>(L.head_f32, t->dypred, m->B, L.H, L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, T.g);
+      SSDK_COUNT_LAUNCH(ctx);
+    }
+    if (d.op == SSDK_OP_MAXPOOL) {
+      if (prod_needs_grad) {
+        const size_t total = (size_t)PL.out.B * PL.out.H * PL.out.W * PL.out.C;
+        pool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(PL.out, T.g, PT.g, L.H, L.W, d.kh, d.kw, d.stride, d.pad_t, d.pad_l,
+                                                                         relu_mask, written[pi] ? 1 : 0);
+        SSDK_COUNT_LAUNCH(ctx);
+        written[pi] = 1;
+      }
+      continue;
+    }
+    if (d.op == SSDK_OP_L2NORM) {
+      if (prod_needs_grad) {
+        const size_t total = (size_t)PL.out.B * PL.out.H * PL.out.W;
+        l2norm_bwd_kernel<<<(unsigned)((total + 7) / 8), 256, 0, s>>>(PL.out, T.g, PT.g, L.gamma, t->grad + T.off_g, relu_mask, written[pi] ? 1 : 0);
+        SSDK_COUNT_LAUNCH(ctx);
+        written[pi] = 1;
+      }
+      continue;
+    }
+    // ---- convolution / head: weight + bias gradients
+    if (L.direct) {
+      const int K = T.taps * T.cin;
+      const size_t smem = (size_t)K * T.cout * sizeof(float);
+      const size_t total = (size_t)T.g.B * T.g.H * T.g.W;
+      const int ppb = 2048;
+      wgrad_direct_kernel<<<(unsigned)((total + ppb - 1) / ppb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, ppb);
+      SSDK_COUNT_LAUNCH(ctx);
+      // bias: through the transposed gradient like the other layers
+      const long long Kv = (long long)m->B * T.g.Hp() * T.g.Wp();
+      const long long ldT = (Kv + 7) / 8 * 8 + 64;
+      if ((long long)T.g.Cs * ldT <= t->dyT_elems) {
+        TMap id{1, 0, 0, 0, 0, 0, 0, 0};
+        rc = do_transpose(t, T.g.hi, T.g.lo, T.g.Cs, (long long)T.g.rows(), id, Kv, T.cout, t->dyT_hi, t->dyT_lo, ldT, s); if (rc) return rc;
+        dim3 gr(64, T.cout);
+        rowsum_kernel<<<gr, 256, 0, s>>>(t->dyT_hi, t->dyT_lo, ldT, Kv, t->grad + T.off_b);
+        SSDK_COUNT_LAUNCH(ctx);
+      } else { set_error("internal: transposed-gradient scratch too small for the image-facing layer"); return SSDK_ERR_INVALID; }
+    } else {
+      // transposed operands
+      rc = do_transpose(t, T.g.hi, T.g.lo, T.g.Cs, (long long)T.g.rows(), T.dy_map, T.Kv, T.cout, t->dyT_hi, t->dyT_lo, T.ldT, s); if (rc) return rc;
+      if (L.im2col) {
+        rc = do_transpose(t, L.col_hi, L.col_lo, L.Kpad, T.Kv, T.x_map, T.Kv, L.Kpad, t->xT_hi, t->xT_lo, T.ldT, s); if (rc) return rc;
+        rc = launch_conv(ctx, T.wgrad[0], s); if (rc) return rc;
+      } else {
+        for (int r = 0; r < 8; ++r) {
+          bool any = false;
+          for (size_t tp = 0; tp < T.wgrad.size(); ++tp) any |= (T.wgrad_res[tp] == r);
+          if (!any) continue;
+          rc = do_transpose(t, PL.out.hi, PL.out.lo, PL.out.Cs, (long long)PL.out.rows(), T.x_map, T.Kv, T.cin, t->xT_hi, t->xT_lo, T.ldT, s, r);
+          if (rc) return rc;
+          for (size_t tp = 0; tp < T.wgrad.size(); ++tp)
+            if (T.wgrad_res[tp] == r) { rc = launch_conv(ctx, T.wgrad[tp], s); if (rc) return rc; }
+        }
+      }
+      dim3 gr(64, T.cout);
+      rowsum_kernel<<<gr, 256, 0, s>>>(t->dyT_hi, t->dyT_lo, T.ldT, T.Kv, t->grad + T.off_b);
+      SSDK_COUNT_LAUNCH(ctx);
+    }
+    // ---- data gradient
+    if (T.has_dgrad && T.dgrad_strided) {
+      rc = launch_conv(ctx, T.dgrad, s); if (rc) return rc;
+      const size_t total = (size_t)PT.g.B * PT.g.H * PT.g.W * PT.g.C;
+      col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(T.dcol, L.H, L.W, d.kh, d.kw, d.stride, d.dilation, d.pad_t, d.pad_l, T.dcol_ld,
+                                                                     PL.out, PT.g, relu_mask, written[pi] ? 1 : 0);
+      SSDK_COUNT_LAUNCH(ctx);
+      written[pi] = 1;
+    } else if (T.has_dgrad && !getenv("SSDK_SKIP_DGRAD")) {
+      T.dgrad.args.accumulate = written[pi] ? 1 : 0;
+      rc = launch_conv(ctx, T.dgrad, s); if (rc) return rc;
+      written[pi] = 1;
+    }
+  }
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float l2_reg, float grad_scale, void* stream_) {
+  SSDK_REQUIRE(t, "ssdk_train_apply: NULL trainer");
+  ssdk_model* m = t->m;
+  ssdk_ctx* ctx = m->ctx;
+  cudaStream_t s = (cudaStream_t)stream_;
+  int rc;
+  for (size_t i = 0; i < t->tl.size(); ++i) {
+    TLayer& T = t->tl[i];
+    LayerPlan& L = m->layers[i];
+    if (T.off_g >= 0) {
+      sgd_kernel_flat<<<(unsigned)((L.C + 255) / 256), 256, 0, s>>>(L.gamma, T.vgamma, t->grad + T.off_g, (size_t)L.C, lr, momentum, grad_scale);
+      SSDK_COUNT_LAUNCH(ctx);
+    }
+    if (T.off_w < 0) continue;
+    const size_t nw = (size_t)T.taps * T.cin * T.cout;
+    sgd_kernel_w<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(L.w_f32, T.vw, t->grad + T.off_w, T.taps, T.cin, T.cout, lr, momentum, l2_reg, grad_scale);
+    SSDK_COUNT_LAUNCH(ctx);
+    sgd_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bias, T.vb, t->grad + T.off_b, (size_t)T.cout, lr, momentum, grad_scale);
+    SSDK_COUNT_LAUNCH(ctx);
+    if (!L.direct) {
+      rc = launch_repack(ctx, L.w_f32, T.taps, T.cin, T.cout, L.im2col ? 1 : 0, L.kblocks, L.w_krow, T.cout, L.w_hi, L.w_lo, s); if (rc) return rc;
+    }
+    if (T.has_dgrad) {
+      if (T.dgrad_strided) rc = launch_repack(ctx, L.w_f32, T.taps, T.cin, T.cout, 3, T.w2_kblocks, T.w2_krow, T.taps * T.cin, T.w2_hi, T.w2_lo, s);
+      else rc = launch_repack(ctx, L.w_f32, T.taps, T.cin, T.cout, 2, T.w2_kblocks, T.w2_krow, T.cin, T.w2_hi, T.w2_lo, s);
+      if (rc) return rc;
+    }
+  }
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_trainer_read_params(ssdk_trainer* t, float* out_dev, void* stream_) {
+  SSDK_REQUIRE(t && out_dev, "ssdk_trainer_read_params: NULL argument");
+  ssdk_model* m = t->m;
+  cudaStream_t s = (cudaStream_t)stream_;
+  for (size_t i = 0; i < t->tl.size(); ++i) {
+    TLayer& T = t->tl[i];
+    LayerPlan& L = m->layers[i];
+    if (T.off_g >= 0) SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev + T.off_g, L.gamma, (size_t)L.C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (T.off_w < 0) continue;
+    const size_t nw = (size_t)T.taps * T.cin * T.cout;
+    hwio_to_ohwi_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(L.w_f32, T.taps, T.cin, T.cout, out_dev + T.off_w);
+    SSDK_COUNT_LAUNCH(m->ctx);
+    SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev + T.off_b, L.bias, (size_t)T.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}

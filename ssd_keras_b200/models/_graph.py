@@ -179,9 +179,10 @@ class SSDModel:
         except Exception:
             pass
 
-    def _plan(self, batch):
-        if batch in self._plans:
-            return self._plans[batch]
+    def _plan(self, batch, training=False):
+        key = (batch, bool(training))
+        if key in self._plans:
+            return self._plans[key]
         n = len(self.specs)
         descs = (_ffi.LayerDesc * n)()
         keep = []
@@ -221,20 +222,20 @@ class SSDModel:
         anc = np.ascontiguousarray(self.anchors_f32)
         md = _ffi.ModelDesc(int(batch), self.img_height, self.img_width, self.img_channels, self.n_classes, n, descs,
                             0 if self.precision == 'bf16x3' else 1, _ffi.np_ptr(anc, C.c_float),
-                            (C.c_float * 4)(*[float(v) for v in self.variances]))
+                            (C.c_float * 4)(*[float(v) for v in self.variances]), 1 if training else 0)
         h = C.c_void_p()
         _ffi.check(_ffi.lib().ssdk_model_create(_ffi.context(), C.byref(md), C.byref(h)))
         P = C.c_int()
         _ffi.check(_ffi.lib().ssdk_model_num_priors(h, C.byref(P)))
         assert P.value == self.n_boxes_total, (P.value, self.n_boxes_total)
-        self._plans[batch] = {'handle': h}
-        return self._plans[batch]
+        self._plans[key] = {'handle': h}
+        return self._plans[key]
 
-    def forward_device(self, images):
+    def forward_device(self, images, training=False):
         """images: float32 CUDA tensor (B,H,W,3) -> y_pred float32 CUDA tensor (B,P,C+12) (raw predictions)."""
         import torch
         B = images.shape[0]
-        plan = self._plan(B)
+        plan = self._plan(B, training)
         images = images.to(dtype=torch.float32).contiguous()
         y = torch.empty((B, self.n_boxes_total, self.n_classes + 12), dtype=torch.float32, device=images.device)
         _ffi.check(_ffi.lib().ssdk_model_forward(plan['handle'], _ffi.dptr(images), _ffi.dptr(y), _ffi.stream_ptr()))

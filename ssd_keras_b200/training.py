@@ -1,0 +1,113 @@
+"""Training step on B200: what ``model.compile(optimizer=SGD(lr, momentum), loss=SSDLoss().compute_loss)`` +
+``train_on_batch`` do in the reference (``ssd300_training.ipynb:169-173``), through ``ssdk_train_backward`` /
+``ssdk_train_apply`` (``csrc/train.cu``).  Data-parallel: every rank runs the same step on its shard and the flat
+gradient buffer is summed with ONE NCCL all-reduce before the update (replica-local loss).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+
+
+class SSDTrainer:
+    def __init__(self, model, batch_size, lr=1e-3, momentum=0.9, l2_regularization=None, neg_pos_ratio=3, n_neg_min=0,
+                 alpha=1.0):
+        import torch
+        self.model = model
+        self.batch = int(batch_size)
+        self.lr, self.momentum = float(lr), float(momentum)
+        self.l2 = float(model.l2_regularization if l2_regularization is None else l2_regularization)
+        self.neg_pos_ratio, self.n_neg_min, self.alpha = int(neg_pos_ratio), int(n_neg_min), float(alpha)
+        self.plan = model._plan(self.batch, training=True)
+        # the flat gradient buffer is a torch tensor so that torch.distributed can all-reduce it in place
+        self.n_params = int(sum(int(np.prod(s)) for s in model.weight_shapes().values()))
+        self.grad = torch.zeros((self.n_params,), dtype=torch.float32, device='cuda')
+        self.handle = C.c_void_p()
+        _ffi.check(_ffi.lib().ssdk_trainer_create(self.plan['handle'], _ffi.dptr(self.grad), C.byref(self.handle)))
+        n = C.c_longlong()
+        _ffi.check(_ffi.lib().ssdk_trainer_num_params(self.handle, C.byref(n)))
+        assert int(n.value) == self.n_params, (n.value, self.n_params)
+        self._spans = None
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                _ffi.lib().ssdk_trainer_destroy(self.handle)
+        except Exception:
+            pass
+
+    # -- one step ------------------------------------------------------------------------------
+    def forward_backward(self, images, y_true):
+        """images (B,H,W,3), y_true (B,P,C+12): float32 CUDA tensors.  Returns (loss (B,), y_pred); gradients in self.grad."""
+        import torch
+        y_pred = self.model.forward_device(images, training=True)
+        loss = torch.empty((self.batch,), dtype=torch.float32, device=images.device)
+        y_true = y_true.to(dtype=torch.float32).contiguous()
+        _ffi.check(_ffi.lib().ssdk_train_backward(self.handle, _ffi.dptr(y_true), _ffi.dptr(y_pred), self.neg_pos_ratio,
+                                                  self.n_neg_min, self.alpha, _ffi.dptr(loss), _ffi.stream_ptr()))
+        return loss, y_pred
+
+    def apply(self, grad_scale=1.0):
+        _ffi.check(_ffi.lib().ssdk_train_apply(self.handle, self.lr, self.momentum, self.l2, float(grad_scale), _ffi.stream_ptr()))
+
+    def train_on_batch(self, images, y_true):
+        """forward + loss + backward + (all-reduce) + SGD update.  Returns the per-image loss tensor (B,)."""
+        import torch.distributed as dist
+        loss, _ = self.forward_backward(images, y_true)
+        scale = 1.0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad)                     # one all-reduce for all 26 M gradients
+            scale = 1.0 / dist.get_world_size()
+        self.apply(scale)
+        return loss
+
+    # -- introspection (tests) -------------------------------------------------------------------
+    def spans(self):
+        if self._spans is None:
+            out = {}
+            for i, s in enumerate(self.model.specs):
+                for which, tag in ((0, 'kernel'), (1, 'bias'), (2, 'gamma')):
+                    o, c = C.c_longlong(), C.c_longlong()
+                    _ffi.check(_ffi.lib().ssdk_trainer_param_span(self.handle, i, which, C.byref(o), C.byref(c)))
+                    if c.value > 0:
+                        out[(s.name, tag)] = (int(o.value), int(c.value))
+            self._spans = out
+        return self._spans
+
+    def _unflatten(self, flat):
+        """flat float32 ndarray -> dict with Keras names / layouts (kernels HWIO, head kernels split into conf / loc)."""
+        m = self.model
+        res = {}
+        Ct = m.n_classes
+        for s in m.specs:
+            if s.op == _ffi.OP_CONV:
+                cin = m._shapes[m.index[s.inp]][2]
+                o, c = self.spans()[(s.name, 'kernel')]
+                res[s.name + '/kernel'] = flat[o:o + c].reshape(s.cout, s.kh, s.kw, cin).transpose(1, 2, 3, 0).copy()
+                o, c = self.spans()[(s.name, 'bias')]
+                res[s.name + '/bias'] = flat[o:o + c].copy()
+            elif s.op == _ffi.OP_HEAD:
+                cin = m._shapes[m.index[s.inp]][2]
+                nb = s.n_boxes
+                o, c = self.spans()[(s.name, 'kernel')]
+                w = flat[o:o + c].reshape(nb, Ct + 4, 3, 3, cin)            # fused per box: [C logits | 4 offsets]
+                res[s.params['conf_name'] + '/kernel'] = w[:, :Ct].reshape(nb * Ct, 3, 3, cin).transpose(1, 2, 3, 0).copy()
+                res[s.params['loc_name'] + '/kernel'] = w[:, Ct:].reshape(nb * 4, 3, 3, cin).transpose(1, 2, 3, 0).copy()
+                o, c = self.spans()[(s.name, 'bias')]
+                b = flat[o:o + c].reshape(nb, Ct + 4)
+                res[s.params['conf_name'] + '/bias'] = b[:, :Ct].reshape(-1).copy()
+                res[s.params['loc_name'] + '/bias'] = b[:, Ct:].reshape(-1).copy()
+            elif s.op == _ffi.OP_L2NORM:
+                o, c = self.spans()[(s.name, 'gamma')]
+                res[s.name + '/gamma'] = flat[o:o + c].copy()
+        return res
+
+    def gradients(self):
+        return self._unflatten(self.grad.cpu().numpy())
+
+    def get_weights(self):
+        import torch
+        out = torch.empty_like(self.grad)
+        _ffi.check(_ffi.lib().ssdk_trainer_read_params(self.handle, _ffi.dptr(out), _ffi.stream_ptr()))
+        return self._unflatten(out.cpu().numpy())
