@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const __nv_bfloat16* __r
     if (v < Kv) {
       if (mp.identity) row = v + row_off;
       else {
-        const int n = (int)(v / mp.rows_per_img); const int rr = (int)(v - (long long)n * mp.rows_per_img);
+        const long long vs = v + row_off;
+        const int n = (int)(vs / mp.rows_per_img); const int rr = (int)(vs - (long long)n * mp.rows_per_img);
         const int y = rr / mp.Wp, x = rr - y * mp.Wp;
         if (y < mp.Ho && x < mp.Wo) row = ((long long)n * mp.src_Hp + (y + mp.src_pad)) * mp.src_Wp + (x + mp.src_pad);
       }
@@ -136,16 +137,41 @@ __global__ void head_bwd_kernel(const float* __restrict__ head, const float* __r
 }
 
 // Max-pool backward (gather form): gin(n,y,x,c) (+)= sum over windows whose FIRST maximum is (y,x) of gout; optional ReLU' mask.
-__global__ void pool_bwd_kernel(ActBuf in, ActBuf gout, ActBuf gin, int Hout, int Wout, int KH, int KW, int stride, int pad_t, int pad_l,
-                                int relu_mask, int accumulate) {
+// One thread per (input pixel, 8 channels): 16-byte loads of the hi / lo planes.
+__device__ __forceinline__ void ld8(const ActBuf& a, size_t i, float (&v)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(a.hi + i);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { v[2 * e] = __uint_as_float(hw[e] << 16); v[2 * e + 1] = __uint_as_float(hw[e] & 0xffff0000u); }
+  if (a.lo) {
+    const uint4 l = *reinterpret_cast<const uint4*>(a.lo + i);
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[2 * e] += __uint_as_float(lw[e] << 16); v[2 * e + 1] += __uint_as_float(lw[e] & 0xffff0000u); }
+  }
+}
+__device__ __forceinline__ void st8(const ActBuf& a, size_t i, const float (&v)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+    hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * e] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v[2 * e + 1] - __bfloat162float(h1));
+    lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(a.hi + i) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if (a.lo) *reinterpret_cast<uint4*>(a.lo + i) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+__global__ void __launch_bounds__(256) pool_bwd_kernel(ActBuf in, ActBuf gout, ActBuf gin, int Hout, int Wout, int KH, int KW, int stride,
+                                                       int pad_t, int pad_l, int relu_mask, int accumulate) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)in.B * in.H * in.W * in.C;
+  const int CG = in.C >> 3;
+  const size_t total = (size_t)in.B * in.H * in.W * CG;
   if (i >= total) return;
-  const int c = (int)(i % in.C); const size_t pix = i / in.C;
+  const int c = (int)(i % CG) * 8; const size_t pix = i / CG;
   const int x = (int)(pix % in.W); const int y = (int)((pix / in.W) % in.H); const int n = (int)(pix / ((size_t)in.W * in.H));
-  const size_t me = aidx(in, n, y, x) + c;
-  const float v = ld2(in, me);
-  float acc = 0.f;
+  float v[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  ld8(in, aidx(in, n, y, x) + c, v);
   const int yo_lo = max(0, (y + pad_t - KH + stride) / stride), yo_hi = min(Hout - 1, (y + pad_t) / stride);
   const int xo_lo = max(0, (x + pad_l - KW + stride) / stride), xo_hi = min(Wout - 1, (x + pad_l) / stride);
   for (int yo = yo_lo; yo <= yo_hi; ++yo) {
@@ -154,26 +180,41 @@ __global__ void pool_bwd_kernel(ActBuf in, ActBuf gout, ActBuf gin, int Hout, in
     for (int xo = xo_lo; xo <= xo_hi; ++xo) {
       const int x0 = xo * stride - pad_l;
       if (x < x0 || x >= x0 + KW) continue;
-      // is (y, x) the first maximum of this window (row-major scan, strict '>')?
-      bool first = true;
+      // per channel: is (y, x) the first maximum of this window (row-major scan, strict '>')?
+      unsigned first = 0xffu;
       for (int ky = 0; ky < KH && first; ++ky) {
         const int yy = y0 + ky;
         if (yy < 0 || yy >= in.H) continue;
         for (int kx = 0; kx < KW; ++kx) {
           const int xx = x0 + kx;
-          if (xx < 0 || xx >= in.W) continue;
-          const float u = ld2(in, aidx(in, n, yy, xx) + c);
+          if (xx < 0 || xx >= in.W || (yy == y && xx == x)) continue;
+          float u[8];
+          ld8(in, aidx(in, n, yy, xx) + c, u);
           const bool before = (yy < y) || (yy == y && xx < x);
-          if (u > v || (u == v && before)) { first = false; break; }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) if (u[e] > v[e] || (u[e] == v[e] && before)) first &= ~(1u << e);
         }
       }
-      if (first) acc += ld2(gout, aidx(gout, n, yo, xo) + c);
+      if (first) {
+        float g[8];
+        ld8(gout, aidx(gout, n, yo, xo) + c, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (first & (1u << e)) acc[e] += g[e];
+      }
     }
   }
-  if (relu_mask && !(v > 0.f)) acc = 0.f;
   const size_t o = aidx(gin, n, y, x) + c;
-  if (accumulate) acc += ld2(gin, o);
-  st2(gin, o, acc);
+  if (relu_mask) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) if (!(v[e] > 0.f)) acc[e] = 0.f;
+  }
+  if (accumulate) {
+    float old[8];
+    ld8(gin, o, old);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += old[e];
+  }
+  st8(gin, o, acc);
 }
 
 // L2Normalization backward (y_c = gamma_c * x_c * s, s = rsqrt(max(sum x^2, 1e-12))): one warp per pixel.
@@ -234,27 +275,33 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, int Ho, int Wo, in
 }
 
 // Weight gradient of the image-facing conv (Cin <= 4): gw[co][tap][ci] += sum_pix dZ[pix][co] * X[pix + tap][ci].
+// A block owns `rows_per_block` output rows; thread -> (k = tap*cin + ci, 8 output channels), 16-byte loads of dZ.
 __global__ void __launch_bounds__(256) wgrad_direct_kernel(ActBuf in, ActBuf g, float* __restrict__ gw, int KH, int KW, int dil,
-                                                           int pad_t, int pad_l, int pix_per_block) {
+                                                           int pad_t, int pad_l, int rows_per_block) {
   extern __shared__ float s_acc[];               // [K][Cout]
   const int K = KH * KW * in.C, Cout = g.C;
   for (int i = threadIdx.x; i < K * Cout; i += 256) s_acc[i] = 0.f;
   __syncthreads();
-  const size_t total = (size_t)g.B * g.H * g.W;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
-  // thread -> (k, group of co); loops over the block's pixels
+  const int total_rows = g.B * g.H;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(total_rows, r0 + rows_per_block);
   for (int idx = threadIdx.x; idx < K * (Cout / 8); idx += 256) {
     const int k = idx / (Cout / 8), cg = (idx % (Cout / 8)) * 8;
     const int c = k % in.C, tap = k / in.C, kw = tap % KW, kh = tap / KW;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t p = p0; p < min(total, p0 + (size_t)pix_per_block); ++p) {
-      const int xo = (int)(p % g.W); const int yo = (int)((p / g.W) % g.H); const int n = (int)(p / ((size_t)g.W * g.H));
-      const int y = yo + kh * dil - pad_t, x = xo + kw * dil - pad_l;
-      if (y < 0 || y >= in.H || x < 0 || x >= in.W) continue;
-      const float xv = ld2(in, aidx(in, n, y, x) + c);
-      const size_t go = aidx(g, n, yo, xo) + cg;
+    for (int r = r0; r < r1; ++r) {
+      const int n = r / g.H, yo = r - n * g.H;
+      const int y = yo + kh * dil - pad_t;
+      if (y < 0 || y >= in.H) continue;
+      const int xo_lo = max(0, pad_l - kw * dil), xo_hi = min(g.W, in.W + pad_l - kw * dil);
+      size_t xi = aidx(in, n, y, xo_lo + kw * dil - pad_l) + c;
+      size_t go = aidx(g, n, yo, xo_lo) + cg;
+      for (int xo = xo_lo; xo < xo_hi; ++xo, xi += in.Cs, go += g.Cs) {
+        const float xv = ld2(in, xi);
+        float gv[8];
+        ld8(g, go, gv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += xv * ld2(g, go + e);
+        for (int e = 0; e < 8; ++e) acc[e] += xv * gv[e];
+      }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) s_acc[k * Cout + cg + e] += acc[e];
@@ -342,6 +389,7 @@ struct TLayer {
   float* dcol = nullptr; int dcol_ld = 0;
   // weight gradient
   std::vector<ConvLaunch> wgrad;            // one per tap (or one for the im2col path)
+  int Wq = 0;                               // row pitch of the transposed operands' pixel grid
   std::vector<int> wgrad_res;               // tap shift mod 8: TMA needs 16-byte aligned K offsets, so XT is built once per residue
   long long Kv = 0, ldT = 0;
   TMap dy_map{}, x_map{};
@@ -498,9 +546,13 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
       T.x_map = TMap{1, 0, 0, 0, 0, 0, 0, 0};
       max_xT = std::max(max_xT, (long long)L.Kpad * ((Kv + 7) / 8 * 8 + 64));
     } else {
-      Kv = (long long)m->B * X.Hp() * X.Wp();
-      T.dy_map = TMap{0, X.Hp() * X.Wp(), X.Wp(), L.H, L.W, T.g.Hp(), T.g.Wp(), T.g.pad};
-      T.x_map = TMap{1, 0, 0, 0, 0, 0, 0, 0};
+      // the GEMM's pixel axis runs over X's padded grid with the row pitch rounded up to 8 elements: tap shifts are then
+      // kh*Wq + kw (+ const) and only the kw part can break TMA's 16-byte alignment -> one XT copy per distinct kw residue
+      const int Wq = (X.Wp() + 7) / 8 * 8;
+      T.Wq = Wq;
+      Kv = (long long)m->B * X.Hp() * Wq;
+      T.dy_map = TMap{0, X.Hp() * Wq, Wq, L.H, L.W, T.g.Hp(), T.g.Wp(), T.g.pad};
+      T.x_map = TMap{0, X.Hp() * Wq, Wq, X.Hp(), X.Wp(), X.Hp(), X.Wp(), 0};
       max_xT = std::max(max_xT, (long long)X.Cs * ((Kv + 7) / 8 * 8 + 64));
     }
     T.Kv = Kv; T.ldT = (Kv + 7) / 8 * 8 + 64;
@@ -540,7 +592,7 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
       else {
         const int kh = tp / d.kw, kw = tp % d.kw;
         a.out_ld = T.taps * T.cin; a.out_col_off = tp * T.cin;
-        const int shift = (kh * d.dilation - d.pad_t + X.pad) * X.Wp() + (kw * d.dilation - d.pad_l + X.pad);
+        const int shift = (kh * d.dilation - d.pad_t + X.pad) * T.Wq + (kw * d.dilation - d.pad_l + X.pad);
         T.wgrad_res[tp] = shift & 7;                 // XT_r[c][v] = X[v + r][c], read at the aligned offset shift - r
         a.b_k_offset = shift - (shift & 7);
       }
@@ -636,7 +688,8 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
     }
     if (d.op == SSDK_OP_MAXPOOL) {
       if (prod_needs_grad) {
-        const size_t total = (size_t)PL.out.B * PL.out.H * PL.out.W * PL.out.C;
+        if (PL.out.C % 8) { set_error("training: max-pool channels must be a multiple of 8"); return SSDK_ERR_UNSUPPORTED; }
+        const size_t total = (size_t)PL.out.B * PL.out.H * PL.out.W * (PL.out.C / 8);
         pool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(PL.out, T.g, PT.g, L.H, L.W, d.kh, d.kw, d.stride, d.pad_t, d.pad_l,
                                                                          relu_mask, written[pi] ? 1 : 0);
         SSDK_COUNT_LAUNCH(ctx);
@@ -657,9 +710,9 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
     if (L.direct) {
       const int K = T.taps * T.cin;
       const size_t smem = (size_t)K * T.cout * sizeof(float);
-      const size_t total = (size_t)T.g.B * T.g.H * T.g.W;
-      const int ppb = 2048;
-      wgrad_direct_kernel<<<(unsigned)((total + ppb - 1) / ppb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, ppb);
+      const int total_rows = T.g.B * T.g.H;
+      const int rpb = std::max(1, (total_rows + 8 * ctx->sm_count - 1) / (8 * ctx->sm_count));
+      wgrad_direct_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, rpb);
       SSDK_COUNT_LAUNCH(ctx);
       // bias: through the transposed gradient like the other layers
       const long long Kv = (long long)m->B * T.g.Hp() * T.g.Wp();
