@@ -27,6 +27,7 @@ SOURCES = {
     'conv.cu': [],
     'model.cu': [],
     'train.cu': [],
+    'wgrad.cu': [],
 }
 
 

@@ -71,6 +71,8 @@ struct ConvLaunch {
 int tma_init();   // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows);
+// 4-D map over a bf16 NHWC tensor, dims / box innermost first (channels, x, y, image); 128B swizzle, zero fill
+int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint32_t box[4]);
 size_t conv_smem_bytes(const ConvArgs& a);
 void conv_pick_stages(ConvArgs& a);
 int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream);

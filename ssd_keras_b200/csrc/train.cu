@@ -11,6 +11,7 @@
 // Operands stay bf16 hi+lo (three MMAs per product) like the forward pass.  Small pieces (max-pool routing, L2Normalization,
 // softmax/concat head, bias sums, image-facing 3-channel conv, SGD, re-packing of the bf16 planes) are plain CUDA kernels.
 #include "model.cuh"
+#include "wgrad.cuh"
 #include <climits>
 
 using namespace ssdk;
@@ -388,7 +389,9 @@ struct TLayer {
   bool dgrad_strided = false;               // stride != 1: col-gradient GEMM (dZ * W^T) + col2im
   float* dcol = nullptr; int dcol_ld = 0;
   // weight gradient
-  std::vector<ConvLaunch> wgrad;            // one per tap (or one for the im2col path)
+  bool wg_native = false;                   // stride-1 layers: wgrad.cu reads dZ / X in place (no transposed copies)
+  WgradLaunch wg;
+  std::vector<ConvLaunch> wgrad;            // fallback: one GEMM per tap (or one for the im2col path) on transposed operands
   int Wq = 0;                               // row pitch of the transposed operands' pixel grid
   std::vector<int> wgrad_res;               // tap shift mod 8: TMA needs 16-byte aligned K offsets, so XT is built once per residue
   long long Kv = 0, ldT = 0;
@@ -540,6 +543,12 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
     if (L.direct) continue;                     // handled by wgrad_direct_kernel
     const ActBuf& X = PL.out;
     long long Kv;
+    if (!L.im2col && !getenv("SSDK_WGRAD_TRANSPOSED") && wgrad_supported(X, T.g, d.kh, d.kw, d.stride, d.dilation)) {
+      T.wg_native = true;
+      rc = plan_wgrad(m->ctx, T.wg, X, T.g, L.H, L.W, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, m->split, nullptr);
+      if (rc) return fail(rc);
+      continue;
+    }
     if (L.im2col) {
       Kv = (long long)m->B * L.H * L.W;
       T.dy_map = TMap{0, L.H * L.W, L.W, L.H, L.W, T.g.Hp(), T.g.Wp(), T.g.pad};
@@ -570,6 +579,7 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
     LayerPlan& L = m->layers[i];
     TLayer& T = t->tl[i];
     if (!is_conv(L.d.op) || L.direct) continue;
+    if (T.wg_native) { T.wg.args.dw = t->grad + T.off_w; continue; }
     const ssdk_layer_desc& d = L.d;
     const ActBuf& X = m->layers[d.input].out;
     const int n_gemm = L.im2col ? 1 : T.taps;
@@ -714,16 +724,10 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
       const int rpb = std::max(1, (total_rows + 8 * ctx->sm_count - 1) / (8 * ctx->sm_count));
       wgrad_direct_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, rpb);
       SSDK_COUNT_LAUNCH(ctx);
-      // bias: through the transposed gradient like the other layers
-      const long long Kv = (long long)m->B * T.g.Hp() * T.g.Wp();
-      const long long ldT = (Kv + 7) / 8 * 8 + 64;
-      if ((long long)T.g.Cs * ldT <= t->dyT_elems) {
-        TMap id{1, 0, 0, 0, 0, 0, 0, 0};
-        rc = do_transpose(t, T.g.hi, T.g.lo, T.g.Cs, (long long)T.g.rows(), id, Kv, T.cout, t->dyT_hi, t->dyT_lo, ldT, s); if (rc) return rc;
-        dim3 gr(64, T.cout);
-        rowsum_kernel<<<gr, 256, 0, s>>>(t->dyT_hi, t->dyT_lo, ldT, Kv, t->grad + T.off_b);
-        SSDK_COUNT_LAUNCH(ctx);
-      } else { set_error("internal: transposed-gradient scratch too small for the image-facing layer"); return SSDK_ERR_INVALID; }
+      rc = launch_bias_grad(ctx, T.g, t->grad + T.off_b, s); if (rc) return rc;
+    } else if (T.wg_native) {
+      rc = launch_wgrad(ctx, T.wg, s); if (rc) return rc;
+      rc = launch_bias_grad(ctx, T.g, t->grad + T.off_b, s); if (rc) return rc;
     } else {
       // transposed operands
       rc = do_transpose(t, T.g.hi, T.g.lo, T.g.Cs, (long long)T.g.rows(), T.dy_map, T.Kv, T.cout, t->dyT_hi, t->dyT_lo, T.ldT, s); if (rc) return rc;
