@@ -93,9 +93,10 @@ def test_ssd300_step_matches_autograd():
     print('ssd300 B=2: worst gradient median err %.2e, max-norm %.2e' % (worst_med, worst_max))
     tr.apply(1.0)
     new_w = tr.get_weights()
-    ref_w, _ = og.sgd_step(w, {k: params[k].grad.numpy() for k in w}, {}, lr, mom, l2)
+    # the optimiser arithmetic, on the gradients the device produced (their own error is bounded above)
+    ref_w, _ = og.sgd_step(w, grads, {}, lr, mom, l2)
     for k in w:
-        assert np.abs(new_w[k] - ref_w[k]).max() <= 2e-5 * np.abs(ref_w[k]).max() + 1e-9, k
+        assert np.abs(new_w[k] - ref_w[k]).max() <= 2e-6 * np.abs(ref_w[k]).max() + 1e-9, k
 
 
 def test_ssd300_loss_decreases():
