@@ -201,6 +201,23 @@ def micro_benchmarks(peaks):
     bytes_ = Bm * (100000 * 20 + 200 * 4)
     out['nms_micro_p1e5'] = {'batch': Bm, 'ms': ms, 'boxes_per_s': Bm * 1e5 / ms * 1e3, 'algorithmic_GB': bytes_ / 1e9,
                              'GBps': bytes_ / ms / 1e6, 'frac_hbm': bytes_ / ms / 1e6 / hbm}
+    del boxes, scores, gm
+    # --- config 3: SSD300 training step, B = 32 per GPU (forward + loss + backward + SGD-momentum update; no all-reduce here,
+    #     this leg runs on rank 0 only)
+    from ssd_keras_b200.models.keras_ssd300 import ssd_300
+    from ssd_keras_b200.training import SSDTrainer
+    Bt = 32
+    mt = ssd_300((300, 300, 3), 20, mode='training', scales=SC300)
+    tr = SSDTrainer(mt, Bt, lr=1e-4, momentum=0.9)
+    xt = torch.from_numpy(synth.synth_images(0, Bt, 300, 300)).cuda()
+
+    def train_step():
+        tr.forward_backward(xt, y_true)
+        tr.apply(1.0)
+    ms = _time_cuda(train_step, iters=5, warm=2)
+    fl = 3.0 * mt.flops(Bt)[0]
+    out['train_step_ssd300_b32'] = {'ms': ms, 'images_per_s': Bt * 1e3 / ms, 'algorithmic_TFLOPs': fl / ms / 1e9,
+                                    'frac_tensor_peak': fl / ms / 1e9 / peaks['bf16_tflops_sustained'], 'n_params': tr.n_params}
     return out
 
 
