@@ -81,7 +81,8 @@ static constexpr int kBM = 128;          // UMMA M (rows per tile)
 static constexpr int kBK = 64;           // channels per k-block = one 128-byte swizzle atom of bf16
 static constexpr int kATile = kBM * kBK * 2;   // 16 KB
 
-static size_t slot_a_bytes(const ConvArgs& a) { return (size_t)a.slab_rows * kBK * 2 * (a.split ? 2 : 1); }
+static int mt_of(const ConvArgs& a) { return a.mt > 1 ? a.mt : 1; }
+static size_t slot_a_bytes(const ConvArgs& a) { return (size_t)(a.slab_rows + (mt_of(a) - 1) * kBM) * kBK * 2 * (a.split ? 2 : 1); }
 static size_t slot_b_bytes(const ConvArgs& a) { return (size_t)a.BN * kBK * 2 * (a.split ? 2 : 1); }
 static size_t epi_param_bytes(const ConvArgs& a) { return ((size_t)a.cout * 3 * sizeof(float) + 127) / 128 * 128; }   // bias | bn scale | bn shift
 size_t conv_smem_bytes(const ConvArgs& a) { return 1024 + slot_a_bytes(a) * a.stages_a + slot_b_bytes(a) * a.stages_b + 512 + epi_param_bytes(a); }
@@ -116,6 +117,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int bo_mode = 
   d |= (uint64_t)2 << 61;                            // [61,64) layout = SWIZZLE_128B
   return d;
 }
+// constant upper part of that descriptor: SBO = 1024 B at [32,46), version 1 at [46,48), SWIZZLE_128B at [61,64)
+static constexpr uint64_t kDescHi = ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   // c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -124,6 +127,56 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == SSDK_ACT_RELU) return fmaxf(x, 0.f);
   if (act == SSDK_ACT_ELU) return x > 0.f ? x : expm1f(x);
   return x;
+}
+
+// Epilogue of the activation-producing launches: bias / folded BatchNorm / activation -> bf16 hi+lo planes, 8 channels per
+// 16-byte store.  BWD adds what the data-gradient launches need: ReLU'(forward value) mask and accumulation into the output.
+template <bool BWD>
+__device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, int ncols, int n0, size_t o, bool valid,
+                                          const float* s_bias, const float* s_scale, const float* s_shift) {
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    uint32_t vr[32];
+    tmem_ld32(t_row + (uint32_t)c0, vr);
+    if (!valid) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (c0 + g * 8 < ncols) {
+        uint32_t ph[4], pl[4];
+        uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), oh = make_uint4(0, 0, 0, 0), ol = oh;
+        if (BWD) {
+          if (args.mask_hi) mk = *reinterpret_cast<const uint4*>(args.mask_hi + o + c0 + g * 8);
+          if (args.accumulate) {
+            oh = *reinterpret_cast<const uint4*>(args.out_hi + o + c0 + g * 8);
+            if (args.out_lo) ol = *reinterpret_cast<const uint4*>(args.out_lo + o + c0 + g * 8);
+          }
+        }
+        const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w}, ohw[4] = {oh.x, oh.y, oh.z, oh.w}, olw[4] = {ol.x, ol.y, ol.z, ol.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = n0 + c0 + g * 8 + j * 2 + e;
+            float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + s_bias[col];
+            if (args.bn_scale) xv = xv * s_scale[col] + s_shift[col];
+            xv = apply_act(xv, args.act);
+            if (BWD) {
+              if (!(__uint_as_float(((mkw[j] >> (e * 16)) & 0xffffu) << 16) > 0.f)) xv = 0.f;       // ReLU'(forward value)
+              xv += __uint_as_float(((ohw[j] >> (e * 16)) & 0xffffu) << 16) + __uint_as_float(((olw[j] >> (e * 16)) & 0xffffu) << 16);
+            }
+            f[e] = xv;
+          }
+          __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
+          __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0));
+          __nv_bfloat16 l1 = __float2bfloat16_rn(f[1] - __bfloat162float(h1));
+          ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(args.out_hi + o + c0 + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (args.out_lo) *reinterpret_cast<uint4*>(args.out_lo + o + c0 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,7 +190,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SA = args.stages_a, SB = args.stages_b, BN = args.BN, split = args.split;
-  const uint32_t a_plane = (uint32_t)args.slab_rows * kBK * 2;        // one A slab plane (hi or lo)
+  const int MT = args.mt > 1 ? args.mt : 1;                            // m-tiles per work unit
+  const uint32_t a_plane = (uint32_t)(args.slab_rows + (MT - 1) * kBM) * kBK * 2;   // one A slab plane (hi or lo)
+  const uint32_t a_box = (uint32_t)args.slab_rows * kBK * 2;           // bytes one TMA box delivers
   const uint32_t b_tile = (uint32_t)BN * kBK * 2;
   const uint32_t slot_a = a_plane * (split ? 2 : 1), slot_b = b_tile * (split ? 2 : 1);
   const uint32_t ring_b = smem_base + slot_a * SA;
@@ -161,7 +216,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   }
 
   int tmem_cols = 32;
-  while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+  while (tmem_cols < 2 * MT * BN) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a_hi)) : "memory");
@@ -204,9 +259,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(emptyA(sa), pa ^ 1u);
             const uint32_t da = smem_base + slot_a * sa;
-            mbar_expect_tx(fullA(sa), slot_a);
-            tma_load_2d(da, &tm_a_hi, kb * kBK, row0, fullA(sa));
-            if (split) tma_load_2d(da + a_plane, &tm_a_lo, kb * kBK, row0, fullA(sa));
+            mbar_expect_tx(fullA(sa), a_box * (uint32_t)MT * (split ? 2u : 1u));
+            for (int mt = 0; mt < MT; ++mt) {                // the second box overlaps the first by slab_rows-128 identical rows
+              tma_load_2d(da + mt * kATile, &tm_a_hi, kb * kBK, row0 + mt * kBM, fullA(sa));
+              if (split) tma_load_2d(da + a_plane + mt * kATile, &tm_a_lo, kb * kBK, row0 + mt * kBM, fullA(sa));
+            }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
             for (int kw = 0; kw < args.KW; ++kw) {
               mbar_wait(emptyB(sb), pb ^ 1u);
@@ -237,7 +294,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       int n_eff = args.cout - n0;
       n_eff = n_eff > BN ? BN : ((n_eff + 15) & ~15);
       const uint32_t idesc = make_idesc(n_eff);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BN);
       uint32_t accumulate = 0;
       for (int kh = 0; kh < args.KH; ++kh) {
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -248,16 +305,27 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             mbar_wait(fullB(sb), pb);
             tc_fence_after();
             if (lane == 0) {
-              const uint32_t b_hi = ring_b + slot_b * sb, b_lo = b_hi + b_tile;
-              const uint32_t arow = (uint32_t)(kw * args.kw_rows) * 128u;     // tap kw = the same slab, kw*dil rows further down
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t ko = (uint32_t)k * 32u;       // 16 bf16 = 32 bytes along K inside the swizzle atom
-                const uint64_t da = make_smem_desc(a_hi + arow + ko, args.bo_mode), db = make_smem_desc(b_hi + ko);
-                tc_mma(d_tmem, da, db, idesc, accumulate);
-                accumulate = 1;
-                if (split) {
-                  tc_mma(d_tmem, da, make_smem_desc(b_lo + ko), idesc, 1);
-                  tc_mma(d_tmem, make_smem_desc(a_lo + arow + ko, args.bo_mode), db, idesc, 1);
+              // The issuing thread is a single in-order instruction stream: for N <= 128 an MMA retires in 32-64 clocks, so the
+              // descriptor arithmetic between two issues must be a couple of integer adds.  Only the 14-bit start-address field
+              // (address >> 4) changes: +2 per k-step (32 B), +8*rows for a row-shifted tap, +1024 for the second m-tile.
+              const uint32_t bh = (ring_b + slot_b * sb) >> 4, bl = bh + (b_tile >> 4);
+              const uint32_t ah = (a_hi + (uint32_t)(kw * args.kw_rows) * 128u) >> 4, al = ah + (a_plane >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  const uint64_t db = kDescHi | (uint64_t)(bh + 2 * k), dbl = kDescHi | (uint64_t)(bl + 2 * k);
+#pragma unroll
+                  for (int mt = 0; mt < 2; ++mt) {
+                    if (mt < MT) {
+                      const uint64_t da = kDescHi | (uint64_t)(ah + mt * (kATile >> 4) + 2 * k);
+                      tc_mma(d_tmem + mt * BN, da, db, idesc, accumulate);
+                      if (split) {
+                        tc_mma(d_tmem + mt * BN, da, dbl, idesc, 1);
+                        tc_mma(d_tmem + mt * BN, kDescHi | (uint64_t)(al + mt * (kATile >> 4) + 2 * k), db, idesc, 1);
+                      }
+                    }
+                  }
+                  accumulate = 1;
                 }
               }
               tc_commit(emptyB(sb));                        // weight slot is free once these MMAs retire
@@ -284,7 +352,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int v = m0 + q * 32 + lane;                    // virtual row of this thread
+      for (int mt = 0; mt < MT; ++mt) {
+      const int v = m0 + mt * kBM + q * 32 + lane;         // virtual row of this thread
       bool valid = v < args.M_total;
       int n = 0, y = 0, x = 0;
       if (valid) {
@@ -296,49 +365,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
       int ncols = args.cout - n0;
       ncols = ncols > BN ? BN : ncols;
-      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_row = tmem_base + (uint32_t)((acc * MT + mt) * BN) + ((uint32_t)(q * 32) << 16);
       if (args.epi == EPI_SPLIT) {
         const size_t o = (((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad)) * args.out_Cs + n0;
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t vr[32];
-          tmem_ld32(t_row + (uint32_t)c0, vr);
-          if (valid) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (c0 + g * 8 < ncols) {
-                uint32_t ph[4], pl[4];
-                uint4 mk = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), oh = make_uint4(0, 0, 0, 0), ol = oh;
-                if (args.mask_hi) mk = *reinterpret_cast<const uint4*>(args.mask_hi + o + c0 + g * 8);
-                if (args.accumulate) {
-                  oh = *reinterpret_cast<const uint4*>(args.out_hi + o + c0 + g * 8);
-                  if (args.out_lo) ol = *reinterpret_cast<const uint4*>(args.out_lo + o + c0 + g * 8);
-                }
-                const uint32_t mkw[4] = {mk.x, mk.y, mk.z, mk.w}, ohw[4] = {oh.x, oh.y, oh.z, oh.w}, olw[4] = {ol.x, ol.y, ol.z, ol.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float f[2];
-#pragma unroll
-                  for (int e = 0; e < 2; ++e) {
-                    const int col = n0 + c0 + g * 8 + j * 2 + e;
-                    float xv = __uint_as_float(vr[g * 8 + j * 2 + e]) + s_bias[col];
-                    if (args.bn_scale) xv = xv * s_scale[col] + s_shift[col];
-                    xv = apply_act(xv, args.act);
-                    if (!(__uint_as_float(((mkw[j] >> (e * 16)) & 0xffffu) << 16) > 0.f)) xv = 0.f;       // ReLU'(forward value)
-                    xv += __uint_as_float(((ohw[j] >> (e * 16)) & 0xffffu) << 16) + __uint_as_float(((olw[j] >> (e * 16)) & 0xffffu) << 16);
-                    f[e] = xv;
-                  }
-                  __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
-                  __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0));
-                  __nv_bfloat16 l1 = __float2bfloat16_rn(f[1] - __bfloat162float(h1));
-                  ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                  pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                *reinterpret_cast<uint4*>(args.out_hi + o + c0 + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                if (args.out_lo) *reinterpret_cast<uint4*>(args.out_lo + o + c0 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              }
-            }
-          }
-        }
+        if (args.mask_hi || args.accumulate) epi_split<true>(args, t_row, ncols, n0, o, valid, s_bias, s_scale, s_shift);
+        else epi_split<false>(args, t_row, ncols, n0, o, valid, s_bias, s_scale, s_shift);
       } else if (args.epi == EPI_ATOMIC) {
         float* dstp = args.out_f32 + (size_t)v * args.out_ld + args.out_col_off + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -367,6 +398,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
       }
+      }   // mt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));

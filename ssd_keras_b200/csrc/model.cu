@@ -173,14 +173,19 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   a.n_tiles_n = (g.cout + a.BN - 1) / a.BN;
   a.split = m->split;
   a.k_split = 1;
+  // two m-tiles per work unit when the accumulators fit (2 buffers x 2 tiles x BN <= 512 TMEM columns): the 64/128-channel
+  // layers are bound by re-fetching the weight tiles from L2 for every m-tile, pairing halves that traffic
+  const int n_m = (a.M_total + 127) / 128;
+  a.mt = 1;
+  { const char* e = getenv("SSDK_MT"); const int want = e ? atoi(e) : 2;
+    if (want >= 2 && g.in && a.BN <= 128 && n_m >= 8 * m->ctx->sm_count) a.mt = 2; }
   conv_pick_stages(a);
   { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
   // m-tiles that hold at least one valid output row
   std::vector<int> tiles;
-  const int n_m = (a.M_total + 127) / 128;
-  for (int t = 0; t < n_m; ++t) {
+  for (int t = 0; t < n_m; t += a.mt) {
     bool any = false;
-    for (int r = 0; r < 128 && !any; ++r) {
+    for (int r = 0; r < 128 * a.mt && !any; ++r) {
       long long v = (long long)t * 128 + r;
       if (v >= a.M_total) break;
       int rr = (int)(v % a.rows_per_img);
@@ -207,7 +212,7 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   double issued = 0;
   for (int nt = 0; nt < a.n_tiles_n; ++nt) {
     int ne = std::min(a.BN, ((g.cout - nt * a.BN) + 15) / 16 * 16);
-    issued += 2.0 * a.n_tiles_m * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
+    issued += 2.0 * a.n_tiles_m * a.mt * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
   }
   cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
   return SSDK_OK;

@@ -314,6 +314,67 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(ActBuf in, ActBuf g, 
   }
 }
 
+// Fast path of the above for the 3x3x3 image-facing kernel (conv1_1): thread -> (2 output channels, pixel lane), all 27
+// accumulators per channel in registers; the 3-channel input is read through 8-byte broadcast loads, dZ through coalesced
+// 4-byte loads.
+__global__ void __launch_bounds__(256) wgrad_direct3x3_kernel(ActBuf in, ActBuf g, float* __restrict__ gw, int pad_t, int pad_l,
+                                                              int rows_per_block) {
+  extern __shared__ float s_acc[];               // [27][Cout]
+  const int Cout = g.C, CG = Cout >> 1, PL = 256 / CG;
+  for (int i = threadIdx.x; i < 27 * Cout; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int cq = threadIdx.x % CG, pl = threadIdx.x / CG;
+  if (pl < PL) {
+    float acc[27][2];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) { acc[k][0] = 0.f; acc[k][1] = 0.f; }
+    const int total_rows = g.B * g.H;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(total_rows, r0 + rows_per_block);
+    for (int r = r0; r < r1; ++r) {
+      const int n = r / g.H, yo = r - n * g.H;
+      for (int xo = pl; xo < g.W; xo += PL) {
+        const size_t go = aidx(g, n, yo, xo) + 2 * cq;
+        const uint32_t gh = *reinterpret_cast<const uint32_t*>(g.hi + go);
+        float g0 = __uint_as_float(gh << 16), g1 = __uint_as_float(gh & 0xffff0000u);
+        if (g.lo) {
+          const uint32_t gl = *reinterpret_cast<const uint32_t*>(g.lo + go);
+          g0 += __uint_as_float(gl << 16); g1 += __uint_as_float(gl & 0xffff0000u);
+        }
+        if (g0 == 0.f && g1 == 0.f) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int y = yo + kh - pad_t, x = xo + kw - pad_l;
+            if (y < 0 || y >= in.H || x < 0 || x >= in.W) continue;
+            const size_t xi = (((size_t)n * in.Hp() + (y + in.pad)) * in.Wp() + (x + in.pad)) * in.Cs;
+            const uint2 xh = *reinterpret_cast<const uint2*>(in.hi + xi);
+            float x0 = __uint_as_float(xh.x << 16), x1 = __uint_as_float(xh.x & 0xffff0000u), x2 = __uint_as_float(xh.y << 16);
+            if (in.lo) {
+              const uint2 xl = *reinterpret_cast<const uint2*>(in.lo + xi);
+              x0 += __uint_as_float(xl.x << 16); x1 += __uint_as_float(xl.x & 0xffff0000u); x2 += __uint_as_float(xl.y << 16);
+            }
+            const int k = (kh * 3 + kw) * 3;
+            acc[k][0] += x0 * g0; acc[k][1] += x0 * g1;
+            acc[k + 1][0] += x1 * g0; acc[k + 1][1] += x1 * g1;
+            acc[k + 2][0] += x2 * g0; acc[k + 2][1] += x2 * g1;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      atomicAdd(&s_acc[k * Cout + 2 * cq], acc[k][0]);
+      atomicAdd(&s_acc[k * Cout + 2 * cq + 1], acc[k][1]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * Cout; i += 256) {
+    const int k = i / Cout, co = i % Cout;
+    atomicAdd(gw + (size_t)co * 27 + k, s_acc[i]);
+  }
+}
+
 // SGD with momentum (Keras: v = m*v - lr*g; w += v); kernels get the l2 regulariser's gradient 2*l2*w.
 // `w` is HWIO [taps][cin][cout]; the gradient is OHWI [cout][taps][cin].
 __global__ void sgd_kernel_w(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, int taps, int cin, int cout,
@@ -722,7 +783,9 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
       const size_t smem = (size_t)K * T.cout * sizeof(float);
       const int total_rows = T.g.B * T.g.H;
       const int rpb = std::max(1, (total_rows + 8 * ctx->sm_count - 1) / (8 * ctx->sm_count));
-      wgrad_direct_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, rpb);
+      const bool fast3 = d.kh == 3 && d.kw == 3 && d.dilation == 1 && T.cin == 3 && PL.out.Cs >= 4 && T.cout % 2 == 0 && T.cout <= 512;
+      if (fast3) wgrad_direct3x3_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.pad_t, d.pad_l, rpb);
+      else wgrad_direct_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, rpb);
       SSDK_COUNT_LAUNCH(ctx);
       rc = launch_bias_grad(ctx, T.g, t->grad + T.off_b, s); if (rc) return rc;
     } else if (T.wg_native) {

@@ -118,6 +118,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_c
     int it = 0;
     const uint32_t idesc = make_idesc_mn(BNc);
     const int slab_w = args.bw + (KW - 1) * args.dil;
+    const uint64_t desc_a = make_desc_mn(0, kBoxA), desc_b = make_desc_mn(0, args.slab_bytes);
+    uint32_t krow[4];                                       // first slab line (in 16-byte units) of each 16-pixel k-step
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int line = (k * 16) / args.bw; krow[k] = (uint32_t)(line * slab_w + (k * 16 - line * args.bw)) * 8u; }
     for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
       const int ks = u % args.k_split;
       const int p0 = ks * args.patches_per_split, p1 = min(args.total_patches, p0 + args.patches_per_split);
@@ -128,20 +132,19 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_c
         mbar_wait(full(s), ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_hi = smem_base + stage_bytes * s, a_lo = a_hi + a_plane;
-          const uint32_t b_hi = a_hi + (split ? 2u : 1u) * a_plane, b_lo = b_hi + b_plane;
+          // descriptor = constant upper word | (address >> 4): a couple of integer adds between two MMA issues
+          const uint32_t a_hi = (smem_base + stage_bytes * s) >> 4, a_lo = a_hi + (a_plane >> 4);
+          const uint32_t b_hi = a_hi + (((split ? 2u : 1u) * a_plane) >> 4), b_lo = b_hi + (b_plane >> 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                       // 4 UMMA k-steps of 16 pixels
-            const int line = (k * 16) / args.bw, xin = (k * 16) - line * args.bw;
-            const uint32_t ao = (uint32_t)k * 2048u;
-            const uint64_t dah = make_desc_mn(a_hi + ao, kBoxA), dal = make_desc_mn(a_lo + ao, kBoxA);
+            const uint64_t dah = desc_a | (uint64_t)(a_hi + 128u * k), dal = desc_a | (uint64_t)(a_lo + 128u * k);
             for (int kw = 0; kw < KW; ++kw) {
-              const uint32_t bo = (uint32_t)(line * slab_w + xin + kw * args.dil) * 128u;
-              const uint64_t dbh = make_desc_mn(b_hi + bo, args.slab_bytes);
+              const uint32_t bo = krow[k] + (uint32_t)(kw * args.dil) * 8u;
+              const uint64_t dbh = desc_b | (uint64_t)(b_hi + bo);
               const uint32_t d_tmem = tmem_base + (uint32_t)(kw * BNc);
               tc_mma(d_tmem, dah, dbh, idesc, accumulate);
               if (split) {
-                tc_mma(d_tmem, dah, make_desc_mn(b_lo + bo, args.slab_bytes), idesc, 1);
+                tc_mma(d_tmem, dah, desc_b | (uint64_t)(b_lo + bo), idesc, 1);
                 tc_mma(d_tmem, dal, dbh, idesc, 1);
               }
             }
