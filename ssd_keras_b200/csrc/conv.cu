@@ -246,7 +246,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tt = t / KS, ks = t - tt * KS;
@@ -304,7 +304,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           for (int kw = 0; kw < args.KW; ++kw) {
             mbar_wait(fullB(sb), pb);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               // The issuing thread is a single in-order instruction stream: for N <= 128 an MMA retires in 32-64 clocks, so the
               // descriptor arithmetic between two issues must be a couple of integer adds.  Only the 14-bit start-address field
               // (address >> 4) changes: +2 per k-step (32 B), +8*rows for a row-shifted tap, +1024 for the second m-tile.
@@ -337,7 +337,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
       }
-      if (lane == 0) tc_commit(tfull_bar(acc));
+      if (elect_one()) tc_commit(tfull_bar(acc));
       __syncwarp();
     }
   } else if (warp >= 4) {

@@ -86,7 +86,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int s = 0; uint32_t ph = 0;
       for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
         const int ks = u % args.k_split; int r = u / args.k_split;
@@ -131,7 +131,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_c
       for (int p = p0; p < p1; ++p) {
         mbar_wait(full(s), ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           // descriptor = constant upper word | (address >> 4): a couple of integer adds between two MMA issues
           const uint32_t a_hi = (smem_base + stage_bytes * s) >> 4, a_lo = a_hi + (a_plane >> 4);
           const uint32_t b_hi = a_hi + (((split ? 2u : 1u) * a_plane) >> 4), b_lo = b_hi + (b_plane >> 4);
@@ -155,7 +155,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_g_hi, const __grid_c
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
-      if (lane == 0) tc_commit(tfull);
+      if (elect_one()) tc_commit(tfull);
       __syncwarp();
     }
   } else if (warp >= 4) {
