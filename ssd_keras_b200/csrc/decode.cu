@@ -292,8 +292,14 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
         bx = prepare_box<T, LAYER>(boxes + (size_t)idx * 4, dd);
       }
       const int k_start = s_K;
-      for (int t = 0; t < k_start && alive; ++t)
-        if (suppressed<T, LAYER>(bx, kept_box(t), thr)) alive = false;
+      // four kept boxes per iteration: the tests are independent, so their shared-memory loads and min/max chains overlap
+      for (int t = 0; t < k_start && alive; t += 4) {
+        bool sup = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (t + u < k_start) sup |= suppressed<T, LAYER>(bx, kept_box(t + u), thr);
+        if (sup) alive = false;
+      }
       __syncthreads();
       // warps take turns (ascending candidate order) to settle intra-chunk suppression
       for (int w = 0; w < NW; ++w) {
