@@ -137,41 +137,48 @@ __device__ __forceinline__ double iou_value(const Box& g, const Box& a, double i
 
 struct RowDecision { int match_g; bool neutral; };
 
-// Write one target row: [one-hot class | 4 offsets | 4 anchor coords | 4 variances] (ssd_input_encoder.py:363,396-410).
-template <typename Store>
-__device__ __forceinline__ void emit_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec,
-                                         Store store) {
-  for (int c = 0; c < p.C; ++c) store(c, 0.f);
-  float o4[4] = {0.f, 0.f, 0.f, 0.f};
+// One target row [one-hot class | 4 offsets | 4 anchor coords | 4 variances] (ssd_input_encoder.py:363,396-410) in compact form:
+// the class vector has at most one 1 (index `one`, -1: none).
+struct RowCompact { int one; float o4[4]; };
+__device__ __forceinline__ RowCompact make_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec) {
+  RowCompact r;
+  r.one = -1; r.o4[0] = r.o4[1] = r.o4[2] = r.o4[3] = 0.f;
   if (dec.match_g >= 0) {
     double gtc[4]; int cls;
     gt_template(gt_rows + (size_t)(g0 + dec.match_g) * 5, p, gtc, cls);
-    if (cls >= 0 && cls < p.C) store(cls, 1.f);
+    if (cls >= 0 && cls < p.C) r.one = cls;
     if (p.coords == SSDK_COORDS_CENTROIDS) {                // :396-400
-      o4[0] = (float)__ddiv_rn(__dsub_rn(gtc[0], at[0]), __dmul_rn(at[2], p.var[0]));
-      o4[1] = (float)__ddiv_rn(__dsub_rn(gtc[1], at[1]), __dmul_rn(at[3], p.var[1]));
-      o4[2] = (float)__ddiv_rn(log(__ddiv_rn(gtc[2], at[2])), p.var[2]);
-      o4[3] = (float)__ddiv_rn(log(__ddiv_rn(gtc[3], at[3])), p.var[3]);
+      r.o4[0] = (float)__ddiv_rn(__dsub_rn(gtc[0], at[0]), __dmul_rn(at[2], p.var[0]));
+      r.o4[1] = (float)__ddiv_rn(__dsub_rn(gtc[1], at[1]), __dmul_rn(at[3], p.var[1]));
+      r.o4[2] = (float)__ddiv_rn(log(__ddiv_rn(gtc[2], at[2])), p.var[2]);
+      r.o4[3] = (float)__ddiv_rn(log(__ddiv_rn(gtc[3], at[3])), p.var[3]);
     } else if (p.coords == SSDK_COORDS_CORNERS) {           // :401-405
       double w = __dsub_rn(at[2], at[0]), h = __dsub_rn(at[3], at[1]);
-      o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
-      o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), h), p.var[1]);
-      o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), w), p.var[2]);
-      o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
+      r.o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
+      r.o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), h), p.var[1]);
+      r.o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), w), p.var[2]);
+      r.o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
     } else {                                                // minmax :406-410
       double w = __dsub_rn(at[1], at[0]), h = __dsub_rn(at[3], at[2]);
-      o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
-      o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), w), p.var[1]);
-      o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), h), p.var[2]);
-      o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
+      r.o4[0] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[0], at[0]), w), p.var[0]);
+      r.o4[1] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[1], at[1]), w), p.var[1]);
+      r.o4[2] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[2], at[2]), h), p.var[2]);
+      r.o4[3] = (float)__ddiv_rn(__ddiv_rn(__dsub_rn(gtc[3], at[3]), h), p.var[3]);
     }
-    if (dec.neutral) store(p.bg, 0.f);                      // neg_iou_limit <= 0 corner case
-  } else {
-    store(p.bg, dec.neutral ? 0.f : 1.f);
+    if (dec.neutral && r.one == p.bg) r.one = -1;           // neg_iou_limit <= 0 corner case: the background entry is zeroed last
+  } else if (!dec.neutral) {
+    r.one = p.bg;
   }
+  return r;
+}
+template <typename Store>
+__device__ __forceinline__ void emit_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec,
+                                         Store store) {
+  const RowCompact r = make_row(p, gt_rows, g0, at, dec);
+  for (int c = 0; c < p.C; ++c) store(c, c == r.one ? 1.f : 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    store(p.C + k, o4[k]);
+    store(p.C + k, r.o4[k]);
     store(p.C + 4 + k, (float)at[k]);
     store(p.C + 8 + k, (float)p.var[k]);
   }
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const flo
   const int W = p.C + 12;
   // shared layout: rows[kTile*W] f32 | cand f32 bounds 4*G (float4 aligned) | cand boxes 5*G f64 | per-warp tile bests 8*G f64 |
   //                cand idx G | per-warp tile-best idx 8*G | cand slot of gt G
+  // (staging compact rows and expanding them in the copy loop was measured slower on B200: 45 us vs 22 us for SSD300 B=32)
   float* rows = reinterpret_cast<float*>(smem_raw);
   size_t off = ((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15;
   float* cf = reinterpret_cast<float*>(smem_raw + off); off += (size_t)4 * Gs * sizeof(float);
@@ -250,7 +258,6 @@ __global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const flo
   const int ncand = s_ncand;
   const int a = a0 + threadIdx.x;
   const bool live = a < p.P;
-  float* my = rows + (size_t)threadIdx.x * W;
   double at[4] = {0, 0, 0, 0};
   Box ab{};
   float fx0 = 0, fy0 = 0, fx1 = 0, fy1 = 0;
@@ -287,6 +294,7 @@ __global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const flo
       if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
       if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
     }
+    float* my = rows + (size_t)threadIdx.x * W;
     emit_row(p, gt, g0, at, dec, [&](int k, float v) { my[k] = v; });
     if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
   }
@@ -502,8 +510,12 @@ struct ssdk_encoder {
   double* d_anchors = nullptr;
   double* d_bbox = nullptr;
   Scratch rows;        // per-(gt, tile) bests + matches + offsets
-  int* h_offsets = nullptr;   // pinned staging
+  // pinned staging ring for the gt offsets: a slot is reused only after the copy issued from it has completed (no stream sync)
+  static constexpr int kSlots = 8;
+  int* h_offsets = nullptr;   // kSlots * h_offsets_cap ints
   int h_offsets_cap = 0;
+  cudaEvent_t slot_done[kSlots] = {};
+  int next_slot = 0;
 };
 
 extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, const double* anchors_host, ssdk_encoder** out) {
@@ -538,6 +550,7 @@ extern "C" int ssdk_encoder_destroy(ssdk_encoder* e) {
   cudaFree(e->d_anchors); cudaFree(e->d_bbox);
   e->rows.release();
   if (e->h_offsets) cudaFreeHost(e->h_offsets);
+  for (int i = 0; i < ssdk_encoder::kSlots; ++i) if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
   delete e;
   return SSDK_OK;
 }
@@ -589,14 +602,19 @@ extern "C" int ssdk_encode(ssdk_encoder* e, const float* gt_boxes_dev, const int
   int* matches = tb_idx + nt;
   int* d_offsets = matches + n;
   if (e->h_offsets_cap < B + 1) {
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
     if (e->h_offsets) cudaFreeHost(e->h_offsets);
-    SSDK_CHECK_CUDA(cudaMallocHost(&e->h_offsets, (size_t)(B + 1) * sizeof(int)));
+    SSDK_CHECK_CUDA(cudaMallocHost(&e->h_offsets, (size_t)ssdk_encoder::kSlots * (B + 1) * sizeof(int)));
     e->h_offsets_cap = B + 1;
   }
-  // the pinned staging buffer is reused across calls: wait for the previous copy to be consumed
-  SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
-  memcpy(e->h_offsets, gt_offsets_host, (size_t)(B + 1) * sizeof(int));
-  SSDK_CHECK_CUDA(cudaMemcpyAsync(d_offsets, e->h_offsets, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  const int slot = e->next_slot;
+  e->next_slot = (slot + 1) % ssdk_encoder::kSlots;
+  if (!e->slot_done[slot]) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&e->slot_done[slot], cudaEventDisableTiming));
+  else SSDK_CHECK_CUDA(cudaEventSynchronize(e->slot_done[slot]));
+  int* h_off = e->h_offsets + (size_t)slot * e->h_offsets_cap;
+  memcpy(h_off, gt_offsets_host, (size_t)(B + 1) * sizeof(int));
+  SSDK_CHECK_CUDA(cudaMemcpyAsync(d_offsets, h_off, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  SSDK_CHECK_CUDA(cudaEventRecord(e->slot_done[slot], stream));
   const int W = p.C + 12;
   const size_t gs = (size_t)(max_g > 0 ? max_g : 1);
   const size_t sm_m = (((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15) + gs * (5 * 8 + 8 * 8 + 4 * 4 + 4 + 8 * 4 + 4 + 8 * 4) + 64;
