@@ -341,13 +341,13 @@ __global__ void __launch_bounds__(256) wgrad_direct3x3_kernel(ActBuf in, ActBuf 
           g0 += __uint_as_float(gl << 16); g1 += __uint_as_float(gl & 0xffff0000u);
         }
         if (g0 == 0.f && g1 == 0.f) continue;
+        // window origin; the buffer's zero border (>= 2 - pad) makes every tap a constant offset from it
+        const size_t x00 = (((size_t)n * in.Hp() + (yo - pad_t + in.pad)) * in.Wp() + (xo - pad_l + in.pad)) * in.Cs;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            const int y = yo + kh - pad_t, x = xo + kw - pad_l;
-            if (y < 0 || y >= in.H || x < 0 || x >= in.W) continue;
-            const size_t xi = (((size_t)n * in.Hp() + (y + in.pad)) * in.Wp() + (x + in.pad)) * in.Cs;
+            const size_t xi = x00 + (size_t)(kh * in.Wp() + kw) * in.Cs;
             const uint2 xh = *reinterpret_cast<const uint2*>(in.hi + xi);
             float x0 = __uint_as_float(xh.x << 16), x1 = __uint_as_float(xh.x & 0xffff0000u), x2 = __uint_as_float(xh.y << 16);
             if (in.lo) {
@@ -783,7 +783,8 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
       const size_t smem = (size_t)K * T.cout * sizeof(float);
       const int total_rows = T.g.B * T.g.H;
       const int rpb = std::max(1, (total_rows + 8 * ctx->sm_count - 1) / (8 * ctx->sm_count));
-      const bool fast3 = d.kh == 3 && d.kw == 3 && d.dilation == 1 && T.cin == 3 && PL.out.Cs >= 4 && T.cout % 2 == 0 && T.cout <= 512;
+      const bool fast3 = d.kh == 3 && d.kw == 3 && d.dilation == 1 && T.cin == 3 && PL.out.Cs >= 4 && T.cout % 2 == 0 && T.cout <= 512 &&
+                         PL.out.pad >= d.pad_t && PL.out.pad >= d.pad_l && PL.out.pad >= 2 - d.pad_t && PL.out.pad >= 2 - d.pad_l;
       if (fast3) wgrad_direct3x3_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.pad_t, d.pad_l, rpb);
       else wgrad_direct_kernel<<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem, s>>>(PL.out, T.g, t->grad + T.off_w, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, rpb);
       SSDK_COUNT_LAUNCH(ctx);
