@@ -356,9 +356,16 @@ def run_ours(args):
     conv_ms = float(np.median(conv_ms))
     fl_algo, fl_issued = model.flops(BATCH)
     peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')          # from one ncu --set full capture of this workload
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get('dram_bytes_per_step'), 'profiles/r01_conv_traffic.json (dram read+write bytes of the %d conv launches of one step, ncu --set full)' % tj.get('launches_per_step', 0)
     roofline = {'bound': 'tensor', 'kernel': 'conv_tcgen05_kernel (all conv launches of one step)',
                 'achieved': fl_algo / conv_ms / 1e9, 'peak': peak, 'unit': 'TFLOP/s', 'frac': fl_algo / conv_ms / 1e9 / peak,
-                'peak_source': peaks_src + ', bf16_tflops_sustained', 'traffic': None,
+                'peak_source': peaks_src + ', bf16_tflops_sustained', 'traffic': traffic, 'traffic_unit': 'bytes per step',
+                'traffic_source': traffic_src,
                 'algorithmic_tflop_per_step': fl_algo / 1e12, 'issued_mma_tflop_per_step': fl_issued / 1e12,
                 'issued_tflops': fl_issued / conv_ms / 1e9, 'issued_frac': fl_issued / conv_ms / 1e9 / peak,
                 'conv_ms_per_step': conv_ms}
