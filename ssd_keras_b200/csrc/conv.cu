@@ -89,6 +89,12 @@ size_t conv_smem_bytes(const ConvArgs& a) { return 1024 + slot_a_bytes(a) * a.st
 // Two rings: A slabs (one per (kh, channel block), shared by the KW taps of that row) and weight tiles (one per tap).
 void conv_pick_stages(ConvArgs& a) {
   const size_t budget = 218 * 1024 - 1536 - epi_param_bytes(a);
+  if (a.resident_b) {                       // weights resident: stages_b counts the tiles, the rest goes to A slabs
+    a.stages_b = a.KH * a.KW * a.kblocks;
+    a.stages_a = 2;
+    while (a.stages_a < 4 && slot_a_bytes(a) * (a.stages_a + 1) + slot_b_bytes(a) * a.stages_b <= budget) ++a.stages_a;
+    return;
+  }
   a.stages_a = 2; a.stages_b = 2;
   int max_a = 4, max_b = 6;
   if (const char* e = getenv("SSDK_SA_MAX")) max_a = atoi(e);
@@ -248,6 +254,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ===================== TMA producer =====================
     if (elect_one()) {
       int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      if (args.resident_b && (int)blockIdx.x < total_tiles) {      // every weight tile once, each on its own barrier
+        for (int i = 0; i < SB; ++i) {
+          const uint32_t db = ring_b + slot_b * i;
+          mbar_expect_tx(fullB(i), slot_b);
+          tma_load_2d(db, &tm_b_hi, i * kBK + args.b_k_offset, 0, fullB(i));
+          if (split) tma_load_2d(db + b_tile, &tm_b_lo, i * kBK + args.b_k_offset, 0, fullB(i));
+        }
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tt = t / KS, ks = t - tt * KS;
         const int m0 = args.tile_list[tt / args.n_tiles_n] * kBM;
@@ -265,7 +279,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               if (split) tma_load_2d(da + a_plane + mt * kATile, &tm_a_lo, kb * kBK, row0 + mt * kBM, fullA(sa));
             }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
-            for (int kw = 0; kw < args.KW; ++kw) {
+            for (int kw = 0; kw < args.KW && !args.resident_b; ++kw) {
               mbar_wait(emptyB(sb), pb ^ 1u);
               const uint32_t db = ring_b + slot_b * sb;
               mbar_expect_tx(fullB(sb), slot_b);
@@ -302,13 +316,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           const uint32_t a_hi = smem_base + slot_a * sa, a_lo = a_hi + a_plane;
           const int ksteps = (kb == args.kblocks - 1) ? args.last_ksteps : 4;
           for (int kw = 0; kw < args.KW; ++kw) {
-            mbar_wait(fullB(sb), pb);
+            int sbi = sb;
+            if (args.resident_b) { sbi = (kh * args.KW + kw) * args.kblocks + kb; if (it == 0) mbar_wait(fullB(sbi), 0); }
+            else mbar_wait(fullB(sb), pb);
             tc_fence_after();
             if (elect_one()) {
               // The issuing thread is a single in-order instruction stream: for N <= 128 an MMA retires in 32-64 clocks, so the
               // descriptor arithmetic between two issues must be a couple of integer adds.  Only the 14-bit start-address field
               // (address >> 4) changes: +2 per k-step (32 B), +8*rows for a row-shifted tap, +1024 for the second m-tile.
-              const uint32_t bh = (ring_b + slot_b * sb) >> 4, bl = bh + (b_tile >> 4);
+              const uint32_t bh = (ring_b + slot_b * sbi) >> 4, bl = bh + (b_tile >> 4);
               const uint32_t ah = (a_hi + (uint32_t)(kw * args.kw_rows) * 128u) >> 4, al = ah + (a_plane >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -328,11 +344,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                   accumulate = 1;
                 }
               }
-              tc_commit(emptyB(sb));                        // weight slot is free once these MMAs retire
+              if (!args.resident_b) tc_commit(emptyB(sb));   // weight slot is free once these MMAs retire
               if (kw == args.KW - 1) tc_commit(emptyA(sa));  // ... and the slab after its last tap
             }
             __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1u; }
+            if (!args.resident_b && ++sb == SB) { sb = 0; pb ^= 1u; }
           }
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }

@@ -214,6 +214,9 @@ __device__ __forceinline__ PBox<T> prepare_box(const T* q, T d) {
 template <typename T, bool LAYER>
 __device__ __forceinline__ bool suppressed(const PBox<T>& c, const PBox<T>& m, T thr) {
   if constexpr (LAYER) {
+    // disjoint boxes (the vast majority of candidate x kept pairs): the intersection below is 0 (or NaN), which never
+    // suppresses for thr >= 0 -- four compares instead of the full IoU
+    if (thr >= (T)0 && (c.x1 <= m.x0 || m.x1 <= c.x0 || c.y1 <= m.y0 || m.y1 <= c.y0)) return false;
     if (c.a <= (T)0 || m.a <= (T)0) return false;
     T ih = tf_max((float)sub_rn(tf_min((float)c.y1, (float)m.y1), tf_max((float)c.y0, (float)m.y0)), 0.f);
     T iw = tf_max((float)sub_rn(tf_min((float)c.x1, (float)m.x1), tf_max((float)c.x0, (float)m.x0)), 0.f);

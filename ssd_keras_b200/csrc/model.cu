@@ -179,6 +179,14 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   a.mt = 1;
   { const char* e = getenv("SSDK_MT"); const int want = e ? atoi(e) : 2;
     if (want >= 2 && g.in && a.BN <= 128 && n_m >= 8 * m->ctx->sm_count) a.mt = 2; }
+  // 64 -> 64 channel layers (conv1_2 and its data gradient): all nine weight tiles fit in shared memory next to two A slabs.
+  // Keeping them resident removes ~40% of the layer's L2->SM traffic, but forces one m-tile per unit and measured SLOWER on
+  // B200 (7.69 vs 7.56 ms/step): the layer is bound by the shared-memory operand bandwidth of N = 64 MMAs, not by L2.
+  // Kept behind SSDK_RESIDENT=1 for experiments.
+  { const char* e = getenv("SSDK_RESIDENT"); const int want = e ? atoi(e) : 0;
+    const size_t wbytes = (size_t)a.KH * a.KW * kblocks * a.BN * 64 * 2 * (a.split ? 2 : 1);
+    const size_t abytes = (size_t)a.slab_rows * 64 * 2 * (a.split ? 2 : 1);
+    if (want && g.in && a.n_tiles_n == 1 && a.BN == 64 && n_m >= 8 * m->ctx->sm_count && wbytes + 2 * abytes + 4096 <= 218 * 1024) { a.resident_b = 1; a.mt = 1; } }
   conv_pick_stages(a);
   { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
   // m-tiles that hold at least one valid output row
