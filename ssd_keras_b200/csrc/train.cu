@@ -821,7 +821,7 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
                                                                      PL.out, PT.g, relu_mask, written[pi] ? 1 : 0);
       SSDK_COUNT_LAUNCH(ctx);
       written[pi] = 1;
-    } else if (T.has_dgrad && !getenv("SSDK_SKIP_DGRAD")) {
+    } else if (T.has_dgrad) {
       T.dgrad.args.accumulate = written[pi] ? 1 : 0;
       rc = launch_conv(ctx, T.dgrad, s); if (rc) return rc;
       written[pi] = 1;
