@@ -125,17 +125,10 @@ __global__ void __launch_bounds__(kSelThreads) loss_select_kernel(const float* _
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
-    // warp-aggregated histogram: the losses share their leading bytes, so most lanes of a warp hit the same bin; one atomic
-    // per distinct bin per warp instead of one per element (the hot bins serialised the old version: 238 us -> see profiles/)
-    for (int base = 0; base < N; base += kSelThreads) {
-      const int i = base + tid;
-      uint32_t bin = 0xffffffffu;
-      if (i < N) {
-        const uint32_t key = okey(negl[i]);
-        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
-      }
-      const unsigned peers = __match_any_sync(0xffffffffu, bin);
-      if (bin != 0xffffffffu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
+    // (a __match_any_sync-aggregated variant was measured slower on B200: 0.45 vs 0.28 ms for the whole loss forward)
+    for (int i = tid; i < N; i += kSelThreads) {
+      uint32_t key = okey(negl[i]);
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
     }
     __syncthreads();
     if (tid == 0) {
