@@ -110,3 +110,42 @@ def test_ssd300_loss_decreases():
     losses = [float(tr.train_on_batch(xd, ytd).mean().item()) for _ in range(10)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+def test_ssd512_step_matches_autograd():
+    """SSD512, batch 1: exercises the geometries SSD300 does not have (64x64 ... 1x1 maps, the 4x4 'valid' conv10_2 whose
+    weight gradient takes the transposed-operand fallback, seven heads).  Same bars as the SSD300 check."""
+    import torch
+    from oracle import graph as og
+    from oracle import synth
+    from oracle.encoder import OracleEncoder
+    from ssd_keras_b200.models.keras_ssd512 import ssd_512
+    from ssd_keras_b200.training import SSDTrainer
+    sc = [0.04, 0.1, 0.26, 0.42, 0.58, 0.74, 0.9, 1.06]
+    m = ssd_512((512, 512, 3), 20, mode='training', scales=sc, divide_by_stddev=[64.0] * 3, weights_seed=3)
+    w = m.get_weights()
+    rng = np.random.default_rng(3)
+    for k in w:
+        if k.endswith('/bias'):
+            w[k] = (rng.standard_normal(w[k].shape) * 0.05).astype(np.float32)
+    m.set_weights(w)
+    enc = OracleEncoder(512, 512, 20, m.predictor_sizes, scales=sc, aspect_ratios_per_layer=m.anchor_cfg['aspect_ratios_per_layer'],
+                        steps=[8, 16, 32, 64, 128, 256, 512], variances=[0.1, 0.1, 0.2, 0.2])
+    assert np.array_equal(enc.anchors, m.anchors)
+    x = synth.synth_images(9, 1, 512, 512)
+    y_true = enc(synth.synth_gt(10, 1, 6, 512, 512, 20)).astype(np.float32)
+    tr = SSDTrainer(m, 1, lr=1e-3, momentum=0.9, l2_regularization=5e-4)
+    loss, _ = tr.forward_backward(torch.from_numpy(x).cuda(), torch.from_numpy(y_true).cuda())
+    torch.cuda.synchronize()
+    grads = tr.gradients()
+    params = og.make_params(m.specs, w, dtype=torch.float64)
+    yp, _ = og.forward(m.specs, params, x, 21, m.anchors, [0.1, 0.1, 0.2, 0.2], dtype=torch.float64)
+    lvec = og.ssd_loss_torch(y_true, yp)
+    lvec.mean().backward()
+    ref_l = lvec.detach().numpy()
+    assert np.abs(loss.cpu().numpy() - ref_l).max() <= 5e-4 * np.abs(ref_l).max()
+    assert set(grads) == set(w)
+    for k in sorted(grads):
+        ref = params[k].grad.numpy()
+        e = np.abs(grads[k] - ref).ravel() / (np.abs(ref).max() + 1e-30)
+        assert np.median(e) < 2e-3 and e.max() < 2e-2, 'gradient %s: median err %.3e, max err %.3e' % (k, np.median(e), e.max())
