@@ -275,7 +275,7 @@ int plan_wgrad(ssdk_ctx* ctx, WgradLaunch& L, const ActBuf& X, const ActBuf& G, 
   L.smem = 1024 + stage * a.stages + 256;
   const int base_units = a.co_tiles * a.ci_tiles * KH;
   int ks = std::max(1, (2 * ctx->sm_count + base_units - 1) / base_units);
-  ks = std::min(ks, std::max(1, a.total_patches / 16));
+  ks = std::min(ks, std::max(1, a.total_patches / 4));
   a.patches_per_split = (a.total_patches + ks - 1) / ks;
   a.k_split = (a.total_patches + a.patches_per_split - 1) / a.patches_per_split;
   L.grid = std::min(base_units * a.k_split, ctx->sm_count);
