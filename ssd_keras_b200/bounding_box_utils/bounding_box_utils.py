@@ -1,7 +1,6 @@
 """``convert_coordinates`` and ``iou`` with the reference signatures (``bounding_box_utils/bounding_box_utils.py:24-87,
 283-383``).  ``iou`` runs on the GPU (``ssdk_iou``, float64, same operation order as NumPy, including the quirk that
 the intersection ignores ``border_pixels``); ``convert_coordinates`` is host-side index shuffling, as in the reference."""
-import ctypes as C
 
 import numpy as np
 

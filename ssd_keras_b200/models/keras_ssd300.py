@@ -2,7 +2,6 @@
 
 Returns an ``SSDModel`` (see ``_graph.py``) instead of a Keras ``Model``: VGG-16 (atrous fc6/fc7) + extra
 layers + L2Normalization + six fused conf/loc predictor heads, executed as tcgen05 implicit-GEMM kernels."""
-import numpy as np
 
 from .. import _ffi
 from ._graph import SSDModel, Spec, resolve_box_args, same_pad, tf_same_pool_pad

@@ -4,9 +4,9 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..')); sys.path.insert(0, ROOT)
 import bench
-import ctypes as C
+
 from oracle import synth
-from ssd_keras_b200 import _ffi
+
 from ssd_keras_b200.models.keras_ssd300 import ssd_300
 prec = 'bf16' if 'fast' in sys.argv else 'bf16x3'
 model = ssd_300((300, 300, 3), 20, mode='training', scales=bench.SC300, precision=prec)

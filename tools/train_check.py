@@ -29,7 +29,7 @@ CASES = [
 
 def build(case):
     from ssd_keras_b200 import _ffi
-    from ssd_keras_b200.models._graph import SSDModel, Spec, same_pad, tf_same_pool_pad
+    from ssd_keras_b200.models._graph import SSDModel, Spec, same_pad
     name, hw, B, layers = case
     specs = [Spec('input', _ffi.OP_INPUT, params={'mean': [127.5] * 3, 'stddev': [64.0] * 3, 'swap': [2, 1, 0]})]
     prev = 'input'
@@ -76,7 +76,6 @@ def small_gt(seed, B, G, hw, ncls):
 def run_case(i):
     import torch
     from oracle import graph as og
-    from oracle import synth
     from oracle.encoder import OracleEncoder
     from ssd_keras_b200.training import SSDTrainer
     case = CASES[i]
