@@ -135,14 +135,26 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Accumulator read: 32 columns of this thread's TMEM lane; with a separate cross-term accumulator (`xoff` columns further)
+// the two partial sums are added here in fp32 round-to-nearest.
+__device__ __forceinline__ void ld_acc32(uint32_t taddr, uint32_t xoff, uint32_t (&v)[32]) {
+  tmem_ld32(taddr, v);
+  if (xoff) {
+    uint32_t w[32];
+    tmem_ld32(taddr + xoff, w);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+  }
+}
+
 // Epilogue of the activation-producing launches: bias / folded BatchNorm / activation -> bf16 hi+lo planes, 8 channels per
 // 16-byte store.  BWD adds what the data-gradient launches need: ReLU'(forward value) mask and accumulation into the output.
 template <bool BWD>
-__device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, int ncols, int n0, size_t o, bool valid,
+__device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, uint32_t xoff, int ncols, int n0, size_t o, bool valid,
                                           const float* s_bias, const float* s_scale, const float* s_shift) {
   for (int c0 = 0; c0 < ncols; c0 += 32) {
     uint32_t vr[32];
-    tmem_ld32(t_row + (uint32_t)c0, vr);
+    ld_acc32(t_row + (uint32_t)c0, xoff, vr);
     if (!valid) continue;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -222,7 +234,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   }
 
   int tmem_cols = 32;
-  while (tmem_cols < 2 * MT * BN) tmem_cols <<= 1;
+  const int XS = args.acc_split ? 2 : 1;                               // accumulators per output tile (main | cross terms)
+  const int NB = args.acc_bufs == 1 ? 1 : 2;                           // accumulator sets
+  while (tmem_cols < NB * XS * MT * BN) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a_hi)) : "memory");
@@ -301,14 +315,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int n0 = (tt % args.n_tiles_n) * BN;
       const int kb0 = KS > 1 ? ks * args.kb_per : 0;
       const int kb1 = KS > 1 ? min(args.kblocks, kb0 + args.kb_per) : args.kblocks;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = NB == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = (uint32_t)(NB == 2 ? (it >> 1) : it) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       int n_eff = args.cout - n0;
       n_eff = n_eff > BN ? BN : ((n_eff + 15) & ~15);
       const uint32_t idesc = make_idesc(n_eff);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * XS * MT * BN);
+      const uint32_t x_cols = (uint32_t)((XS - 1) * BN);     // column offset of the cross-term accumulator
       uint32_t accumulate = 0;
       for (int kh = 0; kh < args.KH; ++kh) {
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -334,10 +349,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
                   for (int mt = 0; mt < 2; ++mt) {
                     if (mt < MT) {
                       const uint64_t da = kDescHi | (uint64_t)(ah + mt * (kATile >> 4) + 2 * k);
-                      tc_mma(d_tmem + mt * BN, da, db, idesc, accumulate);
+                      const uint32_t d_main = d_tmem + (uint32_t)(mt * XS * BN);
+                      tc_mma(d_main, da, db, idesc, accumulate);
                       if (split) {
-                        tc_mma(d_tmem + mt * BN, da, dbl, idesc, 1);
-                        tc_mma(d_tmem + mt * BN, kDescHi | (uint64_t)(al + mt * (kATile >> 4) + 2 * k), db, idesc, 1);
+                        tc_mma(d_main + x_cols, da, dbl, idesc, XS == 2 ? accumulate : 1u);
+                        tc_mma(d_main + x_cols, kDescHi | (uint64_t)(al + mt * (kATile >> 4) + 2 * k), db, idesc, 1);
                       }
                     }
                   }
@@ -364,8 +380,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const int tt = t / KS;
       const int m0 = args.tile_list[tt / args.n_tiles_n] * kBM;
       const int n0 = (tt % args.n_tiles_n) * BN;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int acc = NB == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = (uint32_t)(NB == 2 ? (it >> 1) : it) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int mt = 0; mt < MT; ++mt) {
@@ -381,16 +397,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
       int ncols = args.cout - n0;
       ncols = ncols > BN ? BN : ncols;
-      const uint32_t t_row = tmem_base + (uint32_t)((acc * MT + mt) * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_row = tmem_base + (uint32_t)((acc * MT + mt) * XS * BN) + ((uint32_t)(q * 32) << 16);
+      const uint32_t xoff = (uint32_t)((XS - 1) * BN);
       if (args.epi == EPI_SPLIT) {
         const size_t o = (((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad)) * args.out_Cs + n0;
-        if (args.mask_hi || args.accumulate) epi_split<true>(args, t_row, ncols, n0, o, valid, s_bias, s_scale, s_shift);
-        else epi_split<false>(args, t_row, ncols, n0, o, valid, s_bias, s_scale, s_shift);
+        if (args.mask_hi || args.accumulate) epi_split<true>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
+        else epi_split<false>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
       } else if (args.epi == EPI_ATOMIC) {
         float* dstp = args.out_f32 + (size_t)v * args.out_ld + args.out_col_off + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t vr[32];
-          tmem_ld32(t_row + (uint32_t)c0, vr);
+          ld_acc32(t_row + (uint32_t)c0, xoff, vr);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -401,7 +418,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         const size_t o = (((size_t)n * args.Ho + y) * args.Wo + x) * (size_t)args.cout + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t vr[32];
-          tmem_ld32(t_row + (uint32_t)c0, vr);
+          ld_acc32(t_row + (uint32_t)c0, xoff, vr);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {

@@ -37,6 +37,8 @@ struct ConvArgs {
   int kw_rows;          // rows between consecutive kw taps (= dilation); tap kw reads slab rows [kw*kw_rows, +128)
   int slab_rows;        // rows per A slab = round_up8(128 + (KW-1)*kw_rows) <= 256
   int stages_a, stages_b;
+  int acc_split;        // 1: the two cross terms (hi*lo, lo*hi) accumulate in their own TMEM columns and are added in the epilogue
+  int acc_bufs;         // accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1; 1 when columns run out)
   int resident_b;       // 1: all KH*KW*kblocks weight tiles of the (single) n-tile stay in shared memory for the whole launch
   int mt;               // m-tiles per work unit (1 or 2): with 2, every weight tile feeds two 128-row MMAs (halves the weight traffic)
   int bo_mode;          // how the UMMA descriptor's base-offset field is filled for row-shifted A tiles (debug knob)

@@ -4,9 +4,9 @@ update of ``ssdk_train_backward`` / ``ssdk_train_apply`` against float64 torch a
 
 Tolerance: the backward GEMMs run in the same bf16x3 mode as the forward pass (~16 significant bits per product, fp32
 accumulation); gradients are compared at 2e-3 of the tensor's max magnitude (measured 5e-6 .. 2e-4), updated weights at
-1e-5 relative.  Losses: 1e-4 relative on the small graphs; 5e-4 for the loss at the end of the full 23-layer SSD300 forward
-(measured 1.2e-4 against float64 -- the loss kernel itself is checked at 1e-6 on identical y_pred in test_gpu_codec.py; the
-remainder is the forward pass's accumulated rounding)."""
+1e-5 relative.  Losses: 1e-4 relative, also at the end of the full 23-layer SSD300 forward (measured 3.9e-5 against float64
+with the cross-term accumulator of DESIGN.md section 3.1, 1.2e-4 without it; the loss kernel itself is checked at 1e-6 on
+identical y_pred in test_gpu_codec.py); 5e-4 for SSD512."""
 import importlib.util
 import os
 
@@ -77,7 +77,7 @@ def test_ssd300_step_matches_autograd():
     lvec = og.ssd_loss_torch(y_true, yp)
     lvec.mean().backward()
     ref_l = lvec.detach().numpy()
-    assert np.abs(loss.cpu().numpy() - ref_l).max() <= 5e-4 * np.abs(ref_l).max()
+    assert np.abs(loss.cpu().numpy() - ref_l).max() <= 1e-4 * np.abs(ref_l).max()      # measured 3.9e-5
     assert set(grads) == set(w)
     # Deep in the backbone the comparison is ill-conditioned: a forward value within rounding distance of 0 flips its ReLU'
     # mask and moves one gradient entry by O(1e-3) of the tensor's max (tools/train_diag.py: conv6_1/bias has exactly one
