@@ -12,6 +12,9 @@ Keras-layer semantics (PARITY UNPINNED: TensorFlow 1.x is not installable here):
   ``tf.image.non_max_suppression`` (greedy, descending score, suppress iff IoU > thr,
   IoU of a non-positive-area box = 0, stops at max_output_size; ties -> lower index,
   the rule TF adopted explicitly in later releases) and ``tf.nn.top_k`` (ties -> lower index).
+  Cross-pinned (tests/test_oracle_layer_vs_reference_cpu.py): on the golden y_pred tensors they return the same detections
+  as the real reference's NumPy twins above; what stays unpinned is TensorFlow-specific behaviour the twins do not share
+  (the nms_max_output_size cap, tie order, NaN handling, float32 rounding at the thresholds).
 """
 import numpy as np
 
