@@ -5,7 +5,9 @@ NumPy API (pinned against the real reference by make_golden.py):
   * ``decode_detections_fast``  :228-333 (+ ``_greedy_nms2`` :94-109)
   * ``greedy_nms``              :27-75
 
-Keras-layer semantics (PARITY UNPINNED: TensorFlow 1.x is not installable here):
+Keras-layer semantics (TensorFlow 1.x is not installable here; pinned against the reference's own layer source run over
+a NumPy stand-in for the TF primitives -- tests/golden/make_tf_golden.py, tests/test_oracle_tf_shim_golden.py: classes,
+confidences, row order and padding exact):
   * ``decode_layer``       keras_layers/keras_layer_DecodeDetections.py:109-265
   * ``decode_layer_fast``  keras_layers/keras_layer_DecodeDetectionsFast.py:111-248
   They restate float32 arithmetic plus the published behaviour of

@@ -1,4 +1,6 @@
-"""SSD multibox loss (oracle, float32 NumPy).  PARITY UNPINNED against a running TensorFlow.
+"""SSD multibox loss (oracle, float32 NumPy).  Not checkable against a running TensorFlow (not installable offline); PINNED
+against the reference's own compute_loss source executed over a NumPy stand-in for the TensorFlow primitives it calls
+(tests/golden/make_tf_golden.py, tests/test_oracle_tf_shim_golden.py: seven cases at 2e-6).
 
 Restates ``keras_loss_function/keras_ssd_loss.py``:
   * ``smooth_L1_loss`` :53-75, ``log_loss`` :77-96, ``compute_loss`` :98-211.

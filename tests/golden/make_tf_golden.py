@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Golden vectors for the TensorFlow/Keras half of the reference, produced by executing THE REFERENCE'S OWN SOURCE
+(keras_loss_function/keras_ssd_loss.py, keras_layers/keras_layer_{DecodeDetections,DecodeDetectionsFast,L2Normalization,
+AnchorBoxes}.py) over tests/golden/tf_shim.py, a NumPy stand-in for the ~45 TensorFlow / Keras primitives that code calls
+(TensorFlow itself cannot be installed here).  Run in the build container only:
+
+    python tests/golden/make_tf_golden.py        # writes tests/golden/ref_tf_shim_golden.npz
+
+What the vectors pin and what they assume is spelled out in tf_shim.py.  Inputs are stored next to the outputs (they are
+small) so that tests/test_oracle_tf_shim_golden.py needs neither the reference nor the shim.
+"""
+import os
+import sys
+
+import numpy as np
+
+np.float = float   # noqa  the reference targets NumPy < 1.24 (caller-side aliases, as in make_golden.py)
+np.int = int       # noqa
+
+REF = os.environ.get('SSD_REFERENCE_ROOT', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.abspath(os.path.join(HERE, '..', '..')))
+
+import tf_shim  # noqa: E402
+
+tf_shim.install()
+
+from keras_layers.keras_layer_AnchorBoxes import AnchorBoxes                      # noqa: E402  (the reference's files)
+from keras_layers.keras_layer_DecodeDetections import DecodeDetections            # noqa: E402
+from keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast    # noqa: E402
+from keras_layers.keras_layer_L2Normalization import L2Normalization              # noqa: E402
+from keras_loss_function.keras_ssd_loss import SSDLoss                            # noqa: E402
+
+from oracle import synth                                                           # noqa: E402
+from oracle.encoder import OracleEncoder                                           # noqa: E402
+
+TINY = dict(img_height=120, img_width=160, n_classes=3, predictor_sizes=[(6, 8), (3, 4)], scales=[0.2, 0.45, 0.8],
+            aspect_ratios_global=[0.5, 1.0, 2.0], two_boxes_for_ar1=True, variances=[0.1, 0.1, 0.2, 0.2],
+            pos_iou_threshold=0.5, neg_iou_limit=0.3, normalize_coords=True)
+
+
+def main():
+    arrays = {}
+    enc = OracleEncoder(**TINY)                                   # pinned bit-exact against the real SSDInputEncoder
+    P, C = enc.anchors.shape[0], enc.n_classes
+
+    # ---- SSDLoss.compute_loss (keras_ssd_loss.py:98-211) -------------------------------------------------
+    def loss_case(key, y_true, y_pred, **kw):
+        L = SSDLoss(**kw)
+        out = L.compute_loss(np.asarray(y_true, np.float32), np.asarray(y_pred, np.float32))
+        arrays['loss/%s/y_true' % key] = np.asarray(y_true, np.float32)
+        arrays['loss/%s/y_pred' % key] = np.asarray(y_pred, np.float32)
+        arrays['loss/%s/kw' % key] = np.array([kw.get('neg_pos_ratio', 3), kw.get('n_neg_min', 0), kw.get('alpha', 1.0)], np.float64)
+        arrays['loss/%s/out' % key] = np.asarray(out, np.float32)
+
+    yt, yp = synth.synth_y_true_pred_for_loss(31, enc, 3, 4, 3, sharp=2.0)
+    loss_case('plain', yt, yp)
+    loss_case('ratio2_alpha', yt, yp, neg_pos_ratio=2, alpha=0.5)
+    yt0 = yt.copy(); yt0[:, :, :C] = 0; yt0[:, :, 0] = 1                        # background only -> n_positive = 0
+    loss_case('no_pos', yt0, yp)
+    loss_case('no_pos_negmin', yt0, yp, n_neg_min=7)
+    ypt = yp.copy(); ypt[:, :, :C] = np.array([0.5, 0.25, 0.125, 0.125], np.float32)   # every negative loss identical: top_k ties
+    loss_case('ties', yt, ypt)
+    ytn = yt.copy(); ytn[0, :20, :C] = 0                                         # neutral boxes
+    loss_case('neutral', ytn, yp)
+    yp1 = yp.copy(); yp1[:, :, :C] = 0; yp1[:, :, 0] = 1                         # all negative losses are exactly zero
+    loss_case('zero_neg_losses', yt, yp1)
+
+    # ---- DecodeDetections / DecodeDetectionsFast (.call) ----------------------------------------------------
+    ypd = synth.synth_y_pred(21, 3, enc.anchors, C, sharp=3.0, loc_scale=1.0)
+    arrays['dec/y_pred'] = ypd
+
+    def dec_case(key, cls, **kw):
+        layer = cls(**kw)
+        arrays['dec/%s/out' % key] = np.asarray(layer.call(np.asarray(ypd, np.float32)), np.float32)
+        arrays['dec/%s/kw' % key] = np.array([kw['confidence_thresh'], kw['iou_threshold'], kw['top_k'], kw['nms_max_output_size'],
+                                              1.0 if kw.get('normalize_coords', True) else 0.0], np.float64)
+
+    for name, cls in (('layer', DecodeDetections), ('fast', DecodeDetectionsFast)):
+        dec_case(name + '_default', cls, confidence_thresh=0.01, iou_threshold=0.45, top_k=200, nms_max_output_size=400,
+                 normalize_coords=True, img_height=120, img_width=160)
+        dec_case(name + '_cap', cls, confidence_thresh=0.05, iou_threshold=0.6, top_k=10, nms_max_output_size=5,
+                 normalize_coords=True, img_height=120, img_width=160)
+        dec_case(name + '_topk_small', cls, confidence_thresh=0.2, iou_threshold=0.3, top_k=4, nms_max_output_size=400,
+                 normalize_coords=True, img_height=120, img_width=160)
+        dec_case(name + '_nonorm', cls, confidence_thresh=0.3, iou_threshold=0.45, top_k=50, nms_max_output_size=100,
+                 normalize_coords=False, img_height=120, img_width=160)
+        dec_case(name + '_none', cls, confidence_thresh=0.999, iou_threshold=0.45, top_k=20, nms_max_output_size=30,
+                 normalize_coords=True, img_height=120, img_width=160)
+
+    # ---- L2Normalization (.call, keras_layer_L2Normalization.py:61-63) ----------------------------------------
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((2, 5, 4, 16)) * 3).astype(np.float32)
+    x[0, 0, 0] = 0                                                 # an all-zero pixel: the epsilon clamp
+    l2 = L2Normalization(gamma_init=20)
+    arrays['l2norm/x'] = x
+    arrays['l2norm/out'] = np.asarray(l2(x), np.float32)
+
+    # ---- AnchorBoxes (.call, keras_layer_AnchorBoxes.py:133-255) ----------------------------------------------
+    def anchor_case(key, fmap, **kw):
+        layer = AnchorBoxes(**kw)
+        out = layer.call(tf_shim.keras_tensor(np.zeros((2,) + fmap + (8,), np.float32)))
+        arrays['anchors/%s/out' % key] = np.asarray(out, np.float32)
+
+    anchor_case('tiny0', (6, 8), img_height=120, img_width=160, this_scale=0.2, next_scale=0.45, aspect_ratios=[0.5, 1.0, 2.0],
+                two_boxes_for_ar1=True, variances=[0.1, 0.1, 0.2, 0.2], coords='centroids', normalize_coords=True)
+    anchor_case('tiny1_clip_corners', (3, 4), img_height=120, img_width=160, this_scale=0.45, next_scale=0.8,
+                aspect_ratios=[0.5, 3.0], two_boxes_for_ar1=False, this_steps=(40, 41), this_offsets=(0.4, 0.6), clip_boxes=True,
+                variances=[0.1, 0.1, 0.2, 0.2], coords='corners', normalize_coords=False)
+    anchor_case('ssd300_conv4_3', (38, 38), img_height=300, img_width=300, this_scale=0.1, next_scale=0.2,
+                aspect_ratios=[1.0, 2.0, 0.5], two_boxes_for_ar1=True, this_steps=8, this_offsets=0.5, clip_boxes=False,
+                variances=[0.1, 0.1, 0.2, 0.2], coords='centroids', normalize_coords=True)
+
+    np.savez_compressed(os.path.join(HERE, 'ref_tf_shim_golden.npz'), **arrays)
+    print('wrote %d arrays' % len(arrays))
+
+
+if __name__ == '__main__':
+    main()
