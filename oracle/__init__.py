@@ -16,9 +16,13 @@ Parity pins
 * TF/Keras half (AnchorBoxes, L2Normalization, DecodeDetections(+Fast) layers,
   SSDLoss, model graphs): TensorFlow 1.x / Keras 2.x cannot be installed here,
   and the reference has no tests or golden vectors of its own for them
-  (SURVEY.md section 4).  These restatements follow the cited reference lines
-  and the published semantics of the TF ops they call; they are **parity
-  unpinned** against a running TF and say so in their module headers.
+  (SURVEY.md section 4).  They cannot be checked against a running TensorFlow;
+  they ARE pinned against the reference's own source: ``tests/golden/make_tf_golden.py``
+  imports the reference's loss / layer classes and model builders unmodified and
+  executes them eagerly over ``tests/golden/tf_shim.py``, a NumPy/torch-CPU stand-in
+  for the TensorFlow / Keras primitives they call; the outputs are the committed
+  fixture ``tests/golden/ref_tf_shim_golden.npz`` (tests/test_oracle_tf_shim_golden.py).
+  What stays assumed is the semantics of those primitives (listed in tf_shim.py).
 
 Every function cites the reference file:line it restates (paths relative to the
 reference repository root).

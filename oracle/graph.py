@@ -1,4 +1,5 @@
-"""Generic torch-CPU executor for a layer-spec graph (oracle; test infrastructure).  PARITY UNPINNED.
+"""Generic torch-CPU executor for a layer-spec graph (oracle; test infrastructure).  Checked against oracle/model.py and
+oracle/loss.py (tests/test_oracle_graph_cpu.py), which are pinned to the reference's code (tests/test_oracle_tf_shim_golden.py).
 
 Executes the same ``Spec`` list the product's builders produce (ops INPUT / CONV / MAXPOOL / L2NORM / HEAD) with
 torch.nn.functional in float32 or float64, keeping the autograd graph so that gradients of the SSD loss with respect to

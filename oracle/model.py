@@ -1,4 +1,6 @@
-"""SSD300 / SSD512 / SSD7 forward graphs (oracle, torch-CPU float32).  PARITY UNPINNED.
+"""SSD300 / SSD512 / SSD7 forward graphs (oracle, torch-CPU float32).  Not checkable against Keras itself (not installable
+offline); PINNED against the outputs of the reference's real builders executed over eager stand-in Keras layers
+(tests/golden/make_tf_golden.py, tests/test_oracle_tf_shim_golden.py).
 
 TensorFlow 1.x / Keras 2.x cannot be installed offline, so these restate the graphs from
   * models/keras_ssd300.py:263-419

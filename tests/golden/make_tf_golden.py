@@ -33,8 +33,13 @@ from keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast  
 from keras_layers.keras_layer_L2Normalization import L2Normalization              # noqa: E402
 from keras_loss_function.keras_ssd_loss import SSDLoss                            # noqa: E402
 
+from models.keras_ssd300 import ssd_300                                            # noqa: E402  (the reference's builders)
+from models.keras_ssd512 import ssd_512                                            # noqa: E402
+from models.keras_ssd7 import build_model                                          # noqa: E402
+
 from oracle import synth                                                           # noqa: E402
 from oracle.encoder import OracleEncoder                                           # noqa: E402
+from oracle.model import ssd7_weight_shapes, vgg_weight_shapes                     # noqa: E402
 
 TINY = dict(img_height=120, img_width=160, n_classes=3, predictor_sizes=[(6, 8), (3, 4)], scales=[0.2, 0.45, 0.8],
             aspect_ratios_global=[0.5, 1.0, 2.0], two_boxes_for_ar1=True, variances=[0.1, 0.1, 0.2, 0.2],
@@ -112,6 +117,56 @@ def main():
     anchor_case('ssd300_conv4_3', (38, 38), img_height=300, img_width=300, this_scale=0.1, next_scale=0.2,
                 aspect_ratios=[1.0, 2.0, 0.5], two_boxes_for_ar1=True, this_steps=8, this_offsets=0.5, clip_boxes=False,
                 variances=[0.1, 0.1, 0.2, 0.2], coords='centroids', normalize_coords=True)
+
+    # ---- the model builders themselves (models/keras_ssd300.py, keras_ssd512.py, keras_ssd7.py), executed eagerly ---------
+    # Keras layers are eager NumPy/torch-CPU stand-ins (tf_shim.make_keras_layers); weights and the image are synthetic and
+    # regenerated from their seeds in the test.  Stored: every `stride`-th prior row of the (1, P, C+12) output, plus the
+    # decoded (1, top_k, 6) output of mode='inference' / 'inference_fast'.
+    def run_builder(builder, x, w, **kw):
+        tf_shim.STATE['input'], tf_shim.STATE['weights'] = x, w
+        return np.asarray(builder(**kw).output, np.float32)
+
+    def vgg_w(seed, variant, n_cls):
+        w = synth.synth_weights(seed, vgg_weight_shapes(variant, n_cls), bias_scale=0.02)
+        w['conv4_3_norm/gamma'] = np.random.default_rng(seed).uniform(10, 30, 512).astype(np.float32)
+        return w
+
+    pre = dict(subtract_mean=[123, 117, 104], divide_by_stddev=[64, 64, 64], swap_channels=[2, 1, 0])
+    sc300 = [0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05]
+    x = synth.synth_images(41, 1, 300, 300)
+    w = vgg_w(42, 300, 20)
+    common = dict(image_size=(300, 300, 3), n_classes=20, scales=sc300, **pre)
+    y = run_builder(ssd_300, x, w, mode='training', **common)
+    assert y.shape == (1, 8732, 33), y.shape
+    arrays['model/ssd300/rows7'] = y[:, ::7]
+    arrays['model/ssd300/colsum'] = y.astype(np.float64).sum(axis=1)
+    arrays['model/ssd300/inference'] = run_builder(ssd_300, x, w, mode='inference', confidence_thresh=0.01, iou_threshold=0.45,
+                                                   top_k=200, nms_max_output_size=400, **common)
+    arrays['model/ssd300/inference_fast'] = run_builder(ssd_300, x, w, mode='inference_fast', confidence_thresh=0.01,
+                                                        iou_threshold=0.45, top_k=200, nms_max_output_size=400, **common)
+
+    sc512 = [0.04, 0.1, 0.26, 0.42, 0.58, 0.74, 0.9, 1.06]
+    x = synth.synth_images(43, 1, 512, 512)
+    w = vgg_w(44, 512, 20)
+    y = run_builder(ssd_512, x, w, mode='training', image_size=(512, 512, 3), n_classes=20, scales=sc512, **pre)
+    assert y.shape == (1, 24564, 33), y.shape
+    arrays['model/ssd512/rows16'] = y[:, ::16]
+    arrays['model/ssd512/colsum'] = y.astype(np.float64).sum(axis=1)
+
+    x = synth.synth_images(45, 1, 300, 480)
+    w = synth.synth_weights(46, ssd7_weight_shapes(5), bias_scale=0.05)
+    rng = np.random.default_rng(47)
+    for i in range(1, 8):
+        c = w['conv%d/bias' % i].shape[0]
+        w['bn%d/gamma' % i] = rng.uniform(0.8, 1.2, c).astype(np.float32)
+        w['bn%d/beta' % i] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        w['bn%d/moving_mean' % i] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        w['bn%d/moving_variance' % i] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    y = run_builder(build_model, x, w, mode='training', image_size=(300, 480, 3), n_classes=5, scales=[0.08, 0.16, 0.32, 0.64, 0.96],
+                    normalize_coords=True, subtract_mean=127.5, divide_by_stddev=127.5)
+    arrays['model/ssd7/rows5'] = y[:, ::5]
+    arrays['model/ssd7/colsum'] = y.astype(np.float64).sum(axis=1)
+    arrays['model/ssd7/shape'] = np.array(y.shape)
 
     np.savez_compressed(os.path.join(HERE, 'ref_tf_shim_golden.npz'), **arrays)
     print('wrote %d arrays' % len(arrays))

@@ -167,6 +167,7 @@ def make_keras():
     K.tile = lambda x, n: np.tile(x, [int(v) for v in n])
     K.expand_dims = lambda x, axis=-1: np.expand_dims(x, axis)
     K.concatenate = lambda tensors, axis=-1: np.concatenate(tensors, axis=axis)
+    K.stack = lambda xs, axis=0: np.stack([np.asarray(v) for v in xs], axis=axis)
 
     def l2_normalize(x, axis=None):
         x = np.asarray(x, dtype=F)
@@ -196,12 +197,160 @@ def make_keras():
         def __call__(self, x, **kw):
             if not self.built:
                 self.build(tuple(np.asarray(x).shape))
-            return self.call(x, **kw)
+                W = STATE.get('weights') or {}
+                if hasattr(self, 'gamma') and (self.name + '/gamma') in W:       # L2Normalization: trained scale by layer name
+                    self.gamma = np.asarray(W[self.name + '/gamma'], dtype=F)
+            return keras_tensor(np.asarray(self.call(x, **kw), dtype=F))
 
     topology.InputSpec, topology.Layer = InputSpec, Layer
     engine.topology = topology
     keras.backend, keras.engine = K, engine
     return {'keras': keras, 'keras.backend': K, 'keras.engine': engine, 'keras.engine.topology': topology}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Eager stand-ins for the Keras functional-API layers the reference's model builders use (models/keras_ssd300.py etc.):
+# `Input` returns the concrete image batch stored in STATE['input'], every layer call computes its output immediately
+# (float32, NHWC; convolutions through torch on the CPU), weights come from STATE['weights'] by Keras layer name.
+# ---------------------------------------------------------------------------------------------------------------
+STATE = {'input': None, 'weights': None}
+
+
+def _same_pad(size, k, s, d=1):
+    """TensorFlow 'SAME': total padding so that out = ceil(size / s); the extra pixel goes to the end."""
+    ke = (k - 1) * d + 1
+    out = -(-size // s)
+    total = max((out - 1) * s + ke - size, 0)
+    return total // 2, total - total // 2
+
+
+def _pair2(v):
+    return (int(v), int(v)) if np.isscalar(v) else (int(v[0]), int(v[1]))
+
+
+def make_keras_layers():
+    import torch
+    import torch.nn.functional as Fn
+    L = types.ModuleType('keras.layers')
+
+    class _Base(object):
+        def __init__(self, name=None, **kw):
+            self.name = name
+
+    def Input(shape=None, **kw):
+        x = keras_tensor(STATE['input'])
+        assert tuple(x.shape[1:]) == tuple(shape), (x.shape, shape)
+        return x
+
+    class Lambda(_Base):
+        def __init__(self, function, output_shape=None, name=None, **kw):
+            _Base.__init__(self, name); self.fn = function
+
+        def __call__(self, x):
+            return keras_tensor(np.asarray(self.fn(np.asarray(x)), dtype=F))   # Keras casts NumPy constants to the tensor's dtype
+
+    class Conv2D(_Base):
+        def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', dilation_rate=(1, 1), activation=None,
+                     kernel_initializer=None, kernel_regularizer=None, name=None, **kw):
+            _Base.__init__(self, name)
+            self.filters, self.k, self.s, self.d = filters, _pair2(kernel_size), _pair2(strides), _pair2(dilation_rate)
+            self.padding, self.activation = padding, activation
+
+        def __call__(self, x):
+            w = np.asarray(STATE['weights'][self.name + '/kernel'], dtype=F)      # HWIO
+            b = np.asarray(STATE['weights'][self.name + '/bias'], dtype=F)
+            assert w.shape[:2] == self.k and w.shape[3] == self.filters, (self.name, w.shape)
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(x))).permute(0, 3, 1, 2)
+            if self.padding == 'same':
+                pt, pb = _same_pad(t.shape[2], self.k[0], self.s[0], self.d[0])
+                pl, pr = _same_pad(t.shape[3], self.k[1], self.s[1], self.d[1])
+                t = Fn.pad(t, (pl, pr, pt, pb))
+            else:
+                assert self.padding == 'valid'
+            y = Fn.conv2d(t, torch.from_numpy(w).permute(3, 2, 0, 1).contiguous(), torch.from_numpy(b), stride=self.s, dilation=self.d)
+            if self.activation == 'relu':
+                y = torch.relu(y)
+            else:
+                assert self.activation is None, self.activation
+            return keras_tensor(y.permute(0, 2, 3, 1).contiguous().numpy())
+
+    class MaxPooling2D(_Base):
+        def __init__(self, pool_size=(2, 2), strides=None, padding='valid', name=None, **kw):
+            _Base.__init__(self, name)
+            self.k = _pair2(pool_size); self.s = _pair2(strides if strides is not None else pool_size); self.padding = padding
+
+        def __call__(self, x):
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(x))).permute(0, 3, 1, 2)
+            if self.padding == 'same':
+                pt, pb = _same_pad(t.shape[2], self.k[0], self.s[0])
+                pl, pr = _same_pad(t.shape[3], self.k[1], self.s[1])
+                t = Fn.pad(t, (pl, pr, pt, pb), value=float('-inf'))
+            y = Fn.max_pool2d(t, self.k, self.s)
+            return keras_tensor(y.permute(0, 2, 3, 1).contiguous().numpy())
+
+    class ZeroPadding2D(_Base):
+        def __init__(self, padding=(1, 1), name=None, **kw):
+            _Base.__init__(self, name)
+            p = padding
+            self.p = ((p, p), (p, p)) if np.isscalar(p) else tuple((q, q) if np.isscalar(q) else tuple(q) for q in p)
+
+        def __call__(self, x):
+            (t, b), (l, r) = self.p
+            return keras_tensor(np.pad(np.asarray(x), ((0, 0), (t, b), (l, r), (0, 0))))
+
+    class Reshape(_Base):
+        def __init__(self, target_shape, name=None, **kw):
+            _Base.__init__(self, name); self.shape = tuple(target_shape)
+
+        def __call__(self, x):
+            x = np.asarray(x)
+            return keras_tensor(x.reshape((x.shape[0],) + self.shape))
+
+    class Concatenate(_Base):
+        def __init__(self, axis=-1, name=None, **kw):
+            _Base.__init__(self, name); self.axis = axis
+
+        def __call__(self, xs):
+            return keras_tensor(np.concatenate([np.asarray(v, dtype=F) for v in xs], axis=self.axis))
+
+    class Activation(_Base):
+        def __init__(self, activation, name=None, **kw):
+            _Base.__init__(self, name); self.a = activation
+
+        def __call__(self, x):
+            assert self.a == 'softmax'
+            return keras_tensor(torch.softmax(torch.from_numpy(np.ascontiguousarray(np.asarray(x))), dim=-1).numpy())
+
+    class BatchNormalization(_Base):            # inference phase: moving statistics, Keras default epsilon 1e-3
+        def __init__(self, axis=-1, momentum=0.99, epsilon=1e-3, name=None, **kw):
+            _Base.__init__(self, name); self.eps = epsilon; assert axis in (3, -1)
+
+        def __call__(self, x):
+            W = STATE['weights']; n = self.name
+            g, b = np.asarray(W[n + '/gamma'], F), np.asarray(W[n + '/beta'], F)
+            mu, var = np.asarray(W[n + '/moving_mean'], F), np.asarray(W[n + '/moving_variance'], F)
+            return keras_tensor((np.asarray(x) - mu) / np.sqrt(var + F(self.eps)) * g + b)
+
+    class ELU(_Base):
+        def __init__(self, alpha=1.0, name=None, **kw):
+            _Base.__init__(self, name); self.alpha = F(alpha)
+
+        def __call__(self, x):
+            x = np.asarray(x)
+            return keras_tensor(np.where(x > 0, x, self.alpha * np.expm1(np.minimum(x, F(0)))))
+
+    for k, v in dict(Input=Input, Lambda=Lambda, Conv2D=Conv2D, MaxPooling2D=MaxPooling2D, ZeroPadding2D=ZeroPadding2D, Reshape=Reshape,
+                     Concatenate=Concatenate, Activation=Activation, BatchNormalization=BatchNormalization, ELU=ELU).items():
+        setattr(L, k, v)
+    models = types.ModuleType('keras.models')
+
+    class Model(object):
+        def __init__(self, inputs=None, outputs=None, **kw):
+            self.inputs, self.output = inputs, outputs
+    models.Model = Model
+    reg = types.ModuleType('keras.regularizers')
+    reg.l2 = lambda v=0.01: ('l2', v)
+    return {'keras.layers': L, 'keras.models': models, 'keras.regularizers': reg}
 
 
 def install():
@@ -212,7 +361,11 @@ def install():
     tf = make_tf()
     tf._ssd_b200_shim = True
     sys.modules['tensorflow'] = tf
-    for k, v in make_keras().items():
+    mods = make_keras()
+    mods.update(make_keras_layers())
+    for k, v in mods.items():
         v._ssd_b200_shim = True
         sys.modules[k] = v
+    for sub in ('layers', 'models', 'regularizers'):
+        setattr(mods['keras'], sub, mods['keras.' + sub])
     return tf

@@ -65,3 +65,76 @@ def test_anchor_boxes_layer_matches_reference_code(key, fmap, kw):
     for b in range(ref.shape[0]):                                   # tiled over the batch
         np.testing.assert_array_equal(ref[b, ..., :4], a.astype(np.float32))
         np.testing.assert_array_equal(ref[b, ..., 4:], np.broadcast_to(np.float32([0.1, 0.1, 0.2, 0.2]), ref[b, ..., 4:].shape))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The model graphs: oracle/model.py against the outputs of the reference's REAL builders (models/keras_ssd300.py,
+# keras_ssd512.py, keras_ssd7.py) executed eagerly over stand-in Keras layers (tf_shim.make_keras_layers).  Pins which layer
+# feeds which, paddings, the dilated fc6, pooling modes, reshape / concatenate order, L2Normalization placement, the
+# AnchorBoxes arguments per source layer and the decoder wiring of mode='inference' / 'inference_fast'.
+# ---------------------------------------------------------------------------------------------------------------
+def _vgg_w(seed, variant, n_cls):
+    from oracle import synth
+    from oracle.model import vgg_weight_shapes
+    w = synth.synth_weights(seed, vgg_weight_shapes(variant, n_cls), bias_scale=0.02)
+    w['conv4_3_norm/gamma'] = np.random.default_rng(seed).uniform(10, 30, 512).astype(np.float32)
+    return w
+
+
+PRE = dict(subtract_mean=[123, 117, 104], divide_by_stddev=[64, 64, 64], swap_channels=[2, 1, 0])
+
+
+@pytest.fixture(scope='module')
+def ssd300_oracle_output():
+    from oracle import synth
+    from oracle.model import ssd_vgg_forward
+    x = synth.synth_images(41, 1, 300, 300)
+    return ssd_vgg_forward(x, _vgg_w(42, 300, 20), 300, 20, scales=[0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05], **PRE)
+
+
+def test_ssd300_graph_matches_reference_builder(ssd300_oracle_output):
+    y = ssd300_oracle_output
+    assert y.shape == (1, 8732, 33)
+    np.testing.assert_allclose(y[:, ::7], G['model/ssd300/rows7'], rtol=2e-3, atol=1e-4)     # two float32 evaluation orders, 23 layers
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=1), G['model/ssd300/colsum'], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize('mode', ['inference', 'inference_fast'])
+def test_ssd300_inference_modes_match_reference_builder(ssd300_oracle_output, mode):
+    fn = decode_layer if mode == 'inference' else decode_layer_fast
+    out = fn(ssd300_oracle_output, 0.01, 0.45, 200, 400, True, 300, 300)
+    ref = G['model/ssd300/' + mode]
+    assert out.shape == ref.shape == (1, 200, 6)
+    np.testing.assert_array_equal(out[..., 0], ref[..., 0])
+    np.testing.assert_allclose(out[..., 1], ref[..., 1], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(out[..., 2:], ref[..., 2:], rtol=1e-4, atol=2e-3)
+
+
+def test_ssd512_graph_matches_reference_builder():
+    from oracle import synth
+    from oracle.model import ssd_vgg_forward
+    x = synth.synth_images(43, 1, 512, 512)
+    y = ssd_vgg_forward(x, _vgg_w(44, 512, 20), 512, 20, scales=[0.04, 0.1, 0.26, 0.42, 0.58, 0.74, 0.9, 1.06], **PRE)
+    assert y.shape == (1, 24564, 33)
+    np.testing.assert_allclose(y[:, ::16], G['model/ssd512/rows16'], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=1), G['model/ssd512/colsum'], rtol=1e-5, atol=1e-3)
+
+
+def test_ssd7_graph_matches_reference_builder():
+    """300 x 480 input: also pins the height / width order of every anchor and reshape."""
+    from oracle import synth
+    from oracle.model import ssd7_forward, ssd7_weight_shapes
+    x = synth.synth_images(45, 1, 300, 480)
+    w = synth.synth_weights(46, ssd7_weight_shapes(5), bias_scale=0.05)
+    rng = np.random.default_rng(47)
+    for i in range(1, 8):
+        c = w['conv%d/bias' % i].shape[0]
+        w['bn%d/gamma' % i] = rng.uniform(0.8, 1.2, c).astype(np.float32)
+        w['bn%d/beta' % i] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        w['bn%d/moving_mean' % i] = (rng.standard_normal(c) * 0.1).astype(np.float32)
+        w['bn%d/moving_variance' % i] = rng.uniform(0.5, 1.5, c).astype(np.float32)
+    y = ssd7_forward(x, w, n_classes=5, scales=[0.08, 0.16, 0.32, 0.64, 0.96], normalize_coords=True, subtract_mean=127.5,
+                     divide_by_stddev=127.5)
+    assert tuple(G['model/ssd7/shape']) == y.shape
+    np.testing.assert_allclose(y[:, ::5], G['model/ssd7/rows5'], rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=1), G['model/ssd7/colsum'], rtol=1e-5, atol=1e-3)
