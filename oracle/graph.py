@@ -39,6 +39,10 @@ def forward(specs, params, x_nhwc, n_classes_total, anchors, variances, dtype=to
         if s.op == OP_CONV:
             w = params[s.name + '/kernel'].permute(3, 2, 0, 1)
             y = Fn.conv2d(Fn.pad(xin, (pl, pr, pt, pb)), w, params[s.name + '/bias'], stride=s.stride, dilation=s.dilation)
+            if getattr(s, 'bn', None):          # inference-phase BatchNormalization (Keras epsilon 1e-3) between conv and activation
+                g, b = params[s.bn + '/gamma'], params[s.bn + '/beta']
+                mu, var = params[s.bn + '/moving_mean'], params[s.bn + '/moving_variance']
+                y = (y - mu.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-3) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
             if s.act == ACT_RELU:
                 y = torch.relu(y)
             elif s.act == ACT_ELU:
