@@ -57,6 +57,11 @@ def _check_norm(normalize_coords, img_height, img_width):
                          .format(img_height, img_width))
 
 
+def _check_coords(input_coords, message):
+    if input_coords not in ('centroids', 'minmax', 'corners'):
+        raise ValueError(message)
+
+
 def _ragged(out, counts):
     out = out.cpu().numpy().astype(np.float64)
     counts = counts.cpu().numpy()
@@ -69,6 +74,8 @@ def decode_detections(y_pred, confidence_thresh=0.01, iou_threshold=0.45, top_k=
     When more than ``top_k`` boxes survive, the reference keeps an unordered top-k set (``argpartition``);
     here that set comes back sorted by confidence."""
     _check_norm(normalize_coords, img_height, img_width)
+    _check_coords(input_coords, "Unexpected value for `input_coords`. Supported input coordinate formats are 'minmax', 'corners' "
+                                "and 'centroids'.")                                                   # reference :192
     out, counts = decode_device(_to_device(y_pred), PER_CLASS, False, confidence_thresh, iou_threshold, top_k, 0,
                                 input_coords, normalize_coords, img_height, img_width, border_pixels)
     return _ragged(out, counts)
@@ -78,6 +85,7 @@ def decode_detections_fast(y_pred, confidence_thresh=0.5, iou_threshold=0.45, to
                            normalize_coords=True, img_height=None, img_width=None, border_pixels='half'):
     """Reference :228-333 (class = argmax, one NMS over all classes, ``>=`` confidence test)."""
     _check_norm(normalize_coords, img_height, img_width)
+    _check_coords(input_coords, "Unexpected value for `coords`. Supported values are 'minmax', 'corners' and 'centroids'.")  # :314
     out, counts = decode_device(_to_device(y_pred), FAST, False, confidence_thresh, iou_threshold, top_k, 0,
                                 input_coords, normalize_coords, img_height, img_width, border_pixels)
     res = _ragged(out, counts)
