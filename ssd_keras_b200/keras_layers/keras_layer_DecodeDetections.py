@@ -34,6 +34,10 @@ class DecodeDetections:
 
     __call__ = call
 
+    def build(self, input_shape):
+        """Keras calls this before the first ``call``; nothing is allocated here (reference ``build`` only records the input spec)."""
+        self.input_shape = tuple(input_shape)
+
     def compute_output_shape(self, input_shape):
         return (input_shape[0], self.top_k, 6)
 

@@ -57,6 +57,27 @@ class SSDLoss:
         self.n_neg_min = n_neg_min
         self.alpha = alpha
 
+    @staticmethod
+    def _smooth_l1_t(y_true, y_pred):
+        import torch
+        absolute_loss = torch.abs(y_true - y_pred)
+        square_loss = 0.5 * (y_true - y_pred) ** 2
+        return torch.sum(torch.where(absolute_loss < 1.0, square_loss, absolute_loss - 0.5), dim=-1)
+
+    @staticmethod
+    def _log_loss_t(y_true, y_pred):
+        import torch
+        return -torch.sum(y_true * torch.log(torch.clamp(y_pred, min=1e-15)), dim=-1)
+
+    def smooth_L1_loss(self, y_true, y_pred):
+        """Reference :53-75, (B,P,4) x2 -> (B,P) float32 CUDA tensor.  Stand-alone helper (a few tensor operations on the
+        device); ``compute_loss`` computes the same quantity inside ``ssdk_ssd_loss_fwd``."""
+        return self._smooth_l1_t(_as_cuda(y_true), _as_cuda(y_pred))
+
+    def log_loss(self, y_true, y_pred):
+        """Reference :77-96, (B,P,C) x2 -> (B,P) float32 CUDA tensor (see ``smooth_L1_loss``)."""
+        return self._log_loss_t(_as_cuda(y_true), _as_cuda(y_pred))
+
     def compute_loss(self, y_true, y_pred):
         """(B,P,C+12) x2 -> (B,) float32 CUDA tensor (reference :98-211)."""
         global _FN

@@ -99,6 +99,37 @@ class SSDInputEncoder:
         self._diagnostics()
         self._handle = None
 
+    def generate_anchor_boxes_for_layer(self, feature_map_size, aspect_ratios, this_scale, next_scale, this_steps=None,
+                                        this_offsets=None, diagnostics=False):
+        """Reference :420-548: the anchors of ONE predictor layer as a (feature_map_height, feature_map_width, n_boxes, 4) float64
+        array in this encoder's ``coords`` / ``normalize_coords`` / ``clip_boxes`` convention (same host routine as ``__init__``,
+        ``ssdk_anchors_generate``).  With ``diagnostics`` also returns (centres, wh_list, step, offset) like the reference."""
+        fh, fw = int(feature_map_size[0]), int(feature_map_size[1])
+        a64, _, nb = _ffi.generate_anchors(self.img_height, self.img_width, [(fh, fw)], [this_scale, next_scale], [aspect_ratios],
+                                           self.two_boxes_for_ar1, [this_steps], [this_offsets], self.clip_boxes, self.coords,
+                                           self.normalize_coords)
+        boxes = a64.reshape(fh, fw, nb[0], 4)
+        if not diagnostics:
+            return boxes
+        size = min(self.img_height, self.img_width)
+        wh = []
+        for ar in aspect_ratios:
+            if ar == 1:
+                wh.append((this_scale * size,) * 2)
+                if self.two_boxes_for_ar1:
+                    wh.append((np.sqrt(this_scale * next_scale) * size,) * 2)
+            else:
+                wh.append((this_scale * size * np.sqrt(ar), this_scale * size / np.sqrt(ar)))
+        st_h, st_w = _ffi._pair_or_nan(this_steps)
+        if np.isnan(st_h):
+            st_h, st_w = self.img_height / fh, self.img_width / fw
+        of_h, of_w = _ffi._pair_or_nan(this_offsets)
+        if np.isnan(of_h):
+            of_h = of_w = 0.5
+        cy = np.linspace(of_h * st_h, (of_h + fh - 1) * st_h, fh)
+        cx = np.linspace(of_w * st_w, (of_w + fw - 1) * st_w, fw)
+        return boxes, (cy, cx), np.array(wh), (st_h, st_w), (of_h, of_w)
+
     def _diagnostics(self):
         """wh / steps / offsets / centres per layer, the ``*_diag`` attributes of the reference (:254-275)."""
         self.wh_list_diag, self.steps_diag, self.offsets_diag, self.centers_diag = [], [], [], []

@@ -27,6 +27,11 @@ ENTRY_POINTS = [
     ('keras_layers.keras_layer_DecodeDetections', 'DecodeDetections.__init__'),
     ('keras_layers.keras_layer_DecodeDetectionsFast', 'DecodeDetectionsFast.__init__'),
     ('keras_layers.keras_layer_AnchorBoxes', 'AnchorBoxes.__init__'), ('keras_layers.keras_layer_L2Normalization', 'L2Normalization.__init__'),
+    ('ssd_encoder_decoder.matching_utils', 'match_bipartite_greedy'), ('ssd_encoder_decoder.matching_utils', 'match_multi'),
+    ('bounding_box_utils.bounding_box_utils', 'intersection_area'), ('bounding_box_utils.bounding_box_utils', 'intersection_area_'),
+    ('ssd_encoder_decoder.ssd_input_encoder', 'SSDInputEncoder.generate_anchor_boxes_for_layer'),
+    ('ssd_encoder_decoder.ssd_input_encoder', 'SSDInputEncoder.generate_encoding_template'),
+    ('keras_loss_function.keras_ssd_loss', 'SSDLoss.smooth_L1_loss'), ('keras_loss_function.keras_ssd_loss', 'SSDLoss.log_loss'),
     ('models.keras_ssd300', 'ssd_300'), ('models.keras_ssd512', 'ssd_512'), ('models.keras_ssd7', 'build_model'),
 ]
 
