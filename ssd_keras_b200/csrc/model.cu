@@ -193,6 +193,8 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   { const char* e = getenv("SSDK_ACC_SPLIT"); const int want = e ? atoi(e) : 1;       // on: +3.5% step time, 3x less bias
     if (want && a.split && a.KH * a.KW * kblocks >= 32) {
       a.acc_split = 1;
+      a.mt = 1;                     // paired m-tiles + cross-term accumulator would need 4 accumulators per unit; deep-K layers
+                                    // re-fetch few weight bytes per MMA anyway, so they keep one m-tile and both accumulator sets
       if (2 * 2 * a.mt * a.BN > 512) a.acc_bufs = 1;
       if (a.acc_bufs * 2 * a.mt * a.BN > 512) { a.acc_split = 0; a.acc_bufs = 2; }
     } }
