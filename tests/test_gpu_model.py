@@ -111,6 +111,24 @@ def test_ssd300_forward_layers(precision, tol):
     np.testing.assert_allclose(y[:, :, 21:25], y_ref[:, :, 21:25], atol=max(tol, 2e-4) * np.abs(y_ref[:, :, 21:25]).max())
 
 
+def test_ssd300_batch32_layers():
+    """The benchmark configuration itself (BASELINE configs[1]: batch 32): at this size the 64/128-channel layers run with
+    two m-tiles per work unit and the deep layers with the cross-term accumulator, plans that small batches do not select."""
+    from ssd_keras_b200.models.keras_ssd300 import ssd_300
+    B = 32
+    w = _vgg_weights(5, 300, 20)
+    x = synth.synth_images(6, B, 300, 300)
+    model = ssd_300((300, 300, 3), 20, mode='training', scales=SC300)
+    model.set_weights(w)
+    y = model.predict(x)
+    y_ref, feats = ssd_vgg_forward(x, w, 300, 20, scales=SC300, return_features=True)
+    assert y.shape == (B, 8732, 33)
+    _cmp_layers(model, feats, B, ['conv1_2', 'conv2_1', 'conv2_2', 'conv3_1', 'conv3_3', 'conv4_3', 'fc7', 'conv6_2'], 2e-4)
+    np.testing.assert_array_equal(y[:, :, 25:], y_ref[:, :, 25:])
+    np.testing.assert_allclose(y[:, :, :21], y_ref[:, :, :21], atol=_prob_atol(feats))
+    np.testing.assert_allclose(y[:, :, 21:25], y_ref[:, :, 21:25], atol=2e-4 * np.abs(y_ref[:, :, 21:25]).max())
+
+
 def test_ssd300_inference_mode_matches_layer_oracle():
     """mode='inference': (B,200,6); decoded from identical y_pred the output equals the layer oracle bit for bit in
     survivor set; against the fp32 oracle's own y_pred the boxes agree within 1e-4 relative where survivors coincide."""
