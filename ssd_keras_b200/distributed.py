@@ -60,3 +60,14 @@ def all_gather_ragged(local_rows, group=None):
     out = torch.empty((world * mx,) + tuple(pad.shape[1:]), dtype=pad.dtype, device=pad.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+def all_reduce_gradients_(flat_grad, group=None):
+    """Data-parallel gradient exchange of the training step: ONE all-reduce (sum) over the flat fp32
+    gradient buffer, in place.  Returns the factor the optimiser must scale the summed gradient with (1 / world size), so that
+    the update equals the mean of the replicas' gradients -- what Keras multi-GPU replicas of the reference's loss compute."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 1.0
+    dist.all_reduce(flat_grad, group=group)
+    return 1.0 / dist.get_world_size(group)

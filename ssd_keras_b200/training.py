@@ -53,13 +53,9 @@ class SSDTrainer:
 
     def train_on_batch(self, images, y_true):
         """forward + loss + backward + (all-reduce) + SGD update.  Returns the per-image loss tensor (B,)."""
-        import torch.distributed as dist
+        from .distributed import all_reduce_gradients_
         loss, _ = self.forward_backward(images, y_true)
-        scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad)                     # one all-reduce for all 26 M gradients
-            scale = 1.0 / dist.get_world_size()
-        self.apply(scale)
+        self.apply(all_reduce_gradients_(self.grad))       # one all-reduce for all 26 M gradients, then the update
         return loss
 
     # -- introspection (tests) -------------------------------------------------------------------

@@ -1,4 +1,5 @@
-"""world_size-2 gloo tests of the N>1 host logic (batch sharding + all-gather of decoded boxes), runnable without a GPU."""
+"""world_size-2 gloo tests of the N>1 host logic (batch sharding, all-gather of decoded boxes, gradient all-reduce of the
+training step), runnable without a GPU."""
 import os
 import socket
 
@@ -47,6 +48,10 @@ def _worker(rank, world, port, n_images, q):
         t = torch.tensor([float(rank + 1)])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ok = ok and float(t.item()) == float(world)
+        # gradient exchange of the training step: one all-reduce of the flat buffer, update scaled by 1 / world
+        g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+        scale = D.all_reduce_gradients_(g)
+        ok = ok and scale == 1.0 / world and bool(torch.equal(g, torch.arange(10, dtype=torch.float32) * sum(range(1, world + 1))))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -65,3 +70,8 @@ def test_all_gather_two_ranks_gloo(n_images):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_gradient_exchange_is_identity_without_process_group():
+    g = torch.ones(4)
+    assert D.all_reduce_gradients_(g) == 1.0 and bool(torch.equal(g, torch.ones(4)))
