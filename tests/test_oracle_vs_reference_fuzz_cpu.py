@@ -104,6 +104,7 @@ def test_numpy_decoders_fuzz(ref, seed):
 @pytest.mark.parametrize('seed', range(10))
 def test_box_math_fuzz(ref, seed):
     from oracle.boxes import convert_coordinates, iou
+    from ssd_keras_b200.bounding_box_utils.bounding_box_utils import convert_coordinates as mirror_cc
     rng = np.random.default_rng(3000 + seed)
     m, n = int(rng.integers(1, 9)), int(rng.integers(1, 9))
 
@@ -114,6 +115,7 @@ def test_box_math_fuzz(ref, seed):
     for border in ('half', 'include', 'exclude'):
         for conv in ('minmax2centroids', 'centroids2minmax', 'corners2centroids', 'centroids2corners', 'minmax2corners', 'corners2minmax'):
             np.testing.assert_array_equal(convert_coordinates(b1, 0, conv, border), ref['convert_coordinates'](b1, 0, conv, border))
+            np.testing.assert_array_equal(mirror_cc(b1, 0, conv, border), ref['convert_coordinates'](b1, 0, conv, border))   # product (host side)
         for coords in ('corners', 'minmax', 'centroids'):
             c1 = b1 if coords == 'corners' else ref['convert_coordinates'](b1, 0, 'corners2' + coords)
             c2 = b2 if coords == 'corners' else ref['convert_coordinates'](b2, 0, 'corners2' + coords)
@@ -121,3 +123,19 @@ def test_box_math_fuzz(ref, seed):
             k = min(m, n)
             np.testing.assert_array_equal(iou(c1[:k], c2[:k], coords, 'element-wise', border),
                                           ref['iou'](c1[:k], c2[:k], coords, 'element-wise', border))
+
+
+@pytest.mark.parametrize('seed', range(40))
+def test_product_anchor_generation_fuzz(ref, seed):
+    """PRODUCT code: the library's host-side anchor generator (`ssdk_anchors_generate`, csrc/api.cu) behind the mirror's
+    SSDInputEncoder constructor against the real reference on the same random configurations (no GPU needed)."""
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    rng = np.random.default_rng(1000 + seed)
+    cfg = _random_encoder_cfg(rng)
+    r = ref['SSDInputEncoder'](**cfg)
+    m = SSDInputEncoder(**cfg)
+    np.testing.assert_array_equal(m.anchors, r.generate_encoding_template(1)[0][:, -8:-4])
+    tpl = m.generate_encoding_template(2)
+    np.testing.assert_array_equal(tpl, r.generate_encoding_template(2))
+    for a, b in zip(m.boxes_list, r.boxes_list):
+        np.testing.assert_array_equal(a, b)
