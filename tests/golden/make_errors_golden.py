@@ -86,6 +86,14 @@ def run(fn, args, kw):
 
 def main():
     out = {}
+    # SSDInputEncoder.__call__ on degenerate ground truth (ssd_input_encoder.py:333-336): its own exception class
+    for name, box in (('enc_call_degenerate_x', [1, 10., 10., 10., 50.]), ('enc_call_degenerate_y', [2, 10., 40., 30., 40.])):
+        try:
+            SSDInputEncoder(**ENC)([np.array([[1, 5., 5., 50., 60.]]), np.array([box])])
+            res = ['OK', '']
+        except Exception as e:                                   # DegenerateBoxError
+            res = [type(e).__name__, str(e)]
+        out[name] = dict(target='SSDInputEncoder.__call__', args=[box], kwargs=dict(ENC), result=res)
     for name, (target, args, kw) in CASES.items():
         res = run(TARGETS[target], list(args), dict(kw))
         if target in ('ssd_300', 'ssd_512', 'build_model') and res[0] == 'OK':
