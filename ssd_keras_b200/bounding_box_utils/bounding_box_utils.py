@@ -31,6 +31,20 @@ def convert_coordinates(tensor, start_index, conversion, border_pixels='half'):
     return out
 
 
+def convert_coordinates2(tensor, start_index, conversion):
+    """Reference :89-116: the matrix-product form of the centroids <-> minmax conversion (host side, like the reference)."""
+    if conversion == 'minmax2centroids':
+        M = np.array([[0.5, 0., -1., 0.], [0.5, 0., 1., 0.], [0., 0.5, 0., -1.], [0., 0.5, 0., 1.]])
+    elif conversion == 'centroids2minmax':
+        M = np.array([[1., 1., 0., 0.], [0., 0., 1., 1.], [-0.5, 0.5, 0., 0.], [0., 0., -0.5, 0.5]])
+    else:
+        raise ValueError("Unexpected conversion value. Supported values are 'minmax2centroids' and 'centroids2minmax'.")
+    out = np.array(tensor, dtype=np.float64, copy=True)
+    i = start_index
+    out[..., i:i + 4] = np.dot(out[..., i:i + 4], M)
+    return out
+
+
 def iou(boxes1, boxes2, coords='centroids', mode='outer_product', border_pixels='half'):
     import torch
     b1, b2 = np.asarray(boxes1, dtype=np.float64), np.asarray(boxes2, dtype=np.float64)

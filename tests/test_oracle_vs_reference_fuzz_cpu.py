@@ -18,10 +18,10 @@ def ref():
     np.int = int        # noqa
     sys.path.insert(0, REF)
     try:
-        from bounding_box_utils.bounding_box_utils import convert_coordinates, iou
+        from bounding_box_utils.bounding_box_utils import convert_coordinates, convert_coordinates2, iou
         from ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
         from ssd_encoder_decoder.ssd_output_decoder import decode_detections, decode_detections_fast
-        yield dict(convert_coordinates=convert_coordinates, iou=iou, SSDInputEncoder=SSDInputEncoder,
+        yield dict(convert_coordinates=convert_coordinates, convert_coordinates2=convert_coordinates2, iou=iou, SSDInputEncoder=SSDInputEncoder,
                    decode_detections=decode_detections, decode_detections_fast=decode_detections_fast)
     finally:
         sys.path.remove(REF)
@@ -112,6 +112,10 @@ def test_box_math_fuzz(ref, seed):
         xy = rng.uniform(0, 80, (k, 2)); wh = rng.uniform(0, 40, (k, 2))
         return np.concatenate([xy, xy + wh], axis=1)
     b1, b2 = boxes(m), boxes(n)
+    from ssd_keras_b200.bounding_box_utils.bounding_box_utils import convert_coordinates2 as mirror_cc2
+    wide = np.concatenate([rng.standard_normal((m, 2)), b1], axis=1)          # conversion in the middle of a wider row
+    for conv in ('minmax2centroids', 'centroids2minmax'):
+        np.testing.assert_array_equal(mirror_cc2(wide, 2, conv), ref['convert_coordinates2'](wide, 2, conv))
     for border in ('half', 'include', 'exclude'):
         for conv in ('minmax2centroids', 'centroids2minmax', 'corners2centroids', 'centroids2corners', 'minmax2corners', 'corners2minmax'):
             np.testing.assert_array_equal(convert_coordinates(b1, 0, conv, border), ref['convert_coordinates'](b1, 0, conv, border))
