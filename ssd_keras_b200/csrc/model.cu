@@ -228,6 +228,9 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   const int total_tiles = a.n_tiles_m * a.n_tiles_n;
   cl.grid = std::max(1, std::min(total_tiles, m->ctx->sm_count));
   cl.smem = conv_smem_bytes(a);
+  SSDK_REQUIRE((a.acc_bufs == 1 ? 1 : 2) * (a.acc_split ? 2 : 1) * a.mt * a.BN <= 512,
+               "internal: conv plan needs %d TMEM columns", (a.acc_bufs == 1 ? 1 : 2) * (a.acc_split ? 2 : 1) * a.mt * a.BN);
+  SSDK_REQUIRE(cl.smem <= 227 * 1024, "internal: conv plan needs %zu bytes of shared memory", cl.smem);
   double issued = 0;
   for (int nt = 0; nt < a.n_tiles_n; ++nt) {
     int ne = std::min(a.BN, ((g.cout - nt * a.BN) + 15) / 16 * 16);
