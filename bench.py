@@ -181,7 +181,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_img = 16
+    n_img = int(os.environ.get('SSDK_REF_SAMPLE', '16'))          # images per step of the bounded CPU sample
     ips, dt, threads, t_fwd, t_dec = time_cpu_reference(n_img, args.steps, args.warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
