@@ -51,6 +51,8 @@ int build_conv(ssdk_model* m, int li) {
   SSDK_REQUIRE(taps <= kMaxTaps, "conv kernel %dx%d is larger than the supported %d taps", d.kh, d.kw, kMaxTaps);
   SSDK_REQUIRE(head || cout % 8 == 0, "conv output channels must be a multiple of 8 (got %d)", cout);
   L.direct = !head && cin <= 4 && d.stride == 1 && cout % 16 == 0 && (size_t)taps * cin * cout * 4 <= 96 * 1024 && ia.Cs == 8;
+  // experiment knob (inference plans only): route the image-facing layer through im2col (K = 27 -> 32) + the tcgen05 GEMM instead
+  if (L.direct && !m->training && getenv("SSDK_NO_DIRECT")) L.direct = false;
   if (L.direct) {
     int rc = upload_f32(m, &L.w_f32, d.kernel, (size_t)taps * cin * cout); if (rc) return rc;
     std::vector<float> b0(cout, 0.f);
