@@ -25,6 +25,11 @@ def ref():
                    decode_detections=decode_detections, decode_detections_fast=decode_detections_fast)
     finally:
         sys.path.remove(REF)
+        for alias in ('float', 'int'):
+            if alias in vars(np):
+                delattr(np, alias)
+        for k in [m for m in sys.modules if m.startswith(('bounding_box_utils', 'ssd_encoder_decoder')) and not m.startswith('ssd_keras_b200')]:
+            sys.modules.pop(k, None)
 
 
 def _random_encoder_cfg(rng):

@@ -35,6 +35,9 @@ def ref():
         for k in [m for m in sys.modules if m.startswith(('keras_layers', 'keras_loss_function'))]:
             sys.modules.pop(k, None)
         sys.path.remove(REF); sys.path.remove(os.path.join(HERE, 'golden'))
+        for alias in ('float', 'int'):
+            if alias in vars(np):
+                delattr(np, alias)
 
 
 @pytest.mark.parametrize('seed', range(20))
