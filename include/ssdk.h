@@ -91,7 +91,8 @@ int ssdk_anchors_generate(const ssdk_anchor_cfg* cfg, double* out_f64 /* host [P
  * (bounding_box_utils/bounding_box_utils.py:283-383), match_bipartite_greedy and match_multi
  * (ssd_encoder_decoder/matching_utils.py:22-116) and generate_encoding_template (:550-611).
  * IoU and matching decisions are taken in float64 like the reference; the target tensor is
- * written as float32 (what Keras feeds the loss).
+ * written as float32 (what Keras feeds the loss).  One kernel launch per batch; an encoder object owns
+ * scratch memory and must not be used from two streams at the same time.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int img_height, img_width;
@@ -105,6 +106,13 @@ typedef struct {
   int border_d;              /* 0 'half', 1 'include', -1 'exclude' */
   int normalize_coords;
   double variances[4];
+  /* Optional predictor-layer geometry (prior index = layer offset + (y*fm_width + x)*n_boxes + box): lets the encoder
+   * group priors into compact blocks of feature-map cells, so that fewer ground-truth boxes touch a block.  n_layers = 0
+   * (or NULL arrays): consecutive groups of 256 priors only.  The arrays are read during ssdk_encoder_create. */
+  int n_layers;
+  const int* fm_height;      /* [n_layers] */
+  const int* fm_width;       /* [n_layers] */
+  const int* n_boxes;        /* [n_layers] */
 } ssdk_encode_cfg;
 
 int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, const double* anchors_host /* [P*4], in cfg->coords */,
@@ -117,6 +125,14 @@ int ssdk_encoder_destroy(ssdk_encoder* enc);
  * a batch item with a degenerate box (xmax<=xmin or ymax<=ymin), else left 0 (reference raises :333-336). */
 int ssdk_encode(ssdk_encoder* enc, const float* gt_boxes_dev, const int* gt_offsets_host, int B,
                 float* out_y_dev, int* out_match_dev, int* status_dev, void* stream);
+/* Same with float64 ground-truth rows: the reference converts whatever it is given to float64 (:330), so labels that are
+ * not representable in float32 (sub-pixel coordinates after augmentation) need this entry to stay bit-exact. */
+int ssdk_encode_f64(ssdk_encoder* enc, const double* gt_boxes_dev, const int* gt_offsets_host, int B,
+                    float* out_y_dev, int* out_match_dev, int* status_dev, void* stream);
+/* Same with the row offsets already on the device (the batch was assembled there, see ssdk_assemble_batch): nothing
+ * is read from the host; total_g = gt_offsets[B] and max_g = the largest per-image box count (or an upper bound of it). */
+int ssdk_encode_dev(ssdk_encoder* enc, const float* gt_boxes_dev, const int* gt_offsets_dev, int B, int total_g, int max_g,
+                    float* out_y_dev, int* out_match_dev, int* status_dev, void* stream);
 /* Standalone pieces, used by tests and the micro-benchmark: IoU matrix (G x P, float64, row-major). */
 int ssdk_iou_matrix(ssdk_encoder* enc, const float* gt_boxes_dev, int G, double* out_dev, void* stream);
 /* General IoU, replaces iou() (bounding_box_utils/bounding_box_utils.py:283-383): boxes1 [m*4], boxes2 [n*4] float64 in

@@ -35,7 +35,8 @@ class EncodeCfg(C.Structure):
     _fields_ = [('img_height', C.c_int), ('img_width', C.c_int), ('n_classes_total', C.c_int), ('P', C.c_int),
                 ('background_id', C.c_int), ('coords', C.c_int), ('matching_multi', C.c_int),
                 ('pos_iou_threshold', C.c_double), ('neg_iou_limit', C.c_double), ('border_d', C.c_int),
-                ('normalize_coords', C.c_int), ('variances', C.c_double * 4)]
+                ('normalize_coords', C.c_int), ('variances', C.c_double * 4),
+                ('n_layers', C.c_int), ('fm_height', c_int_p), ('fm_width', c_int_p), ('n_boxes', c_int_p)]
 
 
 class DecodeCfg(C.Structure):
@@ -95,6 +96,8 @@ def lib():
         L.ssdk_encoder_create.argtypes = [vp, C.POINTER(EncodeCfg), c_double_p, C.POINTER(vp)]
         L.ssdk_encoder_destroy.argtypes = [vp]
         L.ssdk_encode.argtypes = [vp, vp, c_int_p, C.c_int, vp, vp, vp, vp]
+        L.ssdk_encode_f64.argtypes = [vp, vp, c_int_p, C.c_int, vp, vp, vp, vp]
+        L.ssdk_encode_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
         L.ssdk_iou_matrix.argtypes = [vp, vp, C.c_int, vp, vp]
         L.ssdk_iou.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.ssdk_decode.argtypes = [vp, C.POINTER(DecodeCfg), vp, C.c_int, vp, vp, vp, vp]
@@ -127,7 +130,7 @@ def lib():
                          'ssdk_train_backward', 'ssdk_train_apply', 'ssdk_trainer_read_params'):
                 getattr(L, name).restype = C.c_int
         for name in ('ssdk_ctx_create', 'ssdk_ctx_destroy', 'ssdk_anchors_count', 'ssdk_anchors_generate',
-                     'ssdk_encoder_create', 'ssdk_encoder_destroy', 'ssdk_encode', 'ssdk_iou_matrix', 'ssdk_iou', 'ssdk_decode',
+                     'ssdk_encoder_create', 'ssdk_encoder_destroy', 'ssdk_encode', 'ssdk_encode_f64', 'ssdk_encode_dev', 'ssdk_iou_matrix', 'ssdk_iou', 'ssdk_decode',
                      'ssdk_nms', 'ssdk_ssd_loss_fwd', 'ssdk_ssd_loss_bwd'):
             getattr(L, name).restype = C.c_int
         _lib = L

@@ -1,36 +1,56 @@
-// SSDInputEncoder hot path on sm_100a: pairwise IoU (float64), greedy bipartite + multi matching,
-// neutral boxes and offset encoding.  Reference: ssd_encoder_decoder/ssd_input_encoder.py:277-418,
+// SSDInputEncoder hot path on sm_100a: pairwise IoU, greedy bipartite + multi matching, neutral boxes and offset
+// encoding in ONE launch per batch.  Reference: ssd_encoder_decoder/ssd_input_encoder.py:277-418,
 // bounding_box_utils/bounding_box_utils.py:283-383, ssd_encoder_decoder/matching_utils.py:22-116.
 //
-// Kernels (all HBM/ALU-bound integer/float64 work, no tensor cores):
-//   enc_fused_kernel   one CTA per (256-anchor tile, image), ONE pass over the IoU pairs: ground-truth boxes that
-//                      can touch the tile form an ordered candidate list; a float32 test on outward-rounded corners
-//                      rejects disjoint pairs before any float64 work; per anchor the best gt (multi-match /
-//                      neutral rule) and per (gt, tile) the best anchor are reduced; the (C+12)-float target rows
-//                      are staged in shared memory and written coalesced.
-//   enc_greedy_kernel  one CTA per image: reduces the per-tile bests to row maxima, then one warp runs the G
-//                      sequential greedy rounds of match_bipartite_greedy (zeroed-row quirk included).  When a
-//                      row loses its best anchor only that anchor's tile (256 IoUs) is re-evaluated.
-//   enc_fix_kernel     one warp per ground-truth box: rewrites the row of its bipartite anchor (last gt wins).
-// Exactness: every decision-relevant value is computed with the reference's float64 operation order using
-// non-contracting intrinsics (__dmul_rn/__dadd_rn/...); arg-max decisions compare the float64 quotients.
+// enc_tiles_kernel   grid (tile groups, images).  A tile is <= 256 anchors: either 256 consecutive priors ("linear" tile set)
+//                    or a compact block of feature-map cells ("spatial" tile set, fewer ground-truth boxes touch a tile).
+//   1. per image: ground-truth boxes -> template coordinates / corner boxes in float64 (shared memory, once per CTA).
+//   2. per tile: ordered list of the boxes whose extent can touch the tile's bounding box.
+//   3. per (anchor, candidate): a RIGOROUS float32 upper bound U of the float64 IoU (directed rounding on
+//      outward-rounded corners, MUFU reciprocal with a safety factor).  Nothing float64 happens unless U reaches
+//      min(pos_iou_threshold, neg_iou_limit) -- only then can the pair influence the anchor's row -- in which case the
+//      reference's float64 arithmetic is evaluated operation for operation (non-contracting intrinsics).
+//      The per-(ground truth, tile) maximum of U (one REDUX per warp and candidate) goes to global memory: it bounds
+//      the best IoU any anchor of that tile has with that box, which is all match_bipartite_greedy needs to find the
+//      exact row maxima later by evaluating one or two tiles per box.
+//   4. the (C+12)-float target rows are staged in shared memory and leave with cp.async.bulk (one bulk store per
+//      contiguous run of priors; plain coalesced stores when a run is not 16-byte aligned).
+//   5. the LAST CTA of an image (atomic ticket) runs match_bipartite_greedy for that image: exact float64 row maxima
+//      from the bounded tiles, the G greedy rounds (in parallel when no two boxes compete for the same anchor, which is
+//      the common case; otherwise the reference's sequential rounds incl. its zeroed-row quirk), then rewrites the
+//      <= G rows whose bipartite match overrides the multi-match row.
+// Exactness: every decision is taken on float64 values computed with the reference's operation order; float32 is only
+// used for bounds that can skip work, never for a comparison the result depends on.
 #include "common.cuh"
 #include <climits>
 #include <cmath>
+#include <vector>
 
 using namespace ssdk;
 
 namespace {
 
-constexpr int kTile = 256;      // anchors per CTA tile == threads per CTA
+constexpr int kTile = 256;      // anchor slots per tile == threads per CTA
+constexpr int kMaxRuns = 16;    // contiguous prior runs per tile
+constexpr int kRunRec = 1 + 2 * kMaxRuns;
+constexpr int kInlineB = 1024;  // batch sizes up to this pass the ground-truth offsets as a kernel argument (no H2D copy)
 
 struct EncParams {
   const double* anchors;        // [P*4] template coords (format = coords)
-  const double* tile_bbox;      // [n_tiles*4] corner bbox of each anchor tile
-  int P, n_tiles, C, bg, coords, multi, d, normalize;
+  int P, C, bg, coords, multi, d, normalize;
   double pos_thr, neg_lim, img_w, img_h;
   double var[4];
+  float thr_adj;                // pairs whose IoU bound is below this cannot change an anchor's row
 };
+
+struct TileSetDev {
+  int n_tiles;
+  const int* map;               // [n_tiles*kTile] prior index of a slot, -1: empty
+  const int* runs;              // [n_tiles*kRunRec]: n_runs, then (first prior, length) pairs; slots follow run order
+  const double* bbox;           // [n_tiles*4] corner bounding box of the tile's anchors
+};
+
+struct OffsArg { int v[kInlineB + 1]; };
 
 struct Box { double x0, y0, x1, y1, area; };
 
@@ -50,11 +70,23 @@ __device__ __forceinline__ Box corners_from_template(const double t[4], int coor
   return b;
 }
 
-// Ground-truth row (class,xmin,ymin,xmax,ymax) float32 pixels -> template coords in `coords` format
-// (ssd_input_encoder.py:330-347).  Returns false for a degenerate box (:333).
-__device__ __forceinline__ bool gt_template(const float* row, const EncParams& p, double t[4], int& cls) {
-  double xmin = (double)row[1], ymin = (double)row[2], xmax = (double)row[3], ymax = (double)row[4];
-  cls = (int)row[0];
+// Ground-truth row (class,xmin,ymin,xmax,ymax), float32 or float64 pixels.
+__device__ __forceinline__ void load_gt(const void* gt, int f64, size_t row, double r[5]) {
+  if (f64) {
+    const double* q = reinterpret_cast<const double*>(gt) + row * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r[k] = q[k];
+  } else {
+    const float* q = reinterpret_cast<const float*>(gt) + row * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) r[k] = (double)q[k];
+  }
+}
+
+// -> template coords in `coords` format (ssd_input_encoder.py:330-347).  Returns false for a degenerate box (:333).
+__device__ __forceinline__ bool gt_template(const double r[5], const EncParams& p, double t[4], int& cls) {
+  double xmin = r[1], ymin = r[2], xmax = r[3], ymax = r[4];
+  cls = (int)r[0];
   bool ok = (__dsub_rn(xmax, xmin) > 0.0) && (__dsub_rn(ymax, ymin) > 0.0);
   if (p.normalize) {
     ymin = __ddiv_rn(ymin, p.img_h); ymax = __ddiv_rn(ymax, p.img_h);
@@ -83,11 +115,18 @@ __device__ __forceinline__ double inter_area(const Box& a, const Box& b) {
 __device__ __forceinline__ double union_area(const Box& g, const Box& a, double inter) {
   return __dsub_rn(__dadd_rn(g.area, a.area), inter);
 }
+__device__ __forceinline__ double iou_value(const Box& g, const Box& a, double inter) {
+  return __ddiv_rn(inter, union_area(g, a, inter));
+}
 
-__device__ __forceinline__ Box load_anchor(const EncParams& p, int a) {
+__device__ __forceinline__ void load_anchor_t(const EncParams& p, int a, double at[4]) {
   const double2* q = reinterpret_cast<const double2*>(p.anchors + (size_t)a * 4);
   double2 u = __ldg(q), v = __ldg(q + 1);
-  double t[4] = {u.x, u.y, v.x, v.y};
+  at[0] = u.x; at[1] = u.y; at[2] = v.x; at[3] = v.y;
+}
+__device__ __forceinline__ Box load_anchor(const EncParams& p, int a) {
+  double t[4];
+  load_anchor_t(p, a, t);
   return corners_from_template(t, p.coords, p.d);
 }
 
@@ -102,8 +141,9 @@ __global__ void iou_matrix_kernel(EncParams p, const float* __restrict__ gt, int
   int a = blockIdx.x * blockDim.x + threadIdx.x;
   int g = blockIdx.y;
   if (a >= p.P || g >= G) return;
-  double t[4]; int cls;
-  gt_template(gt + (size_t)g * 5, p, t, cls);
+  double r[5], t[4]; int cls;
+  load_gt(gt, 0, (size_t)g, r);
+  gt_template(r, p, t, cls);
   Box gb = corners_from_template(t, p.coords, p.d);
   Box ab = load_anchor(p, a);
   double inter = inter_area(gb, ab);
@@ -129,23 +169,21 @@ __global__ void iou_general_kernel(const double* __restrict__ b1, int m, const d
 }
 
 // ------------------------------------------------------------------------------------------
-// shared helpers
+// target rows
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double iou_value(const Box& g, const Box& a, double inter) {
-  return __ddiv_rn(inter, union_area(g, a, inter));
-}
-
 struct RowDecision { int match_g; bool neutral; };
 
 // One target row [one-hot class | 4 offsets | 4 anchor coords | 4 variances] (ssd_input_encoder.py:363,396-410) in compact form:
 // the class vector has at most one 1 (index `one`, -1: none).
 struct RowCompact { int one; float o4[4]; };
-__device__ __forceinline__ RowCompact make_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec) {
+__device__ __forceinline__ RowCompact make_row(const EncParams& p, const void* gt, int gt_f64, int g0, const double at[4],
+                                               RowDecision dec) {
   RowCompact r;
   r.one = -1; r.o4[0] = r.o4[1] = r.o4[2] = r.o4[3] = 0.f;
   if (dec.match_g >= 0) {
-    double gtc[4]; int cls;
-    gt_template(gt_rows + (size_t)(g0 + dec.match_g) * 5, p, gtc, cls);
+    double raw[5], gtc[4]; int cls;
+    load_gt(gt, gt_f64, (size_t)(g0 + dec.match_g), raw);
+    gt_template(raw, p, gtc, cls);
     if (cls >= 0 && cls < p.C) r.one = cls;
     if (p.coords == SSDK_COORDS_CENTROIDS) {                // :396-400
       r.o4[0] = (float)__ddiv_rn(__dsub_rn(gtc[0], at[0]), __dmul_rn(at[2], p.var[0]));
@@ -171,16 +209,15 @@ __device__ __forceinline__ RowCompact make_row(const EncParams& p, const float* 
   }
   return r;
 }
-template <typename Store>
-__device__ __forceinline__ void emit_row(const EncParams& p, const float* gt_rows, int g0, const double at[4], RowDecision dec,
-                                         Store store) {
-  const RowCompact r = make_row(p, gt_rows, g0, at, dec);
-  for (int c = 0; c < p.C; ++c) store(c, c == r.one ? 1.f : 0.f);
+__device__ __forceinline__ void emit_row(const EncParams& p, const void* gt, int gt_f64, int g0, const double at[4],
+                                         RowDecision dec, float* dst) {
+  const RowCompact r = make_row(p, gt, gt_f64, g0, at, dec);
+  for (int c = 0; c < p.C; ++c) dst[c] = (c == r.one) ? 1.f : 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    store(p.C + k, r.o4[k]);
-    store(p.C + 4 + k, (float)at[k]);
-    store(p.C + 8 + k, (float)p.var[k]);
+    dst[p.C + k] = r.o4[k];
+    dst[p.C + 4 + k] = (float)at[k];
+    dst[p.C + 8 + k] = (float)p.var[k];
   }
 }
 
@@ -194,133 +231,14 @@ __device__ __forceinline__ void warp_argmax(double& val, int& idx) {
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// enc_fused_kernel
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile) enc_fused_kernel(EncParams p, const float* __restrict__ gt,
-                                                          const int* __restrict__ gt_offsets,
-                                                          double* __restrict__ tb_val, int* __restrict__ tb_idx,
-                                                          float* __restrict__ out_y, int* __restrict__ out_match,
-                                                          int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tile = blockIdx.x, b = blockIdx.y;
-  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
-  const int Gs = G > 0 ? G : 1;
-  const int W = p.C + 12;
-  // shared layout: rows[kTile*W] f32 | cand f32 bounds 4*G (float4 aligned) | cand boxes 5*G f64 | per-warp tile bests 8*G f64 |
-  //                cand idx G | per-warp tile-best idx 8*G | cand slot of gt G
-  // (staging compact rows and expanding them in the copy loop was measured slower on B200: 45 us vs 22 us for SSD300 B=32)
-  float* rows = reinterpret_cast<float*>(smem_raw);
-  size_t off = ((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15;
-  float* cf = reinterpret_cast<float*>(smem_raw + off); off += (size_t)4 * Gs * sizeof(float);
-  double* cb = reinterpret_cast<double*>(smem_raw + off); off += (size_t)5 * Gs * sizeof(double);
-  double* wv = reinterpret_cast<double*>(smem_raw + off); off += (size_t)8 * Gs * sizeof(double);
-  int* cidx = reinterpret_cast<int*>(smem_raw + off); off += (size_t)Gs * sizeof(int);
-  int* wi = reinterpret_cast<int*>(smem_raw + off); off += (size_t)8 * Gs * sizeof(int);
-  int* slot_of = reinterpret_cast<int*>(smem_raw + off); off += (size_t)Gs * sizeof(int);
-  int* s_wfirst = reinterpret_cast<int*>(smem_raw + off);   // [8*G] first anchor index attaining the per-warp best
-  __shared__ int s_ncand;
-
-  const int a0 = tile * kTile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) slot_of[g] = -1;
-  if (threadIdx.x == 0) s_ncand = 0;
-  __syncthreads();
-  // ordered candidate list (ascending gt index) built by warp 0
-  if (warp == 0) {
-    const double* bb = p.tile_bbox + (size_t)tile * 4;
-    int n = 0;
-    bool bad = false;
-    for (int base = 0; base < G; base += 32) {
-      int g = base + lane;
-      bool hit = false; Box gb{};
-      if (g < G) {
-        double t[4]; int cls;
-        bad |= !gt_template(gt + (size_t)(g0 + g) * 5, p, t, cls);
-        gb = corners_from_template(t, p.coords, p.d);
-        hit = bbox_hits(bb, gb);
-      }
-      unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        int pos = n + __popc(m & ((1u << lane) - 1));
-        cb[pos * 5 + 0] = gb.x0; cb[pos * 5 + 1] = gb.y0; cb[pos * 5 + 2] = gb.x1; cb[pos * 5 + 3] = gb.y1; cb[pos * 5 + 4] = gb.area;
-        // outward-rounded float32 corners: disjoint here => disjoint in float64
-        cf[pos * 4 + 0] = __double2float_rd(gb.x0); cf[pos * 4 + 1] = __double2float_rd(gb.y0);
-        cf[pos * 4 + 2] = __double2float_ru(gb.x1); cf[pos * 4 + 3] = __double2float_ru(gb.y1);
-        cidx[pos] = g; slot_of[g] = pos;
-      }
-      n += __popc(m);
-    }
-    if (lane == 0) s_ncand = n;
-    if (tile == 0 && status && __any_sync(0xffffffffu, bad) && lane == 0) atomicMax(status, b + 1);
-  }
-  __syncthreads();
-  const int ncand = s_ncand;
-  const int a = a0 + threadIdx.x;
-  const bool live = a < p.P;
-  double at[4] = {0, 0, 0, 0};
-  Box ab{};
-  float fx0 = 0, fy0 = 0, fx1 = 0, fy1 = 0;
-  if (live) {
-    const double2* q = reinterpret_cast<const double2*>(p.anchors + (size_t)a * 4);
-    double2 u = __ldg(q), v = __ldg(q + 1);
-    at[0] = u.x; at[1] = u.y; at[2] = v.x; at[3] = v.y;
-    ab = corners_from_template(at, p.coords, p.d);
-    fx0 = __double2float_rd(ab.x0); fy0 = __double2float_rd(ab.y0); fx1 = __double2float_ru(ab.x1); fy1 = __double2float_ru(ab.y1);
-  }
-  double best = 0.0; int best_g = -1;
-  for (int c = 0; c < ncand; ++c) {
-    double val = 0.0;
-    const float4 gf = *reinterpret_cast<const float4*>(cf + c * 4);
-    const bool maybe = live && (fminf(fx1, gf.z) > fmaxf(fx0, gf.x)) && (fminf(fy1, gf.w) > fmaxf(fy0, gf.y));
-    if (maybe) {
-      Box gb; gb.x0 = cb[c * 5]; gb.y0 = cb[c * 5 + 1]; gb.x1 = cb[c * 5 + 2]; gb.y1 = cb[c * 5 + 3]; gb.area = cb[c * 5 + 4];
-      double inter = inter_area(gb, ab);
-      if (inter > 0.0) val = iou_value(gb, ab, inter);
-    }
-    if (val > best) { best = val; best_g = cidx[c]; }          // strict '>' keeps the first gt on ties (np.argmax)
-    // best anchor of this gt inside the warp's 32 anchors (first index on ties)
-    if (__any_sync(0xffffffffu, val > 0.0)) {
-      double rv = val; int ri = (val > 0.0) ? a : INT_MAX;
-      warp_argmax(rv, ri);
-      if (lane == 0) { wv[warp * Gs + c] = rv; s_wfirst[warp * Gs + c] = ri; }
-    } else if (lane == 0) { wv[warp * Gs + c] = 0.0; s_wfirst[warp * Gs + c] = INT_MAX; }
-  }
-  if (live) {
-    RowDecision dec{-1, false};
-    double val = best;
-    if (G > 0) {
-      const int arg = best_g >= 0 ? best_g : 0;                // np.argmax of an all-zero column is 0
-      if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
-      if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
-    }
-    float* my = rows + (size_t)threadIdx.x * W;
-    emit_row(p, gt, g0, at, dec, [&](int k, float v) { my[k] = v; });
-    if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
-  }
-  __syncthreads();
-  // per (gt, tile) best anchor -> global
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double v = 0.0; int i = INT_MAX;
-    const int c = slot_of[g];
-    if (c >= 0) {
-      for (int w = 0; w < 8; ++w) {                             // warps are in ascending anchor order: strict '>' keeps the first
-        double ov = wv[w * Gs + c];
-        if (ov > v) { v = ov; i = s_wfirst[w * Gs + c]; }
-      }
-    }
-    tb_val[(size_t)(g0 + g) * p.n_tiles + tile] = v;
-    tb_idx[(size_t)(g0 + g) * p.n_tiles + tile] = (v > 0.0) ? i : INT_MAX;
-  }
-  // coalesced copy of the staged rows
-  const int n_rows = min(kTile, p.P - a0);
-  const size_t n_f = (size_t)n_rows * W;
-  float* dst = out_y + ((size_t)b * p.P + a0) * W;
-  for (size_t i = threadIdx.x; i < n_f; i += blockDim.x) dst[i] = rows[i];
+__device__ __forceinline__ float rcp_approx(float x) {          // MUFU.RCP: at most 1 ulp off
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------
-// enc_greedy_kernel: match_bipartite_greedy (matching_utils.py:63-77) for one image
+// match_bipartite_greedy (matching_utils.py:63-77) pieces, run by the last CTA of an image
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
   bool r = false;
@@ -328,178 +246,407 @@ __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
   return r;
 }
 
-// Row `g` keeps a COMPACT list of its non-zero per-tile bests (value, anchor index); the tile of an entry is idx / kTile.
-// Re-evaluate tile `t` for ground-truth `gb` ignoring removed anchors (one warp) and update the row's entry for that tile.
-__device__ void warp_fix_tile(const EncParams& p, const Box& gb, int t, const int* removed, int n_removed, double* tv, int* ti, int nnz) {
+// One warp: the exact best anchor (largest float64 IoU > 0, lowest prior index on ties) of ground-truth box `gb` among
+// the priors not in `removed`.  `urow[t]` bounds the IoU of every anchor of tile t from above, so tiles are visited in
+// descending-bound order and the scan stops as soon as the next bound is below the best exact value found.
+__device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const float* urow, const int* removed,
+                              int n_removed, double& out_v, int& out_i) {
   const int lane = threadIdx.x & 31;
-  double bv = 0.0; int bi = INT_MAX;
-  for (int k = 0; k < kTile / 32; ++k) {
-    const int a = t * kTile + k * 32 + lane;
-    if (a < p.P) {
-      Box ab = load_anchor(p, a);
-      double inter = inter_area(gb, ab);
-      if (inter > 0.0) {
-        double v = iou_value(gb, ab, inter);
-        if (v > bv && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
-      }
+  double best = 0.0; int bidx = INT_MAX;
+  float cur_u = 0.f; int cur_t = -1; bool first = true;
+  for (;;) {
+    float nu = 0.f; int nt = INT_MAX;                    // next tile after the cursor in (bound desc, tile asc) order
+    for (int t = lane; t < ts.n_tiles; t += 32) {
+      const float u = __ldcg(urow + t);
+      const bool after = first || (u < cur_u) || (u == cur_u && t > cur_t);
+      if (after && u > 0.f && (u > nu || (u == nu && t < nt))) { nu = u; nt = t; }
     }
-  }
-  warp_argmax(bv, bi);
-  for (int e = lane; e < nnz; e += 32) {
-    if (__ldcg(ti + e) / kTile == t) {                       // exactly one entry per tile
-      tv[e] = bv;
-      if (bv > 0.0) ti[e] = bi;                              // keep the old index (tile id) when the tile is exhausted
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ou = __shfl_xor_sync(0xffffffffu, nu, o);
+      const int ot = __shfl_xor_sync(0xffffffffu, nt, o);
+      if (ou > nu || (ou == nu && ot < nt)) { nu = ou; nt = ot; }
     }
-  }
-  __syncwarp();
-}
-
-__device__ void warp_row_reduce(const double* tv, const int* ti, int nnz, double& val, int& idx) {
-  const int lane = threadIdx.x & 31;
-  double bv = 0.0; int bi = INT_MAX;
-  for (int e = lane; e < nnz; e += 32) {
-    double v = __ldcg(tv + e); int i = __ldcg(ti + e);
-    if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
-  }
-  warp_argmax(bv, bi);
-  val = bv; idx = bi;
-}
-
-__global__ void __launch_bounds__(256) enc_greedy_kernel(EncParams p, const float* __restrict__ gt,
-                                                         const int* __restrict__ gt_offsets, double* tb_val, int* tb_idx,
-                                                         int* __restrict__ matches) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int b = blockIdx.x;
-  const int g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0;
-  if (G <= 0) return;
-  double* rv = reinterpret_cast<double*>(smem_raw);          // [G] current row maximum
-  double* gbox = rv + G;                                      // [5*G] corner boxes of the ground truth
-  int* ra = reinterpret_cast<int*>(gbox + 5 * (size_t)G);     // [G] its (first) anchor index
-  int* removed = ra + G;                                      // [G] anchors taken so far
-  int* nnz = removed + G;                                     // [G] entries in the row's compact tile list
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // phase A (one warp per row): compact the non-zero per-tile bests in place, row maximum, cached gt box
-  for (int g = warp; g < G; g += (blockDim.x >> 5)) {
-    double* tv = tb_val + (size_t)(g0 + g) * p.n_tiles;
-    int* ti = tb_idx + (size_t)(g0 + g) * p.n_tiles;
-    int k = 0;
+    if (nt == INT_MAX) break;
+    if ((double)nu < best) break;                        // no anchor of the remaining tiles can reach (or tie) the best
     double bv = 0.0; int bi = INT_MAX;
-    for (int base = 0; base < p.n_tiles; base += 32) {
-      const int t = base + lane;
-      double v = 0.0; int i = INT_MAX;
-      if (t < p.n_tiles) { v = __ldcg(tv + t); i = __ldcg(ti + t); }
-      const bool nz = v > 0.0;
-      const unsigned m = __ballot_sync(0xffffffffu, nz);
-      __syncwarp();
-      if (nz) {
-        const int pos = k + __popc(m & ((1u << lane) - 1));
-        tv[pos] = v; ti[pos] = i;
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    for (int s = lane; s < kTile; s += 32) {
+      const int a = __ldg(ts.map + (size_t)nt * kTile + s);
+      if (a < 0) continue;
+      const Box ab = load_anchor(p, a);
+      const double inter = inter_area(gb, ab);
+      if (inter > 0.0) {
+        const double v = iou_value(gb, ab, inter);
+        if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
       }
-      k += __popc(m);
-      __syncwarp();
     }
     warp_argmax(bv, bi);
-    double t4[4]; int cls;
-    gt_template(gt + (size_t)(g0 + g) * 5, p, t4, cls);
-    Box gb = corners_from_template(t4, p.coords, p.d);
-    if (lane == 0) {
-      rv[g] = bv; ra[g] = (bv > 0.0) ? bi : 0; nnz[g] = k; matches[g0 + g] = 0;    // argmax of an all-zero row is 0
-      gbox[g * 5] = gb.x0; gbox[g * 5 + 1] = gb.y0; gbox[g * 5 + 2] = gb.x1; gbox[g * 5 + 3] = gb.y1; gbox[g * 5 + 4] = gb.area;
-    }
+    if (bv > best || (bv == best && bv > 0.0 && bi < bidx)) { best = bv; bidx = bi; }
+    cur_u = nu; cur_t = nt; first = false;
   }
-  __threadfence_block();
-  __syncthreads();
-  if (warp != 0) return;
-  // phase B: the G sequential rounds, one warp
-  int n_removed = 0;
-  for (int round = 0; round < G; ++round) {
-    double v = -1.0; int gi = INT_MAX;
-    for (int g = lane; g < G; g += 32)
-      if (rv[g] > v) { v = rv[g]; gi = g; }                   // ascending g per lane: first index kept
-    warp_argmax(v, gi);
-    const int a_star = ra[gi];
-    __syncwarp();
-    if (lane == 0) { matches[g0 + gi] = a_star; rv[gi] = 0.0; ra[gi] = 0; removed[n_removed] = a_star; }
-    ++n_removed;
-    __syncwarp();
-    if (!(v > 0.0)) continue;                                  // nothing left to match: no row can point at a_star
-    // rows that pointed at the taken anchor: fix that tile, re-reduce, repeat while the new best is itself stale
-    for (int base = 0; base < G; base += 32) {
-      const int g = base + lane;
-      unsigned need = __ballot_sync(0xffffffffu, g < G && rv[g] > 0.0 && ra[g] == a_star);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const int gg = base + src;
-        Box gb; gb.x0 = gbox[gg * 5]; gb.y0 = gbox[gg * 5 + 1]; gb.x1 = gbox[gg * 5 + 2]; gb.y1 = gbox[gg * 5 + 3]; gb.area = gbox[gg * 5 + 4];
-        double* tv = tb_val + (size_t)(g0 + gg) * p.n_tiles;
-        int* ti = tb_idx + (size_t)(g0 + gg) * p.n_tiles;
-        const int nz = nnz[gg];
-        int stale = a_star;
-        double nv; int ni;
-        while (true) {
-          warp_fix_tile(p, gb, stale / kTile, removed, n_removed, tv, ti, nz);
-          __threadfence_block();
-          warp_row_reduce(tv, ti, nz, nv, ni);
-          if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
-          stale = ni;                                          // a tile entry recorded before that anchor was taken
-        }
-        if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
-        __syncwarp();
-      }
-    }
-    __syncwarp();
-  }
+  out_v = best; out_i = bidx;
 }
 
-// ------------------------------------------------------------------------------------------
-// enc_fix_kernel: y_encoded[i, bipartite_matches, :-8] = labels_one_hot (:363), last writer wins
-// ------------------------------------------------------------------------------------------
-__global__ void enc_fix_kernel(EncParams p, const float* __restrict__ gt, const int* __restrict__ gt_offsets, int B,
-                               int total_g, const int* __restrict__ matches, float* __restrict__ out_y,
-                               int* __restrict__ out_match) {
-  const int gg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (gg >= total_g) return;
-  int lo = 0, hi = B;                                         // image of this gt row
-  while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gt_offsets[mid] <= gg) lo = mid; else hi = mid; }
-  const int b = lo, g0 = gt_offsets[b], G = gt_offsets[b + 1] - g0, g = gg - g0;
-  const int a = matches[gg];
-  bool last = true;
-  for (int g2 = g + 1 + lane; g2 < G; g2 += 32) last &= (matches[g0 + g2] != a);
-  last = __all_sync(0xffffffffu, last);
-  if (!last) return;
-  const double2* q = reinterpret_cast<const double2*>(p.anchors + (size_t)a * 4);
-  double2 u = __ldg(q), v = __ldg(q + 1);
-  const double at[4] = {u.x, u.y, v.x, v.y};
-  RowDecision dec{g, 0.0 >= p.neg_lim};                       // the matched column is all zero
-  float* dst = out_y + ((size_t)b * p.P + a) * (p.C + 12);
-  if (lane == 0) {
-    emit_row(p, gt, g0, at, dec, [&](int k, float v2) { dst[k] = v2; });
+__device__ void finish_image(const EncParams& p, const TileSetDev& ts, const void* gt, int gt_f64, int g0, int G, int b,
+                             const double* s_gbox, unsigned char* scratch, const float* ub, float* __restrict__ out_y,
+                             int* __restrict__ out_match) {
+  __shared__ int s_flag[2];
+  double* rv = reinterpret_cast<double*>(scratch);           // [G] current row maximum
+  int* ra = reinterpret_cast<int*>(rv + G);                   // [G] its (first) prior index
+  int* removed = ra + G;                                      // [G] priors taken so far
+  int* matches = removed + G;                                 // [G]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = p.C + 12;
+  auto gbox = [&](int g) {
+    Box q; q.x0 = s_gbox[g * 5]; q.y0 = s_gbox[g * 5 + 1]; q.x1 = s_gbox[g * 5 + 2]; q.y1 = s_gbox[g * 5 + 3]; q.area = s_gbox[g * 5 + 4];
+    return q;
+  };
+  // exact row maxima, one warp per ground-truth box
+  for (int g = warp; g < G; g += kTile / 32) {
+    double v; int i;
+    warp_row_best(p, ts, gbox(g), ub + (size_t)(g0 + g) * ts.n_tiles, nullptr, 0, v, i);
+    if (lane == 0) { rv[g] = v; ra[g] = (v > 0.0) ? i : 0; }   // argmax of an all-zero row is 0
+  }
+  if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
+  __syncthreads();
+  for (int g = tid; g < G; g += kTile) {
+    if (!(rv[g] > 0.0)) { s_flag[1] = 1; continue; }           // an all-zero row: the zero rounds come last and hit matches[0]
+    const int a = ra[g];
+    for (int g2 = 0; g2 < g; ++g2)
+      if (rv[g2] > 0.0 && ra[g2] == a) { s_flag[0] = 1; break; }
+  }
+  __syncthreads();
+  if (!s_flag[0]) {
+    // no two boxes want the same prior: the G rounds commute, every positive row keeps its arg-max; rounds in which
+    // all remaining rows are zero select (gt 0, prior 0) (np.argmax of zeros), and rows never selected keep the initial 0
+    for (int g = tid; g < G; g += kTile) matches[g] = ra[g];
+    __syncthreads();
+    if (tid == 0 && s_flag[1]) matches[0] = 0;
+  } else if (warp == 0) {
+    // the reference's G sequential rounds (one warp)
+    for (int g = lane; g < G; g += 32) matches[g] = 0;
+    __syncwarp();
+    int n_removed = 0;
+    for (int round = 0; round < G; ++round) {
+      double v = -1.0; int gi = INT_MAX;
+      for (int g = lane; g < G; g += 32)
+        if (rv[g] > v) { v = rv[g]; gi = g; }                   // ascending g per lane: first index kept
+      warp_argmax(v, gi);
+      const int a_star = ra[gi];
+      __syncwarp();
+      if (lane == 0) { matches[gi] = a_star; rv[gi] = 0.0; ra[gi] = 0; removed[n_removed] = a_star; }
+      ++n_removed;
+      __syncwarp();
+      if (!(v > 0.0)) continue;                                  // nothing left to match: no row can point at a_star
+      for (int base = 0; base < G; base += 32) {
+        const int g = base + lane;
+        unsigned need = __ballot_sync(0xffffffffu, g < G && rv[g] > 0.0 && ra[g] == a_star);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int gg = base + src;
+          double nv; int ni;
+          warp_row_best(p, ts, gbox(gg), ub + (size_t)(g0 + gg) * ts.n_tiles, removed, n_removed, nv, ni);
+          if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // y_encoded[i, bipartite_matches, :-8] = labels_one_hot (:363): last writer wins; the matched column is all zero afterwards
+  for (int g = tid; g < G; g += kTile) {
+    const int a = matches[g];
+    bool last = true;
+    for (int g2 = g + 1; g2 < G; ++g2) last &= (matches[g2] != a);
+    if (!last) continue;
+    double at[4];
+    load_anchor_t(p, a, at);
+    RowDecision dec{g, 0.0 >= p.neg_lim};
+    emit_row(p, gt, gt_f64, g0, at, dec, out_y + ((size_t)b * p.P + a) * W);
     if (out_match) out_match[(size_t)b * p.P + a] = g;
   }
 }
 
-__global__ void anchor_tile_bbox_kernel(EncParams p, double* __restrict__ bbox) {
-  __shared__ double s[4][8];
-  int tile = blockIdx.x;
-  int a = tile * kTile + threadIdx.x;
+// ------------------------------------------------------------------------------------------
+// enc_tiles_kernel
+// ------------------------------------------------------------------------------------------
+struct EncSmem {            // byte offsets inside the dynamic shared memory
+  size_t rows, gbox, cf, ca, wmax, slot, total;
+};
+__host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
+  EncSmem s;
+  const size_t gs = (size_t)(G > 0 ? G : 1);
+  size_t rows_bytes = ((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15;
+  const size_t fin = (gs * 20 + 15) & ~(size_t)15;            // finish_image scratch lives in the row staging area
+  if (fin > rows_bytes) rows_bytes = fin;
+  auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  s.rows = 0;
+  s.gbox = rows_bytes;                                        // [G*5] f64
+  s.cf = up16(s.gbox + gs * 40);                              // [G] float4: outward-rounded corners of a candidate
+  s.ca = up16(s.cf + gs * 16);                                // [G] float2: (area rounded down, gt index)
+  s.wmax = up16(s.ca + gs * 8);                               // [8*G] u32: per-warp maximum of the IoU bound
+  s.slot = up16(s.wmax + gs * 32);                            // [G] candidate slot of a gt (-1: not a candidate)
+  s.total = up16(s.slot + gs * 4) + 16;
+  return s;
+}
+
+template <bool INLINE_OFFS>
+__global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant__ EncParams p, const __grid_constant__ TileSetDev ts,
+                                                          const __grid_constant__ OffsArg offs_arg, const int* __restrict__ offs_dev,
+                                                          const void* __restrict__ gt, int gt_f64, int tpc, float* __restrict__ ub,
+                                                          int* __restrict__ counters, float* __restrict__ out_y,
+                                                          int* __restrict__ out_match, int* __restrict__ status) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_wcnt[kTile / 32];
+  __shared__ int s_last;
+  const int b = blockIdx.y;
+  const int g0 = INLINE_OFFS ? offs_arg.v[b] : offs_dev[b];
+  const int G = (INLINE_OFFS ? offs_arg.v[b + 1] : offs_dev[b + 1]) - g0;
+  const int Gs = G > 0 ? G : 1;
+  const int W = p.C + 12;
+  const EncSmem L = enc_smem_layout(W, G);
+  float* rows = reinterpret_cast<float*>(smem_raw + L.rows);
+  double* s_gbox = reinterpret_cast<double*>(smem_raw + L.gbox);
+  float4* s_cf = reinterpret_cast<float4*>(smem_raw + L.cf);
+  float2* s_ca = reinterpret_cast<float2*>(smem_raw + L.ca);
+  unsigned* s_wmax = reinterpret_cast<unsigned*>(smem_raw + L.wmax);
+  int* slot_of = reinterpret_cast<int*>(smem_raw + L.slot);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- 1. ground truth of this image -> float64 corner boxes ----
+  bool bad = false;
+  for (int g = tid; g < G; g += kTile) {
+    double r[5], t[4]; int cls;
+    load_gt(gt, gt_f64, (size_t)(g0 + g), r);
+    bad |= !gt_template(r, p, t, cls);
+    const Box gb = corners_from_template(t, p.coords, p.d);
+    s_gbox[g * 5] = gb.x0; s_gbox[g * 5 + 1] = gb.y0; s_gbox[g * 5 + 2] = gb.x1; s_gbox[g * 5 + 3] = gb.y1; s_gbox[g * 5 + 4] = gb.area;
+  }
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);          // also publishes s_gbox
+  if (blockIdx.x == 0 && tid == 0 && any_bad && status) atomicMax(status, b + 1);
+
+  const int tile0 = blockIdx.x * tpc;
+  const int tile1 = min(ts.n_tiles, tile0 + tpc);
+  bool store_pending = false;
+  for (int tile = tile0; tile < tile1; ++tile) {
+    // ---- 2. ordered candidate list (ascending gt index) ----
+    const double bb[4] = {ts.bbox[tile * 4], ts.bbox[tile * 4 + 1], ts.bbox[tile * 4 + 2], ts.bbox[tile * 4 + 3]};
+    int ncand = 0;
+    for (int gbase = 0; gbase < G; gbase += kTile) {
+      const int g = gbase + tid;
+      bool hit = false; Box gb{};
+      if (g < G) {
+        gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
+        hit = bbox_hits(bb, gb);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_wcnt[warp] = __popc(m);
+      __syncthreads();
+      int wbase = ncand, total = 0;
+#pragma unroll
+      for (int w = 0; w < kTile / 32; ++w) { const int c = s_wcnt[w]; if (w < warp) wbase += c; total += c; }
+      if (hit) {
+        const int pos = wbase + __popc(m & ((1u << lane) - 1));
+        // outward-rounded float32 corners, area rounded down: ingredients of an IoU bound that can only err upwards
+        s_cf[pos] = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
+        s_ca[pos] = make_float2(__double2float_rd(gb.area), __int_as_float(g));
+        slot_of[g] = pos;
+      } else if (g < G) {
+        slot_of[g] = -1;
+      }
+      ncand += total;
+      __syncthreads();
+    }
+    // ---- 3. this thread's anchor ----
+    const int a = __ldg(ts.map + (size_t)tile * kTile + tid);
+    const bool live = a >= 0;
+    float fx0 = 0.f, fy0 = 0.f, fx1 = -INFINITY, fy1 = -INFINITY, fa = 0.f;
+    if (live) {
+      const Box ab = load_anchor(p, a);
+      fx0 = __double2float_rd(ab.x0); fy0 = __double2float_rd(ab.y0);
+      fx1 = __double2float_ru(ab.x1); fy1 = __double2float_ru(ab.y1);
+      fa = __double2float_rd(ab.area);
+    }
+    double best = 0.0; int best_g = -1;
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 gf = s_cf[c];
+      const float2 ga = s_ca[c];
+      // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
+      const float iw = fmaxf(__fsub_ru(fminf(fx1, gf.z), fmaxf(fx0, gf.x)), 0.f);
+      const float ih = fmaxf(__fsub_ru(fminf(fy1, gf.w), fmaxf(fy0, gf.y)), 0.f);
+      const float inter = __fmul_ru(iw, ih);
+      const float un = fmaxf(__fsub_rd(__fadd_rd(fa, ga.x), inter), 1e-30f);
+      const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst; see thr_adj and the 1+2^-21 factor
+      const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
+      if (lane == 0) s_wmax[warp * Gs + c] = wm;
+      if (live && U >= p.thr_adj) {                           // rare: the pair may matter for this anchor's row -> exact float64 IoU
+        const int g = __float_as_int(ga.y);
+        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
+        const Box ab = load_anchor(p, a);
+        const double inter64 = inter_area(gb, ab);
+        if (inter64 > 0.0) {
+          const double val = iou_value(gb, ab, inter64);
+          if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
+        }
+      }
+    }
+    // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
+    if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    // ---- per (gt, tile) bound -> global ----
+    for (int g = tid; g < G; g += kTile) {
+      const int c = slot_of[g];
+      float u = 0.f;
+      if (c >= 0) {
+        unsigned m = 0;
+#pragma unroll
+        for (int w = 0; w < kTile / 32; ++w) m = max(m, s_wmax[w * Gs + c]);
+        u = __fmul_ru(__uint_as_float(m), 1.0f + 4.76837158203125e-7f);     // (1 + 2^-21) covers the reciprocal's 1 ulp
+      }
+      ub[(size_t)(g0 + g) * ts.n_tiles + tile] = u;
+    }
+    // ---- 4. this anchor's row ----
+    if (live) {
+      RowDecision dec{-1, false};
+      double val = best;
+      if (G > 0) {
+        const int arg = best_g >= 0 ? best_g : 0;                // np.argmax of an all-zero column is 0
+        if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
+        if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
+      }
+      double at[4];
+      load_anchor_t(p, a, at);
+      emit_row(p, gt, gt_f64, g0, at, dec, rows + (size_t)tid * W);
+      if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the rows -> visible to the bulk copy engine
+    __syncthreads();
+    // ---- 5. rows leave: one bulk store per contiguous run of priors ----
+    const int* rn = ts.runs + (size_t)tile * kRunRec;
+    const int nruns = rn[0];
+    int slot0 = 0;
+    bool issued = false;
+    for (int r = 0; r < nruns; ++r) {
+      const int start = rn[1 + 2 * r], len = rn[2 + 2 * r];
+      float* dst = out_y + ((size_t)b * p.P + start) * W;
+      const float* src = rows + (size_t)slot0 * W;
+      const size_t n_f = (size_t)len * W;
+      const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (((n_f * 4) & 15) == 0) && ((((size_t)slot0 * W * 4) & 15) == 0);
+      if (aligned) {
+        if (tid == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"((uint32_t)(n_f * 4)) : "memory");
+        }
+        issued = true;
+      } else {
+        for (size_t i = tid; i < n_f; i += kTile) dst[i] = src[i];
+      }
+      slot0 += len;
+    }
+    if (issued && tid == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    store_pending = issued;
+  }
+  // ---- 6. last CTA of the image: bipartite matching ----
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (G <= 0) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int old = atomicAdd(counters + b, 1);
+    const int last = (old == (int)gridDim.x - 1);
+    if (last) counters[b] = 0;                                  // ready for the next launch
+    __threadfence();
+    s_last = last;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  finish_image(p, ts, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, ub, out_y, out_match);
+}
+
+__global__ void tile_bbox_kernel(EncParams p, const int* __restrict__ map, double* __restrict__ bbox) {
+  __shared__ double s[4][kTile / 32];
+  const int tile = blockIdx.x;
+  const int a = map[(size_t)tile * kTile + threadIdx.x];
   double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-  if (a < p.P) { Box ab = load_anchor(p, a); x0 = ab.x0; y0 = ab.y0; x1 = ab.x1; y1 = ab.y1; }
+  if (a >= 0) { Box ab = load_anchor(p, a); x0 = ab.x0; y0 = ab.y0; x1 = ab.x1; y1 = ab.y1; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o));
     x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
   }
-  int w = threadIdx.x >> 5;
+  const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) { s[0][w] = x0; s[1][w] = y0; s[2][w] = x1; s[3][w] = y1; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) { x0 = fmin(x0, s[0][i]); y0 = fmin(y0, s[1][i]); x1 = fmax(x1, s[2][i]); y1 = fmax(y1, s[3][i]); }
+    for (int i = 1; i < kTile / 32; ++i) { x0 = fmin(x0, s[0][i]); y0 = fmin(y0, s[1][i]); x1 = fmax(x1, s[2][i]); y1 = fmax(y1, s[3][i]); }
     bbox[tile * 4 + 0] = x0; bbox[tile * 4 + 1] = y0; bbox[tile * 4 + 2] = x1; bbox[tile * 4 + 3] = y1;
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// host side: tile sets
+// ------------------------------------------------------------------------------------------
+struct TileSetHost {
+  std::vector<int> map, runs;
+  int n_tiles = 0;
+  void begin_tile() { runs.resize((size_t)(n_tiles + 1) * kRunRec, 0); map.resize((size_t)(n_tiles + 1) * kTile, -1); fill = 0; }
+  void add_run(int start, int len) {
+    int* r = runs.data() + (size_t)n_tiles * kRunRec;
+    r[1 + 2 * r[0]] = start; r[2 + 2 * r[0]] = len; ++r[0];
+    for (int i = 0; i < len; ++i) map[(size_t)n_tiles * kTile + fill + i] = start + i;
+    fill += len;
+  }
+  void end_tile() { ++n_tiles; }
+  int fill = 0;
+};
+
+void linear_tiles(TileSetHost& t, int first, int count) {
+  for (int o = 0; o < count; o += kTile) {
+    t.begin_tile();
+    t.add_run(first + o, std::min(kTile, count - o));
+    t.end_tile();
+  }
+}
+
+// Compact blocks of feature-map cells per predictor layer (prior index = off + (y*W + x)*nb + box).
+void spatial_tiles(TileSetHost& t, int n_layers, const int* fh, const int* fw, const int* nbx) {
+  int off = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const int H = fh[l], Wd = fw[l], nb = nbx[l];
+    const int count = H * Wd * nb;
+    if (nb > kTile || nb <= 0) { linear_tiles(t, off, count); off += count; continue; }
+    const int cells_max = kTile / nb;
+    int bw = (int)std::floor(std::sqrt((double)cells_max));
+    if (bw < 1) bw = 1;
+    if (bw >= Wd) {                                            // whole rows fit: a tile is bh full rows = one contiguous run
+      const int bh = std::max(1, std::min(H, cells_max / Wd));
+      for (int y0 = 0; y0 < H; y0 += bh) {
+        t.begin_tile();
+        t.add_run(off + y0 * Wd * nb, std::min(bh, H - y0) * Wd * nb);
+        t.end_tile();
+      }
+    } else {
+      const int bh = std::max(1, std::min(std::min(H, cells_max / bw), kMaxRuns));
+      for (int y0 = 0; y0 < H; y0 += bh)
+        for (int x0 = 0; x0 < Wd; x0 += bw) {
+          t.begin_tile();
+          for (int y = y0; y < std::min(H, y0 + bh); ++y) t.add_run(off + (y * Wd + x0) * nb, std::min(bw, Wd - x0) * nb);
+          t.end_tile();
+        }
+    }
+    off += count;
+  }
+}
+
+struct TileSetOwned {
+  TileSetDev dev{};
+  int* d_map = nullptr; int* d_runs = nullptr; double* d_bbox = nullptr;
+  void release() { cudaFree(d_map); cudaFree(d_runs); cudaFree(d_bbox); d_map = d_runs = nullptr; d_bbox = nullptr; dev = TileSetDev{}; }
+};
 
 }  // namespace
 
@@ -508,15 +655,48 @@ struct ssdk_encoder {
   ssdk_encode_cfg cfg{};
   EncParams p{};
   double* d_anchors = nullptr;
-  double* d_bbox = nullptr;
-  Scratch rows;        // per-(gt, tile) bests + matches + offsets
-  // pinned staging ring for the gt offsets: a slot is reused only after the copy issued from it has completed (no stream sync)
+  TileSetOwned linear, spatial;     // spatial.dev.n_tiles == 0: no layer geometry was given
+  Scratch ub;                       // per-(gt, tile) IoU bounds
+  Scratch counters;                 // per-image tickets (self-resetting)
+  size_t counters_n = 0;
+  Scratch offsets;                  // device copy of the offsets for batches larger than kInlineB
+  // pinned staging ring for those offsets: a slot is reused only after the copy issued from it has completed (no stream sync)
   static constexpr int kSlots = 8;
   int* h_offsets = nullptr;   // kSlots * h_offsets_cap ints
   int h_offsets_cap = 0;
   cudaEvent_t slot_done[kSlots] = {};
   int next_slot = 0;
+  size_t smem_attr[2] = {0, 0};
+  OffsArg offs_arg{};               // ground-truth offsets passed by value with the launch (B <= kInlineB)
 };
+
+namespace {
+
+int upload_tiles(ssdk_encoder* e, const TileSetHost& h, TileSetOwned& o) {
+  SSDK_CHECK_CUDA(cudaMalloc(&o.d_map, h.map.size() * sizeof(int)));
+  SSDK_CHECK_CUDA(cudaMalloc(&o.d_runs, h.runs.size() * sizeof(int)));
+  SSDK_CHECK_CUDA(cudaMalloc(&o.d_bbox, (size_t)h.n_tiles * 4 * sizeof(double)));
+  SSDK_CHECK_CUDA(cudaMemcpy(o.d_map, h.map.data(), h.map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  SSDK_CHECK_CUDA(cudaMemcpy(o.d_runs, h.runs.data(), h.runs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  tile_bbox_kernel<<<h.n_tiles, kTile>>>(e->p, o.d_map, o.d_bbox);
+  SSDK_COUNT_LAUNCH(e->ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  o.dev.n_tiles = h.n_tiles; o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.bbox = o.d_bbox;
+  return SSDK_OK;
+}
+
+bool tiles_cover(const TileSetHost& h, int P) {
+  std::vector<char> seen((size_t)P, 0);
+  for (int a : h.map) {
+    if (a < 0) continue;
+    if (a >= P || seen[a]) return false;
+    seen[a] = 1;
+  }
+  for (char c : seen) if (!c) return false;
+  return true;
+}
+
+}  // namespace
 
 extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, const double* anchors_host, ssdk_encoder** out) {
   SSDK_REQUIRE(ctx && cfg && anchors_host && out, "ssdk_encoder_create: NULL argument");
@@ -527,28 +707,56 @@ extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, co
   SSDK_CHECK_CUDA(cudaSetDevice(ctx->device));
   ssdk_encoder* e = new ssdk_encoder();
   e->ctx = ctx; e->cfg = *cfg;
+  e->cfg.fm_height = e->cfg.fm_width = e->cfg.n_boxes = nullptr;     // the caller's arrays are only read here
   EncParams& p = e->p;
-  p.P = cfg->P; p.n_tiles = ceil_div(cfg->P, kTile); p.C = cfg->n_classes_total; p.bg = cfg->background_id;
+  p.P = cfg->P; p.C = cfg->n_classes_total; p.bg = cfg->background_id;
   p.coords = cfg->coords; p.multi = cfg->matching_multi; p.d = cfg->border_d; p.normalize = cfg->normalize_coords;
   p.pos_thr = cfg->pos_iou_threshold; p.neg_lim = cfg->neg_iou_limit;
   p.img_w = (double)cfg->img_width; p.img_h = (double)cfg->img_height;
   for (int i = 0; i < 4; ++i) p.var[i] = cfg->variances[i];
-  SSDK_CHECK_CUDA(cudaMalloc(&e->d_anchors, (size_t)p.P * 4 * sizeof(double)));
-  SSDK_CHECK_CUDA(cudaMalloc(&e->d_bbox, (size_t)p.n_tiles * 4 * sizeof(double)));
-  SSDK_CHECK_CUDA(cudaMemcpy(e->d_anchors, anchors_host, (size_t)p.P * 4 * sizeof(double), cudaMemcpyHostToDevice));
-  p.anchors = e->d_anchors; p.tile_bbox = e->d_bbox;
-  anchor_tile_bbox_kernel<<<p.n_tiles, kTile>>>(p, e->d_bbox);
-  SSDK_COUNT_LAUNCH(ctx);
-  SSDK_CHECK_CUDA(cudaGetLastError());
-  SSDK_CHECK_CUDA(cudaDeviceSynchronize());
+  {
+    // a pair can change an anchor's row only if its IoU reaches the smaller of the thresholds that are tested (:375,389);
+    // the float32 bound is compared against a value safely below it (the bound may be 2^-23 short of the true maximum)
+    double thr = p.multi ? std::min(p.pos_thr, p.neg_lim) : p.neg_lim;
+    float t = 0.f;
+    if (thr > 0.0 && std::isfinite(thr)) {
+      t = (float)(thr * (1.0 - 9.5367431640625e-7));           // 1 - 2^-20
+      t = std::nextafterf(t, 0.f);
+      if (!(t > 0.f)) t = 0.f;
+    }
+    p.thr_adj = t;                                             // 0: every overlapping pair is evaluated exactly
+  }
+  auto fail = [&](int code) { ssdk_encoder_destroy(e); return code; };
+  if (cudaMalloc(&e->d_anchors, (size_t)p.P * 4 * sizeof(double)) != cudaSuccess) { set_error("ssdk_encoder_create: cudaMalloc failed"); return fail(SSDK_ERR_NOMEM); }
+  if (cudaMemcpy(e->d_anchors, anchors_host, (size_t)p.P * 4 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("ssdk_encoder_create: anchor upload failed"); return fail(SSDK_ERR_CUDA);
+  }
+  p.anchors = e->d_anchors;
+  int rc;
+  {
+    TileSetHost h;
+    linear_tiles(h, 0, p.P);
+    rc = upload_tiles(e, h, e->linear); if (rc) return fail(rc);
+  }
+  if (cfg->n_layers > 0 && cfg->fm_height && cfg->fm_width && cfg->n_boxes) {
+    long long tot = 0;
+    for (int l = 0; l < cfg->n_layers; ++l) tot += (long long)cfg->fm_height[l] * cfg->fm_width[l] * cfg->n_boxes[l];
+    if (tot != p.P) { set_error("ssdk_encoder_create: layer geometry describes %lld priors, P is %d", tot, p.P); return fail(SSDK_ERR_INVALID); }
+    TileSetHost h;
+    spatial_tiles(h, cfg->n_layers, cfg->fm_height, cfg->fm_width, cfg->n_boxes);
+    if (!tiles_cover(h, p.P)) { set_error("internal: spatial tiles do not cover the priors exactly once"); return fail(SSDK_ERR_INVALID); }
+    rc = upload_tiles(e, h, e->spatial); if (rc) return fail(rc);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("ssdk_encoder_create: tile setup failed"); return fail(SSDK_ERR_CUDA); }
   *out = e;
   return SSDK_OK;
 }
 
 extern "C" int ssdk_encoder_destroy(ssdk_encoder* e) {
   if (!e) return SSDK_OK;
-  cudaFree(e->d_anchors); cudaFree(e->d_bbox);
-  e->rows.release();
+  cudaFree(e->d_anchors);
+  e->linear.release(); e->spatial.release();
+  e->ub.release(); e->counters.release(); e->offsets.release();
   if (e->h_offsets) cudaFreeHost(e->h_offsets);
   for (int i = 0; i < ssdk_encoder::kSlots; ++i) if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
   delete e;
@@ -577,60 +785,118 @@ extern "C" int ssdk_iou(ssdk_ctx* ctx, const double* boxes1_dev, int m, const do
   return SSDK_OK;
 }
 
+namespace {
+
+// Common launch path.  offs_host (B+1 ints) may be NULL when offs_dev is given together with total_g / max_g.
+int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* offs_host, const int* offs_dev, int B, int total_g,
+                  int max_g, float* out_y_dev, int* out_match_dev, int* status_dev, cudaStream_t stream) {
+  const EncParams& p = e->p;
+  const int W = p.C + 12;
+  SSDK_REQUIRE(total_g == 0 || gt_dev, "ssdk_encode: gt_boxes_dev is NULL");
+  SSDK_REQUIRE((reinterpret_cast<uintptr_t>(out_y_dev) & 3) == 0, "ssdk_encode: out_y_dev is not float aligned");
+  // tile set: compact cell blocks pay off once many boxes compete per tile; consecutive priors give full tiles and one
+  // 16-byte aligned run each, which is what matters when the kernel is purely store bound
+  int spatial_min = 24;
+  if (const char* s = getenv("SSDK_ENC_SPATIAL_MIN")) spatial_min = atoi(s);
+  const bool use_spatial = e->spatial.dev.n_tiles > 0 && max_g >= spatial_min;
+  const TileSetDev& ts = use_spatial ? e->spatial.dev : e->linear.dev;
+  int tpc = max_g <= 16 ? 1 : (max_g <= 48 ? 2 : 4);
+  if (const char* s = getenv("SSDK_ENC_TPC")) tpc = std::max(1, atoi(s));
+  while (tpc > 1 && (long long)ceil_div(ts.n_tiles, tpc) * B < 8ll * e->ctx->sm_count) tpc >>= 1;
+  // scratch
+  const size_t n = (size_t)(total_g > 0 ? total_g : 1);
+  int rc = e->ub.ensure(n * (size_t)ts.n_tiles * sizeof(float));
+  if (rc) return rc;
+  if (e->counters_n < (size_t)B) {
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
+    rc = e->counters.ensure((size_t)B * sizeof(int));
+    if (rc) return rc;
+    SSDK_CHECK_CUDA(cudaMemset(e->counters.ptr, 0, e->counters.bytes));
+    e->counters_n = e->counters.bytes / sizeof(int);
+  }
+  const EncSmem L = enc_smem_layout(W, max_g);
+  SSDK_REQUIRE(L.total <= 227 * 1024, "ssdk_encode: n_classes (%d) / gt count (%d) need %zu bytes of shared memory", p.C, max_g, L.total);
+  dim3 grid(ceil_div(ts.n_tiles, tpc), B);
+  const bool inline_offs = offs_host != nullptr && B <= kInlineB;
+  if (inline_offs) {
+    if (L.total > 48 * 1024 && L.total > e->smem_attr[0]) {
+      SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      e->smem_attr[0] = L.total;
+    }
+    OffsArg& arg = e->offs_arg;
+    memcpy(arg.v, offs_host, (size_t)(B + 1) * sizeof(int));
+    enc_tiles_kernel<true><<<grid, kTile, L.total, stream>>>(p, ts, arg, nullptr, gt_dev, gt_f64, tpc, reinterpret_cast<float*>(e->ub.ptr),
+                                                             reinterpret_cast<int*>(e->counters.ptr), out_y_dev, out_match_dev, status_dev);
+  } else {
+    const int* d_offs = offs_dev;
+    if (!d_offs) {                                         // large batch with host offsets: pinned ring + async copy
+      rc = e->offsets.ensure((size_t)(B + 1) * sizeof(int));
+      if (rc) return rc;
+      if (e->h_offsets_cap < B + 1) {
+        SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
+        if (e->h_offsets) cudaFreeHost(e->h_offsets);
+        SSDK_CHECK_CUDA(cudaMallocHost(&e->h_offsets, (size_t)ssdk_encoder::kSlots * (B + 1) * sizeof(int)));
+        e->h_offsets_cap = B + 1;
+      }
+      const int slot = e->next_slot;
+      e->next_slot = (slot + 1) % ssdk_encoder::kSlots;
+      if (!e->slot_done[slot]) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&e->slot_done[slot], cudaEventDisableTiming));
+      else SSDK_CHECK_CUDA(cudaEventSynchronize(e->slot_done[slot]));
+      int* h_off = e->h_offsets + (size_t)slot * e->h_offsets_cap;
+      memcpy(h_off, offs_host, (size_t)(B + 1) * sizeof(int));
+      SSDK_CHECK_CUDA(cudaMemcpyAsync(e->offsets.ptr, h_off, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+      SSDK_CHECK_CUDA(cudaEventRecord(e->slot_done[slot], stream));
+      d_offs = reinterpret_cast<const int*>(e->offsets.ptr);
+    }
+    if (L.total > 48 * 1024 && L.total > e->smem_attr[1]) {
+      SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      e->smem_attr[1] = L.total;
+    }
+    enc_tiles_kernel<false><<<grid, kTile, L.total, stream>>>(p, ts, e->offs_arg, d_offs, gt_dev, gt_f64, tpc, reinterpret_cast<float*>(e->ub.ptr),
+                                                              reinterpret_cast<int*>(e->counters.ptr), out_y_dev, out_match_dev, status_dev);
+  }
+  SSDK_COUNT_LAUNCH(e->ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+int scan_offsets(const int* offs, int B, int* total_g, int* max_g) {
+  SSDK_REQUIRE(offs[0] == 0 && offs[B] >= 0, "ssdk_encode: gt_offsets must start at 0 and be non-decreasing");
+  int mg = 0;
+  for (int b = 0; b < B; ++b) {
+    const int g = offs[b + 1] - offs[b];
+    SSDK_REQUIRE(g >= 0, "ssdk_encode: gt_offsets must be non-decreasing");
+    mg = g > mg ? g : mg;
+  }
+  *total_g = offs[B]; *max_g = mg;
+  return SSDK_OK;
+}
+
+}  // namespace
+
 extern "C" int ssdk_encode(ssdk_encoder* e, const float* gt_boxes_dev, const int* gt_offsets_host, int B,
                            float* out_y_dev, int* out_match_dev, int* status_dev, void* stream_) {
   SSDK_REQUIRE(e && gt_offsets_host && out_y_dev && B > 0, "ssdk_encode: bad argument");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const EncParams& p = e->p;
-  const int total_g = gt_offsets_host[B];
-  SSDK_REQUIRE(gt_offsets_host[0] == 0 && total_g >= 0, "ssdk_encode: gt_offsets must start at 0 and be non-decreasing");
-  int max_g = 0;
-  for (int b = 0; b < B; ++b) {
-    int g = gt_offsets_host[b + 1] - gt_offsets_host[b];
-    SSDK_REQUIRE(g >= 0, "ssdk_encode: gt_offsets must be non-decreasing");
-    max_g = g > max_g ? g : max_g;
-  }
-  SSDK_REQUIRE(total_g == 0 || gt_boxes_dev, "ssdk_encode: gt_boxes_dev is NULL");
-  // scratch: tile-best values [total_g * n_tiles] f64 | tile-best indices [total_g * n_tiles] | matches[total_g] | offsets[B+1]
-  const size_t n = (size_t)(total_g > 0 ? total_g : 1);
-  const size_t nt = n * (size_t)p.n_tiles;
-  const size_t bytes = nt * 8 + nt * 4 + n * 4 + (size_t)(B + 1) * 4 + 64;
-  int rc = e->rows.ensure(bytes);
+  int total_g, max_g;
+  int rc = scan_offsets(gt_offsets_host, B, &total_g, &max_g);
   if (rc) return rc;
-  double* tb_val = reinterpret_cast<double*>(e->rows.ptr);
-  int* tb_idx = reinterpret_cast<int*>(tb_val + nt);
-  int* matches = tb_idx + nt;
-  int* d_offsets = matches + n;
-  if (e->h_offsets_cap < B + 1) {
-    SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
-    if (e->h_offsets) cudaFreeHost(e->h_offsets);
-    SSDK_CHECK_CUDA(cudaMallocHost(&e->h_offsets, (size_t)ssdk_encoder::kSlots * (B + 1) * sizeof(int)));
-    e->h_offsets_cap = B + 1;
-  }
-  const int slot = e->next_slot;
-  e->next_slot = (slot + 1) % ssdk_encoder::kSlots;
-  if (!e->slot_done[slot]) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&e->slot_done[slot], cudaEventDisableTiming));
-  else SSDK_CHECK_CUDA(cudaEventSynchronize(e->slot_done[slot]));
-  int* h_off = e->h_offsets + (size_t)slot * e->h_offsets_cap;
-  memcpy(h_off, gt_offsets_host, (size_t)(B + 1) * sizeof(int));
-  SSDK_CHECK_CUDA(cudaMemcpyAsync(d_offsets, h_off, (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-  SSDK_CHECK_CUDA(cudaEventRecord(e->slot_done[slot], stream));
-  const int W = p.C + 12;
-  const size_t gs = (size_t)(max_g > 0 ? max_g : 1);
-  const size_t sm_m = (((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15) + gs * (5 * 8 + 8 * 8 + 4 * 4 + 4 + 8 * 4 + 4 + 8 * 4) + 64;
-  SSDK_REQUIRE(sm_m <= 227 * 1024, "ssdk_encode: n_classes (%d) / gt count (%d) need %zu bytes of shared memory", p.C, max_g, sm_m);
-  if (sm_m > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_m));
-  dim3 grid(p.n_tiles, B);
-  enc_fused_kernel<<<grid, kTile, sm_m, stream>>>(p, gt_boxes_dev, d_offsets, tb_val, tb_idx, out_y_dev, out_match_dev, status_dev);
-  SSDK_COUNT_LAUNCH(e->ctx);
-  if (total_g > 0) {
-    const size_t sm_b = (size_t)max_g * (8 + 40 + 4 + 4 + 4) + 16;
-    if (sm_b > 48 * 1024) SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
-    enc_greedy_kernel<<<B, 256, sm_b, stream>>>(p, gt_boxes_dev, d_offsets, tb_val, tb_idx, matches);
-    SSDK_COUNT_LAUNCH(e->ctx);
-    enc_fix_kernel<<<ceil_div(total_g, 8), 256, 0, stream>>>(p, gt_boxes_dev, d_offsets, B, total_g, matches, out_y_dev, out_match_dev);
-    SSDK_COUNT_LAUNCH(e->ctx);
-  }
-  SSDK_CHECK_CUDA(cudaGetLastError());
-  return SSDK_OK;
+  return encode_launch(e, gt_boxes_dev, 0, gt_offsets_host, nullptr, B, total_g, max_g, out_y_dev, out_match_dev, status_dev,
+                       (cudaStream_t)stream_);
+}
+
+extern "C" int ssdk_encode_f64(ssdk_encoder* e, const double* gt_boxes_dev, const int* gt_offsets_host, int B,
+                               float* out_y_dev, int* out_match_dev, int* status_dev, void* stream_) {
+  SSDK_REQUIRE(e && gt_offsets_host && out_y_dev && B > 0, "ssdk_encode_f64: bad argument");
+  int total_g, max_g;
+  int rc = scan_offsets(gt_offsets_host, B, &total_g, &max_g);
+  if (rc) return rc;
+  return encode_launch(e, gt_boxes_dev, 1, gt_offsets_host, nullptr, B, total_g, max_g, out_y_dev, out_match_dev, status_dev,
+                       (cudaStream_t)stream_);
+}
+
+extern "C" int ssdk_encode_dev(ssdk_encoder* e, const float* gt_boxes_dev, const int* gt_offsets_dev, int B, int total_g, int max_g,
+                               float* out_y_dev, int* out_match_dev, int* status_dev, void* stream_) {
+  SSDK_REQUIRE(e && gt_offsets_dev && out_y_dev && B > 0 && total_g >= 0 && max_g >= 0, "ssdk_encode_dev: bad argument");
+  return encode_launch(e, gt_boxes_dev, 0, nullptr, gt_offsets_dev, B, total_g, max_g, out_y_dev, out_match_dev, status_dev,
+                       (cudaStream_t)stream_);
 }

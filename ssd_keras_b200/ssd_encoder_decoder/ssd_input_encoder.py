@@ -96,8 +96,10 @@ class SSDInputEncoder:
         for (h, w), b in zip(predictor_sizes, nb):
             self.boxes_list.append(a64[o:o + h * w * b].reshape(h, w, b, 4))
             o += h * w * b
+        self._n_boxes_per_layer = list(nb)
         self._diagnostics()
         self._handle = None
+        self._status = None
 
     def generate_anchor_boxes_for_layer(self, feature_map_size, aspect_ratios, this_scale, next_scale, this_steps=None,
                                         this_offsets=None, diagnostics=False):
@@ -157,10 +159,15 @@ class SSDInputEncoder:
     # -----------------------------------------------------------------------------------------
     def _encoder(self):
         if self._handle is None:
+            ps = np.ascontiguousarray(np.asarray(self.predictor_sizes, dtype=np.int32).reshape(-1, 2))
+            fm_h = np.ascontiguousarray(ps[:, 0]); fm_w = np.ascontiguousarray(ps[:, 1])
+            nb = np.ascontiguousarray(np.asarray(self._n_boxes_per_layer, dtype=np.int32))
+            self._geom = (fm_h, fm_w, nb)                     # read during ssdk_encoder_create only
             cfg = _ffi.EncodeCfg(int(self.img_height), int(self.img_width), int(self.n_classes), int(self.anchors.shape[0]),
                                  int(self.background_id), _ffi.COORDS[self.coords], 1 if self.matching_type == 'multi' else 0,
                                  float(self.pos_iou_threshold), float(self.neg_iou_limit), _ffi.BORDER_D[self.border_pixels],
-                                 int(bool(self.normalize_coords)), (C.c_double * 4)(*[float(v) for v in self.variances]))
+                                 int(bool(self.normalize_coords)), (C.c_double * 4)(*[float(v) for v in self.variances]),
+                                 int(ps.shape[0]), _ffi.np_ptr(fm_h, C.c_int), _ffi.np_ptr(fm_w, C.c_int), _ffi.np_ptr(nb, C.c_int))
             h = C.c_void_p()
             anc = np.ascontiguousarray(self.anchors)
             _ffi.check(_ffi.lib().ssdk_encoder_create(_ffi.context(), C.byref(cfg), _ffi.np_ptr(anc, C.c_double), C.byref(h)))
@@ -174,24 +181,56 @@ class SSDInputEncoder:
         except Exception:
             pass
 
-    def encode_device(self, gt_boxes_dev, gt_offsets, return_matches=False):
-        """Hot path: ``gt_boxes_dev`` float32 CUDA tensor (sum G_i, 5), ``gt_offsets`` host int32 (B+1,).
-        Returns the float32 CUDA tensor (B,P,C+12) (and, optionally, the int32 match tensor (B,P)).
-        Asynchronous; degenerate boxes are reported through ``self.last_status`` (a CUDA int32 tensor)."""
+    @property
+    def last_status(self):
+        """int32 CUDA tensor (1,): 0, or the 1-based index of a batch item with a degenerate box seen by ``encode_device``
+        since the flag was last read (the kernel raises it with an atomic; reading synchronises and clears it)."""
+        import torch
+        if self._status is None:
+            return torch.zeros((1,), dtype=torch.int32, device='cuda')
+        out = self._status.clone()
+        if int(out.item()) != 0:
+            self._status.zero_()
+        return out
+
+    def encode_device(self, gt_boxes_dev, gt_offsets, return_matches=False, out=None):
+        """Hot path: ``gt_boxes_dev`` float32 (or float64) CUDA tensor (sum G_i, 5), ``gt_offsets`` host int32 (B+1,), or an
+        int32 CUDA tensor together with ``(total_g, max_g)`` -- see ``encode_device_offsets``.  Returns the float32 CUDA tensor
+        (B,P,C+12) (``out`` if given) and, optionally, the int32 match tensor (B,P).  ONE kernel launch, asynchronous;
+        degenerate boxes are reported through ``self.last_status``."""
         import torch
         offs = np.ascontiguousarray(np.asarray(gt_offsets, dtype=np.int32))
         B = offs.shape[0] - 1
         P, W = self.anchors.shape[0], self.n_classes + 12
         dev = gt_boxes_dev.device if gt_boxes_dev is not None else torch.device('cuda')
-        y = torch.empty((B, P, W), dtype=torch.float32, device=dev)
+        y = out if out is not None else torch.empty((B, P, W), dtype=torch.float32, device=dev)
+        if tuple(y.shape) != (B, P, W) or y.dtype != torch.float32 or not y.is_contiguous():
+            raise ValueError('`out` must be a contiguous float32 tensor of shape %s' % ((B, P, W),))
         match = torch.empty((B, P), dtype=torch.int32, device=dev) if return_matches else None
-        self.last_status = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _ffi.check(_ffi.lib().ssdk_encode(self._encoder(), _ffi.dptr(gt_boxes_dev), _ffi.np_ptr(offs, C.c_int), B,
-                                          _ffi.dptr(y), _ffi.dptr(match), _ffi.dptr(self.last_status), _ffi.stream_ptr()))
+        if self._status is None:
+            self._status = torch.zeros((1,), dtype=torch.int32, device=dev)
+        f64 = gt_boxes_dev is not None and gt_boxes_dev.dtype == torch.float64
+        fn = _ffi.lib().ssdk_encode_f64 if f64 else _ffi.lib().ssdk_encode
+        _ffi.check(fn(self._encoder(), _ffi.dptr(gt_boxes_dev), _ffi.np_ptr(offs, C.c_int), B,
+                      _ffi.dptr(y), _ffi.dptr(match), _ffi.dptr(self._status), _ffi.stream_ptr()))
         return (y, match) if return_matches else y
 
+    def encode_device_offsets(self, gt_boxes_dev, gt_offsets_dev, total_g, max_g, out=None):
+        """Like ``encode_device`` for a batch that was assembled on the device (``data_generator.assemble_batch_device``):
+        the row offsets are an int32 CUDA tensor (B+1,), nothing is read from the host."""
+        import torch
+        B = gt_offsets_dev.shape[0] - 1
+        P, W = self.anchors.shape[0], self.n_classes + 12
+        y = out if out is not None else torch.empty((B, P, W), dtype=torch.float32, device=gt_offsets_dev.device)
+        if self._status is None:
+            self._status = torch.zeros((1,), dtype=torch.int32, device=gt_offsets_dev.device)
+        _ffi.check(_ffi.lib().ssdk_encode_dev(self._encoder(), _ffi.dptr(gt_boxes_dev), _ffi.dptr(gt_offsets_dev), B, int(total_g),
+                                              int(max_g), _ffi.dptr(y), _ffi.dptr(None), _ffi.dptr(self._status), _ffi.stream_ptr()))
+        return y
+
     def __call__(self, ground_truth_labels, diagnostics=False):
-        """Reference call (:277): list of ``(k_i, 5)`` arrays -> ``(B, P, C+12)`` float64 ndarray."""
+        """Reference call (:277): list of ``(k_i, 5)`` arrays -> ``(B, P, C+12)`` float64 ndarray.  The labels go to the
+        device as float64, which is what the reference computes on (:330)."""
         import torch
         rows, offs = [], [0]
         for i, g in enumerate(ground_truth_labels):
@@ -205,7 +244,13 @@ class SSDInputEncoder:
                                          "bounding boxes {}, i.e. bounding boxes where xmax <= xmin and/or ymax <= ymin. "
                                          "Degenerate ground truth bounding boxes will lead to NaN errors during the training."
                                          .format(i, lab))
-            rows.append(lab.astype(np.float32))
+            cls = lab[:, 0].astype(np.int64)                   # class_vectors[labels[:, class_id].astype(np.int)] (:349)
+            if np.any(cls >= self.n_classes) or np.any(cls < -self.n_classes):
+                bad = cls[(cls >= self.n_classes) | (cls < -self.n_classes)][0]
+                raise IndexError("index {} is out of bounds for axis 0 with size {}".format(int(bad), self.n_classes))
+            lab = lab.copy()
+            lab[:, 0] = np.where(cls < 0, cls + self.n_classes, cls)   # NumPy's negative indices wrap around
+            rows.append(lab)
             offs.append(offs[-1] + lab.shape[0])
         gt_dev = None
         if rows:

@@ -102,6 +102,92 @@ def test_encode_edge_cases(configs):
     _check_encode(cfg, big)
 
 
+@pytest.mark.parametrize('spatial_min', ['0', '100000'])
+def test_encode_both_tile_sets(configs, monkeypatch, spatial_min):
+    """The encoder groups priors either into runs of 256 consecutive priors or into compact blocks of feature-map cells
+    (picked by the number of boxes per image); both groupings must give the reference's result on every kind of input."""
+    monkeypatch.setenv('SSDK_ENC_SPATIAL_MIN', spatial_min)
+    gts = synth.synth_gt(2, 4, 8, 300, 300, 20)
+    _check_encode(configs['ssd300'], gts)
+    cfg = dict(configs['ssd300']); cfg['neg_iou_limit'] = 0.3
+    _check_encode(cfg, synth.synth_gt(12, 3, 40, 300, 300, 20))
+    _check_encode(configs['ssd512'], synth.synth_gt(7, 2, 30, 512, 512, 80))
+    _check_encode(configs['ssd7'], synth.synth_gt(8, 3, 12, 300, 300, 5))
+    tiny = synth.synth_gt(5, 6, 3, 160, 120, 3)
+    tiny[0] = np.zeros((0, 5), np.float32)
+    tiny[2] = np.repeat(tiny[2][:1], 4, axis=0)
+    tiny[3] = np.array([[1, 0, 0, 3, 3], [2, 1, 1, 2.5, 2.5], [3, 150, 110, 159, 119]], np.float32)
+    _check_encode(configs['tiny'], tiny)
+    _check_encode(configs['tiny_clip_abs'], tiny)
+    _check_encode(configs['tiny'], synth.synth_gt(9, 2, 300, 160, 120, 3))      # 300 boxes on 240 priors: contested priors
+    for tpc in ('1', '4'):
+        monkeypatch.setenv('SSDK_ENC_TPC', tpc)
+        _check_encode(configs['ssd300'], synth.synth_gt(13, 2, 60, 300, 300, 20))
+    monkeypatch.delenv('SSDK_ENC_TPC')
+
+
+def test_encode_integer_pixel_labels_ties(configs):
+    """Integer pixel coordinates on a regular prior grid produce exact IoU ties between neighbouring priors (and between
+    tiles): np.argmax's first-index rule must hold in both matching stages."""
+    rng = np.random.default_rng(77)
+    gts = []
+    for _ in range(4):
+        n = 12
+        x0 = rng.integers(0, 200, n) // 4 * 4; y0 = rng.integers(0, 200, n) // 4 * 4
+        w = rng.integers(2, 20, n) * 8; h = rng.integers(2, 20, n) * 8
+        gts.append(np.stack([rng.integers(1, 21, n), x0, y0, np.minimum(x0 + w, 299), np.minimum(y0 + h, 299)], 1).astype(np.float32))
+    _check_encode(configs['ssd300'], gts)
+    cfg = dict(configs['ssd7']); cfg['neg_iou_limit'] = 0.3
+    g7 = []
+    for g in gts:
+        g = g.copy(); g[:, 0] = (g[:, 0] - 1) % 5 + 1
+        g7.append(g)
+    _check_encode(cfg, g7)
+
+
+def test_encode_float64_labels(configs):
+    """Labels that float32 cannot hold: the reference computes on float64 copies (:330) and so does ssdk_encode_f64."""
+    rng = np.random.default_rng(3)
+    gts = []
+    for _ in range(3):
+        n = 6
+        x0 = rng.uniform(0, 200, n); y0 = rng.uniform(0, 200, n)
+        gts.append(np.stack([rng.integers(1, 21, n).astype(np.float64), x0, y0, x0 + rng.uniform(10, 90, n),
+                             y0 + rng.uniform(10, 90, n)], 1))
+    assert any((g.astype(np.float32).astype(np.float64) != g).any() for g in gts)
+    enc = _enc(configs['ssd300'])
+    y = enc(gts)
+    y_ref = OracleEncoder(**configs['ssd300'])(gts)
+    np.testing.assert_array_equal(y[:, :, :21], y_ref[:, :, :21])
+    np.testing.assert_allclose(y[:, :, 21:], y_ref[:, :, 21:].astype(np.float32).astype(np.float64), rtol=2e-7, atol=1e-7)
+    with pytest.raises(IndexError):
+        enc([np.array([[21, 10., 10., 50., 60.]])])               # class id outside [0, n_classes]: np.eye row gather fails
+
+
+def test_encode_large_batch_and_device_offsets(configs):
+    """B > 1024: the offsets no longer fit the launch arguments and travel through the pinned ring; and the entry that
+    takes offsets which already live on the device."""
+    import torch
+    cfg = configs['tiny']
+    gts = synth.synth_gt(21, 1100, 2, 160, 120, 3)
+    enc = _enc(cfg)
+    y = enc(gts)
+    y_ref = OracleEncoder(**cfg)(gts)
+    np.testing.assert_array_equal(y[:, :, :4], y_ref[:, :, :4])
+    np.testing.assert_allclose(y[:, :, 4:], y_ref[:, :, 4:].astype(np.float32).astype(np.float64), rtol=2e-7, atol=1e-7)
+    gts = synth.synth_gt(22, 5, 7, 160, 120, 3)
+    offs = np.cumsum([0] + [g.shape[0] for g in gts]).astype(np.int32)
+    gd = torch.from_numpy(np.concatenate(gts)).cuda()
+    yd = enc.encode_device_offsets(gd, torch.from_numpy(offs).cuda(), int(offs[-1]), 7).cpu().numpy()
+    np.testing.assert_array_equal(yd, enc.encode_device(gd, offs).cpu().numpy())
+    out = torch.empty((5, enc.anchors.shape[0], enc.n_classes + 12), dtype=torch.float32, device='cuda')
+    assert enc.encode_device(gd, offs, out=out) is out
+    np.testing.assert_array_equal(out.cpu().numpy(), yd)
+    # repeated launches reuse the per-image tickets
+    for _ in range(3):
+        np.testing.assert_array_equal(enc.encode_device(gd, offs).cpu().numpy(), yd)
+
+
 def test_encode_degenerate_raises(configs):
     from ssd_keras_b200.ssd_encoder_decoder.ssd_input_encoder import DegenerateBoxError
     enc = _enc(configs['tiny'])
