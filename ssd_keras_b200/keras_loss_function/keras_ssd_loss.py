@@ -12,7 +12,9 @@ def _as_cuda(t):
     import torch
     if isinstance(t, np.ndarray):
         return torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).pin_memory().cuda(non_blocking=True)
-    return t.to(dtype=torch.float32).contiguous()
+    if not torch.is_tensor(t):
+        raise ValueError('expected a NumPy array or a torch tensor, got %s' % type(t).__name__)
+    return t.to(device='cuda', dtype=torch.float32).contiguous()
 
 
 def _make_fn():
@@ -84,8 +86,11 @@ class SSDLoss:
         if _FN is None:
             _FN = _make_fn()
         yt, yp = _as_cuda(y_true), _as_cuda(y_pred)
-        if yt.shape != yp.shape or yt.dim() != 3:
-            raise ValueError("y_true and y_pred must both have shape (batch, #boxes, #classes + 12)")
+        if yt.shape != yp.shape or yt.dim() != 3 or yt.shape[-1] < 14:
+            raise ValueError("y_true and y_pred must both have shape (batch, #boxes, #classes + 12) with at least two classes, "
+                             "got %s and %s" % (tuple(yt.shape), tuple(yp.shape)))
+        if yt.device != yp.device:
+            raise ValueError("y_true and y_pred must live on the same device")
         return _FN.apply(yt, yp, self.neg_pos_ratio, self.n_neg_min, self.alpha)
 
     def loss_and_stats(self, y_true, y_pred):

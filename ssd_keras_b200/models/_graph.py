@@ -58,6 +58,7 @@ class SSDModel:
         self.l2_regularization = l2_reg
         self.precision = precision
         self._plans = {}
+        self._trainers = []                        # weak references to the SSDTrainer objects attached to this model
         self._shapes = self._infer_shapes()
         self.predictor_sizes = np.array([self._shapes[self.index[s.name]][:2] for s in specs if s.op == _ffi.OP_HEAD])
         a64, a32, nb = _ffi.generate_anchors(img_height, img_width, self.predictor_sizes, **anchor_cfg)
@@ -154,7 +155,32 @@ class SSDModel:
         self._release()
 
     def get_weights(self):
+        self._sync_trained()
         return dict(self.weights)
+
+    # -- trained weights: the model owns them ---------------------------------------------------
+    def _live_trainers(self):
+        out = []
+        for r in self._trainers:
+            t = r()
+            if t is not None:
+                out.append(t)
+        return out
+
+    def _sync_trained(self):
+        """An attached ``SSDTrainer`` updates float32 master weights on the device (its training plan).  Before anything else
+        looks at the weights -- ``get_weights`` / ``save_weights``, or a plan for another batch size / mode -- they are copied
+        back into ``self.weights`` and the plans built from the old values are dropped (Keras' ``train_on_batch`` mutates the
+        model; so does this)."""
+        for t in self._live_trainers():
+            if t._dirty:
+                self.weights.update(t.get_weights())
+                t._dirty = False
+                keep = t.plan
+                for key, h in list(self._plans.items()):
+                    if h is not keep:
+                        _ffi.lib().ssdk_model_destroy(h['handle'])
+                        del self._plans[key]
 
     def load_weights(self, path, by_name=True):
         """Loads an ``.npz`` with Keras layer names as keys (h5py is not available offline; see INTEGRATION.md
@@ -165,10 +191,15 @@ class SSDModel:
             self.set_weights({k: f[k] for k in f.files})
 
     def save_weights(self, path):
+        self._sync_trained()
         np.savez(path, **self.weights)
 
     # -- execution ---------------------------------------------------------------------------
     def _release(self):
+        # trainers hold a raw pointer into their training plan: detach them first (they re-attach, with fresh optimiser
+        # state, the next time they are used)
+        for t in self._live_trainers():
+            t._detach()
         for h in self._plans.values():
             _ffi.lib().ssdk_model_destroy(h['handle'])
         self._plans = {}
@@ -181,6 +212,11 @@ class SSDModel:
 
     def _plan(self, batch, training=False):
         key = (batch, bool(training))
+        if key in self._plans:
+            hit = self._plans[key]
+            if not any(t._dirty and t.plan is not hit for t in self._live_trainers()):
+                return hit
+        self._sync_trained()
         if key in self._plans:
             return self._plans[key]
         n = len(self.specs)

@@ -4,6 +4,7 @@
 gradient buffer is summed with ONE NCCL all-reduce before the update (replica-local loss).
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -19,16 +20,46 @@ class SSDTrainer:
         self.lr, self.momentum = float(lr), float(momentum)
         self.l2 = float(model.l2_regularization if l2_regularization is None else l2_regularization)
         self.neg_pos_ratio, self.n_neg_min, self.alpha = int(neg_pos_ratio), int(n_neg_min), float(alpha)
-        self.plan = model._plan(self.batch, training=True)
         # the flat gradient buffer is a torch tensor so that torch.distributed can all-reduce it in place
-        self.n_params = int(sum(int(np.prod(s)) for s in model.weight_shapes().values()))
+        self.n_params = self._count_trainable(model)
         self.grad = torch.zeros((self.n_params,), dtype=torch.float32, device='cuda')
-        self.handle = C.c_void_p()
-        _ffi.check(_ffi.lib().ssdk_trainer_create(self.plan['handle'], _ffi.dptr(self.grad), C.byref(self.handle)))
+        self.handle = None
+        self.plan = None
+        self._spans = None
+        self._dirty = False                      # device master weights are ahead of model.weights
+        model._trainers.append(weakref.ref(self))
+        self._attach()
+
+    @staticmethod
+    def _count_trainable(model):
+        n = 0
+        for k, shp in model.weight_shapes().items():
+            if k.endswith(('/moving_mean', '/moving_variance')):
+                continue
+            n += int(np.prod(shp))
+        return n
+
+    def _attach(self):
+        """(Re-)create the training plan from the model's current weights and the native trainer on top of it."""
+        if self.handle is not None:
+            return
+        self.plan = self.model._plan(self.batch, training=True)
+        h = C.c_void_p()
+        _ffi.check(_ffi.lib().ssdk_trainer_create(self.plan['handle'], _ffi.dptr(self.grad), C.byref(h)))
+        self.handle = h
         n = C.c_longlong()
         _ffi.check(_ffi.lib().ssdk_trainer_num_params(self.handle, C.byref(n)))
         assert int(n.value) == self.n_params, (n.value, self.n_params)
         self._spans = None
+
+    def _detach(self):
+        """Called by the model before it destroys its plans (``set_weights`` / ``load_weights``): the native trainer points
+        into the training plan.  Optimiser state (momentum) does not survive; the next step starts from the new weights."""
+        if self.handle is not None:
+            _ffi.lib().ssdk_trainer_destroy(self.handle)
+        self.handle = None
+        self.plan = None
+        self._dirty = False
 
     def __del__(self):
         try:
@@ -41,6 +72,14 @@ class SSDTrainer:
     def forward_backward(self, images, y_true):
         """images (B,H,W,3), y_true (B,P,C+12): float32 CUDA tensors.  Returns (loss (B,), y_pred); gradients in self.grad."""
         import torch
+        self._attach()
+        P, W = self.model.n_boxes_total, self.model.n_classes + 12
+        if images.shape[0] != self.batch or tuple(y_true.shape) != (self.batch, P, W):
+            raise ValueError('this trainer was built for batches of %d images: images %s / y_true %s do not match (%d, H, W, 3) / %s; '
+                             'build another SSDTrainer for a different batch size (e.g. the last, smaller batch of an epoch)'
+                             % (self.batch, tuple(images.shape), tuple(y_true.shape), self.batch, (self.batch, P, W)))
+        if not (images.is_cuda and y_true.is_cuda):
+            raise ValueError('images and y_true must be CUDA tensors')
         y_pred = self.model.forward_device(images, training=True)
         loss = torch.empty((self.batch,), dtype=torch.float32, device=images.device)
         y_true = y_true.to(dtype=torch.float32).contiguous()
@@ -49,6 +88,8 @@ class SSDTrainer:
         return loss, y_pred
 
     def apply(self, grad_scale=1.0):
+        self._attach()
+        self._dirty = True
         _ffi.check(_ffi.lib().ssdk_train_apply(self.handle, self.lr, self.momentum, self.l2, float(grad_scale), _ffi.stream_ptr()))
 
     def train_on_batch(self, images, y_true):
@@ -104,6 +145,7 @@ class SSDTrainer:
 
     def get_weights(self):
         import torch
+        self._attach()
         out = torch.empty_like(self.grad)
         _ffi.check(_ffi.lib().ssdk_trainer_read_params(self.handle, _ffi.dptr(out), _ffi.stream_ptr()))
         return self._unflatten(out.cpu().numpy())

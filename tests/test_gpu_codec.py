@@ -328,6 +328,32 @@ def test_nms_microbench_semantics():
         assert cnt[b] == len(order)
 
 
+def test_nms_config5_full_size():
+    """config 5 NMS part at its stated size: 100 000 boxes per image (the micro-benchmark's prior grid as corner boxes),
+    uniform scores, conf 0.01 / iou 0.45, cap 400, top_k 200."""
+    import torch
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_output_decoder import nms_device
+    cfg = dict(img_height=1000, img_width=1600, n_classes=20, predictor_sizes=[(125, 200)], scales=[0.1, 0.2],
+               aspect_ratios_global=[0.5, 1.0, 2.0], coords='corners', normalize_coords=False)
+    anc = OracleEncoder(**cfg).anchors.astype(np.float32)
+    n = anc.shape[0]
+    assert n == 100000
+    B = 2
+    scores = np.stack([np.random.default_rng(5 + i).uniform(0, 1, n) for i in range(B)]).astype(np.float32)
+    boxes = np.broadcast_to(anc[None], (B, n, 4)).copy()
+    out, cnt, idx = nms_device(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.01, 0.45, 400, 200, return_index=True)
+    out, cnt, idx = out.cpu().numpy(), cnt.cpu().numpy(), idx.cpu().numpy()
+    for b in range(B):
+        m = np.nonzero(scores[b] > np.float32(0.01))[0]
+        sel = odec.tf_nms_fast(boxes[b, m], scores[b, m], 400, 0.45)
+        keep = m[sel]
+        order = np.lexsort((np.arange(len(keep)), -scores[b, keep].astype(np.float64)))[:200]
+        np.testing.assert_array_equal(idx[b, :len(order)], keep[order])
+        assert cnt[b] == len(order)
+        np.testing.assert_array_equal(out[b, :len(order), 1], scores[b, keep[order]])
+        np.testing.assert_array_equal(out[b, :len(order), 2:], boxes[b, keep[order]])
+
+
 def test_nms_large_n_multi_band():
     """n = 40000 random boxes > band capacity; uncapped enough to need several bands."""
     import torch

@@ -149,3 +149,44 @@ def test_ssd512_step_matches_autograd():
         ref = params[k].grad.numpy()
         e = np.abs(grads[k] - ref).ravel() / (np.abs(ref).max() + 1e-30)
         assert np.median(e) < 2e-3 and e.max() < 2e-2, 'gradient %s: median err %.3e, max err %.3e' % (k, np.median(e), e.max())
+
+
+def test_trained_weights_belong_to_the_model(tmp_path):
+    """Keras' train_on_batch mutates the model: after SSDTrainer steps, predict() with another batch size, get_weights() and
+    save_weights() must see the trained weights; set_weights() after building a trainer must not leave it pointing at a freed
+    plan; a batch of the wrong size is refused instead of read out of bounds."""
+    import torch
+    from ssd_keras_b200.models.keras_ssd300 import ssd_300
+    from ssd_keras_b200.training import SSDTrainer
+    B = 2
+    m, w, x, y_true = _ssd300(B)
+    xd, ytd = torch.from_numpy(x).cuda(), torch.from_numpy(y_true).cuda()
+    tr = SSDTrainer(m, B, lr=1e-3, momentum=0.9, l2_regularization=5e-4)
+    y0 = m.predict(x[:1])                                   # an inference-side plan (batch 1) built from the initial weights
+    l_first = tr.train_on_batch(xd, ytd).cpu().numpy()
+    tr.train_on_batch(xd, ytd)
+    w_tr, w_m = tr.get_weights(), m.get_weights()
+    assert set(w_tr) <= set(w_m)
+    for k in w_tr:
+        np.testing.assert_array_equal(w_tr[k], w_m[k])
+    assert any(not np.array_equal(w_m[k], w[k]) for k in w_tr if k.endswith('/kernel'))
+    y1 = m.predict(x[:1])
+    assert not np.allclose(y0[:, :, :25], y1[:, :, :25])    # the stale batch-1 plan was rebuilt
+    sc = [0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05]
+    m2 = ssd_300((300, 300, 3), 20, mode='training', scales=sc, divide_by_stddev=[64.0] * 3)
+    m2.set_weights(w_m)
+    np.testing.assert_array_equal(m2.predict(x[:1]), y1)    # same weights, same kernels -> same bits
+    p = str(tmp_path / 'trained.npz')
+    m.save_weights(p)
+    with np.load(p) as f:
+        for k in w_tr:
+            np.testing.assert_array_equal(f[k], w_tr[k])
+    # the sync kept the training plan (and its momentum): training goes on
+    assert np.isfinite(tr.train_on_batch(xd, ytd).cpu().numpy()).all()
+    # new weights under a live trainer: it re-attaches to a fresh plan; the first step equals the very first step above
+    m.set_weights(w)
+    np.testing.assert_allclose(tr.train_on_batch(xd, ytd).cpu().numpy(), l_first, rtol=1e-6)
+    with pytest.raises(ValueError):
+        tr.forward_backward(xd[:1], ytd[:1])
+    with pytest.raises(ValueError):
+        tr.forward_backward(xd, ytd[:, :100])
