@@ -666,7 +666,6 @@ struct ssdk_encoder {
   int h_offsets_cap = 0;
   cudaEvent_t slot_done[kSlots] = {};
   int next_slot = 0;
-  size_t smem_attr[2] = {0, 0};
   OffsArg offs_arg{};               // ground-truth offsets passed by value with the launch (B <= kInlineB)
 };
 
@@ -787,6 +786,8 @@ extern "C" int ssdk_iou(ssdk_ctx* ctx, const double* boxes1_dev, int m, const do
 
 namespace {
 
+size_t g_smem_attr[2] = {0, 0};
+
 // Common launch path.  offs_host (B+1 ints) may be NULL when offs_dev is given together with total_g / max_g.
 int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* offs_host, const int* offs_dev, int B, int total_g,
                   int max_g, float* out_y_dev, int* out_match_dev, int* status_dev, cudaStream_t stream) {
@@ -819,9 +820,9 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   dim3 grid(ceil_div(ts.n_tiles, tpc), B);
   const bool inline_offs = offs_host != nullptr && B <= kInlineB;
   if (inline_offs) {
-    if (L.total > 48 * 1024 && L.total > e->smem_attr[0]) {
+    if (L.total > 48 * 1024 && L.total > g_smem_attr[0]) {   // the attribute belongs to the kernel, not to an encoder: only ever raise it
       SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-      e->smem_attr[0] = L.total;
+      g_smem_attr[0] = L.total;
     }
     OffsArg& arg = e->offs_arg;
     memcpy(arg.v, offs_host, (size_t)(B + 1) * sizeof(int));
@@ -848,9 +849,9 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
       SSDK_CHECK_CUDA(cudaEventRecord(e->slot_done[slot], stream));
       d_offs = reinterpret_cast<const int*>(e->offsets.ptr);
     }
-    if (L.total > 48 * 1024 && L.total > e->smem_attr[1]) {
+    if (L.total > 48 * 1024 && L.total > g_smem_attr[1]) {
       SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-      e->smem_attr[1] = L.total;
+      g_smem_attr[1] = L.total;
     }
     enc_tiles_kernel<false><<<grid, kTile, L.total, stream>>>(p, ts, e->offs_arg, d_offs, gt_dev, gt_f64, tpc, reinterpret_cast<float*>(e->ub.ptr),
                                                               reinterpret_cast<int*>(e->counters.ptr), out_y_dev, out_match_dev, status_dev);
