@@ -183,7 +183,8 @@ int ssdk_nms(ssdk_ctx* ctx, const float* boxes_dev, const float* scores_dev, int
 /* ------------------------------------------------------------------------------------------
  * SSD loss.  Replaces SSDLoss.compute_loss (keras_loss_function/keras_ssd_loss.py:98-211).
  * out_loss_dev [B] float32.  bwd writes d(sum_b upstream[b]*loss[b])/d y_pred with the hard-negative
- * mask held constant (upstream_dev NULL = 1/B each, the Keras batch mean).
+ * mask held constant (upstream_dev NULL = 1/B each, the Keras batch mean).  One cooperative kernel launch per call
+ * (csrc/loss.cu): per-box losses, batch-global top-k by a two-level histogram select, masked sums / gradient.
  * ------------------------------------------------------------------------------------------ */
 int ssdk_ssd_loss_fwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pred_dev, int B, int P, int n_classes_total,
                       int neg_pos_ratio, int n_neg_min, float alpha, float* out_loss_dev,
@@ -191,6 +192,33 @@ int ssdk_ssd_loss_fwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pre
 int ssdk_ssd_loss_bwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pred_dev, int B, int P, int n_classes_total,
                       int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream_dev,
                       float* out_grad_dev /* [B*P*(C+12)] */, void* stream);
+/* Loss and gradient from ONE launch of the same kernel (what a training step needs). */
+int ssdk_ssd_loss_fwd_bwd(ssdk_ctx* ctx, const float* y_true_dev, const float* y_pred_dev, int B, int P, int n_classes_total,
+                          int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream_dev, float* out_loss_dev,
+                          int* out_stats_dev, float* out_grad_dev, void* stream);
+
+/* Multi-GPU, global-batch-exact loss.  The reference's n_positive (:143) and hard-negative top-k (:179-183) run over the
+ * WHOLE batch; when the batch is sharded over ranks the kernel's phases are launched one by one on a caller-provided
+ * workspace and the integer counts / histograms inside it are summed over the ranks (NCCL all-reduce) in between:
+ *   zero the workspace; phase 0; all-reduce(sum) counts + hist1; phase 1; all-reduce(sum) hist2; phase 2; phase 3;
+ *   all-gather the int32 at ties_offset (one per rank, rank order = global image order) -> ties_all_dev; phase 4.
+ * Phase 4 writes the (B,) losses of this rank's images (normalised by the global n_positive and multiplied by global_B
+ * like :204-209) and / or the gradient with respect to this rank's y_pred.  Boxes whose loss equals the k-th largest are
+ * taken in global flat-index order, like tf.nn.top_k on the single-process batch. */
+typedef struct {
+  long long bytes;            /* size of the workspace */
+  long long counts_offset;    /* int64[counts_n] */
+  long long counts_n;
+  long long hist1_offset;     /* int32[hist_n] */
+  long long hist2_offset;     /* int32[hist_n] */
+  long long hist_n;
+  long long ties_offset;      /* int32[1], valid after phase 3 */
+} ssdk_loss_ws_layout;
+int ssdk_ssd_loss_ws_layout(int B, int P, ssdk_loss_ws_layout* out);
+int ssdk_ssd_loss_phase(ssdk_ctx* ctx, int phase, const float* y_true_dev, const float* y_pred_dev, int B, int P,
+                        int n_classes_total, int neg_pos_ratio, int n_neg_min, float alpha, void* ws_dev, int global_B,
+                        const int* ties_all_dev /* [world], phase 4 */, int rank, const float* upstream_dev,
+                        float* out_loss_dev, int* out_stats_dev, float* out_grad_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Model graph.  Replaces ssd_300 (models/keras_ssd300.py:31-457), ssd_512 (models/keras_ssd512.py:31-477)
@@ -276,6 +304,9 @@ int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int which, long lo
 float* ssdk_trainer_grad_buffer(ssdk_trainer* t);
 int ssdk_train_backward(ssdk_trainer* t, const float* y_true_dev, const float* y_pred_dev, int neg_pos_ratio, int n_neg_min,
                         float alpha, float* out_loss_dev /* [B] */, void* stream);
+/* The same backward pass from a gradient the caller computed: dypred_dev = d loss / d y_pred, (B,P,C+12) float32 (used with the
+ * multi-GPU global-batch-exact loss, whose phases run between NCCL collectives, see ssdk_ssd_loss_phase). */
+int ssdk_train_backward_dy(ssdk_trainer* t, const float* dypred_dev, void* stream);
 int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float l2_reg, float grad_scale, void* stream);
 /* Copy the current float32 master parameters (same order / layout as the gradients) to out_dev. */
 int ssdk_trainer_read_params(ssdk_trainer* t, float* out_dev, void* stream);

@@ -46,6 +46,11 @@ class DecodeCfg(C.Structure):
                 ('img_height', C.c_int), ('img_width', C.c_int), ('border_d', C.c_int), ('max_out', C.c_int)]
 
 
+class LossWsLayout(C.Structure):
+    _fields_ = [('bytes', C.c_longlong), ('counts_offset', C.c_longlong), ('counts_n', C.c_longlong), ('hist1_offset', C.c_longlong),
+                ('hist2_offset', C.c_longlong), ('hist_n', C.c_longlong), ('ties_offset', C.c_longlong)]
+
+
 class LayerDesc(C.Structure):
     _fields_ = [('op', C.c_int), ('input', C.c_int), ('cout', C.c_int), ('kh', C.c_int), ('kw', C.c_int),
                 ('stride', C.c_int), ('dilation', C.c_int), ('pad_t', C.c_int), ('pad_l', C.c_int),
@@ -104,6 +109,12 @@ def lib():
         L.ssdk_nms.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp, vp]
         L.ssdk_ssd_loss_fwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]
         L.ssdk_ssd_loss_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]
+        L.ssdk_ssd_loss_fwd_bwd.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp]
+        L.ssdk_ssd_loss_ws_layout.argtypes = [C.c_int, C.c_int, C.POINTER(LossWsLayout)]
+        L.ssdk_ssd_loss_phase.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp,
+                                          C.c_int, vp, vp, vp, vp, vp]
+        for name in ('ssdk_ssd_loss_fwd_bwd', 'ssdk_ssd_loss_ws_layout', 'ssdk_ssd_loss_phase'):
+            getattr(L, name).restype = C.c_int
         L.ssdk_l2_normalize.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp]
         L.ssdk_l2_normalize.restype = C.c_int
         if hasattr(L, 'ssdk_model_create'):
@@ -124,6 +135,8 @@ def lib():
             L.ssdk_trainer_grad_buffer.argtypes = [vp]
             L.ssdk_trainer_grad_buffer.restype = vp
             L.ssdk_train_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]
+            L.ssdk_train_backward_dy.argtypes = [vp, vp, vp]
+            L.ssdk_train_backward_dy.restype = C.c_int
             L.ssdk_train_apply.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
             L.ssdk_trainer_read_params.argtypes = [vp, vp, vp]
             for name in ('ssdk_trainer_create', 'ssdk_trainer_destroy', 'ssdk_trainer_num_params', 'ssdk_trainer_param_span',

@@ -55,6 +55,8 @@ struct ssdk_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   ssdk::Scratch ws[4];          // decode / loss / nms workspaces
+  long long loss_ws_shape = -1; // (B, P) the loss workspace is laid out for
+  int loss_parity = 0;          // which of its two histogram sets the next loss call uses (the other one is being cleared)
   cudaDeviceProp prop{};
 };
 

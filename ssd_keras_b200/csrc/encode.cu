@@ -1,24 +1,31 @@
 // SSDInputEncoder hot path on sm_100a: pairwise IoU, greedy bipartite + multi matching, neutral boxes and offset
-// encoding in ONE launch per batch.  Reference: ssd_encoder_decoder/ssd_input_encoder.py:277-418,
+// encoding.  Reference: ssd_encoder_decoder/ssd_input_encoder.py:277-418,
 // bounding_box_utils/bounding_box_utils.py:283-383, ssd_encoder_decoder/matching_utils.py:22-116.
 //
-// enc_tiles_kernel   grid (tile groups, images).  A tile is <= 256 anchors: either 256 consecutive priors ("linear" tile set)
-//                    or a compact block of feature-map cells ("spatial" tile set, fewer ground-truth boxes touch a tile).
+// enc_tiles_kernel   ONE launch per batch, grid (tile groups, images).  A tile is <= 256 anchors: 256 consecutive priors
+//                    ("linear" tile set) or a compact block of feature-map cells ("spatial" tile set: fewer ground-truth
+//                    boxes touch a tile; threads are ordered box-shape-major so that the anchors of one shape share warps).
 //   1. per image: ground-truth boxes -> template coordinates / corner boxes in float64 (shared memory, once per CTA).
 //   2. per tile: ordered list of the boxes whose extent can touch the tile's bounding box.
 //   3. per (anchor, candidate): a RIGOROUS float32 upper bound U of the float64 IoU (directed rounding on
-//      outward-rounded corners, MUFU reciprocal with a safety factor).  Nothing float64 happens unless U reaches
-//      min(pos_iou_threshold, neg_iou_limit) -- only then can the pair influence the anchor's row -- in which case the
-//      reference's float64 arithmetic is evaluated operation for operation (non-contracting intrinsics).
-//      The per-(ground truth, tile) maximum of U (one REDUX per warp and candidate) goes to global memory: it bounds
-//      the best IoU any anchor of that tile has with that box, which is all match_bipartite_greedy needs to find the
-//      exact row maxima later by evaluating one or two tiles per box.
+//      outward-rounded corners, MUFU reciprocal with a safety factor).  The reference's float64 arithmetic is evaluated
+//      -- operation for operation, non-contracting intrinsics -- only where a decision can depend on it:
+//        * U reaches min(pos_iou_threshold, neg_iou_limit): the pair may matter for the anchor's own row;
+//        * U reaches a lower bound LB[g] of the best IoU ground-truth box g has with ANY anchor: the pair may be the
+//          row maximum match_bipartite_greedy looks for.  (Anchors that lie inside a large box all have IoU
+//          area_anchor / area_box up to rounding noise, and np.argmax picks the first maximum of that noise: those few
+//          hundred pairs per box must be exact, the other ~99.5 % need not.)
+//      Exact per-(box, tile) bests (value, first prior index) and the per-(box, tile) maximum of U go to global memory.
 //   4. the (C+12)-float target rows are staged in shared memory and leave with cp.async.bulk (one bulk store per
 //      contiguous run of priors; plain coalesced stores when a run is not 16-byte aligned).
-//   5. the LAST CTA of an image (atomic ticket) runs match_bipartite_greedy for that image: exact float64 row maxima
-//      from the bounded tiles, the G greedy rounds (in parallel when no two boxes compete for the same anchor, which is
-//      the common case; otherwise the reference's sequential rounds incl. its zeroed-row quirk), then rewrites the
-//      <= G rows whose bipartite match overrides the multi-match row.
+//   5. the LAST CTA of an image (atomic ticket) runs match_bipartite_greedy for that image: one thread per box reduces the
+//      tile bests to the exact row maxima; the G greedy rounds commute when no two boxes compete for the same anchor
+//      (the common case); otherwise the reference's sequential rounds run, incl. its zeroed-row quirk, re-evaluating only
+//      the tile of a taken anchor (and, if a row falls below its LB, the tiles in descending-U order); then the <= G
+//      rows whose bipartite match overrides the multi-match row are rewritten.
+// enc_lb_kernel      (only for images with many boxes) LB[g] = best exact IoU of box g among the anchors of the tiles whose
+//                    bounding box contains the box centre.  Any exact IoU is a valid lower bound: the choice of tiles
+//                    affects speed, never the result.  With few boxes per image LB = 0 (every overlapping pair is exact).
 // Exactness: every decision is taken on float64 values computed with the reference's operation order; float32 is only
 // used for bounds that can skip work, never for a comparison the result depends on.
 #include "common.cuh"
@@ -43,10 +50,21 @@ struct EncParams {
   float thr_adj;                // pairs whose IoU bound is below this cannot change an anchor's row
 };
 
+struct EncScratch {             // per call, global memory; TG = total number of ground-truth boxes in the batch
+  float* tU;                    // [n_tiles*TG] upper bound of the best IoU between a box and the anchors of a tile
+  double* tV;                   // [n_tiles*TG] best EXACT IoU among the evaluated pairs (0: none)
+  int* tI;                      // [n_tiles*TG] its prior index (lowest on ties)
+  const float* lb;              // [TG] lower bound of each box's row maximum, or NULL (= 0)
+  int* counters;                // [B] tickets
+  int TG;
+};
+
 struct TileSetDev {
   int n_tiles;
-  const int* map;               // [n_tiles*kTile] prior index of a slot, -1: empty
-  const int* runs;              // [n_tiles*kRunRec]: n_runs, then (first prior, length) pairs; slots follow run order
+  int linear;                   // 1: tile t holds priors [256 t, 256 t + 256), thread == staging slot, one run: nothing to load
+  const int2* map;              // [n_tiles*kTile] (prior index of a thread or -1, its staging slot)
+  const int* runs;              // [n_tiles*kRunRec]: n_runs, then (first prior, length) pairs; staging slots follow run order
+  const int* tile_of;           // [P] tile of a prior
   const double* bbox;           // [n_tiles*4] corner bounding box of the tile's anchors
 };
 
@@ -238,18 +256,46 @@ __device__ __forceinline__ float rcp_approx(float x) {          // MUFU.RCP: at 
 }
 
 // ------------------------------------------------------------------------------------------
-// match_bipartite_greedy (matching_utils.py:63-77) pieces, run by the last CTA of an image
+// tiles
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tile_anchor(const TileSetDev& ts, int tile, int s, int P, int& pos) {
+  if (ts.linear) { const int a = tile * kTile + s; pos = s; return a < P ? a : -1; }
+  const int2 m = __ldg(ts.map + (size_t)tile * kTile + s);
+  pos = m.y;
+  return m.x;
+}
+__device__ __forceinline__ int tile_of_prior(const TileSetDev& ts, int a) { return ts.linear ? a / kTile : __ldg(ts.tile_of + a); }
+
 __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
   bool r = false;
   for (int i = 0; i < n; ++i) r |= (removed[i] == a);
   return r;
 }
 
-// One warp: the exact best anchor (largest float64 IoU > 0, lowest prior index on ties) of ground-truth box `gb` among
-// the priors not in `removed`.  `urow[t]` bounds the IoU of every anchor of tile t from above, so tiles are visited in
-// descending-bound order and the scan stops as soon as the next bound is below the best exact value found.
-__device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const float* urow, const int* removed,
+// One warp: best exact IoU (> 0, lowest prior index on ties) of box `gb` among the anchors of `tile` not in `removed`.
+__device__ void warp_tile_best(const EncParams& p, const TileSetDev& ts, const Box& gb, int tile, const int* removed, int n_removed,
+                               double& out_v, int& out_i) {
+  const int lane = threadIdx.x & 31;
+  double bv = 0.0; int bi = INT_MAX;
+  for (int s = lane; s < kTile; s += 32) {
+    int pos;
+    const int a = tile_anchor(ts, tile, s, p.P, pos);
+    if (a < 0) continue;
+    const Box ab = load_anchor(p, a);
+    const double inter = inter_area(gb, ab);
+    if (inter > 0.0) {
+      const double v = iou_value(gb, ab, inter);
+      if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
+    }
+  }
+  warp_argmax(bv, bi);
+  out_v = bv; out_i = bi;
+}
+
+// One warp: the exact best anchor of `gb` over ALL tiles, ignoring `removed`, from the per-tile upper bounds alone: tiles are
+// visited in descending-bound order until the next bound is below the best exact value found.  General and exact, but slow
+// when many tiles tie at the maximum -- only used when a row drops below its lower bound during the sequential rounds.
+__device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const float* ucol, int stride, const int* removed,
                               int n_removed, double& out_v, int& out_i) {
   const int lane = threadIdx.x & 31;
   double best = 0.0; int bidx = INT_MAX;
@@ -257,7 +303,7 @@ __device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Bo
   for (;;) {
     float nu = 0.f; int nt = INT_MAX;                    // next tile after the cursor in (bound desc, tile asc) order
     for (int t = lane; t < ts.n_tiles; t += 32) {
-      const float u = __ldcg(urow + t);
+      const float u = __ldcg(ucol + (size_t)t * stride);
       const bool after = first || (u < cur_u) || (u == cur_u && t > cur_t);
       if (after && u > 0.f && (u > nu || (u == nu && t < nt))) { nu = u; nt = t; }
     }
@@ -269,43 +315,81 @@ __device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Bo
     }
     if (nt == INT_MAX) break;
     if ((double)nu < best) break;                        // no anchor of the remaining tiles can reach (or tie) the best
-    double bv = 0.0; int bi = INT_MAX;
-    for (int s = lane; s < kTile; s += 32) {
-      const int a = __ldg(ts.map + (size_t)nt * kTile + s);
-      if (a < 0) continue;
-      const Box ab = load_anchor(p, a);
-      const double inter = inter_area(gb, ab);
-      if (inter > 0.0) {
-        const double v = iou_value(gb, ab, inter);
-        if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
-      }
-    }
-    warp_argmax(bv, bi);
+    double bv; int bi;
+    warp_tile_best(p, ts, gb, nt, removed, n_removed, bv, bi);
     if (bv > best || (bv == best && bv > 0.0 && bi < bidx)) { best = bv; bidx = bi; }
     cur_u = nu; cur_t = nt; first = false;
   }
   out_v = best; out_i = bidx;
 }
 
-__device__ void finish_image(const EncParams& p, const TileSetDev& ts, const void* gt, int gt_f64, int g0, int G, int b,
-                             const double* s_gbox, unsigned char* scratch, const float* ub, float* __restrict__ out_y,
-                             int* __restrict__ out_match) {
+// ------------------------------------------------------------------------------------------
+// enc_lb_kernel: lower bounds of the row maxima (one warp per ground-truth box)
+// ------------------------------------------------------------------------------------------
+template <bool INLINE_OFFS>
+__global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ EncParams p, const __grid_constant__ TileSetDev ts,
+                                                       const __grid_constant__ OffsArg offs_arg, const int* __restrict__ offs_dev,
+                                                       const void* __restrict__ gt, int gt_f64, float* __restrict__ lb) {
+  const int b = blockIdx.y;
+  const int g0 = INLINE_OFFS ? offs_arg.v[b] : offs_dev[b];
+  const int G = (INLINE_OFFS ? offs_arg.v[b + 1] : offs_dev[b + 1]) - g0;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * (kTile / 32) + (threadIdx.x >> 5);
+  if (g >= G) return;
+  double r[5], t[4]; int cls;
+  load_gt(gt, gt_f64, (size_t)(g0 + g), r);
+  gt_template(r, p, t, cls);
+  const Box gb = corners_from_template(t, p.coords, p.d);
+  const double cx = 0.5 * (gb.x0 + gb.x1), cy = 0.5 * (gb.y0 + gb.y1);
+  double best = 0.0;
+  for (int base = 0; base < ts.n_tiles; base += 32) {
+    const int tile = base + lane;
+    bool inside = false;
+    if (tile < ts.n_tiles) {
+      const double* bb = ts.bbox + (size_t)tile * 4;
+      inside = bb[0] <= cx && cx <= bb[2] && bb[1] <= cy && cy <= bb[3];
+    }
+    unsigned m = __ballot_sync(0xffffffffu, inside);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      double v; int i;
+      warp_tile_best(p, ts, gb, base + src, nullptr, 0, v, i);
+      best = fmax(best, v);
+    }
+  }
+  if (lane == 0) lb[g0 + g] = __double2float_rd(best);
+}
+
+// ------------------------------------------------------------------------------------------
+// match_bipartite_greedy (matching_utils.py:63-77), run by the last CTA of an image
+// ------------------------------------------------------------------------------------------
+__device__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
+                             int b, const double* s_gbox, unsigned char* scratch, float* __restrict__ out_y, int* __restrict__ out_match) {
   __shared__ int s_flag[2];
   double* rv = reinterpret_cast<double*>(scratch);           // [G] current row maximum
   int* ra = reinterpret_cast<int*>(rv + G);                   // [G] its (first) prior index
   int* removed = ra + G;                                      // [G] priors taken so far
   int* matches = removed + G;                                 // [G]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W = p.C + 12;
+  const int W = p.C + 12, TG = sc.TG;
   auto gbox = [&](int g) {
     Box q; q.x0 = s_gbox[g * 5]; q.y0 = s_gbox[g * 5 + 1]; q.x1 = s_gbox[g * 5 + 2]; q.y1 = s_gbox[g * 5 + 3]; q.area = s_gbox[g * 5 + 4];
     return q;
   };
-  // exact row maxima, one warp per ground-truth box
-  for (int g = warp; g < G; g += kTile / 32) {
-    double v; int i;
-    warp_row_best(p, ts, gbox(g), ub + (size_t)(g0 + g) * ts.n_tiles, nullptr, 0, v, i);
-    if (lane == 0) { rv[g] = v; ra[g] = (v > 0.0) ? i : 0; }   // argmax of an all-zero row is 0
+  // exact row maxima: one thread per box over the tile bests (coalesced: consecutive threads read consecutive boxes)
+  for (int g = tid; g < G; g += kTile) {
+    double bv = 0.0; int bi = INT_MAX;
+    const size_t col = (size_t)(g0 + g);
+#pragma unroll 4
+    for (int t = 0; t < ts.n_tiles; ++t) {
+      const double v = __ldcg(sc.tV + (size_t)t * TG + col);
+      if (v > 0.0) {
+        const int i = __ldcg(sc.tI + (size_t)t * TG + col);
+        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+      }
+    }
+    rv[g] = bv; ra[g] = (bv > 0.0) ? bi : 0;                    // argmax of an all-zero row is 0
   }
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
   __syncthreads();
@@ -345,8 +429,33 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const voi
           const int src = __ffs(need) - 1;
           need &= need - 1;
           const int gg = base + src;
+          const size_t col = (size_t)(g0 + gg);
+          const Box gb = gbox(gg);
+          // the row lost its best anchor: re-evaluate that anchor's tile without the taken priors, reduce the row again;
+          // repeat while the new best is itself a taken prior recorded by another tile
+          int stale = a_star;
           double nv; int ni;
-          warp_row_best(p, ts, gbox(gg), ub + (size_t)(g0 + gg) * ts.n_tiles, removed, n_removed, nv, ni);
+          for (;;) {
+            const int st = tile_of_prior(ts, stale);
+            double tv; int ti;
+            warp_tile_best(p, ts, gb, st, removed, n_removed, tv, ti);
+            if (lane == 0) { sc.tV[(size_t)st * TG + col] = tv; sc.tI[(size_t)st * TG + col] = ti; }
+            __syncwarp();
+            nv = 0.0; ni = INT_MAX;
+            for (int t = lane; t < ts.n_tiles; t += 32) {
+              const double v2 = (t == st) ? tv : __ldcg(sc.tV + (size_t)t * TG + col);
+              if (v2 > 0.0) {
+                const int i2 = (t == st) ? ti : __ldcg(sc.tI + (size_t)t * TG + col);
+                if (v2 > nv || (v2 == nv && i2 < ni)) { nv = v2; ni = i2; }
+              }
+            }
+            warp_argmax(nv, ni);
+            if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
+            stale = ni;
+          }
+          // pairs below the row's lower bound were never evaluated: if the best that is left fell below it, search all tiles
+          const float lbg = sc.lb ? __ldg(sc.lb + col) : 0.f;
+          if (nv < (double)lbg) warp_row_best(p, ts, gb, sc.tU + col, TG, removed, n_removed, nv, ni);
           if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
           __syncwarp();
         }
@@ -373,7 +482,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const voi
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, cf, ca, wmax, slot, total;
+  size_t rows, gbox, cf, cq, wU, wV, wI, slot, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
@@ -383,21 +492,23 @@ __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   if (fin > rows_bytes) rows_bytes = fin;
   auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   s.rows = 0;
-  s.gbox = rows_bytes;                                        // [G*5] f64
+  s.gbox = rows_bytes;                                        // [G*5] f64 corner boxes of the ground truth
   s.cf = up16(s.gbox + gs * 40);                              // [G] float4: outward-rounded corners of a candidate
-  s.ca = up16(s.cf + gs * 16);                                // [G] float2: (area rounded down, gt index)
-  s.wmax = up16(s.ca + gs * 8);                               // [8*G] u32: per-warp maximum of the IoU bound
-  s.slot = up16(s.wmax + gs * 32);                            // [G] candidate slot of a gt (-1: not a candidate)
+  s.cq = up16(s.cf + gs * 16);                                // [G] float4: (area rounded down, gt index, exact-evaluation threshold, -)
+  s.wV = up16(s.cq + gs * 16);                                // [8*G] f64: per-warp best exact IoU
+  s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-warp maximum of the IoU bound
+  s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-warp prior index of the best exact IoU
+  s.slot = up16(s.wI + gs * 32);                              // [G] candidate slot of a gt (-1: not a candidate)
   s.total = up16(s.slot + gs * 4) + 16;
   return s;
 }
 
 template <bool INLINE_OFFS>
-__global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant__ EncParams p, const __grid_constant__ TileSetDev ts,
-                                                          const __grid_constant__ OffsArg offs_arg, const int* __restrict__ offs_dev,
-                                                          const void* __restrict__ gt, int gt_f64, int tpc, float* __restrict__ ub,
-                                                          int* __restrict__ counters, float* __restrict__ out_y,
-                                                          int* __restrict__ out_match, int* __restrict__ status) {
+__global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_constant__ EncParams p, const __grid_constant__ TileSetDev ts,
+                                                             const __grid_constant__ OffsArg offs_arg, const int* __restrict__ offs_dev,
+                                                             const void* __restrict__ gt, int gt_f64, int tpc,
+                                                             const __grid_constant__ EncScratch sc, float* __restrict__ out_y,
+                                                             int* __restrict__ out_match, int* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_wcnt[kTile / 32];
   __shared__ int s_last;
@@ -405,15 +516,25 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
   const int g0 = INLINE_OFFS ? offs_arg.v[b] : offs_dev[b];
   const int G = (INLINE_OFFS ? offs_arg.v[b + 1] : offs_dev[b + 1]) - g0;
   const int Gs = G > 0 ? G : 1;
-  const int W = p.C + 12;
+  const int W = p.C + 12, TG = sc.TG;
   const EncSmem L = enc_smem_layout(W, G);
   float* rows = reinterpret_cast<float*>(smem_raw + L.rows);
   double* s_gbox = reinterpret_cast<double*>(smem_raw + L.gbox);
   float4* s_cf = reinterpret_cast<float4*>(smem_raw + L.cf);
-  float2* s_ca = reinterpret_cast<float2*>(smem_raw + L.ca);
-  unsigned* s_wmax = reinterpret_cast<unsigned*>(smem_raw + L.wmax);
+  float4* s_cq = reinterpret_cast<float4*>(smem_raw + L.cq);
+  double* s_wV = reinterpret_cast<double*>(smem_raw + L.wV);
+  unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
+  int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
   int* slot_of = reinterpret_cast<int*>(smem_raw + L.slot);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const int tile0 = blockIdx.x * tpc;
+  const int tile1 = min(ts.n_tiles, tile0 + tpc);
+  // the first tile's anchor: issued before anything else so that its latency hides behind the ground-truth set-up
+  int pos = 0;
+  int a = tile_anchor(ts, tile0, tid, p.P, pos);
+  double at[4] = {0, 0, 0, 0};
+  if (a >= 0) load_anchor_t(p, a, at);
 
   // ---- 1. ground truth of this image -> float64 corner boxes ----
   bool bad = false;
@@ -427,10 +548,12 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
   const int any_bad = __syncthreads_or(bad ? 1 : 0);          // also publishes s_gbox
   if (blockIdx.x == 0 && tid == 0 && any_bad && status) atomicMax(status, b + 1);
 
-  const int tile0 = blockIdx.x * tpc;
-  const int tile1 = min(ts.n_tiles, tile0 + tpc);
   bool store_pending = false;
   for (int tile = tile0; tile < tile1; ++tile) {
+    if (tile != tile0) {
+      a = tile_anchor(ts, tile, tid, p.P, pos);
+      if (a >= 0) load_anchor_t(p, a, at);
+    }
     // ---- 2. ordered candidate list (ascending gt index) ----
     const double bb[4] = {ts.bbox[tile * 4], ts.bbox[tile * 4 + 1], ts.bbox[tile * 4 + 2], ts.bbox[tile * 4 + 3]};
     int ncand = 0;
@@ -448,23 +571,31 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
 #pragma unroll
       for (int w = 0; w < kTile / 32; ++w) { const int c = s_wcnt[w]; if (w < warp) wbase += c; total += c; }
       if (hit) {
-        const int pos = wbase + __popc(m & ((1u << lane) - 1));
+        const int cpos = wbase + __popc(m & ((1u << lane) - 1));
         // outward-rounded float32 corners, area rounded down: ingredients of an IoU bound that can only err upwards
-        s_cf[pos] = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
-        s_ca[pos] = make_float2(__double2float_rd(gb.area), __int_as_float(g));
-        slot_of[g] = pos;
+        s_cf[cpos] = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
+        // exact evaluation is needed from the smaller of: the threshold an anchor's own row depends on, and the lower bound of
+        // this box's row maximum (both lowered by more than the bound's own slack; never below "any overlap at all")
+        float q = 1.401298464e-45f;
+        if (sc.lb) {
+          const float lbg = __ldg(sc.lb + g0 + g);
+          if (lbg > 0.f) q = fmaxf(q, nextafterf(lbg * 0.99999905f, 0.f));
+        }
+        q = fminf(q, p.thr_adj);
+        s_cq[cpos] = make_float4(__double2float_rd(gb.area), __int_as_float(g), q, 0.f);
+        slot_of[g] = cpos;
       } else if (g < G) {
         slot_of[g] = -1;
       }
       ncand += total;
       __syncthreads();
     }
-    // ---- 3. this thread's anchor ----
-    const int a = __ldg(ts.map + (size_t)tile * kTile + tid);
+    // ---- 3. this thread's anchor against the candidates ----
     const bool live = a >= 0;
     float fx0 = 0.f, fy0 = 0.f, fx1 = -INFINITY, fy1 = -INFINITY, fa = 0.f;
+    Box ab{};
     if (live) {
-      const Box ab = load_anchor(p, a);
+      ab = corners_from_template(at, p.coords, p.d);
       fx0 = __double2float_rd(ab.x0); fy0 = __double2float_rd(ab.y0);
       fx1 = __double2float_ru(ab.x1); fy1 = __double2float_ru(ab.y1);
       fa = __double2float_rd(ab.area);
@@ -473,40 +604,53 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
 #pragma unroll 2
     for (int c = 0; c < ncand; ++c) {
       const float4 gf = s_cf[c];
-      const float2 ga = s_ca[c];
+      const float4 gq = s_cq[c];
       // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
       const float iw = fmaxf(__fsub_ru(fminf(fx1, gf.z), fmaxf(fx0, gf.x)), 0.f);
       const float ih = fmaxf(__fsub_ru(fminf(fy1, gf.w), fmaxf(fy0, gf.y)), 0.f);
       const float inter = __fmul_ru(iw, ih);
-      const float un = fmaxf(__fsub_rd(__fadd_rd(fa, ga.x), inter), 1e-30f);
-      const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst; see thr_adj and the 1+2^-21 factor
+      const float un = fmaxf(__fsub_rd(__fadd_rd(fa, gq.x), inter), 1e-30f);
+      const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst (thresholds and the stored tile
+                                                             // maximum account for it)
       const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
-      if (lane == 0) s_wmax[warp * Gs + c] = wm;
-      if (live && U >= p.thr_adj) {                           // rare: the pair may matter for this anchor's row -> exact float64 IoU
-        const int g = __float_as_int(ga.y);
+      double val = 0.0;
+      if (live && U >= gq.z) {                                // rare: the pair may decide something -> the reference's float64 IoU
+        const int g = __float_as_int(gq.y);
         Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
-        const Box ab = load_anchor(p, a);
         const double inter64 = inter_area(gb, ab);
         if (inter64 > 0.0) {
-          const double val = iou_value(gb, ab, inter64);
+          val = iou_value(gb, ab, inter64);
           if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
+          if (!(val > 0.0)) val = 0.0;
         }
       }
+      // best exact pair of this warp for the candidate (first prior index on ties)
+      double rvv = 0.0; int rii = INT_MAX;
+      if (__any_sync(0xffffffffu, val > 0.0)) {
+        rvv = val; rii = (val > 0.0) ? a : INT_MAX;
+        warp_argmax(rvv, rii);
+      }
+      if (lane == 0) { s_wU[warp * Gs + c] = wm; s_wV[warp * Gs + c] = rvv; s_wI[warp * Gs + c] = rii; }
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
-    // ---- per (gt, tile) bound -> global ----
+    // ---- per (gt, tile) results -> global (consecutive threads write consecutive boxes) ----
     for (int g = tid; g < G; g += kTile) {
       const int c = slot_of[g];
-      float u = 0.f;
+      float u = 0.f; double bv = 0.0; int bi = INT_MAX;
       if (c >= 0) {
         unsigned m = 0;
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) m = max(m, s_wmax[w * Gs + c]);
+        for (int w = 0; w < kTile / 32; ++w) {
+          m = max(m, s_wU[w * Gs + c]);
+          const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
+          if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
+        }
         u = __fmul_ru(__uint_as_float(m), 1.0f + 4.76837158203125e-7f);     // (1 + 2^-21) covers the reciprocal's 1 ulp
       }
-      ub[(size_t)(g0 + g) * ts.n_tiles + tile] = u;
+      const size_t o = (size_t)tile * TG + (size_t)(g0 + g);
+      sc.tU[o] = u; sc.tV[o] = bv; sc.tI[o] = bi;
     }
     // ---- 4. this anchor's row ----
     if (live) {
@@ -517,20 +661,20 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
         if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
         if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
       }
-      double at[4];
-      load_anchor_t(p, a, at);
-      emit_row(p, gt, gt_f64, g0, at, dec, rows + (size_t)tid * W);
+      emit_row(p, gt, gt_f64, g0, at, dec, rows + (size_t)pos * W);
       if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the rows -> visible to the bulk copy engine
     __syncthreads();
     // ---- 5. rows leave: one bulk store per contiguous run of priors ----
-    const int* rn = ts.runs + (size_t)tile * kRunRec;
-    const int nruns = rn[0];
+    int nruns = 1;
+    const int* rn = nullptr;
+    if (!ts.linear) { rn = ts.runs + (size_t)tile * kRunRec; nruns = rn[0]; }
     int slot0 = 0;
     bool issued = false;
     for (int r = 0; r < nruns; ++r) {
-      const int start = rn[1 + 2 * r], len = rn[2 + 2 * r];
+      const int start = ts.linear ? tile * kTile : rn[1 + 2 * r];
+      const int len = ts.linear ? min(kTile, p.P - tile * kTile) : rn[2 + 2 * r];
       float* dst = out_y + ((size_t)b * p.P + start) * W;
       const float* src = rows + (size_t)slot0 * W;
       const size_t n_f = (size_t)len * W;
@@ -552,25 +696,25 @@ __global__ void __launch_bounds__(kTile) enc_tiles_kernel(const __grid_constant_
   // ---- 6. last CTA of the image: bipartite matching ----
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (G <= 0) return;
-  __threadfence();
-  __syncthreads();
+  __syncthreads();                                              // every thread's global writes happen-before thread 0's fence
   if (tid == 0) {
     __threadfence();
-    const int old = atomicAdd(counters + b, 1);
+    const int old = atomicAdd(sc.counters + b, 1);
     const int last = (old == (int)gridDim.x - 1);
-    if (last) counters[b] = 0;                                  // ready for the next launch
+    if (last) sc.counters[b] = 0;                               // ready for the next launch
     __threadfence();
     s_last = last;
   }
   __syncthreads();
   if (!s_last) return;
-  finish_image(p, ts, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, ub, out_y, out_match);
+  finish_image(p, ts, sc, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, out_y, out_match);
 }
 
-__global__ void tile_bbox_kernel(EncParams p, const int* __restrict__ map, double* __restrict__ bbox) {
+__global__ void tile_bbox_kernel(EncParams p, TileSetDev ts, double* __restrict__ bbox) {
   __shared__ double s[4][kTile / 32];
   const int tile = blockIdx.x;
-  const int a = map[(size_t)tile * kTile + threadIdx.x];
+  int pos;
+  const int a = tile_anchor(ts, tile, threadIdx.x, p.P, pos);
   double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
   if (a >= 0) { Box ab = load_anchor(p, a); x0 = ab.x0; y0 = ab.y0; x1 = ab.x1; y1 = ab.y1; }
 #pragma unroll
@@ -591,23 +735,31 @@ __global__ void tile_bbox_kernel(EncParams p, const int* __restrict__ map, doubl
 // host side: tile sets
 // ------------------------------------------------------------------------------------------
 struct TileSetHost {
-  std::vector<int> map, runs;
+  std::vector<int> map, pos, runs;      // map/pos per thread slot
   int n_tiles = 0;
-  void begin_tile() { runs.resize((size_t)(n_tiles + 1) * kRunRec, 0); map.resize((size_t)(n_tiles + 1) * kTile, -1); fill = 0; }
-  void add_run(int start, int len) {
+  int fill = 0;
+  void begin_tile() { runs.resize((size_t)(n_tiles + 1) * kRunRec, 0); map.resize((size_t)(n_tiles + 1) * kTile, -1); pos.resize(map.size(), 0); fill = 0; }
+  // a run of `cells` feature-map cells x nb boxes starting at prior `start`; `cell0` = cells already in this tile, `ncells` = cells
+  // the finished tile will hold: thread = box * ncells + cell (box-shape-major), staging slot = run order
+  void add_run(int start, int cells, int nb, int cell0, int ncells) {
     int* r = runs.data() + (size_t)n_tiles * kRunRec;
-    r[1 + 2 * r[0]] = start; r[2 + 2 * r[0]] = len; ++r[0];
-    for (int i = 0; i < len; ++i) map[(size_t)n_tiles * kTile + fill + i] = start + i;
-    fill += len;
+    r[1 + 2 * r[0]] = start; r[2 + 2 * r[0]] = cells * nb; ++r[0];
+    for (int c = 0; c < cells; ++c)
+      for (int bx = 0; bx < nb; ++bx) {
+        const int thread = bx * ncells + cell0 + c;
+        map[(size_t)n_tiles * kTile + thread] = start + c * nb + bx;
+        pos[(size_t)n_tiles * kTile + thread] = fill + c * nb + bx;
+      }
+    fill += cells * nb;
   }
   void end_tile() { ++n_tiles; }
-  int fill = 0;
 };
 
-void linear_tiles(TileSetHost& t, int first, int count) {
+void linear_layer_tiles(TileSetHost& t, int first, int count) {
   for (int o = 0; o < count; o += kTile) {
     t.begin_tile();
-    t.add_run(first + o, std::min(kTile, count - o));
+    const int n = std::min(kTile, count - o);
+    t.add_run(first + o, n, 1, 0, n);
     t.end_tile();
   }
 }
@@ -618,23 +770,25 @@ void spatial_tiles(TileSetHost& t, int n_layers, const int* fh, const int* fw, c
   for (int l = 0; l < n_layers; ++l) {
     const int H = fh[l], Wd = fw[l], nb = nbx[l];
     const int count = H * Wd * nb;
-    if (nb > kTile || nb <= 0) { linear_tiles(t, off, count); off += count; continue; }
+    if (nb > kTile || nb <= 0) { linear_layer_tiles(t, off, count); off += count; continue; }
     const int cells_max = kTile / nb;
     int bw = (int)std::floor(std::sqrt((double)cells_max));
     if (bw < 1) bw = 1;
     if (bw >= Wd) {                                            // whole rows fit: a tile is bh full rows = one contiguous run
       const int bh = std::max(1, std::min(H, cells_max / Wd));
       for (int y0 = 0; y0 < H; y0 += bh) {
+        const int rws = std::min(bh, H - y0);
         t.begin_tile();
-        t.add_run(off + y0 * Wd * nb, std::min(bh, H - y0) * Wd * nb);
+        t.add_run(off + y0 * Wd * nb, rws * Wd, nb, 0, rws * Wd);
         t.end_tile();
       }
     } else {
       const int bh = std::max(1, std::min(std::min(H, cells_max / bw), kMaxRuns));
       for (int y0 = 0; y0 < H; y0 += bh)
         for (int x0 = 0; x0 < Wd; x0 += bw) {
+          const int cw = std::min(bw, Wd - x0), ch = std::min(bh, H - y0);
           t.begin_tile();
-          for (int y = y0; y < std::min(H, y0 + bh); ++y) t.add_run(off + (y * Wd + x0) * nb, std::min(bw, Wd - x0) * nb);
+          for (int y = 0; y < ch; ++y) t.add_run(off + ((y0 + y) * Wd + x0) * nb, cw, nb, y * cw, cw * ch);
           t.end_tile();
         }
     }
@@ -644,8 +798,8 @@ void spatial_tiles(TileSetHost& t, int n_layers, const int* fh, const int* fw, c
 
 struct TileSetOwned {
   TileSetDev dev{};
-  int* d_map = nullptr; int* d_runs = nullptr; double* d_bbox = nullptr;
-  void release() { cudaFree(d_map); cudaFree(d_runs); cudaFree(d_bbox); d_map = d_runs = nullptr; d_bbox = nullptr; dev = TileSetDev{}; }
+  int2* d_map = nullptr; int* d_runs = nullptr; int* d_tile_of = nullptr; double* d_bbox = nullptr;
+  void release() { cudaFree(d_map); cudaFree(d_runs); cudaFree(d_tile_of); cudaFree(d_bbox); d_map = nullptr; d_runs = d_tile_of = nullptr; d_bbox = nullptr; dev = TileSetDev{}; }
 };
 
 }  // namespace
@@ -656,7 +810,7 @@ struct ssdk_encoder {
   EncParams p{};
   double* d_anchors = nullptr;
   TileSetOwned linear, spatial;     // spatial.dev.n_tiles == 0: no layer geometry was given
-  Scratch ub;                       // per-(gt, tile) IoU bounds
+  Scratch tiles;                    // per-(gt, tile) bounds and exact bests, per-gt lower bounds
   Scratch counters;                 // per-image tickets (self-resetting)
   size_t counters_n = 0;
   Scratch offsets;                  // device copy of the offsets for batches larger than kInlineB
@@ -671,29 +825,61 @@ struct ssdk_encoder {
 
 namespace {
 
-int upload_tiles(ssdk_encoder* e, const TileSetHost& h, TileSetOwned& o) {
-  SSDK_CHECK_CUDA(cudaMalloc(&o.d_map, h.map.size() * sizeof(int)));
-  SSDK_CHECK_CUDA(cudaMalloc(&o.d_runs, h.runs.size() * sizeof(int)));
-  SSDK_CHECK_CUDA(cudaMalloc(&o.d_bbox, (size_t)h.n_tiles * 4 * sizeof(double)));
-  SSDK_CHECK_CUDA(cudaMemcpy(o.d_map, h.map.data(), h.map.size() * sizeof(int), cudaMemcpyHostToDevice));
-  SSDK_CHECK_CUDA(cudaMemcpy(o.d_runs, h.runs.data(), h.runs.size() * sizeof(int), cudaMemcpyHostToDevice));
-  tile_bbox_kernel<<<h.n_tiles, kTile>>>(e->p, o.d_map, o.d_bbox);
+int upload_tiles(ssdk_encoder* e, const TileSetHost* h, int n_linear_tiles, TileSetOwned& o) {
+  const int n_tiles = h ? h->n_tiles : n_linear_tiles;
+  SSDK_CHECK_CUDA(cudaMalloc(&o.d_bbox, (size_t)n_tiles * 4 * sizeof(double)));
+  o.dev.n_tiles = n_tiles; o.dev.linear = h ? 0 : 1;
+  if (h) {
+    std::vector<int2> m(h->map.size());
+    std::vector<int> tile_of((size_t)e->p.P, 0);
+    for (size_t i = 0; i < m.size(); ++i) {
+      m[i] = make_int2(h->map[i], h->pos[i]);
+      if (h->map[i] >= 0) tile_of[h->map[i]] = (int)(i / kTile);
+    }
+    SSDK_CHECK_CUDA(cudaMalloc(&o.d_map, m.size() * sizeof(int2)));
+    SSDK_CHECK_CUDA(cudaMalloc(&o.d_runs, h->runs.size() * sizeof(int)));
+    SSDK_CHECK_CUDA(cudaMalloc(&o.d_tile_of, tile_of.size() * sizeof(int)));
+    SSDK_CHECK_CUDA(cudaMemcpy(o.d_map, m.data(), m.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SSDK_CHECK_CUDA(cudaMemcpy(o.d_runs, h->runs.data(), h->runs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    SSDK_CHECK_CUDA(cudaMemcpy(o.d_tile_of, tile_of.data(), tile_of.size() * sizeof(int), cudaMemcpyHostToDevice));
+    o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.tile_of = o.d_tile_of;
+  }
+  o.dev.bbox = o.d_bbox;
+  tile_bbox_kernel<<<n_tiles, kTile>>>(e->p, o.dev, o.d_bbox);
   SSDK_COUNT_LAUNCH(e->ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
-  o.dev.n_tiles = h.n_tiles; o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.bbox = o.d_bbox;
   return SSDK_OK;
 }
 
+// every prior exactly once, every thread's staging slot inside its tile's runs exactly once
 bool tiles_cover(const TileSetHost& h, int P) {
   std::vector<char> seen((size_t)P, 0);
-  for (int a : h.map) {
-    if (a < 0) continue;
-    if (a >= P || seen[a]) return false;
-    seen[a] = 1;
+  for (int t = 0; t < h.n_tiles; ++t) {
+    std::vector<char> slot(kTile, 0);
+    int fill = 0;
+    const int* r = h.runs.data() + (size_t)t * kRunRec;
+    for (int i = 0; i < r[0]; ++i) fill += r[2 + 2 * i];
+    if (fill > kTile || r[0] > kMaxRuns) return false;
+    for (int s = 0; s < kTile; ++s) {
+      const int a = h.map[(size_t)t * kTile + s];
+      if (a < 0) continue;
+      const int ps = h.pos[(size_t)t * kTile + s];
+      if (a >= P || seen[a] || ps < 0 || ps >= fill || slot[ps]) return false;
+      seen[a] = 1; slot[ps] = 1;
+      // the staging slot must be the prior's place in run order
+      int base = 0, want = -1;
+      for (int i = 0; i < r[0]; ++i) {
+        if (a >= r[1 + 2 * i] && a < r[1 + 2 * i] + r[2 + 2 * i]) { want = base + (a - r[1 + 2 * i]); break; }
+        base += r[2 + 2 * i];
+      }
+      if (want != ps) return false;
+    }
   }
   for (char c : seen) if (!c) return false;
   return true;
 }
+
+size_t g_smem_attr[2] = {0, 0};
 
 }  // namespace
 
@@ -723,7 +909,7 @@ extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, co
       t = std::nextafterf(t, 0.f);
       if (!(t > 0.f)) t = 0.f;
     }
-    p.thr_adj = t;                                             // 0: every overlapping pair is evaluated exactly
+    p.thr_adj = t;                                             // 0: every pair is evaluated exactly
   }
   auto fail = [&](int code) { ssdk_encoder_destroy(e); return code; };
   if (cudaMalloc(&e->d_anchors, (size_t)p.P * 4 * sizeof(double)) != cudaSuccess) { set_error("ssdk_encoder_create: cudaMalloc failed"); return fail(SSDK_ERR_NOMEM); }
@@ -731,12 +917,8 @@ extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, co
     set_error("ssdk_encoder_create: anchor upload failed"); return fail(SSDK_ERR_CUDA);
   }
   p.anchors = e->d_anchors;
-  int rc;
-  {
-    TileSetHost h;
-    linear_tiles(h, 0, p.P);
-    rc = upload_tiles(e, h, e->linear); if (rc) return fail(rc);
-  }
+  int rc = upload_tiles(e, nullptr, ceil_div(p.P, kTile), e->linear);
+  if (rc) return fail(rc);
   if (cfg->n_layers > 0 && cfg->fm_height && cfg->fm_width && cfg->n_boxes) {
     long long tot = 0;
     for (int l = 0; l < cfg->n_layers; ++l) tot += (long long)cfg->fm_height[l] * cfg->fm_width[l] * cfg->n_boxes[l];
@@ -744,7 +926,7 @@ extern "C" int ssdk_encoder_create(ssdk_ctx* ctx, const ssdk_encode_cfg* cfg, co
     TileSetHost h;
     spatial_tiles(h, cfg->n_layers, cfg->fm_height, cfg->fm_width, cfg->n_boxes);
     if (!tiles_cover(h, p.P)) { set_error("internal: spatial tiles do not cover the priors exactly once"); return fail(SSDK_ERR_INVALID); }
-    rc = upload_tiles(e, h, e->spatial); if (rc) return fail(rc);
+    rc = upload_tiles(e, &h, 0, e->spatial); if (rc) return fail(rc);
   }
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("ssdk_encoder_create: tile setup failed"); return fail(SSDK_ERR_CUDA); }
   *out = e;
@@ -755,7 +937,7 @@ extern "C" int ssdk_encoder_destroy(ssdk_encoder* e) {
   if (!e) return SSDK_OK;
   cudaFree(e->d_anchors);
   e->linear.release(); e->spatial.release();
-  e->ub.release(); e->counters.release(); e->offsets.release();
+  e->tiles.release(); e->counters.release(); e->offsets.release();
   if (e->h_offsets) cudaFreeHost(e->h_offsets);
   for (int i = 0; i < ssdk_encoder::kSlots; ++i) if (e->slot_done[i]) cudaEventDestroy(e->slot_done[i]);
   delete e;
@@ -786,8 +968,6 @@ extern "C" int ssdk_iou(ssdk_ctx* ctx, const double* boxes1_dev, int m, const do
 
 namespace {
 
-size_t g_smem_attr[2] = {0, 0};
-
 // Common launch path.  offs_host (B+1 ints) may be NULL when offs_dev is given together with total_g / max_g.
 int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* offs_host, const int* offs_dev, int B, int total_g,
                   int max_g, float* out_y_dev, int* out_match_dev, int* status_dev, cudaStream_t stream) {
@@ -795,19 +975,29 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   const int W = p.C + 12;
   SSDK_REQUIRE(total_g == 0 || gt_dev, "ssdk_encode: gt_boxes_dev is NULL");
   SSDK_REQUIRE((reinterpret_cast<uintptr_t>(out_y_dev) & 3) == 0, "ssdk_encode: out_y_dev is not float aligned");
-  // tile set: compact cell blocks pay off once many boxes compete per tile; consecutive priors give full tiles and one
-  // 16-byte aligned run each, which is what matters when the kernel is purely store bound
-  int spatial_min = 24;
+  // tile set: compact cell blocks pay off once many boxes compete per tile; consecutive priors give full tiles, one aligned
+  // run each and nothing to look up, which is what matters when the kernel is purely store / latency bound
+  int spatial_min = 24, lb_min = 17;
   if (const char* s = getenv("SSDK_ENC_SPATIAL_MIN")) spatial_min = atoi(s);
+  if (const char* s = getenv("SSDK_ENC_LB_MIN")) lb_min = atoi(s);
   const bool use_spatial = e->spatial.dev.n_tiles > 0 && max_g >= spatial_min;
   const TileSetDev& ts = use_spatial ? e->spatial.dev : e->linear.dev;
+  const bool use_lb = max_g >= lb_min && total_g > 0;
   int tpc = max_g <= 16 ? 1 : (max_g <= 48 ? 2 : 4);
   if (const char* s = getenv("SSDK_ENC_TPC")) tpc = std::max(1, atoi(s));
   while (tpc > 1 && (long long)ceil_div(ts.n_tiles, tpc) * B < 8ll * e->ctx->sm_count) tpc >>= 1;
-  // scratch
-  const size_t n = (size_t)(total_g > 0 ? total_g : 1);
-  int rc = e->ub.ensure(n * (size_t)ts.n_tiles * sizeof(float));
+  // scratch: tV (f64) | tU (f32) | tI (i32) each [n_tiles * TG], lb [TG]
+  const size_t TG = (size_t)(total_g > 0 ? total_g : 1);
+  const size_t nt = TG * (size_t)ts.n_tiles;
+  int rc = e->tiles.ensure(nt * 16 + TG * 4 + 64);
   if (rc) return rc;
+  EncScratch sc{};
+  sc.tV = reinterpret_cast<double*>(e->tiles.ptr);
+  sc.tU = reinterpret_cast<float*>(sc.tV + nt);
+  sc.tI = reinterpret_cast<int*>(sc.tU + nt);
+  float* lb = reinterpret_cast<float*>(sc.tI + nt);
+  sc.lb = use_lb ? lb : nullptr;
+  sc.TG = (int)TG;
   if (e->counters_n < (size_t)B) {
     SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
     rc = e->counters.ensure((size_t)B * sizeof(int));
@@ -815,9 +1005,11 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
     SSDK_CHECK_CUDA(cudaMemset(e->counters.ptr, 0, e->counters.bytes));
     e->counters_n = e->counters.bytes / sizeof(int);
   }
+  sc.counters = reinterpret_cast<int*>(e->counters.ptr);
   const EncSmem L = enc_smem_layout(W, max_g);
   SSDK_REQUIRE(L.total <= 227 * 1024, "ssdk_encode: n_classes (%d) / gt count (%d) need %zu bytes of shared memory", p.C, max_g, L.total);
   dim3 grid(ceil_div(ts.n_tiles, tpc), B);
+  dim3 grid_lb(ceil_div(max_g, kTile / 32), B);
   const bool inline_offs = offs_host != nullptr && B <= kInlineB;
   if (inline_offs) {
     if (L.total > 48 * 1024 && L.total > g_smem_attr[0]) {   // the attribute belongs to the kernel, not to an encoder: only ever raise it
@@ -826,8 +1018,11 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
     }
     OffsArg& arg = e->offs_arg;
     memcpy(arg.v, offs_host, (size_t)(B + 1) * sizeof(int));
-    enc_tiles_kernel<true><<<grid, kTile, L.total, stream>>>(p, ts, arg, nullptr, gt_dev, gt_f64, tpc, reinterpret_cast<float*>(e->ub.ptr),
-                                                             reinterpret_cast<int*>(e->counters.ptr), out_y_dev, out_match_dev, status_dev);
+    if (use_lb) {
+      enc_lb_kernel<true><<<grid_lb, kTile, 0, stream>>>(p, ts, arg, nullptr, gt_dev, gt_f64, lb);
+      SSDK_COUNT_LAUNCH(e->ctx);
+    }
+    enc_tiles_kernel<true><<<grid, kTile, L.total, stream>>>(p, ts, arg, nullptr, gt_dev, gt_f64, tpc, sc, out_y_dev, out_match_dev, status_dev);
   } else {
     const int* d_offs = offs_dev;
     if (!d_offs) {                                         // large batch with host offsets: pinned ring + async copy
@@ -853,8 +1048,11 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
       SSDK_CHECK_CUDA(cudaFuncSetAttribute(enc_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
       g_smem_attr[1] = L.total;
     }
-    enc_tiles_kernel<false><<<grid, kTile, L.total, stream>>>(p, ts, e->offs_arg, d_offs, gt_dev, gt_f64, tpc, reinterpret_cast<float*>(e->ub.ptr),
-                                                              reinterpret_cast<int*>(e->counters.ptr), out_y_dev, out_match_dev, status_dev);
+    if (use_lb) {
+      enc_lb_kernel<false><<<grid_lb, kTile, 0, stream>>>(p, ts, e->offs_arg, d_offs, gt_dev, gt_f64, lb);
+      SSDK_COUNT_LAUNCH(e->ctx);
+    }
+    enc_tiles_kernel<false><<<grid, kTile, L.total, stream>>>(p, ts, e->offs_arg, d_offs, gt_dev, gt_f64, tpc, sc, out_y_dev, out_match_dev, status_dev);
   }
   SSDK_COUNT_LAUNCH(e->ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());

@@ -1,288 +1,532 @@
-// SSDLoss on sm_100a.  Reference: keras_loss_function/keras_ssd_loss.py:53-211.
+// SSDLoss on sm_100a as ONE kernel (forward, backward, or both).  Reference: keras_loss_function/keras_ssd_loss.py:53-211.
 //
-// HBM-bound: the two (B,P,C+12) tensors are read exactly once per pass by warp-per-row kernels
-// (coalesced row reads, shuffle reductions).  The batch-global hard-negative top-k (tf.nn.top_k over
-// B*P values, :179-183) is a 4-pass radix select on the float bits done by one CTA over the per-box
-// negative losses (B*P floats, L2 resident); ties at the threshold value are resolved by flat index
-// like tf.nn.top_k.  All cross-block sums go through per-block partials reduced in a fixed order, so
-// the result is deterministic.
-//   loss_box_kernel     per-box log-loss / smooth-L1, positives, negatives; per-block partial sums
-//   loss_select_kernel  n_positive, k, threshold key and tie index limit
-//   loss_negsum_kernel  masked negative sums per image
-//   loss_final_kernel   (pos + neg + alpha*loc) / max(1, n_pos) * B
-//   loss_grad_kernel    d loss / d y_pred (mask held constant)
+// ssd_loss_kernel is a persistent cooperative kernel (all CTAs co-resident, grid-wide barriers between phases):
+//   phase A  tiles of 128 prediction rows stream through shared memory with cp.async.bulk + mbarrier (two stages), one thread
+//            per row: log-loss (:93-95), smooth-L1 (:72-75), positives / negatives (:139-140); per-tile partial sums in a
+//            fixed order; the per-box negative losses (B*P floats, L2 resident) and a two-level histogram of their order
+//            keys (65536 fine bins by global atomics, 2048 coarse bins = sums of 32 fine bins).
+//   phase B  every CTA derives k (:166) and the fine bin that holds the k-th largest negative loss from the (small) coarse
+//            histogram; second histogram over the low 16 key bits of the boxes in that bin.
+//   phase C  threshold key T; only if fewer boxes than those equal to T are wanted, the tf.nn.top_k tie rule (lower flat
+//            index first, :179-183) is resolved with per-tile tie counts and one scan.
+//   phase D  masked negative sums per tile, and/or the gradient rows (mask held constant) staged in shared memory and
+//            written with cp.async.bulk; the last CTA to finish (atomic ticket) reduces the tile partials per image:
+//            (pos + neg + alpha*loc) / max(1, n_pos) * B (:204-209).
+// All sums that reach the result are reduced in a fixed order (per tile, then per image), histograms and counts are
+// integers: the output is deterministic.  The same phases run as separate launches (ssdk_ssd_loss_phase) when the batch is
+// spread over several GPUs and the reference's batch-global quantities (n_positive :143, the top-k :179-183) must be
+// global too: the histograms and counts in the caller-provided workspace are summed with NCCL between the phases.
 #include "common.cuh"
+#include "tc.cuh"
+#include <cooperative_groups.h>
 #include <cmath>
 
+namespace cg = cooperative_groups;
 using namespace ssdk;
 
 namespace {
 
-constexpr int kRowsPerBlock = 256;     // 8 warps x 32 rows
-constexpr int kSelThreads = 1024;
+constexpr int kRows = 128;             // rows per tile == threads per CTA
+constexpr int kCoarse = 2048;          // coarse bins: key >> 21 (level 1), (key >> 5) & 2047 (level 2)
+constexpr int kFine = 65536;           // fine bins:   key >> 16 (level 1), key & 65535 (level 2)
+constexpr unsigned kZeroKey = 0x80000000u;
 
-struct SelResult {
-  uint32_t T;        // orderable key of the k-th largest negative loss
-  int limit;         // ties (key == T) are taken iff flat index <= limit
-  int none;          // 1: no negatives are kept (k == 0 or no non-zero negative loss)
-  int k, n_pos, nnz, ties_taken;
-  float inv_norm;    // 1 / max(1, n_positive)
-};
-
-__device__ __forceinline__ uint32_t okey(float f) {
-  uint32_t b = __float_as_uint(f);
+__device__ __forceinline__ unsigned okey(float f) {       // order-preserving key: larger float -> larger unsigned
+  unsigned b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// partial layout per (b, blk): [0] sum cls*pos, [1] sum loc*pos, [2] sum pos, [3] count nonzero(cls*neg)
-__global__ void __launch_bounds__(256) loss_box_kernel(const float* __restrict__ y_true, const float* __restrict__ y_pred,
-                                                       int P, int C, float* __restrict__ cls_out, float* __restrict__ negl_out,
-                                                       double* __restrict__ partial) {
-  __shared__ double s_acc[8][4];
-  const int W = C + 12;
-  const int b = blockIdx.y, blk = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double a_pc = 0, a_loc = 0, a_pos = 0, a_nnz = 0;
-  for (int r = 0; r < 32; ++r) {
-    const int p = blk * kRowsPerBlock + warp * 32 + r;
-    if (p >= P) break;
-    const float* yt = y_true + ((size_t)b * P + p) * W;
-    const float* yp = y_pred + ((size_t)b * P + p) * W;
-    float acc = 0.f, pmax = -INFINITY;
-    for (int c = lane; c < C; c += 32) {
-      float t = yt[c];
-      if (t != 0.f) acc += t * logf(fmaxf(yp[c], 1e-15f));          // :93-95
-      if (c >= 1) pmax = fmaxf(pmax, t);                             // :140
+struct LossArgs {
+  const float* y_true; const float* y_pred;
+  int B, P, C;
+  int tiles_per_img, n_tiles;
+  long long n_total;                   // boxes the selection runs over (B*P, or the global count in multi-GPU mode)
+  int global_B;                        // batch size in the normalisation (:209)
+  int ratio, n_neg_min;
+  float alpha;
+  // workspace
+  float* cls; float* negl;             // [B*P]
+  double* part;                        // [n_tiles*2] sum cls*pos, sum loc*pos
+  double* negpart;                     // [n_tiles]
+  int* tile_ties;                      // [n_tiles + 1]
+  unsigned long long* counts;          // [0] sum of positives in 32.32 fixed point, [1] non-zero negative losses
+  unsigned* hist1;                     // [kCoarse + kFine]
+  unsigned* hist2;                     // [kCoarse + kFine]
+  unsigned* hist_next;                 // the other parity's 2*(kCoarse+kFine) ints, cleared for the next call (or NULL)
+  int* ticket;
+  const int* ties_all; int rank;       // multi-GPU: boxes equal to T on every rank (all-gathered), this rank's index
+  int* ties_local;                     // multi-GPU: out, boxes equal to T on this rank
+  // outputs
+  float* out_loss; int* out_stats; const float* upstream; float* out_grad;
+  int stages;                          // shared-memory stages of phase A / D tile loads (1 or 2)
+  int bulk_ok;                         // rows of a tile start 16-byte aligned: cp.async.bulk is usable
+};
+
+struct Sel {                           // what phases C / D know about the hard-negative selection
+  int none;                            // no negatives are kept
+  int k, n_pos, nnz;
+  float inv_norm;
+  unsigned T;                          // threshold key
+  long long want;                      // boxes equal to T that are kept, in flat-index order
+  long long ties_total;
+};
+
+// ---- shared-memory tile loads ----------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Loads rows [row0, row0+rows) of y_true and y_pred (W floats each) into the stage buffers.  Bulk path: one elected thread
+// issues two copies that complete on the stage's mbarrier; fallback: all threads copy and the caller's __syncthreads publishes.
+__device__ __forceinline__ void tile_load(const LossArgs& a, size_t flat_row0, int rows, float* s_t, float* s_p, uint32_t bar) {
+  const int W = a.C + 12;
+  const float* gt = a.y_true + flat_row0 * W;
+  const float* gp = a.y_pred + flat_row0 * W;
+  const uint32_t bytes = (uint32_t)rows * W * 4u;
+  if (a.bulk_ok) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, 2u * bytes);
+      bulk_load(smem_u32(s_t), gt, bytes, bar);
+      bulk_load(smem_u32(s_p), gp, bytes, bar);
     }
-    float l = 0.f;
-    if (lane < 4) {
-      float d = yt[C + lane] - yp[C + lane];
-      float ad = fabsf(d);
-      l = (ad < 1.0f) ? 0.5f * d * d : ad - 0.5f;                    // :72-74
-    }
-    l += __shfl_xor_sync(0xffffffffu, l, 1);
-    l += __shfl_xor_sync(0xffffffffu, l, 2);
-    acc = warp_sum(acc);
-    pmax = warp_max(pmax);
-    if (lane == 0) {
-      float cls = -acc;
-      float neg = yt[0];                                             // :139
-      float nl = cls * neg;                                          // :151
-      cls_out[(size_t)b * P + p] = cls;
-      negl_out[(size_t)b * P + p] = nl;
-      a_pc += (double)(cls * pmax);
-      a_loc += (double)(l * pmax);
-      a_pos += (double)pmax;
-      a_nnz += (nl != 0.f) ? 1.0 : 0.0;
-    }
-  }
-  if (lane == 0) { s_acc[warp][0] = a_pc; s_acc[warp][1] = a_loc; s_acc[warp][2] = a_pos; s_acc[warp][3] = a_nnz; }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    double t = 0;
-    for (int w = 0; w < 8; ++w) t += s_acc[w][threadIdx.x];
-    partial[((size_t)b * gridDim.x + blk) * 4 + threadIdx.x] = t;
+  } else {
+    for (int i = threadIdx.x; i < rows * W; i += kRows) { s_t[i] = gt[i]; s_p[i] = gp[i]; }
   }
 }
 
-__global__ void __launch_bounds__(kSelThreads) loss_select_kernel(const float* __restrict__ negl, int N, int B, int nblk,
-                                                                  const double* __restrict__ partial, int neg_pos_ratio,
-                                                                  int n_neg_min, SelResult* __restrict__ res) {
-  __shared__ int s_hist[256];
-  __shared__ int s_misc[4];
-  __shared__ double s_red[2];
-  __shared__ int s_w[kSelThreads / 32];
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* s_red) {       // fixed-order block reduction (4 warps), result in every thread
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return s_red[0] + s_red[1] + s_red[2] + s_red[3];
+}
+
+// ---- selection: which bin holds the `want`-th largest key -----------------------------------------------------------
+// hist = [coarse (kCoarse) | fine (kFine)], fine bin f belongs to coarse bin f >> 5.  `zero_fine` (or -1) is a fine bin that
+// additionally holds `n_zero` boxes that were never added atomically (the boxes whose negative loss is exactly 0).
+// Returns the fine bin; `want` becomes the rank inside it, `in_bin` its population.  All threads get the same answer.
+__device__ void select_bin(const unsigned* hist, int zero_fine, long long n_zero, long long& want, long long& in_bin, int& bin,
+                           long long* s_scan) {
+  // coarse: 2048 bins / 128 threads = 16 each, scanned from the top
+  const int t = threadIdx.x;
+  long long mine = 0;
+  const int c_hi = kCoarse - 1 - t * 16;
+  for (int i = 0; i < 16; ++i) {
+    const int c = c_hi - i;
+    mine += __ldcg(hist + c) + ((zero_fine >= 0 && (zero_fine >> 5) == c) ? n_zero : 0);
+  }
+  __syncthreads();
+  s_scan[t] = mine;
+  __syncthreads();
+  if (t == 0) {
+    long long acc = 0; int owner = kRows - 1;
+    for (int i = 0; i < kRows; ++i) { if (acc + s_scan[i] >= want) { owner = i; break; } acc += s_scan[i]; }
+    // inside the owner's 16 coarse bins
+    int c = kCoarse - 1 - owner * 16, csel = c - 15;
+    for (int i = 0; i < 16; ++i, --c) {
+      const long long v = __ldcg(hist + c) + ((zero_fine >= 0 && (zero_fine >> 5) == c) ? n_zero : 0);
+      if (acc + v >= want) { csel = c; break; }
+      acc += v;
+    }
+    // inside the coarse bin: 32 fine bins from the top
+    int f = csel * 32 + 31, fsel = csel * 32; long long pop = 0;
+    for (int i = 0; i < 32; ++i, --f) {
+      const long long v = __ldcg(hist + kCoarse + f) + ((f == zero_fine) ? n_zero : 0);
+      if (acc + v >= want) { fsel = f; pop = v; break; }
+      acc += v;
+    }
+    s_scan[0] = fsel; s_scan[1] = want - acc; s_scan[2] = pop;
+  }
+  __syncthreads();
+  bin = (int)s_scan[0]; want = s_scan[1]; in_bin = s_scan[2];
+  __syncthreads();
+}
+
+__device__ void read_counts(const LossArgs& a, Sel& s) {
+  const unsigned long long pos_fx = __ldcg(a.counts), nnz = __ldcg(a.counts + 1);
+  const float n_pos_f = (float)((double)pos_fx / 4294967296.0);         // tf.reduce_sum(positives) (:143)
+  s.n_pos = (int)n_pos_f;                                                // tf.to_int32
+  s.nnz = (int)nnz;
+  long long k = (long long)a.ratio * s.n_pos;
+  k = k > a.n_neg_min ? k : a.n_neg_min;
+  k = k < (long long)nnz ? k : (long long)nnz;                           // :166
+  s.k = (int)k;
+  s.inv_norm = 1.0f / fmaxf(1.0f, n_pos_f);
+  s.none = (k <= 0 || nnz == 0) ? 1 : 0;
+}
+
+// level 1: returns the high 16 key bits of the k-th largest negative loss and the rank wanted inside that bin
+__device__ void level1(const LossArgs& a, const Sel& s, int& b1, long long& want, long long* s_scan) {
+  long long in_bin;
+  want = s.k;
+  select_bin(a.hist1, (int)(kZeroKey >> 16), a.n_total - s.nnz, want, in_bin, b1, s_scan);
+}
+
+__device__ __forceinline__ bool taken(const Sel& s, unsigned key, long long tie_rank) {
+  if (s.none) return false;
+  return key > s.T || (key == s.T && tie_rank < s.want);
+}
+
+// ---- phase A -----------------------------------------------------------------------------------------------------------
+__device__ void phase_a(const LossArgs& a, unsigned char* smem, uint32_t bar0) {
+  const int W = a.C + 12, C = a.C;
   const int tid = threadIdx.x;
-  {   // n_positive and the number of non-zero negative losses: block reduction of the per-block partials (exact: integer counts)
-    __shared__ double s_part[2][kSelThreads / 32];
-    double np = 0, nz = 0;
-    for (int i = tid; i < B * nblk; i += kSelThreads) { np += partial[(size_t)i * 4 + 2]; nz += partial[(size_t)i * 4 + 3]; }
-    for (int o = 16; o > 0; o >>= 1) { np += __shfl_xor_sync(0xffffffffu, np, o); nz += __shfl_xor_sync(0xffffffffu, nz, o); }
-    if ((tid & 31) == 0) { s_part[0][tid >> 5] = np; s_part[1][tid >> 5] = nz; }
-    __syncthreads();
-    if (tid == 0) {
-      double a = 0, b = 0;
-      for (int w = 0; w < kSelThreads / 32; ++w) { a += s_part[0][w]; b += s_part[1][w]; }
-      s_red[0] = a; s_red[1] = b;
-    }
-    __syncthreads();
-  }
-  const float n_pos_f = (float)s_red[0];
-  const int n_pos = (int)n_pos_f;                                       // tf.to_int32(n_positive)
-  const int nnz = (int)s_red[1];
-  int k = neg_pos_ratio * n_pos;
-  k = k > n_neg_min ? k : n_neg_min;
-  k = k < nnz ? k : nnz;                                                // :166
-  if (tid == 0) {
-    res->k = k; res->n_pos = n_pos; res->nnz = nnz; res->ties_taken = 0;
-    res->inv_norm = 1.0f / fmaxf(1.0f, n_pos_f);
-    res->none = (k <= 0 || nnz == 0) ? 1 : 0;
-    res->T = 0; res->limit = 0x7fffffff;
-  }
-  if (k <= 0 || nnz == 0) return;
-  uint32_t prefix = 0, mask = 0;
-  int want = k, ties_total = 0;
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += kSelThreads) s_hist[i] = 0;
-    __syncthreads();
-    // (a __match_any_sync-aggregated variant was measured slower on B200: 0.45 vs 0.28 ms for the whole loss forward)
-    for (int i = tid; i < N; i += kSelThreads) {
-      uint32_t key = okey(negl[i]);
-      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int acc = 0, bsel = 0;
-      for (int bb = 255; bb >= 0; --bb) {
-        if (acc + s_hist[bb] >= want) { bsel = bb; break; }
-        acc += s_hist[bb];
-      }
-      s_misc[0] = bsel; s_misc[1] = want - acc; s_misc[2] = s_hist[bsel];
-    }
-    __syncthreads();
-    prefix |= ((uint32_t)s_misc[0]) << shift;
-    mask |= 0xFFu << shift;
-    want = s_misc[1];
-    ties_total = s_misc[2];
-    __syncthreads();
-  }
-  const uint32_t T = prefix;
-  int limit = 0x7fffffff;
-  if (want < ties_total) {
-    // ordered scan: flat index of the `want`-th element with key == T (tf.nn.top_k: lower index first)
-    int base_cnt = 0;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int base = 0; base < N; base += kSelThreads) {
-      int i = base + tid;
-      bool tie = (i < N) && (okey(negl[i]) == T);
-      unsigned bal = __ballot_sync(0xffffffffu, tie);
-      if (lane == 0) s_w[warp] = __popc(bal);
-      __syncthreads();
-      int wbase = 0, total = 0;
-      for (int w = 0; w < kSelThreads / 32; ++w) { int c = s_w[w]; if (w < warp) wbase += c; total += c; }
-      int rank = base_cnt + wbase + __popc(bal & ((1u << lane) - 1));   // 0-based rank among ties
-      if (tie && rank == want - 1) s_misc[3] = i;
-      __syncthreads();
-      base_cnt += total;
-      if (base_cnt >= want) break;                                       // uniform
-    }
-    __syncthreads();
-    limit = s_misc[3];
-  }
-  if (tid == 0) { res->T = T; res->limit = limit; res->ties_taken = want; }
-}
-
-__device__ __forceinline__ bool neg_taken(const SelResult& r, float nl, int flat) {
-  if (r.none) return false;
-  uint32_t key = okey(nl);
-  return key > r.T || (key == r.T && flat <= r.limit);
-}
-
-__global__ void __launch_bounds__(256) loss_negsum_kernel(const float* __restrict__ cls, const float* __restrict__ negl, int P,
-                                                          const SelResult* __restrict__ res, double* __restrict__ partial2) {
-  __shared__ double s_acc[8];
-  const SelResult r = *res;
-  const int b = blockIdx.y, blk = blockIdx.x;
-  const int p = blk * 256 + threadIdx.x;
-  double v = 0;
-  if (p < P) {
-    const int flat = b * P + p;
-    if (neg_taken(r, negl[flat], flat)) v = (double)cls[flat];
-  }
-  v = warp_sum(v);
-  if ((threadIdx.x & 31) == 0) s_acc[threadIdx.x >> 5] = v;
+  const size_t stage_floats = (size_t)kRows * W;
+  float* s_buf = reinterpret_cast<float*>(smem);                        // [stages][2][kRows*W]
+  unsigned* s_coarse = reinterpret_cast<unsigned*>(smem + (size_t)a.stages * 2 * stage_floats * 4);   // [kCoarse]
+  __shared__ double s_red[4];
+  __shared__ unsigned long long s_redu[4];
+  for (int i = tid; i < kCoarse; i += kRows) s_coarse[i] = 0;
+  if (a.hist_next)                                                       // clear the other parity's histograms for the next call
+    for (size_t i = (size_t)blockIdx.x * kRows + tid; i < 2ull * (kCoarse + kFine); i += (size_t)gridDim.x * kRows) a.hist_next[i] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int w = 0; w < 8; ++w) t += s_acc[w];
-    partial2[(size_t)b * gridDim.x + blk] = t;
-  }
-}
-
-__global__ void loss_final_kernel(const double* __restrict__ partial, const double* __restrict__ partial2, int B, int nblk,
-                                  int nblk2, float alpha, const SelResult* __restrict__ res, float* __restrict__ out,
-                                  int* __restrict__ stats) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0 && stats) { stats[0] = res->n_pos; stats[1] = res->nnz; stats[2] = res->none ? 0 : res->k; stats[3] = res->ties_taken; }
-  if (b >= B) return;
-  double pc = 0, loc = 0, ng = 0;
-  for (int i = 0; i < nblk; ++i) { pc += partial[((size_t)b * nblk + i) * 4 + 0]; loc += partial[((size_t)b * nblk + i) * 4 + 1]; }
-  for (int i = 0; i < nblk2; ++i) ng += partial2[(size_t)b * nblk2 + i];
-  double total = (pc + ng + (double)alpha * loc) * (double)res->inv_norm;   // :204
-  out[b] = (float)(total * (double)B);                                       // :209
-}
-
-__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ y_true, const float* __restrict__ y_pred,
-                                                        int B, int P, int C, const float* __restrict__ negl,
-                                                        const SelResult* __restrict__ res, const float* __restrict__ upstream,
-                                                        float alpha, float* __restrict__ grad) {
-  const SelResult r = *res;
-  const int W = C + 12;
-  const int b = blockIdx.y, blk = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float up = upstream ? upstream[b] : (1.0f / (float)B);
-  const float scale = up * (float)B * r.inv_norm;
-  for (int rr = 0; rr < 32; ++rr) {
-    const int p = blk * kRowsPerBlock + warp * 32 + rr;
-    if (p >= P) break;
-    const size_t ro = ((size_t)b * P + p) * W;
-    const float* yt = y_true + ro;
-    const float* yp = y_pred + ro;
-    float pmax = -INFINITY;
-    for (int c = lane; c < C; c += 32)
-      if (c >= 1) pmax = fmaxf(pmax, yt[c]);                               // classes 1..C-1
-    pmax = warp_max(pmax);
-    const int flat = b * P + p;
-    float take = neg_taken(r, negl[flat], flat) ? 1.f : 0.f;
-    const float w_cls = (pmax + take) * scale;
-    const float w_loc = pmax * scale * alpha;
-    for (int c = lane; c < W; c += 32) {
-      float g = 0.f;
-      if (c < C) {
-        float t = yt[c];
-        if (t != 0.f) { float q = yp[c]; g = (q >= 1e-15f) ? (-t / q) * w_cls : 0.f; }
-      } else if (c < C + 4) {
-        float d = yp[c] - yt[c];
-        g = ((fabsf(d) < 1.0f) ? d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * w_loc;
-      }
-      grad[ro + c] = g;
+  int it = 0;
+  // prologue: first tile(s) in flight
+  for (int st = 0; st < a.stages; ++st) {
+    const int t = blockIdx.x + st * gridDim.x;
+    if (t < a.n_tiles) {
+      const int b = t / a.tiles_per_img, blk = t - b * a.tiles_per_img;
+      const int rows = min(kRows, a.P - blk * kRows);
+      tile_load(a, (size_t)b * a.P + (size_t)blk * kRows, rows, s_buf + (size_t)st * 2 * stage_floats, s_buf + (size_t)st * 2 * stage_floats + stage_floats,
+                bar0 + 8u * st);
     }
   }
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++it) {
+    const int st = it % a.stages;
+    const uint32_t parity = (uint32_t)(it / a.stages) & 1u;
+    const int b = t / a.tiles_per_img, blk = t - b * a.tiles_per_img;
+    const int rows = min(kRows, a.P - blk * kRows);
+    const float* s_t = s_buf + (size_t)st * 2 * stage_floats;
+    const float* s_p = s_t + stage_floats;
+    if (a.bulk_ok) mbar_wait(bar0 + 8u * st, parity); else __syncthreads();
+    double pc = 0, loc = 0; unsigned long long pos_fx = 0, nz = 0;
+    if (tid < rows) {
+      const float* yt = s_t + (size_t)tid * W;
+      const float* yp = s_p + (size_t)tid * W;
+      float acc = 0.f, pmax = -INFINITY;
+      for (int c = 0; c < C; ++c) {
+        const float tv = yt[c];
+        if (tv != 0.f) acc += tv * logf(fmaxf(yp[c], 1e-15f));          // :93-95
+        if (c >= 1) pmax = fmaxf(pmax, tv);                              // :140
+      }
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = yt[C + j] - yp[C + j];
+        const float ad = fabsf(d);
+        l += (ad < 1.0f) ? 0.5f * d * d : ad - 0.5f;                     // :72-74
+      }
+      const float cls = -acc;
+      const float nl = cls * yt[0];                                      // :139,151
+      const size_t flat = (size_t)b * a.P + (size_t)blk * kRows + tid;
+      a.cls[flat] = cls;
+      a.negl[flat] = nl;
+      pc = (double)(cls * pmax); loc = (double)(l * pmax);
+      pos_fx = (unsigned long long)llrint((double)pmax * 4294967296.0);
+      if (nl != 0.f) {
+        nz = 1;
+        const unsigned key = okey(nl);
+        atomicAdd(a.hist1 + kCoarse + (key >> 16), 1u);
+        atomicAdd(s_coarse + (key >> 21), 1u);
+      }
+    }
+    // the stage is free again once every thread has read its row: refill it with the tile `stages` iterations ahead
+    const int tn = t + a.stages * gridDim.x;
+    pc = block_sum(pc, s_red);
+    loc = block_sum(loc, s_red);
+    {
+      unsigned long long v = pos_fx;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      unsigned long long w = nz;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+      __syncthreads();
+      if ((tid & 31) == 0) { s_redu[tid >> 5] = v; s_red[tid >> 5] = (double)w; }
+      __syncthreads();
+      if (tid == 0) {
+        a.part[(size_t)t * 2] = pc; a.part[(size_t)t * 2 + 1] = loc;
+        const unsigned long long pv = s_redu[0] + s_redu[1] + s_redu[2] + s_redu[3];
+        const unsigned long long nv = (unsigned long long)(s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+        if (pv) atomicAdd(a.counts, pv);
+        if (nv) atomicAdd(a.counts + 1, nv);
+      }
+    }
+    if (tn < a.n_tiles) {                                                // (the block_sum barriers above ordered all row reads before this)
+      const int b2 = tn / a.tiles_per_img, blk2 = tn - b2 * a.tiles_per_img;
+      const int rows2 = min(kRows, a.P - blk2 * kRows);
+      tile_load(a, (size_t)b2 * a.P + (size_t)blk2 * kRows, rows2, s_buf + (size_t)st * 2 * stage_floats,
+                s_buf + (size_t)st * 2 * stage_floats + stage_floats, bar0 + 8u * st);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kCoarse; i += kRows) { const unsigned v = s_coarse[i]; if (v) atomicAdd(a.hist1 + i, v); }
+}
+
+// ---- phase B: histogram of the low key bits inside the level-1 bin ---------------------------------------------------
+__device__ void phase_b(const LossArgs& a, const Sel& s, int b1) {
+  if (s.none) return;
+  const long long n_local = (long long)a.B * a.P;
+  for (long long i = (long long)blockIdx.x * kRows + threadIdx.x; i < n_local; i += (long long)gridDim.x * kRows) {
+    const float nl = __ldcg(a.negl + i);
+    if (nl == 0.f) continue;
+    const unsigned key = okey(nl);
+    if ((int)(key >> 16) != b1) continue;
+    atomicAdd(a.hist2 + kCoarse + (key & 0xffffu), 1u);
+    atomicAdd(a.hist2 + ((key >> 5) & 0x7ffu), 1u);
+  }
+}
+
+// threshold key and tie bookkeeping from the two histograms (every CTA computes the same)
+__device__ void finish_select(const LossArgs& a, Sel& s, int b1, long long want1, long long* s_scan) {
+  s.T = 0; s.want = 0; s.ties_total = 0;
+  if (s.none) return;
+  long long want = want1, in_bin; int lo;
+  const bool zero_bin = (b1 == (int)(kZeroKey >> 16));
+  select_bin(a.hist2, zero_bin ? 0 : -1, zero_bin ? (a.n_total - s.nnz) : 0, want, in_bin, lo, s_scan);
+  s.T = ((unsigned)b1 << 16) | (unsigned)lo;
+  s.want = want; s.ties_total = in_bin;
+}
+
+// per-tile number of boxes whose key equals T (flat order == tile order)
+__device__ void phase_ties(const LossArgs& a, const Sel& s) {
+  __shared__ int s_cnt[4];
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int b = t / a.tiles_per_img, blk = t - b * a.tiles_per_img;
+    const int rows = min(kRows, a.P - blk * kRows);
+    bool tie = false;
+    if ((int)threadIdx.x < rows) tie = okey(__ldcg(a.negl + (size_t)b * a.P + (size_t)blk * kRows + threadIdx.x)) == s.T;
+    const unsigned m = __ballot_sync(0xffffffffu, tie);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) a.tile_ties[t] = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
+  }
+}
+
+// exclusive prefix of tile_ties in place (one CTA); tile_ties[n_tiles] = total
+__device__ void scan_ties(const LossArgs& a) {
+  __shared__ long long s_part[kRows];
+  const int per = (a.n_tiles + kRows - 1) / kRows;
+  const int lo = threadIdx.x * per, hi = min(a.n_tiles, lo + per);
+  long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a.tile_ties[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  long long base = 0;
+  for (int i = 0; i < (int)threadIdx.x; ++i) base += s_part[i];
+  for (int i = lo; i < hi; ++i) { const int v = a.tile_ties[i]; a.tile_ties[i] = (int)base; base += v; }
+  if (threadIdx.x == kRows - 1) a.tile_ties[a.n_tiles] = (int)base;
+}
+
+// ---- phase D: masked negative sums and/or the gradient, then the per-image totals ----------------------------------------
+__device__ void phase_d(const LossArgs& a, const Sel& s, bool ordered_ties, long long tie_base, unsigned char* smem, uint32_t bar0) {
+  const int W = a.C + 12, C = a.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double s_red[4];
+  __shared__ int s_cnt[4];
+  __shared__ int s_is_last;
+  const size_t stage_floats = (size_t)kRows * W;
+  float* s_t = reinterpret_cast<float*>(smem);
+  float* s_p = s_t + stage_floats;
+  float* s_g = s_p + stage_floats;                                       // gradient rows (only with out_grad)
+  uint32_t parity = 0;
+  bool store_pending = false;
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int b = t / a.tiles_per_img, blk = t - b * a.tiles_per_img;
+    const int rows = min(kRows, a.P - blk * kRows);
+    const size_t flat0 = (size_t)b * a.P + (size_t)blk * kRows;
+    if (a.out_grad) tile_load(a, flat0, rows, s_t, s_p, bar0);           // overlaps the mask computation below
+    float nl = 0.f, cls = 0.f; unsigned key = 0; bool tie = false;
+    if (tid < rows) { nl = __ldcg(a.negl + flat0 + tid); cls = __ldcg(a.cls + flat0 + tid); key = okey(nl); tie = (key == s.T); }
+    long long tie_rank = 0;
+    if (ordered_ties) {                                                  // rank of this box among the boxes equal to T, flat order
+      const unsigned m = __ballot_sync(0xffffffffu, tie);
+      __syncthreads();
+      if (lane == 0) s_cnt[warp] = __popc(m);
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += s_cnt[w];
+      tie_rank = tie_base + a.tile_ties[t] + before + __popc(m & ((1u << lane) - 1));
+    }
+    const bool take = (tid < rows) && taken(s, key, tie_rank);
+    if (a.out_loss) {
+      const double v = block_sum(take ? (double)cls : 0.0, s_red);
+      if (tid == 0) a.negpart[t] = v;
+    }
+    if (a.out_grad) {
+      if (store_pending) { if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+      if (a.bulk_ok) mbar_wait(bar0, parity);
+      __syncthreads();
+      parity ^= 1u;
+      if (tid < rows) {
+        const float* yt = s_t + (size_t)tid * W;
+        const float* yp = s_p + (size_t)tid * W;
+        float* g = s_g + (size_t)tid * W;
+        float pmax = -INFINITY;
+        for (int c = 1; c < C; ++c) pmax = fmaxf(pmax, yt[c]);
+        const float up = a.upstream ? a.upstream[b] : (1.0f / (float)a.global_B);
+        const float scale = up * (float)a.global_B * s.inv_norm;
+        const float w_cls = (pmax + (take ? 1.f : 0.f)) * scale;
+        const float w_loc = pmax * scale * a.alpha;
+        for (int c = 0; c < C; ++c) {
+          const float tv = yt[c];
+          float gv = 0.f;
+          if (tv != 0.f) { const float q = yp[c]; gv = (q >= 1e-15f) ? (-tv / q) * w_cls : 0.f; }
+          g[c] = gv;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float d = yp[C + j] - yt[C + j];
+          g[C + j] = ((fabsf(d) < 1.0f) ? d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f))) * w_loc;
+        }
+#pragma unroll
+        for (int j = 4; j < 12; ++j) g[C + j] = 0.f;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      float* dst = a.out_grad + flat0 * W;
+      const size_t n_f = (size_t)rows * W;
+      if (a.bulk_ok && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (((n_f * 4) & 15) == 0)) {
+        if (tid == 0) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(s_g)), "r"((uint32_t)(n_f * 4)) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        store_pending = true;
+      } else {
+        for (size_t i = tid; i < n_f; i += kRows) dst[i] = s_g[i];
+      }
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (!a.out_loss) return;
+  // last CTA: per-image totals in a fixed order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const int old = atomicAdd(a.ticket, 1);
+    s_is_last = (old == (int)gridDim.x - 1);
+    if (s_is_last) *a.ticket = 0;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  for (int b = tid; b < a.B; b += kRows) {
+    double pc = 0, loc = 0, ng = 0;
+    for (int i = 0; i < a.tiles_per_img; ++i) {
+      const size_t t = (size_t)b * a.tiles_per_img + i;
+      pc += __ldcg(a.part + t * 2); loc += __ldcg(a.part + t * 2 + 1); ng += __ldcg(a.negpart + t);
+    }
+    const double total = (pc + ng + (double)a.alpha * loc) * (double)s.inv_norm;    // :204
+    a.out_loss[b] = (float)(total * (double)a.global_B);                            // :209
+  }
+  if (tid == 0 && a.out_stats) {
+    a.out_stats[0] = s.n_pos; a.out_stats[1] = s.nnz; a.out_stats[2] = s.none ? 0 : s.k; a.out_stats[3] = s.none ? 0 : (int)s.want;
+  }
+}
+
+// shared-memory layout (dynamic): phase A: stages * 2 tiles | coarse histogram;  phase D: y_true tile | y_pred tile | grad tile
+__host__ __device__ inline size_t loss_smem_bytes(int W, int stages, bool grad) {
+  const size_t tile = (size_t)kRows * W * 4;
+  const size_t pa = (size_t)stages * 2 * tile + kCoarse * 4;
+  const size_t pd = grad ? 3 * tile : 0;
+  return (pa > pd ? pa : pd) + 128;
+}
+
+__device__ __forceinline__ uint32_t setup_barriers(uint64_t* bars) {
+  const uint32_t bar0 = smem_u32(bars);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  return bar0;
+}
+
+// The fused kernel.  Cooperative launch: grid-wide barriers separate the phases.
+__global__ void __launch_bounds__(kRows) ssd_loss_kernel(const __grid_constant__ LossArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bars[3];
+  __shared__ long long s_scan[kRows];
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t bar0 = setup_barriers(s_bars);
+  phase_a(a, smem, bar0);
+  grid.sync();
+  Sel s;
+  read_counts(a, s);
+  int b1 = 0; long long want1 = 0;
+  if (!s.none) level1(a, s, b1, want1, s_scan);
+  phase_b(a, s, b1);
+  grid.sync();
+  finish_select(a, s, b1, want1, s_scan);
+  const bool ordered = !s.none && s.want < s.ties_total;                 // uniform over the grid
+  if (ordered) {
+    phase_ties(a, s);
+    grid.sync();
+    if (blockIdx.x == 0) scan_ties(a);
+    grid.sync();
+  } else {
+    s.want = s.ties_total;                                               // every box equal to T is kept: no order needed
+  }
+  phase_d(a, s, ordered, 0, smem, bar0 + 16);
+}
+
+// The same phases as separate launches (multi-GPU, global-batch-exact): 0 = A, 1 = B, 2 = threshold + local ties, 3 = scan, 4 = D
+__global__ void __launch_bounds__(kRows) ssd_loss_phase_kernel(const __grid_constant__ LossArgs a, int phase) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t s_bars[3];
+  __shared__ long long s_scan[kRows];
+  const uint32_t bar0 = setup_barriers(s_bars);
+  if (phase == 0) { phase_a(a, smem, bar0); return; }
+  if (phase == 3) { if (blockIdx.x == 0) scan_ties(a); return; }
+  Sel s;
+  read_counts(a, s);
+  int b1 = 0; long long want1 = 0;
+  if (!s.none) level1(a, s, b1, want1, s_scan);
+  if (phase == 1) { phase_b(a, s, b1); return; }
+  finish_select(a, s, b1, want1, s_scan);
+  if (phase == 2) {
+    if (!s.none) phase_ties(a, s); else for (int t = blockIdx.x * kRows + threadIdx.x; t <= a.n_tiles; t += gridDim.x * kRows) a.tile_ties[t] = 0;
+    return;
+  }
+  // phase 4: the boxes equal to T are taken in global flat order: lower ranks first
+  long long before = 0;
+  for (int r = 0; r < a.rank; ++r) before += a.ties_all[r];
+  // ranks hold disjoint index ranges in rank order, so this rank's ties rank from `before`; tile_ties was scanned by phase 3
+  s.want = s.none ? 0 : s.want;
+  Sel s2 = s;
+  s2.want = s.want - before;                                             // may be <= 0 (none of ours) or >= our tie count (all of ours)
+  phase_d(a, s2, !s.none, 0, smem, bar0 + 16);
 }
 
 struct LossWs {
-  float* cls; float* negl; double* partial; double* partial2; SelResult* res;
-  int nblk;
+  float* cls; float* negl; double* part; double* negpart; int* tile_ties; unsigned long long* counts; unsigned* hist; int* ticket;
 };
 
-int loss_prepare(ssdk_ctx* ctx, int B, int P, LossWs& w) {
-  const size_t N = (size_t)B * P;
-  w.nblk = ceil_div(P, kRowsPerBlock);
-  size_t o_cls = 0, o_negl = (N * 4 + 255) / 256 * 256;
-  size_t o_part = o_negl + (N * 4 + 255) / 256 * 256;
-  size_t o_part2 = o_part + ((size_t)B * w.nblk * 4 * 8 + 255) / 256 * 256;
-  size_t o_res = o_part2 + ((size_t)B * w.nblk * 8 + 255) / 256 * 256;
-  size_t total = o_res + 256;
-  int rc = ctx->ws[2].ensure(total);
-  if (rc) return rc;
-  unsigned char* base = reinterpret_cast<unsigned char*>(ctx->ws[2].ptr);
-  w.cls = reinterpret_cast<float*>(base + o_cls); w.negl = reinterpret_cast<float*>(base + o_negl);
-  w.partial = reinterpret_cast<double*>(base + o_part); w.partial2 = reinterpret_cast<double*>(base + o_part2);
-  w.res = reinterpret_cast<SelResult*>(base + o_res);
-  return SSDK_OK;
-}
+size_t al256(size_t v) { return (v + 255) / 256 * 256; }
 
-int loss_common(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C, int ratio, int n_neg_min,
-                LossWs& w, cudaStream_t stream) {
-  int rc = loss_prepare(ctx, B, P, w);
-  if (rc) return rc;
-  dim3 grid(w.nblk, B);
-  loss_box_kernel<<<grid, 256, 0, stream>>>(y_true, y_pred, P, C, w.cls, w.negl, w.partial);
-  SSDK_COUNT_LAUNCH(ctx);
-  loss_select_kernel<<<1, kSelThreads, 0, stream>>>(w.negl, B * P, B, w.nblk, w.partial, ratio, n_neg_min, w.res);
-  SSDK_COUNT_LAUNCH(ctx);
-  SSDK_CHECK_CUDA(cudaGetLastError());
-  return SSDK_OK;
+// Workspace layout (bytes, 256-aligned sections): counts | hist A (2*(coarse+fine)) | hist B | ticket | cls | negl | part | negpart | tile_ties
+struct WsLayout { size_t counts, histA, histB, ticket, cls, negl, part, negpart, ties, total; };
+WsLayout ws_layout(int B, int P) {
+  const size_t N = (size_t)B * P, nt = (size_t)B * ((P + kRows - 1) / kRows);
+  WsLayout L;
+  size_t o = 0;
+  L.counts = o; o += 256;
+  L.histA = o; o += al256(2ull * (kCoarse + kFine) * 4);
+  L.histB = o; o += al256(2ull * (kCoarse + kFine) * 4);
+  L.ticket = o; o += 256;
+  L.cls = o; o += al256(N * 4);
+  L.negl = o; o += al256(N * 4);
+  L.part = o; o += al256(nt * 16);
+  L.negpart = o; o += al256(nt * 8);
+  L.ties = o; o += al256((nt + 1) * 4);
+  L.total = o;
+  return L;
 }
 
 int check_args(ssdk_ctx* ctx, const float* yt, const float* yp, int B, int P, int C) {
@@ -292,39 +536,138 @@ int check_args(ssdk_ctx* ctx, const float* yt, const float* yp, int B, int P, in
   return SSDK_OK;
 }
 
+struct LossPlan { int grid; size_t smem; };
+
+// fills everything of LossArgs that depends on the shapes and the workspace; hist parity chosen by the caller
+int fill_args(ssdk_ctx* ctx, LossArgs& a, const float* y_true, const float* y_pred, int B, int P, int C, int ratio, int n_neg_min,
+              float alpha, unsigned char* ws, int parity, bool grad, LossPlan& plan, bool cooperative) {
+  const WsLayout L = ws_layout(B, P);
+  memset(&a, 0, sizeof(a));
+  a.y_true = y_true; a.y_pred = y_pred; a.B = B; a.P = P; a.C = C;
+  a.tiles_per_img = (P + kRows - 1) / kRows; a.n_tiles = B * a.tiles_per_img;
+  a.n_total = (long long)B * P; a.global_B = B;
+  a.ratio = ratio; a.n_neg_min = n_neg_min; a.alpha = alpha;
+  a.cls = reinterpret_cast<float*>(ws + L.cls); a.negl = reinterpret_cast<float*>(ws + L.negl);
+  a.part = reinterpret_cast<double*>(ws + L.part); a.negpart = reinterpret_cast<double*>(ws + L.negpart);
+  a.tile_ties = reinterpret_cast<int*>(ws + L.ties);
+  a.counts = reinterpret_cast<unsigned long long*>(ws + L.counts);
+  unsigned* hA = reinterpret_cast<unsigned*>(ws + L.histA); unsigned* hB = reinterpret_cast<unsigned*>(ws + L.histB);
+  unsigned* cur = parity ? hB : hA;
+  a.hist1 = cur; a.hist2 = cur + (kCoarse + kFine);
+  a.hist_next = parity ? hA : hB;
+  a.ticket = reinterpret_cast<int*>(ws + L.ticket);
+  const int W = C + 12;
+  // cp.async.bulk needs 16-byte aligned tile starts: image stride P*W*4 and tile stride 128*W*4 (always a multiple of 16)
+  a.bulk_ok = (((size_t)P * W) % 4 == 0) && ((reinterpret_cast<uintptr_t>(y_true) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y_pred) & 15) == 0) ? 1 : 0;
+  a.stages = 2;
+  if (loss_smem_bytes(W, 2, grad) > 100 * 1024) a.stages = 1;
+  plan.smem = loss_smem_bytes(W, a.stages, grad);
+  SSDK_REQUIRE(plan.smem <= 227 * 1024, "ssd_loss: %d classes need %zu bytes of shared memory per CTA", C, plan.smem);
+  static size_t attr[2] = {0, 0};
+  if (plan.smem > 48 * 1024) {
+    if (plan.smem > attr[0]) { SSDK_CHECK_CUDA(cudaFuncSetAttribute(ssd_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem)); attr[0] = plan.smem; }
+    if (plan.smem > attr[1]) { SSDK_CHECK_CUDA(cudaFuncSetAttribute(ssd_loss_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem)); attr[1] = plan.smem; }
+  }
+  int per_sm = 0;
+  if (cooperative) SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssd_loss_kernel, kRows, plan.smem));
+  else SSDK_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssd_loss_phase_kernel, kRows, plan.smem));
+  SSDK_REQUIRE(per_sm > 0, "ssd_loss: the kernel does not fit on an SM (%zu bytes of shared memory)", plan.smem);
+  if (per_sm > 4) per_sm = 4;
+  plan.grid = std::max(1, std::min(a.n_tiles, per_sm * ctx->sm_count));
+  return SSDK_OK;
+}
+
+// context-owned workspace: zeroed when (re)allocated; the histogram parity flips on every call
+int own_ws(ssdk_ctx* ctx, int B, int P, unsigned char** ws, int* parity, cudaStream_t stream) {
+  const WsLayout L = ws_layout(B, P);
+  const size_t before = ctx->ws[2].bytes;
+  int rc = ctx->ws[2].ensure(L.total);
+  if (rc) return rc;
+  if (ctx->ws[2].bytes != before || ctx->loss_ws_shape != ((long long)B << 32 | (unsigned)P)) {
+    SSDK_CHECK_CUDA(cudaMemsetAsync(ctx->ws[2].ptr, 0, ctx->ws[2].bytes, stream));   // layout moved: start from clean histograms
+    ctx->loss_ws_shape = ((long long)B << 32 | (unsigned)P);
+    ctx->loss_parity = 0;
+  }
+  *ws = reinterpret_cast<unsigned char*>(ctx->ws[2].ptr);
+  *parity = ctx->loss_parity;
+  ctx->loss_parity ^= 1;
+  return SSDK_OK;
+}
+
+int launch_fused(ssdk_ctx* ctx, LossArgs& a, const LossPlan& plan, cudaStream_t stream) {
+  // the counts are cleared per call (16 bytes); histograms are self-cleaning (parity), the ticket resets itself
+  SSDK_CHECK_CUDA(cudaMemsetAsync(a.counts, 0, 16, stream));
+  void* params[] = {(void*)&a};
+  SSDK_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)ssd_loss_kernel, dim3(plan.grid), dim3(kRows), params, plan.smem, stream));
+  SSDK_COUNT_LAUNCH(ctx);
+  return SSDK_OK;
+}
+
+int loss_run(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C, int ratio, int n_neg_min, float alpha,
+             const float* upstream, float* out_loss, int* out_stats, float* out_grad, cudaStream_t stream) {
+  int rc = check_args(ctx, y_true, y_pred, B, P, C);
+  if (rc) return rc;
+  unsigned char* ws; int parity;
+  rc = own_ws(ctx, B, P, &ws, &parity, stream);
+  if (rc) return rc;
+  LossArgs a; LossPlan plan;
+  rc = fill_args(ctx, a, y_true, y_pred, B, P, C, ratio, n_neg_min, alpha, ws, parity, out_grad != nullptr, plan, true);
+  if (rc) return rc;
+  a.out_loss = out_loss; a.out_stats = out_stats; a.upstream = upstream; a.out_grad = out_grad;
+  return launch_fused(ctx, a, plan, stream);
+}
+
 }  // namespace
 
 extern "C" int ssdk_ssd_loss_fwd(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C,
                                  int neg_pos_ratio, int n_neg_min, float alpha, float* out_loss, int* out_stats, void* stream_) {
-  int rc = check_args(ctx, y_true, y_pred, B, P, C);
-  if (rc) return rc;
   SSDK_REQUIRE(out_loss != nullptr, "ssd_loss: out_loss is NULL");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  LossWs w;
-  rc = loss_common(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, w, stream);
-  if (rc) return rc;
-  const int nblk2 = ceil_div(P, 256);
-  dim3 grid(nblk2, B);
-  loss_negsum_kernel<<<grid, 256, 0, stream>>>(w.cls, w.negl, P, w.res, w.partial2);
-  SSDK_COUNT_LAUNCH(ctx);
-  loss_final_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(w.partial, w.partial2, B, w.nblk, nblk2, alpha, w.res, out_loss, out_stats);
-  SSDK_COUNT_LAUNCH(ctx);
-  SSDK_CHECK_CUDA(cudaGetLastError());
-  return SSDK_OK;
+  return loss_run(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, alpha, nullptr, out_loss, out_stats, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int ssdk_ssd_loss_bwd(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C,
                                  int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream, float* out_grad,
                                  void* stream_) {
+  SSDK_REQUIRE(out_grad != nullptr, "ssd_loss_bwd: out_grad is NULL");
+  return loss_run(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, alpha, upstream, nullptr, nullptr, out_grad, (cudaStream_t)stream_);
+}
+
+extern "C" int ssdk_ssd_loss_fwd_bwd(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int P, int C,
+                                     int neg_pos_ratio, int n_neg_min, float alpha, const float* upstream, float* out_loss,
+                                     int* out_stats, float* out_grad, void* stream_) {
+  SSDK_REQUIRE(out_loss != nullptr && out_grad != nullptr, "ssdk_ssd_loss_fwd_bwd: out_loss / out_grad is NULL");
+  return loss_run(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, alpha, upstream, out_loss, out_stats, out_grad, (cudaStream_t)stream_);
+}
+
+extern "C" int ssdk_ssd_loss_ws_layout(int B, int P, ssdk_loss_ws_layout* out) {
+  SSDK_REQUIRE(out && B > 0 && P > 0, "ssdk_ssd_loss_ws_layout: bad argument");
+  const WsLayout L = ws_layout(B, P);
+  out->bytes = (long long)L.total;
+  out->counts_offset = (long long)L.counts; out->counts_n = 2;
+  out->hist1_offset = (long long)L.histA; out->hist_n = kCoarse + kFine;
+  out->hist2_offset = (long long)(L.histA + (size_t)(kCoarse + kFine) * 4);
+  out->ties_offset = (long long)(L.ties + (size_t)B * ((P + kRows - 1) / kRows) * 4);
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_ssd_loss_phase(ssdk_ctx* ctx, int phase, const float* y_true, const float* y_pred, int B, int P, int C,
+                                   int neg_pos_ratio, int n_neg_min, float alpha, void* ws_dev, int global_B, const int* ties_all_dev,
+                                   int rank, const float* upstream, float* out_loss, int* out_stats, float* out_grad, void* stream_) {
   int rc = check_args(ctx, y_true, y_pred, B, P, C);
   if (rc) return rc;
-  SSDK_REQUIRE(out_grad != nullptr, "ssd_loss_bwd: out_grad is NULL");
+  SSDK_REQUIRE(ws_dev && phase >= 0 && phase <= 4 && global_B >= B && rank >= 0, "ssdk_ssd_loss_phase: bad argument");
+  SSDK_REQUIRE(phase != 4 || ties_all_dev, "ssdk_ssd_loss_phase: phase 4 needs the all-gathered tie counts");
   cudaStream_t stream = (cudaStream_t)stream_;
-  LossWs w;
-  rc = loss_common(ctx, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, w, stream);
+  LossArgs a; LossPlan plan;
+  rc = fill_args(ctx, a, y_true, y_pred, B, P, C, neg_pos_ratio, n_neg_min, alpha, reinterpret_cast<unsigned char*>(ws_dev), 0,
+                 out_grad != nullptr && phase == 4, plan, false);
   if (rc) return rc;
-  dim3 grid(w.nblk, B);
-  loss_grad_kernel<<<grid, 256, 0, stream>>>(y_true, y_pred, B, P, C, w.negl, w.res, upstream, alpha, out_grad);
+  a.hist_next = nullptr;                                              // the caller zeroes the workspace before phase 0
+  a.global_B = global_B; a.n_total = (long long)global_B * P;
+  a.ties_all = ties_all_dev; a.rank = rank;
+  if (phase == 4) { a.out_loss = out_loss; a.out_stats = out_stats; a.upstream = upstream; a.out_grad = out_grad; }
+  const int grid = phase == 3 ? 1 : plan.grid;
+  ssd_loss_phase_kernel<<<grid, kRows, plan.smem, stream>>>(a, phase);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;

@@ -726,20 +726,36 @@ int do_transpose(ssdk_trainer* t, const __nv_bfloat16* hi, const __nv_bfloat16* 
 
 }  // namespace
 
+namespace {
+int backward_from_dy(ssdk_trainer* t, const float* dypred, cudaStream_t s);
+}
+
 extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const float* y_pred, int neg_pos_ratio, int n_neg_min,
                                    float alpha, float* out_loss, void* stream_) {
   SSDK_REQUIRE(t && y_true && y_pred, "ssdk_train_backward: NULL argument");
   ssdk_model* m = t->m;
   ssdk_ctx* ctx = m->ctx;
-  cudaStream_t s = (cudaStream_t)stream_;
+  int rc;
+  // loss (optional) and d loss / d y_pred from one launch of the fused loss kernel
+  if (out_loss) rc = ssdk_ssd_loss_fwd_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, out_loss, nullptr, t->dypred, stream_);
+  else rc = ssdk_ssd_loss_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, t->dypred, stream_);
+  if (rc) return rc;
+  return backward_from_dy(t, t->dypred, (cudaStream_t)stream_);
+}
+
+extern "C" int ssdk_train_backward_dy(ssdk_trainer* t, const float* dypred_dev, void* stream_) {
+  SSDK_REQUIRE(t && dypred_dev, "ssdk_train_backward_dy: NULL argument");
+  return backward_from_dy(t, dypred_dev, (cudaStream_t)stream_);
+}
+
+namespace {
+
+// every parameter gradient from d loss / d y_pred (B,P,C+12), walking the layers in reverse
+int backward_from_dy(ssdk_trainer* t, const float* dypred, cudaStream_t s) {
+  ssdk_model* m = t->m;
+  ssdk_ctx* ctx = m->ctx;
   int rc;
   SSDK_CHECK_CUDA(cudaMemsetAsync(t->grad, 0, (size_t)t->n_params * sizeof(float), s));
-  if (out_loss) {
-    rc = ssdk_ssd_loss_fwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, out_loss, nullptr, stream_);
-    if (rc) return rc;
-  }
-  rc = ssdk_ssd_loss_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, t->dypred, stream_);
-  if (rc) return rc;
   const int n = (int)m->layers.size();
   std::vector<char> written(n, 0);
   for (int i = n - 1; i >= 0; --i) {
@@ -754,7 +770,7 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
     const int relu_mask = (PL.d.op == SSDK_OP_CONV && PL.d.act == SSDK_ACT_RELU) ? 1 : 0;
     if (d.op == SSDK_OP_HEAD) {
       const size_t total = (size_t)m->B * L.H * L.W * d.n_boxes;
-      head_bwd_kernel<<<(unsigned)((total + 7) / 8), 256, 0, s>>>(L.head_f32, t->dypred, m->B, L.H, L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, T.g);
+      head_bwd_kernel<<<(unsigned)((total + 7) / 8), 256, 0, s>>>(L.head_f32, dypred, m->B, L.H, L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, T.g);
       SSDK_COUNT_LAUNCH(ctx);
     }
     if (d.op == SSDK_OP_MAXPOOL) {
@@ -830,6 +846,8 @@ extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const f
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
 }
+
+}  // namespace
 
 extern "C" int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float l2_reg, float grad_scale, void* stream_) {
   SSDK_REQUIRE(t, "ssdk_train_apply: NULL trainer");

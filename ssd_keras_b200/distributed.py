@@ -71,3 +71,73 @@ def all_reduce_gradients_(flat_grad, group=None):
         return 1.0
     dist.all_reduce(flat_grad, group=group)
     return 1.0 / dist.get_world_size(group)
+
+
+class GlobalLossRun:
+    """One rank's side of the phase-wise loss (``ssdk_ssd_loss_phase``): owns the workspace and exposes the tensors that have
+    to be reduced between the phases.  ``ssd_loss_global`` drives it with torch.distributed; the single-GPU tests drive several
+    instances and add the tensors by hand."""
+
+    def __init__(self, y_true, y_pred, neg_pos_ratio, n_neg_min, alpha, world, rank, return_grad):
+        import ctypes as C
+        import torch
+        from . import _ffi
+        self.yt = y_true.to(device='cuda', dtype=torch.float32).contiguous()
+        self.yp = y_pred.to(device='cuda', dtype=torch.float32).contiguous()
+        self.B, self.P, self.W = self.yp.shape
+        self.cfg = (int(neg_pos_ratio), int(n_neg_min), float(alpha))
+        self.world, self.rank = int(world), int(rank)
+        lay = _ffi.LossWsLayout()
+        _ffi.check(_ffi.lib().ssdk_ssd_loss_ws_layout(self.B, self.P, C.byref(lay)))
+        dev = self.yp.device
+        self.ws = torch.zeros((lay.bytes,), dtype=torch.uint8, device=dev)
+        self.counts = self.ws[lay.counts_offset:lay.counts_offset + 8 * lay.counts_n].view(torch.int64)
+        self.hist1 = self.ws[lay.hist1_offset:lay.hist1_offset + 4 * lay.hist_n].view(torch.int32)
+        self.hist2 = self.ws[lay.hist2_offset:lay.hist2_offset + 4 * lay.hist_n].view(torch.int32)
+        self.ties = self.ws[lay.ties_offset:lay.ties_offset + 4].view(torch.int32)
+        self.ties_all = torch.zeros((self.world,), dtype=torch.int32, device=dev)
+        self.loss = torch.empty((self.B,), dtype=torch.float32, device=dev)
+        self.stats = torch.zeros((4,), dtype=torch.int32, device=dev)
+        self.grad = torch.empty_like(self.yp) if return_grad else None
+
+    def phase(self, i):
+        from . import _ffi
+        final = i == 4
+        r, m, a = self.cfg
+        _ffi.check(_ffi.lib().ssdk_ssd_loss_phase(_ffi.context(self.yp.device.index), i, _ffi.dptr(self.yt), _ffi.dptr(self.yp), self.B,
+                                                  self.P, self.W - 12, r, m, a, _ffi.dptr(self.ws), self.world * self.B,
+                                                  _ffi.dptr(self.ties_all), self.rank, _ffi.dptr(None),
+                                                  _ffi.dptr(self.loss if final else None), _ffi.dptr(self.stats if final else None),
+                                                  _ffi.dptr(self.grad if final else None), _ffi.stream_ptr()))
+
+
+def ssd_loss_global(y_true, y_pred, neg_pos_ratio=3, n_neg_min=0, alpha=1.0, group=None, return_grad=False):
+    """Global-batch-exact ``SSDLoss.compute_loss`` for a batch that is sharded over the ranks of ``group``.
+
+    The reference's ``n_positive`` (keras_ssd_loss.py:143) and its hard-negative top-k (:179-183) run over the WHOLE batch.
+    Every rank holds ``(B_local, P, C+12)`` shards (equal ``B_local``, rank order = image order); the loss kernel's phases run
+    one by one and the integer counts / histograms in its workspace are summed with all-reduces in between (2 x int64, then
+    two histograms of 67 584 int32), ties at the k-th value are resolved by GLOBAL flat index via an all-gather of one int per
+    rank.  Returns the ``(B_local,)`` losses of this rank's images -- exactly the entries the single-process reference
+    computes for them -- and, with ``return_grad``, ``(loss, d(mean over the global batch)/d y_pred of this shard, stats)``.
+    Without an initialised process group this is the single-rank result (phases run back to back)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    run = GlobalLossRun(y_true, y_pred, neg_pos_ratio, n_neg_min, alpha, world, rank, return_grad)
+    run.phase(0)
+    if on:
+        dist.all_reduce(run.counts, group=group)
+        dist.all_reduce(run.hist1, group=group)
+    run.phase(1)
+    if on:
+        dist.all_reduce(run.hist2, group=group)
+    run.phase(2)
+    run.phase(3)
+    if on:
+        dist.all_gather_into_tensor(run.ties_all, run.ties, group=group)
+    else:
+        run.ties_all.copy_(run.ties)
+    run.phase(4)
+    return (run.loss, run.grad, run.stats) if return_grad else run.loss

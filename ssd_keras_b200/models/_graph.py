@@ -236,10 +236,11 @@ class SSDModel:
             d.pad_t, d.pad_l, d.pad_b, d.pad_r = s.pad
             d.act, d.n_boxes = s.act, s.n_boxes
             if s.op == _ffi.OP_INPUT:
+                # the reference broadcasts np.array(subtract_mean) over the channel axis: a scalar is legal
                 if s.params.get('mean') is not None:
-                    d.mean = fptr(s.params['mean'])
+                    d.mean = fptr(np.broadcast_to(np.asarray(s.params['mean'], dtype=np.float32).reshape(-1), (3,)))
                 if s.params.get('stddev') is not None:
-                    d.stddev = fptr(s.params['stddev'])
+                    d.stddev = fptr(np.broadcast_to(np.asarray(s.params['stddev'], dtype=np.float32).reshape(-1), (3,)))
                 if s.params.get('swap'):
                     sw = np.ascontiguousarray(s.params['swap'], dtype=np.int32); keep.append(sw)
                     d.swap = _ffi.np_ptr(sw, C.c_int)

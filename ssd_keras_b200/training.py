@@ -13,7 +13,13 @@ from . import _ffi
 
 class SSDTrainer:
     def __init__(self, model, batch_size, lr=1e-3, momentum=0.9, l2_regularization=None, neg_pos_ratio=3, n_neg_min=0,
-                 alpha=1.0):
+                 alpha=1.0, loss_mode='replica'):
+        """``loss_mode``: 'replica' -- every rank applies the reference loss to its own shard (what Keras data-parallel replicas
+        compute); 'global' -- n_positive and the hard-negative top-k run over the whole sharded batch, so that N
+        ranks reproduce the single-process reference on the full batch (8e(ii), ``distributed.ssd_loss_global``)."""
+        if loss_mode not in ('replica', 'global'):
+            raise ValueError("loss_mode must be 'replica' or 'global'")
+        self.loss_mode = loss_mode
         import torch
         self.model = model
         self.batch = int(batch_size)
@@ -81,8 +87,13 @@ class SSDTrainer:
         if not (images.is_cuda and y_true.is_cuda):
             raise ValueError('images and y_true must be CUDA tensors')
         y_pred = self.model.forward_device(images, training=True)
-        loss = torch.empty((self.batch,), dtype=torch.float32, device=images.device)
         y_true = y_true.to(dtype=torch.float32).contiguous()
+        if self.loss_mode == 'global':
+            from .distributed import ssd_loss_global
+            loss, dy, _ = ssd_loss_global(y_true, y_pred, self.neg_pos_ratio, self.n_neg_min, self.alpha, return_grad=True)
+            _ffi.check(_ffi.lib().ssdk_train_backward_dy(self.handle, _ffi.dptr(dy), _ffi.stream_ptr()))
+            return loss, y_pred
+        loss = torch.empty((self.batch,), dtype=torch.float32, device=images.device)
         _ffi.check(_ffi.lib().ssdk_train_backward(self.handle, _ffi.dptr(y_true), _ffi.dptr(y_pred), self.neg_pos_ratio,
                                                   self.n_neg_min, self.alpha, _ffi.dptr(loss), _ffi.stream_ptr()))
         return loss, y_pred
@@ -96,7 +107,10 @@ class SSDTrainer:
         """forward + loss + backward + (all-reduce) + SGD update.  Returns the per-image loss tensor (B,)."""
         from .distributed import all_reduce_gradients_
         loss, _ = self.forward_backward(images, y_true)
-        self.apply(all_reduce_gradients_(self.grad))       # one all-reduce for all 26 M gradients, then the update
+        scale = all_reduce_gradients_(self.grad)           # one all-reduce for all 26 M gradients, then the update
+        if self.loss_mode == 'global':
+            scale = 1.0                                     # the shards' gradients of the GLOBAL batch mean add up; nothing to average
+        self.apply(scale)
         return loss
 
     # -- introspection (tests) -------------------------------------------------------------------

@@ -424,3 +424,70 @@ def test_loss_ties_and_no_positives(configs):
     np.testing.assert_allclose(loss0, ssd_loss(y_true0, y_pred), atol=1e-7)
     loss1 = SSDLoss(n_neg_min=10).compute_loss(y_true0, y_pred).cpu().numpy()
     np.testing.assert_allclose(loss1, ssd_loss(y_true0, y_pred, n_neg_min=10), rtol=1e-5)
+
+
+def _global_loss_by_hand(y_true, y_pred, shards, ratio=3, n_neg_min=0, alpha=1.0):
+    """The phase-wise loss of `shards` ranks on ONE GPU: the NCCL all-reduces / all-gather replaced by adding the tensors."""
+    import torch
+    from ssd_keras_b200.distributed import GlobalLossRun
+    B = y_true.shape[0]
+    per = B // shards
+    runs = [GlobalLossRun(torch.from_numpy(y_true[r * per:(r + 1) * per]).cuda(), torch.from_numpy(y_pred[r * per:(r + 1) * per]).cuda(),
+                          ratio, n_neg_min, alpha, shards, r, True) for r in range(shards)]
+    for r in runs:
+        r.phase(0)
+    for name in ('counts', 'hist1'):
+        tot = sum(getattr(r, name).clone() for r in runs)
+        for r in runs:
+            getattr(r, name).copy_(tot)
+    for r in runs:
+        r.phase(1)
+    tot = sum(r.hist2.clone() for r in runs)
+    for r in runs:
+        r.hist2.copy_(tot)
+    for r in runs:
+        r.phase(2); r.phase(3)
+    ties = torch.cat([r.ties.clone() for r in runs])
+    for r in runs:
+        r.ties_all.copy_(ties); r.phase(4)
+    return (np.concatenate([r.loss.cpu().numpy() for r in runs]), np.concatenate([r.grad.cpu().numpy() for r in runs]),
+            runs[0].stats.cpu().numpy())
+
+
+@pytest.mark.parametrize('shards', [1, 2, 4])
+def test_loss_global_batch_exact_phases(configs, shards):
+    """The multi-GPU loss mode (n_positive and the top-k over the whole sharded batch): its phase-wise launches, with the
+    collectives emulated, give the single-process loss and gradient of the full batch -- also when every negative ties."""
+    enc = OracleEncoder(**configs['ssd300'])
+    y_true, y_pred = synth.synth_y_true_pred_for_loss(2, enc, 8, 8, 20, sharp=2.0)
+    loss, grad, stats = _global_loss_by_hand(y_true, y_pred, shards)
+    ref, parts = ssd_loss(y_true, y_pred, 3, 0, 1.0, return_parts=True)
+    assert stats[0] == parts['n_positive'] and stats[2] == parts['k']
+    np.testing.assert_allclose(loss, ref, rtol=1e-5)
+    np.testing.assert_allclose(grad, ssd_loss_grad(y_true, y_pred, 3, 0, 1.0), rtol=1e-4, atol=1e-7)
+    tiny = OracleEncoder(**configs['tiny'])
+    yt, _ = synth.synth_y_true_pred_for_loss(61, tiny, 4, 2, 3, sharp=1.0)
+    yp = np.zeros_like(yt); yp[:, :, :4] = 0.25                    # every negative has the same loss: global flat-index order decides
+    loss, grad, _ = _global_loss_by_hand(yt, yp, shards)
+    np.testing.assert_allclose(loss, ssd_loss(yt, yp), rtol=1e-5)
+    np.testing.assert_allclose(grad, ssd_loss_grad(yt, yp), rtol=1e-5, atol=1e-8)
+    yt0 = tiny([np.zeros((0, 5))] * 4).astype(np.float32)          # no positives anywhere
+    loss, _, _ = _global_loss_by_hand(yt0, yp, shards, n_neg_min=10)
+    np.testing.assert_allclose(loss, ssd_loss(yt0, yp, n_neg_min=10), rtol=1e-5)
+
+
+def test_loss_forward_backward_one_launch(configs):
+    """ssdk_ssd_loss_fwd_bwd (what the training step calls): same loss and gradient as the separate entry points."""
+    import ctypes as C
+    import torch
+    from ssd_keras_b200 import _ffi
+    enc = OracleEncoder(**configs['ssd300'])
+    y_true, y_pred = synth.synth_y_true_pred_for_loss(5, enc, 4, 8, 20, sharp=2.0)
+    yt, yp = torch.from_numpy(y_true).cuda(), torch.from_numpy(y_pred).cuda()
+    loss = torch.empty((4,), dtype=torch.float32, device='cuda'); grad = torch.empty_like(yp)
+    n0 = _ffi.launch_count()
+    _ffi.check(_ffi.lib().ssdk_ssd_loss_fwd_bwd(_ffi.context(), _ffi.dptr(yt), _ffi.dptr(yp), 4, yp.shape[1], 21, 3, 0, 1.0, _ffi.dptr(None),
+                                                _ffi.dptr(loss), _ffi.dptr(None), _ffi.dptr(grad), _ffi.stream_ptr()))
+    assert _ffi.launch_count() - n0 == 1
+    np.testing.assert_allclose(loss.cpu().numpy(), ssd_loss(y_true, y_pred), rtol=1e-5)
+    np.testing.assert_allclose(grad.cpu().numpy(), ssd_loss_grad(y_true, y_pred), rtol=1e-4, atol=1e-7)

@@ -86,9 +86,12 @@ def _vgg_w(seed, variant, n_cls):
 
 
 def _close_to_builder(y, rows, colsum, stride):
-    """Same bars as the oracle's own pin against the builders (two float32 evaluation orders through ~23 layers)."""
-    np.testing.assert_allclose(y[:, ::stride], rows, rtol=2e-3, atol=1e-4)
-    np.testing.assert_allclose(y.astype(np.float64).sum(axis=1), colsum, rtol=1e-5, atol=1e-3)
+    """Element-wise: the oracle's own pin against the builders is rtol 2e-3 / atol 1e-4 (two float32 evaluation orders through
+    ~23 layers); the tcgen05 path adds its own <= 1.5e-4 on the probabilities (tests/test_gpu_model.py), hence atol 3e-4.
+    Column sums over all P rows: the bf16x3 accumulation error is systematic (truncating fp32 adds), so it does not average
+    out -- bounded by 3e-5 per row on top of the float32 summation noise."""
+    np.testing.assert_allclose(y[:, ::stride], rows, rtol=2e-3, atol=3e-4)
+    np.testing.assert_allclose(y.astype(np.float64).sum(axis=1), colsum, rtol=1e-5, atol=1e-3 + 3e-5 * y.shape[1])
 
 
 def test_ssd300_model_vs_reference_builder():
