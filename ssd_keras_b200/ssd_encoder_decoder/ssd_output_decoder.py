@@ -104,3 +104,77 @@ def nms_device(boxes, scores, confidence_thresh=0.01, iou_threshold=0.45, nms_ma
                                    B, n, float(confidence_thresh), float(iou_threshold), int(nms_max_output_size), int(top_k),
                                    _ffi.dptr(out), _ffi.dptr(counts), _ffi.dptr(index), _ffi.stream_ptr()))
     return (out, counts, index) if return_index else (out, counts)
+
+
+# ---------------------------------------------------------------------------------------------
+# debug / stand-alone utilities of the reference module (:27-75, :342-530)
+# ---------------------------------------------------------------------------------------------
+def decode_detections_debug(y_pred, confidence_thresh=0.01, iou_threshold=0.45, top_k=200, input_coords='centroids',
+                            normalize_coords=True, img_height=None, img_width=None, variance_encoded_in_target=False,
+                            border_pixels='half'):
+    """Reference :342-455: ``decode_detections`` with the index of the prior that made each detection prepended,
+    rows ``[box_id, class_id, confidence, xmin, ymin, xmax, ymax]``.  Same kernels as ``decode_detections`` -- the
+    prior index is carried through the NMS and top-k stages (``out_index`` of ``ssdk_decode``)."""
+    _check_norm(normalize_coords, img_height, img_width)
+    _check_coords(input_coords, "Unexpected value for `input_coords`. Supported input coordinate formats are 'minmax', 'corners' "
+                                "and 'centroids'.")
+    y = _to_device(y_pred)
+    if variance_encoded_in_target and input_coords == 'centroids':
+        # :404-406: the offsets are used without the variances == the usual formula with variances of exactly 1
+        y = y.clone()
+        y[:, :, -4:] = 1.0
+    out, counts, index = decode_device(y, PER_CLASS, False, confidence_thresh, iou_threshold, top_k, 0, input_coords,
+                                       normalize_coords, img_height, img_width, border_pixels, return_index=True)
+    out = out.cpu().numpy().astype(np.float64)
+    counts = counts.cpu().numpy()
+    index = index.cpu().numpy()
+    res = []
+    for i in range(out.shape[0]):
+        k = int(counts[i])
+        res.append(np.concatenate([index[i, :k, None].astype(np.float64), out[i, :k]], axis=1) if k > 0 else np.zeros((0, 7)))
+    return res
+
+
+def get_num_boxes_per_pred_layer(predictor_sizes, aspect_ratios, two_boxes_for_ar1):
+    """Reference :488-501 (note: like the reference, one extra box per cell whenever ``two_boxes_for_ar1`` is set)."""
+    out = []
+    for i in range(len(predictor_sizes)):
+        n = len(aspect_ratios[i]) + (1 if two_boxes_for_ar1 else 0)
+        out.append(predictor_sizes[i][0] * predictor_sizes[i][1] * n)
+    return out
+
+
+def get_pred_layers(y_pred_decoded, num_boxes_per_pred_layer):
+    """Reference :503-530: for predictions decoded with ``decode_detections_debug``, the index of the predictor layer that
+    made each of them."""
+    cum = np.cumsum(num_boxes_per_pred_layer)
+    res = []
+    for batch_item in y_pred_decoded:
+        ids = np.asarray(batch_item, dtype=np.float64).reshape(-1, 7)[:, 0] if np.size(batch_item) else np.zeros((0,))
+        if np.any(ids < 0) or np.any(ids >= cum[-1]):
+            raise ValueError("Box index is out of bounds of the possible indices as given by the values in `num_boxes_per_pred_layer`.")
+        res.append([int(v) for v in np.searchsorted(cum, ids, side='right')])
+    return res
+
+
+def greedy_nms(y_pred_decoded, iou_threshold=0.45, coords='corners', border_pixels='half'):
+    """Reference :27-75: greedy NMS over already decoded predictions, one ``(k, 6)`` array ``[class_id, score, 4 coordinates]``
+    per batch item; the score column decides, class ids are ignored, boxes with IoU <= ``iou_threshold`` to every kept
+    box survive.  Host loop like the reference, the element-wise IoU of every round is ``ssdk_iou`` (float64, the
+    reference's arithmetic incl. the border_pixels quirk); a utility, not part of the decode hot path."""
+    from ..bounding_box_utils.bounding_box_utils import iou
+    res = []
+    for batch_item in y_pred_decoded:
+        boxes_left = np.array(batch_item, dtype=np.float64, copy=True).reshape(-1, np.shape(batch_item)[-1] if np.ndim(batch_item) > 1 else 6)
+        maxima = []
+        while boxes_left.shape[0] > 0:
+            m = int(np.argmax(boxes_left[:, 1]))
+            box = boxes_left[m].copy()
+            maxima.append(box)
+            boxes_left = np.delete(boxes_left, m, axis=0)
+            if boxes_left.shape[0] == 0:
+                break
+            sim = iou(boxes_left[:, 2:], box[2:], coords=coords, mode='element-wise', border_pixels=border_pixels)
+            boxes_left = boxes_left[sim <= iou_threshold]
+        res.append(np.array(maxima))
+    return res

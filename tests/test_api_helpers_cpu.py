@@ -72,3 +72,32 @@ def test_loss_helpers_match_reference():
     np.testing.assert_allclose(out, X['loss_helpers/l1_out'], rtol=1e-6, atol=1e-7)
     out = SSDLoss._log_loss_t(f(X['loss_helpers/log_true']), f(X['loss_helpers/log_pred'])).numpy()
     np.testing.assert_allclose(out, X['loss_helpers/log_out'], rtol=1e-6, atol=1e-6)
+
+
+def test_pred_layer_helpers_and_inverse_transforms():
+    """get_num_boxes_per_pred_layer / get_pred_layers (ssd_output_decoder.py:488-530) against the real reference's outputs,
+    apply_inverse_transforms (data_generator/object_detection_2d_misc_utils.py:22-73) against its documented behaviour."""
+    import os
+    from ssd_keras_b200.data_generator.object_detection_2d_misc_utils import apply_inverse_transforms
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_output_decoder import get_num_boxes_per_pred_layer, get_pred_layers
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_debug_golden.npz'))
+    nb = get_num_boxes_per_pred_layer([(6, 8), (3, 4)], [[0.5, 1.0, 2.0]] * 2, True)
+    np.testing.assert_array_equal(nb, G['dbg/num_boxes'])
+    np.testing.assert_array_equal(get_num_boxes_per_pred_layer([(38, 38), (19, 19)], [[1.0, 2.0, 0.5], [1.0, 2.0, 0.5, 3.0, 1 / 3]], False),
+                                  G['dbg/num_boxes_one'])
+    dec = [G['dbg/centroids/a/out%d' % i] for i in range(3)]
+    for i, layers in enumerate(get_pred_layers(dec, nb)):
+        np.testing.assert_array_equal(layers, G['dbg/centroids/layers%d' % i])
+    with pytest.raises(ValueError):
+        get_pred_layers([np.array([[1e9, 1, 0.5, 0, 0, 1, 1]])], nb)
+    shift = lambda a: a + np.array([0, 0, 10, 20, 10, 20.])       # noqa: E731
+    lst = [np.ones((2, 6)), np.zeros((0, 6)), np.ones((1, 6))]
+    out = apply_inverse_transforms(lst, [[shift, None], [shift], [shift, shift]])
+    np.testing.assert_array_equal(out[0], np.ones((2, 6)) + [0, 0, 10, 20, 10, 20])
+    assert out[1].shape == (0, 6)
+    np.testing.assert_array_equal(out[2], np.ones((1, 6)) + [0, 0, 20, 40, 20, 40])
+    arr = np.ones((2, 3, 6))
+    out = apply_inverse_transforms(arr, [[shift], [None]])
+    np.testing.assert_array_equal(out[0], arr[0] + [0, 0, 10, 20, 10, 20]); np.testing.assert_array_equal(out[1], arr[1])
+    with pytest.raises(ValueError):
+        apply_inverse_transforms(3, [])
