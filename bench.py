@@ -288,6 +288,142 @@ def micro_benchmarks(peaks):
     return out
 
 
+def _max_over_ranks(ms, dist):
+    import torch
+    t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_extras(world, rank, peaks, model_inf_weights):
+    """Runs on EVERY rank when world > 1 (all collectives are real NCCL calls): BASELINE config 3's training step with the
+    gradient exchange overlapped with the backward pass, the same step with one exchange after the backward pass, a fixed
+    global batch of 32 split over the ranks (strong scaling), and a correctness check of both loss modes against the float64
+    oracle.  Times are CUDA events, max over ranks."""
+    import importlib.util
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    from ssd_keras_b200.distributed import all_gather_detections, all_reduce_buckets_, shard_bounds, ssd_loss_global
+    from ssd_keras_b200.models.keras_ssd300 import ssd_300
+    from ssd_keras_b200.ssd_encoder_decoder.ssd_input_encoder import SSDInputEncoder
+    from ssd_keras_b200.training import SSDTrainer
+    out = {}
+
+    def timed(fn, steps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        dist.barrier(); torch.cuda.synchronize()
+        return _max_over_ranks(a.elapsed_time(b) / steps, dist)
+
+    # --- config 3, weak scaling: 32 images per rank, encode on the device + forward + loss + backward + exchange + update
+    Bt = 32
+    from oracle.model import SSD300_AR
+    mt = ssd_300((300, 300, 3), 20, mode='training', scales=SC300)
+    enc = SSDInputEncoder(300, 300, 20, mt.predictor_sizes, scales=SC300, aspect_ratios_per_layer=SSD300_AR, steps=[8, 16, 32, 64, 100, 300],
+                          offsets=[0.5] * 6, pos_iou_threshold=0.5, neg_iou_limit=0.5)
+    gt = synth.synth_gt(2 + rank, Bt, 8, 300, 300, 20)
+    offs = np.cumsum([0] + [g.shape[0] for g in gt]).astype(np.int32)
+    gdev = torch.from_numpy(np.concatenate(gt)).cuda()
+    xt = torch.from_numpy(synth.synth_images(50 + rank, Bt, 300, 300)).cuda()
+    ybuf = torch.empty((Bt, 8732, 33), dtype=torch.float32, device='cuda')
+    tr = SSDTrainer(mt, Bt, lr=1e-4, momentum=0.9)
+
+    def step():
+        tr.train_on_batch(xt, enc.encode_device(gdev, offs, out=ybuf))
+    ms_overlap = timed(step)
+    tr.bucket_bytes = 1 << 40                                   # one bucket: the exchange starts when the backward pass is over
+    ms_serial = timed(step)
+    tr.bucket_bytes = 24 << 20
+
+    def step_local():                                           # the same step without any exchange (what a single GPU does)
+        loss, _, dy = tr._loss_and_dy(xt, enc.encode_device(gdev, offs, out=ybuf))
+        tr._backward_layers(dy, len(mt.specs) - 1, 0)
+        tr.apply(1.0)
+    ms_local = timed(step_local)
+    nbytes = tr.n_params * 4
+    out['train_step_ssd300_b32_per_gpu'] = {
+        'ms_overlapped_buckets': ms_overlap, 'ms_single_allreduce_after_backward': ms_serial, 'ms_no_exchange': ms_local,
+        'images_per_s': world * Bt * 1e3 / ms_overlap, 'allreduce_MB': nbytes / 1e6, 'buckets': len(tr.buckets()),
+        'exposed_exchange_ms': ms_overlap - ms_local, 'unoverlapped_exchange_ms': ms_serial - ms_local,
+        'allreduce_busbw_GBps_if_serial': (2.0 * (world - 1) / world * nbytes / 1e9) / max((ms_serial - ms_local) * 1e-3, 1e-9),
+        'scaling': 'weak', 'loss_mode': 'replica'}
+    del tr, mt, xt, ybuf
+    torch.cuda.empty_cache()
+
+    # --- configs 1/2 as the survey partitions them: a FIXED global batch of 32 images, 32 / world per rank (strong scaling)
+    if 32 % world == 0:
+        bl = 32 // world
+        ms_ = ssd_300((300, 300, 3), 20, mode='inference', scales=SC300)
+        ms_.set_weights(model_inf_weights)
+        lo, hi = shard_bounds(32, rank, world)
+        xs = [torch.from_numpy(synth.synth_images(200 + i, 32, 300, 300)[lo:hi]).cuda() for i in range(2)]
+        state = {'i': 0}
+
+        def infer():
+            state['i'] += 1
+            return all_gather_detections(ms_.predict_device(xs[state['i'] & 1]))
+        t = timed(infer, steps=10, warm=3)
+        out['strong_b32'] = {'global_batch': 32, 'images_per_rank': bl, 'ms_per_step': t, 'images_per_s': 32e3 / t, 'scaling': 'strong',
+                             'note': 'SSD300 forward + DecodeDetections + all-gather of the (32,200,6) boxes'}
+        del ms_, xs
+        torch.cuda.empty_cache()
+
+    # --- correctness of the exchange against the float64 oracle (small graph, 2 images per rank) and of the global-batch-exact loss
+    spec = importlib.util.spec_from_file_location('train_check', os.path.join(ROOT, 'tools', 'train_check.py'))
+    tc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tc)
+    case = tc.CASES[2]
+    m, w, n_cls = tc.build(case)
+    hw, per = case[1], 2
+    Bg = per * world
+    rng = np.random.default_rng(11)
+    x_all = rng.integers(0, 256, size=(Bg, hw, hw, 3)).astype(np.float32)
+    from oracle.encoder import OracleEncoder
+    oenc = OracleEncoder(hw, hw, n_cls - 1, m.predictor_sizes, scales=m.anchor_cfg['scales'], aspect_ratios_per_layer=m.anchor_cfg['aspect_ratios_per_layer'],
+                         variances=[0.1, 0.1, 0.2, 0.2], pos_iou_threshold=0.3, neg_iou_limit=0.2)
+    y_all = oenc(tc.small_gt(5, Bg, 3, hw, n_cls - 1)).astype(np.float32)
+    lo, hi = rank * per, (rank + 1) * per
+    xd, yd = torch.from_numpy(x_all[lo:hi]).cuda(), torch.from_numpy(y_all[lo:hi]).cuda()
+    check = {}
+    for mode in ('replica', 'global'):
+        trc = SSDTrainer(m, per, lr=1e-3, momentum=0.9, l2_regularization=0.0, loss_mode=mode)
+        loss, y_pred, dy = trc._loss_and_dy(xd, yd)
+        all_reduce_buckets_(trc.grad, trc.buckets(1 << 12), lambda a, b: trc._backward_layers(dy, a, b))
+        torch.cuda.synchronize()
+        grads = trc.gradients()
+        losses = [torch.zeros_like(loss) for _ in range(world)]
+        dist.all_gather(losses, loss)
+        if rank == 0:
+            from oracle import graph as og
+            params = og.make_params(m.specs, w, dtype=torch.float64)
+            yp, _ = og.forward(m.specs, params, x_all, n_cls, m.anchors, [0.1, 0.1, 0.2, 0.2], dtype=torch.float64)
+            if mode == 'replica':                # every rank: the reference loss on its own shard, mean over the shard; gradients summed
+                lv = torch.cat([og.ssd_loss_torch(y_all[r * per:(r + 1) * per], yp[r * per:(r + 1) * per]) for r in range(world)])
+                torch.stack([lv[r * per:(r + 1) * per].mean() for r in range(world)]).sum().backward()
+            else:                                # the single-process reference on the whole batch
+                lv = og.ssd_loss_torch(y_all, yp)
+                lv.mean().backward()
+            ref_l = lv.detach().numpy()
+            got_l = torch.cat(losses).cpu().numpy()
+            gerr = max(float(np.abs(grads[k] - params[k].grad.numpy()).max() / (np.abs(params[k].grad.numpy()).max() + 1e-30)) for k in grads)
+            lerr = float(np.abs(got_l - ref_l).max() / np.abs(ref_l).max())
+            check[mode] = {'loss_rel_err': lerr, 'grad_rel_err_max': gerr, 'pass': bool(lerr < 1e-4 and gerr < 2e-3)}
+        del trc
+    if rank == 0:
+        check['pass'] = bool(all(v['pass'] for v in check.values()))
+        check['what'] = ('%d ranks x 2 images, small SSD graph (conv / l2norm / pool / two heads): all-reduced gradients and gathered '
+                         'losses against float64 autograd of the oracle graph; replica-local loss and global-batch-exact loss' % world)
+        out['nccl_check'] = check
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -409,10 +545,6 @@ def run_ours(args):
                 'issued_tflops': fl_issued / conv_ms / 1e9, 'issued_frac': fl_issued / conv_ms / 1e9 / peak,
                 'conv_ms_per_step': conv_ms}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     line = {'metric': METRIC, 'value': ips, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16x3 (bf16 hi+lo operands, 3 tcgen05 MMAs per product, fp32 accumulate)' if not args.fast else 'bf16',
@@ -425,6 +557,33 @@ def run_ours(args):
                     'note': 'SSDModel.predict_device on pinned-host inputs; the H2D of step i+1 is issued on a copy stream before '
                             'the kernels of step i (K uploads + K downloads inside the timed region)'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline}
+    if world > 1:
+        # every rank takes part in the extras (real NCCL collectives).  They must never cost the headline line: a watchdog
+        # prints it without them and leaves if they hang (a rank that failed while the others wait in a collective)
+        import signal
+
+        def _bail(signum, frame):
+            if rank == 0:
+                line['extra'] = {'error': 'multi-rank extras timed out'}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        if not args.no_micro:
+            signal.signal(signal.SIGALRM, _bail)
+            signal.alarm(int(os.environ.get('SSDK_EXTRAS_TIMEOUT', '420')))
+            try:
+                extra = dist_extras(world, rank, peaks, _weights())
+            except Exception as e:
+                import traceback
+                extra = {'error': repr(e), 'trace': traceback.format_exc()[-1500:]}
+            signal.alarm(0)
+            line['extra'] = extra
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        return
     if world == 1:
         if not args.no_cpu:
             v, dt, threads, t_fwd, t_dec = time_cpu_reference(16, 2, 1)
@@ -438,8 +597,6 @@ def run_ours(args):
             except Exception as e:                    # the headline number must not depend on the extras
                 line['extra'] = {'error': repr(e)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

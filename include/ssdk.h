@@ -304,6 +304,15 @@ int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int which, long lo
 float* ssdk_trainer_grad_buffer(ssdk_trainer* t);
 int ssdk_train_backward(ssdk_trainer* t, const float* y_true_dev, const float* y_pred_dev, int neg_pos_ratio, int n_neg_min,
                         float alpha, float* out_loss_dev /* [B] */, void* stream);
+/* The step in pieces, for overlapping the gradient exchange with the backward pass:
+ *   ssdk_train_backward_begin   loss + d loss / d y_pred (kept inside the trainer), gradient buffer cleared;
+ *   ssdk_train_backward_layers  layers hi .. lo (graph indices, top down, consecutive calls cover n_layers-1 .. 0).  In stream
+ *                               order after the call the parameter gradients of exactly these layers are final, so their
+ *                               span of the flat buffer (ssdk_trainer_param_span) can be all-reduced on another stream while the
+ *                               lower layers are still being differentiated.  dypred_dev NULL = the trainer's own. */
+int ssdk_train_backward_begin(ssdk_trainer* t, const float* y_true_dev, const float* y_pred_dev, int neg_pos_ratio, int n_neg_min,
+                              float alpha, float* out_loss_dev, void* stream);
+int ssdk_train_backward_layers(ssdk_trainer* t, const float* dypred_dev, int hi, int lo, void* stream);
 /* The same backward pass from a gradient the caller computed: dypred_dev = d loss / d y_pred, (B,P,C+12) float32 (used with the
  * multi-GPU global-batch-exact loss, whose phases run between NCCL collectives, see ssdk_ssd_loss_phase). */
 int ssdk_train_backward_dy(ssdk_trainer* t, const float* dypred_dev, void* stream);

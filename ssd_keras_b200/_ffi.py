@@ -137,6 +137,10 @@ def lib():
             L.ssdk_train_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]
             L.ssdk_train_backward_dy.argtypes = [vp, vp, vp]
             L.ssdk_train_backward_dy.restype = C.c_int
+            L.ssdk_train_backward_begin.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]
+            L.ssdk_train_backward_begin.restype = C.c_int
+            L.ssdk_train_backward_layers.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+            L.ssdk_train_backward_layers.restype = C.c_int
             L.ssdk_train_apply.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
             L.ssdk_trainer_read_params.argtypes = [vp, vp, vp]
             for name in ('ssdk_trainer_create', 'ssdk_trainer_destroy', 'ssdk_trainer_num_params', 'ssdk_trainer_param_span',

@@ -470,6 +470,7 @@ struct ssdk_trainer {
   __nv_bfloat16 *xT_hi = nullptr, *xT_lo = nullptr, *dyT_hi = nullptr, *dyT_lo = nullptr;   // scratch, sized for the largest layer
   long long xT_elems = 0, dyT_elems = 0;
   float* dypred = nullptr;                  // [B*P*(C+12)]
+  std::vector<char> written;                // backward pass state: which activations already hold a partial gradient
   std::vector<void*> allocs;
 };
 
@@ -727,38 +728,59 @@ int do_transpose(ssdk_trainer* t, const __nv_bfloat16* hi, const __nv_bfloat16* 
 }  // namespace
 
 namespace {
-int backward_from_dy(ssdk_trainer* t, const float* dypred, cudaStream_t s);
+int backward_layers(ssdk_trainer* t, const float* dypred, int hi, int lo, cudaStream_t s);
+}
+
+// Loss (optional) and d loss / d y_pred from one launch of the fused loss kernel; clears the gradient buffer.
+extern "C" int ssdk_train_backward_begin(ssdk_trainer* t, const float* y_true, const float* y_pred, int neg_pos_ratio, int n_neg_min,
+                                         float alpha, float* out_loss, void* stream_) {
+  SSDK_REQUIRE(t && y_true && y_pred, "ssdk_train_backward_begin: NULL argument");
+  ssdk_model* m = t->m;
+  ssdk_ctx* ctx = m->ctx;
+  int rc;
+  SSDK_CHECK_CUDA(cudaMemsetAsync(t->grad, 0, (size_t)t->n_params * sizeof(float), (cudaStream_t)stream_));
+  if (out_loss) rc = ssdk_ssd_loss_fwd_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, out_loss, nullptr, t->dypred, stream_);
+  else rc = ssdk_ssd_loss_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, t->dypred, stream_);
+  return rc;
+}
+
+// The backward pass of layers hi, hi-1, ..., lo (graph indices; a full pass is n_layers-1 .. 0 in one or several calls, top
+// down).  When it returns (stream order), the parameter gradients of exactly these layers are final -- their span of the
+// flat buffer can be all-reduced while the lower layers are still being differentiated.  dypred_dev NULL: the gradient
+// ssdk_train_backward_begin left in the trainer; otherwise d loss / d y_pred provided by the caller (the buffer is cleared
+// when the pass starts at the top layer).
+extern "C" int ssdk_train_backward_layers(ssdk_trainer* t, const float* dypred_dev, int hi, int lo, void* stream_) {
+  SSDK_REQUIRE(t, "ssdk_train_backward_layers: NULL trainer");
+  const int n = (int)t->m->layers.size();
+  SSDK_REQUIRE(hi < n && lo >= 0 && lo <= hi, "ssdk_train_backward_layers: bad layer range [%d, %d] of %d layers", lo, hi, n);
+  if (dypred_dev && hi == n - 1) SSDK_CHECK_CUDA(cudaMemsetAsync(t->grad, 0, (size_t)t->n_params * sizeof(float), (cudaStream_t)stream_));
+  return backward_layers(t, dypred_dev ? dypred_dev : t->dypred, hi, lo, (cudaStream_t)stream_);
 }
 
 extern "C" int ssdk_train_backward(ssdk_trainer* t, const float* y_true, const float* y_pred, int neg_pos_ratio, int n_neg_min,
                                    float alpha, float* out_loss, void* stream_) {
-  SSDK_REQUIRE(t && y_true && y_pred, "ssdk_train_backward: NULL argument");
-  ssdk_model* m = t->m;
-  ssdk_ctx* ctx = m->ctx;
-  int rc;
-  // loss (optional) and d loss / d y_pred from one launch of the fused loss kernel
-  if (out_loss) rc = ssdk_ssd_loss_fwd_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, out_loss, nullptr, t->dypred, stream_);
-  else rc = ssdk_ssd_loss_bwd(ctx, y_true, y_pred, m->B, m->P, m->Ctot, neg_pos_ratio, n_neg_min, alpha, nullptr, t->dypred, stream_);
+  int rc = ssdk_train_backward_begin(t, y_true, y_pred, neg_pos_ratio, n_neg_min, alpha, out_loss, stream_);
   if (rc) return rc;
-  return backward_from_dy(t, t->dypred, (cudaStream_t)stream_);
+  return backward_layers(t, t->dypred, (int)t->m->layers.size() - 1, 0, (cudaStream_t)stream_);
 }
 
 extern "C" int ssdk_train_backward_dy(ssdk_trainer* t, const float* dypred_dev, void* stream_) {
   SSDK_REQUIRE(t && dypred_dev, "ssdk_train_backward_dy: NULL argument");
-  return backward_from_dy(t, dypred_dev, (cudaStream_t)stream_);
+  return ssdk_train_backward_layers(t, dypred_dev, (int)t->m->layers.size() - 1, 0, stream_);
 }
 
 namespace {
 
-// every parameter gradient from d loss / d y_pred (B,P,C+12), walking the layers in reverse
-int backward_from_dy(ssdk_trainer* t, const float* dypred, cudaStream_t s) {
+// parameter gradients of layers hi .. lo from d loss / d y_pred (B,P,C+12), walking the layers in reverse
+int backward_layers(ssdk_trainer* t, const float* dypred, int hi, int lo, cudaStream_t s) {
   ssdk_model* m = t->m;
   ssdk_ctx* ctx = m->ctx;
   int rc;
-  SSDK_CHECK_CUDA(cudaMemsetAsync(t->grad, 0, (size_t)t->n_params * sizeof(float), s));
   const int n = (int)m->layers.size();
-  std::vector<char> written(n, 0);
-  for (int i = n - 1; i >= 0; --i) {
+  if (hi == n - 1) t->written.assign(n, 0);
+  SSDK_REQUIRE((int)t->written.size() == n, "ssdk_train_backward_layers: a pass must start at the top layer");
+  std::vector<char>& written = t->written;
+  for (int i = hi; i >= lo; --i) {
     LayerPlan& L = m->layers[i];
     TLayer& T = t->tl[i];
     const ssdk_layer_desc& d = L.d;

@@ -73,6 +73,42 @@ def all_reduce_gradients_(flat_grad, group=None):
     return 1.0 / dist.get_world_size(group)
 
 
+def plan_buckets(first, size, bucket_bytes):
+    """Layer ranges for an overlapped gradient exchange, top of the graph first.
+
+    ``first[i]`` / ``size[i]``: offset (in floats; None if the layer has no parameters) and number of parameters of graph
+    layer ``i`` inside the flat gradient buffer, which holds the layers in graph order.  Walking the layers top down, a bucket
+    is closed once it holds ``bucket_bytes`` of float32 gradients.  Returns ``[(hi, lo, offset, count), ...]``: the layers
+    ``hi .. lo`` own the contiguous span ``[offset, offset + count)``; every layer belongs to exactly one bucket."""
+    n = len(size)
+    out, hi, acc, lo_off = [], n - 1, 0, None
+    for i in range(n - 1, -1, -1):
+        if size[i]:
+            acc += size[i]
+            lo_off = first[i] if lo_off is None else min(lo_off, first[i])
+        if acc * 4 >= bucket_bytes or i == 0:
+            out.append((hi, i, lo_off if lo_off is not None else 0, acc))
+            hi, acc, lo_off = i - 1, 0, None
+    return out
+
+
+def all_reduce_buckets_(flat_grad, buckets, produce, group=None):
+    """``for hi, lo, off, cnt in buckets: produce(hi, lo)`` (which enqueues the kernels that finish the gradients of the layers
+    ``hi .. lo``) followed at once by an asynchronous all-reduce (sum) of that bucket's span: the collective of bucket k runs
+    on the communication stream while ``produce`` of bucket k+1 already runs on the compute stream.  Returns after making the
+    current stream (CUDA) / the host (CPU tensors) wait for all of them."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    works = []
+    for hi, lo, off, cnt in buckets:
+        produce(hi, lo)
+        if on and cnt:
+            works.append(dist.all_reduce(flat_grad[off:off + cnt], group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return len(works)
+
+
 class GlobalLossRun:
     """One rank's side of the phase-wise loss (``ssdk_ssd_loss_phase``): owns the workspace and exposes the tensors that have
     to be reduced between the phases.  ``ssd_loss_global`` drives it with torch.distributed; the single-GPU tests drive several

@@ -33,6 +33,8 @@ class SSDTrainer:
         self.plan = None
         self._spans = None
         self._dirty = False                      # device master weights are ahead of model.weights
+        self._buckets = None
+        self.bucket_bytes = 24 << 20
         model._trainers.append(weakref.ref(self))
         self._attach()
 
@@ -75,10 +77,7 @@ class SSDTrainer:
             pass
 
     # -- one step ------------------------------------------------------------------------------
-    def forward_backward(self, images, y_true):
-        """images (B,H,W,3), y_true (B,P,C+12): float32 CUDA tensors.  Returns (loss (B,), y_pred); gradients in self.grad."""
-        import torch
-        self._attach()
+    def _check_batch(self, images, y_true):
         P, W = self.model.n_boxes_total, self.model.n_classes + 12
         if images.shape[0] != self.batch or tuple(y_true.shape) != (self.batch, P, W):
             raise ValueError('this trainer was built for batches of %d images: images %s / y_true %s do not match (%d, H, W, 3) / %s; '
@@ -86,16 +85,30 @@ class SSDTrainer:
                              % (self.batch, tuple(images.shape), tuple(y_true.shape), self.batch, (self.batch, P, W)))
         if not (images.is_cuda and y_true.is_cuda):
             raise ValueError('images and y_true must be CUDA tensors')
+
+    def _loss_and_dy(self, images, y_true):
+        """forward + loss; leaves d loss / d y_pred ready for the layer-wise backward.  Returns (loss, y_pred, dy or None)."""
+        import torch
+        self._attach()
+        self._check_batch(images, y_true)
         y_pred = self.model.forward_device(images, training=True)
         y_true = y_true.to(dtype=torch.float32).contiguous()
         if self.loss_mode == 'global':
             from .distributed import ssd_loss_global
             loss, dy, _ = ssd_loss_global(y_true, y_pred, self.neg_pos_ratio, self.n_neg_min, self.alpha, return_grad=True)
-            _ffi.check(_ffi.lib().ssdk_train_backward_dy(self.handle, _ffi.dptr(dy), _ffi.stream_ptr()))
-            return loss, y_pred
+            return loss, y_pred, dy
         loss = torch.empty((self.batch,), dtype=torch.float32, device=images.device)
-        _ffi.check(_ffi.lib().ssdk_train_backward(self.handle, _ffi.dptr(y_true), _ffi.dptr(y_pred), self.neg_pos_ratio,
-                                                  self.n_neg_min, self.alpha, _ffi.dptr(loss), _ffi.stream_ptr()))
+        _ffi.check(_ffi.lib().ssdk_train_backward_begin(self.handle, _ffi.dptr(y_true), _ffi.dptr(y_pred), self.neg_pos_ratio,
+                                                        self.n_neg_min, self.alpha, _ffi.dptr(loss), _ffi.stream_ptr()))
+        return loss, y_pred, None
+
+    def _backward_layers(self, dy, hi, lo):
+        _ffi.check(_ffi.lib().ssdk_train_backward_layers(self.handle, _ffi.dptr(dy), int(hi), int(lo), _ffi.stream_ptr()))
+
+    def forward_backward(self, images, y_true):
+        """images (B,H,W,3), y_true (B,P,C+12): float32 CUDA tensors.  Returns (loss (B,), y_pred); gradients in self.grad."""
+        loss, y_pred, dy = self._loss_and_dy(images, y_true)
+        self._backward_layers(dy, len(self.model.specs) - 1, 0)
         return loss, y_pred
 
     def apply(self, grad_scale=1.0):
@@ -103,14 +116,42 @@ class SSDTrainer:
         self._dirty = True
         _ffi.check(_ffi.lib().ssdk_train_apply(self.handle, self.lr, self.momentum, self.l2, float(grad_scale), _ffi.stream_ptr()))
 
-    def train_on_batch(self, images, y_true):
-        """forward + loss + backward + (all-reduce) + SGD update.  Returns the per-image loss tensor (B,)."""
-        from .distributed import all_reduce_gradients_
-        loss, _ = self.forward_backward(images, y_true)
-        scale = all_reduce_gradients_(self.grad)           # one all-reduce for all 26 M gradients, then the update
-        if self.loss_mode == 'global':
-            scale = 1.0                                     # the shards' gradients of the GLOBAL batch mean add up; nothing to average
-        self.apply(scale)
+    def buckets(self, bucket_bytes=None):
+        """Layer ranges for the overlapped gradient exchange, top of the graph first: [(hi, lo, offset, count), ...].  The
+        parameters lie in the flat buffer in graph order, so the layers hi..lo own one contiguous span of it; a bucket is closed
+        once it holds ``bucket_bytes`` of gradients (default 24 MB -- large enough that NCCL runs at NVLink bandwidth, small enough
+        that the first exchange starts after ~1/5 of the backward pass of SSD300)."""
+        from .distributed import plan_buckets
+        bucket_bytes = int(self.bucket_bytes if bucket_bytes is None else bucket_bytes)
+        if self._buckets is not None and self._buckets[0] == bucket_bytes:
+            return self._buckets[1]
+        n = len(self.model.specs)
+        first = [None] * n                                       # lowest offset / total count of each layer's parameters
+        size = [0] * n
+        for (name, _), (o, c) in self.spans().items():
+            i = self.model.index[name]
+            first[i] = o if first[i] is None else min(first[i], o)
+            size[i] += c
+        out = plan_buckets(first, size, bucket_bytes)
+        self._buckets = (bucket_bytes, out)
+        return out
+
+    def train_on_batch(self, images, y_true, group=None):
+        """forward + loss + backward + gradient exchange + SGD update.  Returns the per-image loss tensor (B,).
+        With several ranks the flat gradient buffer is all-reduced in buckets, from the top of the network down, each as soon
+        as its layers have been differentiated: NCCL runs on its own stream and overlaps the weight / data gradient kernels of
+        the lower layers."""
+        import torch.distributed as dist
+        on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        loss, _, dy = self._loss_and_dy(images, y_true)
+        if not on:
+            self._backward_layers(dy, len(self.model.specs) - 1, 0)
+            self.apply(1.0)
+            return loss
+        from .distributed import all_reduce_buckets_
+        all_reduce_buckets_(self.grad, self.buckets(), lambda hi, lo: self._backward_layers(dy, hi, lo), group=group)
+        # 'replica': the mean of the replicas' gradients; 'global': the shards' gradients of the GLOBAL batch mean add up
+        self.apply(1.0 if self.loss_mode == 'global' else 1.0 / dist.get_world_size(group))
         return loss
 
     # -- introspection (tests) -------------------------------------------------------------------

@@ -52,6 +52,24 @@ def _worker(rank, world, port, n_images, q):
         g = torch.arange(10, dtype=torch.float32) * (rank + 1)
         scale = D.all_reduce_gradients_(g)
         ok = ok and scale == 1.0 / world and bool(torch.equal(g, torch.arange(10, dtype=torch.float32) * sum(range(1, world + 1))))
+        # bucketed, overlapped exchange: layers are "differentiated" top down, each bucket is reduced as soon as it is complete
+        sizes = [0, 5, 0, 7, 3, 0, 9, 4]                                   # parameters per graph layer (0: pool / input)
+        first, o = [], 0
+        for sz in sizes:
+            first.append(o if sz else None); o += sz
+        buckets = D.plan_buckets(first, sizes, bucket_bytes=40)            # 10 floats per bucket
+        flat = torch.zeros(o)
+        done = []
+
+        def produce(hi, lo):                                               # fills the gradients of layers hi .. lo only
+            for i in range(hi, lo - 1, -1):
+                if sizes[i]:
+                    flat[first[i]:first[i] + sizes[i]] = float(rank + 1) * (i + 1)
+            done.append((hi, lo))
+        n_coll = D.all_reduce_buckets_(flat, buckets, produce)
+        exp = torch.cat([torch.full((sz,), float(sum(range(1, world + 1))) * (i + 1)) for i, sz in enumerate(sizes) if sz])
+        ok = ok and bool(torch.equal(flat, exp)) and n_coll == len([b for b in buckets if b[3]])
+        ok = ok and done[0][0] == len(sizes) - 1 and done[-1][1] == 0 and all(a[1] == b[0] + 1 for a, b in zip(done, done[1:]))
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -75,3 +93,21 @@ def test_all_gather_two_ranks_gloo(n_images):
 def test_gradient_exchange_is_identity_without_process_group():
     g = torch.ones(4)
     assert D.all_reduce_gradients_(g) == 1.0 and bool(torch.equal(g, torch.ones(4)))
+
+
+def test_plan_buckets_partitions_the_layers():
+    sizes = [0, 1728, 36864, 0, 73728, 147456, 0, 2359296, 4718592, 1000, 0, 12]
+    first, o = [], 0
+    for sz in sizes:
+        first.append(o if sz else None); o += sz
+    for bb in (1, 4 * 100000, 4 * 3000000, 1 << 40):
+        b = D.plan_buckets(first, sizes, bb)
+        assert b[0][0] == len(sizes) - 1 and b[-1][1] == 0
+        assert all(x[1] == y[0] + 1 for x, y in zip(b, b[1:]))                      # consecutive, top down, no gaps
+        assert sum(x[3] for x in b) == o
+        for hi, lo, off, cnt in b:                                                 # the span is exactly the layers' parameters
+            owned = [i for i in range(lo, hi + 1) if sizes[i]]
+            if owned:
+                assert off == first[owned[0]] and cnt == sum(sizes[i] for i in owned)
+        if bb == 1 << 40:
+            assert len(b) == 1
