@@ -142,6 +142,31 @@ int ssdk_iou(ssdk_ctx* ctx, const double* boxes1_dev, int m, const double* boxes
              int elementwise, double* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Batch assembly (the hand-off DataGenerator.generate -> label_encoder, data_generator/object_detection_2d_data_generator.py:
+ * 1095-1151) and the box half of the reference's geometric augmentation ops on the device: per image a list of operations
+ * with the parameters the caller's (host-side, random) augmentation logic decided, applied to every box in float64 like
+ * NumPy does, boxes that fail a filter are dropped, the survivors are packed into the encoder's ragged format.
+ *   CROP_PAD  a0=patch_ymin a1=patch_xmin a2=patch_height a3=patch_width; flags bit0: BoxFilter 'center_point' against the
+ *             patch, bit1: clip to the patch      (CropPad.__call__, object_detection_2d_patch_sampling_ops.py:312-330;
+ *             SSDExpand = negative patch origin without filter / clip, SSDRandomCrop = filter + clip)
+ *   FLIP_H    a0=image width   FLIP_V  a0=image height                  (object_detection_2d_geometric_ops.py:186,194)
+ *   RESIZE    a0=in_height a1=in_width a2=out_height a3=out_width; flags bit0: drop degenerate boxes afterwards (:88-100)
+ *   FILTER    flags bit0: drop degenerate boxes (xmax <= xmin or ymax <= ymin), bit1: drop boxes with area < a0
+ *             (BoxFilter, object_detection_2d_image_boxes_validation_utils.py:155-165; also DataGenerator's
+ *             degenerate_box_handling='remove')
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { SSDK_BOXOP_END = 0, SSDK_BOXOP_CROP_PAD = 1, SSDK_BOXOP_FLIP_H = 2, SSDK_BOXOP_FLIP_V = 3, SSDK_BOXOP_RESIZE = 4,
+               SSDK_BOXOP_FILTER = 5 } ssdk_box_op_kind;
+typedef struct { int op; int flags; double a0, a1, a2, a3; } ssdk_box_op;
+/* gt_in_dev [total_in*5] float32 (gt_in_f64 = 0) or float64 (1) rows (class, xmin, ymin, xmax, ymax), offsets_in_dev [B+1]; ops_dev [B*max_ops] (a list ends at
+ * SSDK_BOXOP_END or after max_ops entries; max_ops = 0: pack only).  Outputs: gt_out_dev [<= total_in*5], offsets_out_dev [B+1],
+ * out_stats_dev (optional) [2] = total number of boxes left, largest per-image count.  Everything stays on the device: feed
+ * the result to ssdk_encode_dev with total_in / the input's largest count as upper bounds. */
+int ssdk_assemble_batch(ssdk_ctx* ctx, const void* gt_in_dev, int gt_in_f64, const int* offsets_in_dev, int B, int total_in,
+                        const ssdk_box_op* ops_dev, int max_ops, float* gt_out_dev, int* offsets_out_dev, int* out_stats_dev,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Decoders.
  *   mode PER_CLASS + layer_semantics=1: DecodeDetections.call   (keras_layers/keras_layer_DecodeDetections.py:109-265)
  *   mode FAST      + layer_semantics=1: DecodeDetectionsFast.call (keras_layers/keras_layer_DecodeDetectionsFast.py:111-248)

@@ -46,6 +46,13 @@ class DecodeCfg(C.Structure):
                 ('img_height', C.c_int), ('img_width', C.c_int), ('border_d', C.c_int), ('max_out', C.c_int)]
 
 
+class BoxOp(C.Structure):
+    _fields_ = [('op', C.c_int), ('flags', C.c_int), ('a0', C.c_double), ('a1', C.c_double), ('a2', C.c_double), ('a3', C.c_double)]
+
+
+BOXOP_END, BOXOP_CROP_PAD, BOXOP_FLIP_H, BOXOP_FLIP_V, BOXOP_RESIZE, BOXOP_FILTER = range(6)
+
+
 class LossWsLayout(C.Structure):
     _fields_ = [('bytes', C.c_longlong), ('counts_offset', C.c_longlong), ('counts_n', C.c_longlong), ('hist1_offset', C.c_longlong),
                 ('hist2_offset', C.c_longlong), ('hist_n', C.c_longlong), ('ties_offset', C.c_longlong)]
@@ -115,6 +122,8 @@ def lib():
                                           C.c_int, vp, vp, vp, vp, vp]
         for name in ('ssdk_ssd_loss_fwd_bwd', 'ssdk_ssd_loss_ws_layout', 'ssdk_ssd_loss_phase'):
             getattr(L, name).restype = C.c_int
+        L.ssdk_assemble_batch.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp]
+        L.ssdk_assemble_batch.restype = C.c_int
         L.ssdk_l2_normalize.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp]
         L.ssdk_l2_normalize.restype = C.c_int
         if hasattr(L, 'ssdk_model_create'):

@@ -24,6 +24,7 @@ SOURCES = {
     'encode.cu': ['--fmad=false'],
     'decode.cu': ['--fmad=false'],
     'loss.cu': ['--fmad=false'],
+    'batch.cu': ['--fmad=false'],
     'conv.cu': [],
     'model.cu': [],
     'train.cu': [],

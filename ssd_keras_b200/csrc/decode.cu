@@ -14,6 +14,13 @@
 //                       ballot/shuffle).  With the layer's cap of 400 survivors one band is normally enough.
 //   topk_kernel         one CTA per image: concatenates the per-class survivors (class-major, NMS order),
 //                       selects top_k with the same radix select, sorts and writes (class,conf,box) rows.
+// Only top_k detections per image leave the decoder, so (i) no class ever needs more than top_k survivors, and (ii) a
+// candidate whose score is below the top_k-th best SURVIVOR of the image cannot matter.  The NMS therefore runs in two
+// stages: stage 1 looks at the best few hundred candidates of every class only (one small band) and records the score
+// where it stopped; the top-k stage then checks that every class that was cut short stopped strictly below the score of
+// the top_k-th detection -- if so the result is exactly that of the full scan (the remaining candidates could only have
+// produced lower-scoring detections).  Classes that fail the check (few survivors, heavy suppression) are redone with
+// the full multi-band scan in a third launch whose other CTAs exit at once, and the image's top-k is recomputed.
 // Arithmetic follows the reference operation order with non-contracting intrinsics.
 #include "common.cuh"
 #include <cmath>
@@ -245,6 +252,10 @@ struct NmsParams {
   int strict, use64;
   float thr32; double thr64;
   double iou_thr; int d;
+  int band_cap;            // candidates per band (<= kNmsCap)
+  int max_bands;           // > 0: stop after this many bands even if candidates remain (stage 1)
+  uint32_t* cut_key;       // [B*S] out (stage 1): order key of the last candidate looked at when the scan was cut short, else 0
+  const int* redo;         // [B*S] in (stage 3): only segments with a non-zero flag are (re)done
 };
 
 template <typename T, bool LAYER>
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
 
   const int sidx = blockIdx.x, b = blockIdx.y;
   const int seg = b * prm.S + sidx;
+  if (prm.redo && !prm.redo[seg]) return;
   SegView sv;
   sv.scores = prm.scores + (size_t)seg * prm.n;
   sv.labels = prm.labels ? prm.labels + (size_t)b * prm.n : nullptr;
@@ -280,9 +292,11 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
   BandState st{0u, -1, 1};
   __syncthreads();
   bool done = false;
+  int bands = 0;
+  uint32_t cut = 0;
   while (!done) {
     bool more = false;
-    const int cnt = band_select<NT>(sv, st, kNmsCap, keys, s_hist, s_misc, s_w, more);
+    const int cnt = band_select<NT>(sv, st, prm.band_cap, keys, s_hist, s_misc, s_w, more);
     if (cnt == 0) break;
     bitonic_sort<NT>(keys, cnt);
     for (int c0 = 0; c0 < cnt && !done; c0 += NT) {
@@ -337,15 +351,19 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
       }
       if (s_K >= prm.cap) done = true;
     }
-    if (!more) break;
+    if (!more || done) break;
     // next band starts strictly below the last (smallest) candidate of this band
     const u64 last = keys[cnt - 1];
     st.hi_key = ~(uint32_t)(last >> 32);
     st.hi_idx = (int)(uint32_t)(last & 0xffffffffull);
     st.first = 0;
+    if (prm.max_bands > 0 && ++bands >= prm.max_bands) { cut = st.hi_key ? st.hi_key : 1u; break; }   // cut short: candidates remain
     __syncthreads();
   }
-  if (threadIdx.x == 0) prm.kept_cnt[seg] = s_K;
+  if (threadIdx.x == 0) {
+    prm.kept_cnt[seg] = s_K;
+    if (prm.cut_key) prm.cut_key[seg] = cut;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -450,6 +468,10 @@ struct TopkParams {
   float* cat_score;      // scratch [B*S*kmax]
   int* cat_src;          // scratch [B*S*kmax*2] (s, prior idx)
   float* out; int* out_counts; int* out_index;
+  const uint32_t* cut_key; // stage-1 verification (NULL: none): see the file header
+  int* redo;             // [B*S] out
+  int* any_redo;         // [B] out
+  const int* only_if;    // [B] in (second top-k pass): images without a flag keep their output
 };
 
 __device__ void emit_row(const TopkParams& p, int b, int row_out, int s, int idx, float score) {
@@ -476,6 +498,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_kernel(TopkParams p) {
   __shared__ int s_off[1025];
   const int b = blockIdx.x;
   const int S = p.S;
+  if (p.only_if && !p.only_if[b]) return;
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int s = 0; s < S; ++s) { s_off[s] = acc; acc += p.kept_cnt[b * S + s]; }
@@ -501,6 +524,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_kernel(TopkParams p) {
   if (p.out_index) for (int i = threadIdx.x; i < p.max_out; i += kThreads) p.out_index[(size_t)b * p.max_out + i] = -1;
   __syncthreads();
   int n_out;
+  uint32_t sigma = 0;      // order key of the top_k-th detection (0: fewer than top_k detections so far)
   if (p.top_k <= 0 || (!p.layer && M <= p.top_k)) {
     // NumPy API without top-k filtering: class-major / NMS order, as the reference concatenates them
     n_out = M < p.max_out ? M : p.max_out;
@@ -513,6 +537,7 @@ __global__ void __launch_bounds__(kTopThreads) topk_kernel(TopkParams p) {
     int want = p.top_k < M ? p.top_k : M;
     int cnt = (M > 0) ? band_select<kTopThreads>(sv, st, want, keys, s_hist, s_misc, s_w, more) : 0;
     if (cnt > 0) bitonic_sort<kTopThreads>(keys, cnt);
+    if (cnt > 0 && cnt == p.top_k) sigma = ~(uint32_t)(keys[cnt - 1] >> 32);
     n_out = cnt < p.max_out ? cnt : p.max_out;
     for (int j = threadIdx.x; j < n_out; j += kThreads) {
       int r = (int)(uint32_t)(keys[j] & 0xffffffffull);
@@ -520,6 +545,18 @@ __global__ void __launch_bounds__(kTopThreads) topk_kernel(TopkParams p) {
     }
   }
   if (threadIdx.x == 0) p.out_counts[b] = n_out;
+  if (p.cut_key) {
+    // a class whose scan was cut short is exact iff it stopped strictly below the top_k-th detection of the image
+    int flag = 0;
+    for (int s = threadIdx.x; s < S; s += kThreads) {
+      const uint32_t ck = p.cut_key[b * S + s];
+      const int r = (ck != 0u && !(ck < sigma)) ? 1 : 0;
+      p.redo[b * S + s] = r;
+      flag |= r;
+    }
+    flag = __syncthreads_or(flag);
+    if (threadIdx.x == 0) p.any_redo[b] = flag;
+  }
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -533,39 +570,69 @@ int launch_nms(ssdk_ctx* ctx, const NmsParams& np, int B, cudaStream_t stream) {
   return SSDK_OK;
 }
 
+int stage1_band(int S, int top_k) {
+  int want = 4 * top_k / (S > 0 ? S : 1), b = 256;
+  while (b < want && b < kNmsCap) b <<= 1;
+  return b;
+}
+
 int run_nms_topk(ssdk_ctx* ctx, int B, int n, int S, int layer, int box_f64, int np_f32, const float* scores,
                  const int* labels, const void* boxes, int strict, double conf_thr, double iou_thr, int d, int cap,
                  int top_k, int max_out, unsigned char* scratch, float* out, int* out_counts, int* out_index,
                  cudaStream_t stream) {
+  // only top_k rows leave: no class needs more than top_k survivors (rows beyond the top_k-th of one class never reach
+  // the global top_k: equal scores are ordered class-major / NMS order, so a class's own earlier survivors come first)
+  if (top_k > 0 && top_k < cap) cap = top_k;
   const int kmax = cap;
   size_t o = 0;
   int* kept_idx = reinterpret_cast<int*>(scratch + o); o += align_up((size_t)B * S * kmax * 4, 256);
   int* kept_cnt = reinterpret_cast<int*>(scratch + o); o += align_up((size_t)B * S * 4, 256);
   float* cat_score = reinterpret_cast<float*>(scratch + o); o += align_up((size_t)B * S * kmax * 4, 256);
   int* cat_src = reinterpret_cast<int*>(scratch + o); o += align_up((size_t)B * S * kmax * 8, 256);
+  uint32_t* cut_key = reinterpret_cast<uint32_t*>(scratch + o); o += align_up((size_t)B * S * 4, 256);
+  int* redo = reinterpret_cast<int*>(scratch + o); o += align_up((size_t)B * S * 4, 256);
+  int* any_redo = reinterpret_cast<int*>(scratch + o); o += align_up((size_t)B * 4, 256);
+  const int band1 = stage1_band(S, top_k);
+  bool two_stage = top_k > 0 && n > band1 && band1 < kNmsCap;
+  if (const char* e = getenv("SSDK_NMS_TWO_STAGE")) two_stage = two_stage && atoi(e) != 0;
   NmsParams np{};
   np.scores = scores; np.labels = labels; np.boxes = boxes; np.kept_idx = kept_idx; np.kept_cnt = kept_cnt;
   np.n = n; np.S = S; np.kmax = kmax; np.cap = cap; np.strict = strict; np.use64 = layer ? 0 : 1;
   np.thr32 = (float)conf_thr; np.thr64 = conf_thr; np.iou_thr = iou_thr; np.d = d;
-  int rc;
-  if (layer) rc = launch_nms<float, true>(ctx, np, B, stream);
-  else if (np_f32) rc = launch_nms<float, false>(ctx, np, B, stream);
-  else rc = launch_nms<double, false>(ctx, np, B, stream);
+  np.band_cap = two_stage ? band1 : kNmsCap; np.max_bands = two_stage ? 1 : 0; np.cut_key = two_stage ? cut_key : nullptr; np.redo = nullptr;
+  auto nms = [&](const NmsParams& q) {
+    if (layer) return launch_nms<float, true>(ctx, q, B, stream);
+    if (np_f32) return launch_nms<float, false>(ctx, q, B, stream);
+    return launch_nms<double, false>(ctx, q, B, stream);
+  };
+  int rc = nms(np);
   if (rc) return rc;
   TopkParams tp{};
   tp.scores = scores; tp.labels = labels; tp.boxes = boxes; tp.box_f64 = box_f64; tp.kept_idx = kept_idx; tp.kept_cnt = kept_cnt;
   tp.n = n; tp.S = S; tp.kmax = kmax; tp.top_k = top_k; tp.max_out = max_out; tp.layer = layer;
   tp.cat_score = cat_score; tp.cat_src = cat_src; tp.out = out; tp.out_counts = out_counts; tp.out_index = out_index;
+  if (two_stage) { tp.cut_key = cut_key; tp.redo = redo; tp.any_redo = any_redo; }
   size_t sm = (size_t)kTopCap * sizeof(u64);
-  SSDK_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  static bool attr_set = false;
+  if (!attr_set) { SSDK_CHECK_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr_set = true; }
   topk_kernel<<<B, kTopThreads, sm, stream>>>(tp);
   SSDK_COUNT_LAUNCH(ctx);
+  if (two_stage) {
+    // classes that failed the check: full scan (the other CTAs exit at once), then the top-k of the affected images again
+    np.band_cap = kNmsCap; np.max_bands = 0; np.cut_key = nullptr; np.redo = redo;
+    rc = nms(np);
+    if (rc) return rc;
+    tp.cut_key = nullptr; tp.redo = nullptr; tp.any_redo = nullptr; tp.only_if = any_redo;
+    topk_kernel<<<B, kTopThreads, sm, stream>>>(tp);
+    SSDK_COUNT_LAUNCH(ctx);
+  }
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
 }
 
 size_t nms_scratch_bytes(int B, int S, int kmax) {
-  return align_up((size_t)B * S * kmax * 4, 256) * 2 + align_up((size_t)B * S * 4, 256) + align_up((size_t)B * S * kmax * 8, 256);
+  return align_up((size_t)B * S * kmax * 4, 256) * 2 + align_up((size_t)B * S * 4, 256) * 3 + align_up((size_t)B * S * kmax * 8, 256) +
+         align_up((size_t)B * 4, 256);
 }
 
 }  // namespace
