@@ -167,6 +167,24 @@ int ssdk_assemble_batch(ssdk_ctx* ctx, const void* gt_in_dev, int gt_in_f64, con
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Evaluation.  Replaces the per-prediction Python loop of Evaluator.match_predictions
+ * (eval_utils/average_precision_evaluator.py:538-736, element-wise iou at :679) and the cumulative sums of :726-727.
+ * The caller sorts the predictions twice (stable): by (class, confidence desc) -- the order of the outputs -- and by
+ * (class, image, confidence desc) -- the order of the pred_* inputs, whose (class, image) runs are given by seg_offsets.
+ *   pred_rank[i]   position of input prediction i in the (class, confidence desc) order
+ *   gt_rows        float64 (class, xmin, ymin, xmax, ymax) rows of all images, gt_offsets [n_images+1]
+ *   gt_neutral     optional uint8 flags (eval_neutral, :684), gt_matched uint8 scratch zeroed by the caller
+ *   tp / fp        int32 [n_pred], zeroed by the caller, in (class, confidence desc) order
+ * ssdk_eval_cumsum: inclusive scans of tp / fp inside each of the n_segments ranges class_offsets[c] .. class_offsets[c+1].
+ * ------------------------------------------------------------------------------------------ */
+int ssdk_eval_match(ssdk_ctx* ctx, int n_pred, const int* seg_offsets_dev, int n_seg, const int* pred_image_dev,
+                    const int* pred_class_dev, const float* pred_box_dev, const int* pred_rank_dev, const double* gt_rows_dev,
+                    const int* gt_offsets_dev, const unsigned char* gt_neutral_dev, unsigned char* gt_matched_dev,
+                    double matching_iou_threshold, int border_d, int* tp_dev, int* fp_dev, void* stream);
+int ssdk_eval_cumsum(ssdk_ctx* ctx, const int* tp_dev, const int* fp_dev, const int* class_offsets_dev, int n_segments,
+                     int* ctp_dev, int* cfp_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Decoders.
  *   mode PER_CLASS + layer_semantics=1: DecodeDetections.call   (keras_layers/keras_layer_DecodeDetections.py:109-265)
  *   mode FAST      + layer_semantics=1: DecodeDetectionsFast.call (keras_layers/keras_layer_DecodeDetectionsFast.py:111-248)

@@ -11,7 +11,6 @@ import numpy as np
 
 np.float = float   # noqa
 np.int = int       # noqa
-np.bool = bool     # noqa
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.environ.get('SSD_REFERENCE_ROOT', '/root/reference'))
 
