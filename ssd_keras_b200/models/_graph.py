@@ -183,12 +183,22 @@ class SSDModel:
                         del self._plans[key]
 
     def load_weights(self, path, by_name=True):
-        """Loads an ``.npz`` with Keras layer names as keys (h5py is not available offline; see INTEGRATION.md
-        for the one-line HDF5 -> npz conversion)."""
-        if not str(path).endswith('.npz'):
-            raise NotImplementedError('Only .npz weight files are supported in this build (Keras HDF5 needs h5py).')
-        with np.load(path) as f:
-            self.set_weights({k: f[k] for k in f.files})
+        """``model.load_weights(path, by_name=True)`` (reference ``ssd300_training.ipynb:162``).  Accepts the Keras HDF5 files the
+        reference ships (``README.md:223-239``) -- weights files (``/<layer>/<layer>/kernel:0``) and full-model files
+        (``/model_weights/...``), read by ``misc_utils/hdf5_lite.py`` without h5py -- and ``.npz`` files with Keras weight names
+        as keys.  Matching is by name like Keras' ``by_name=True``: entries for layers this model does not have are skipped,
+        layers without an entry keep their weights; a shape mismatch raises."""
+        p = str(path)
+        if p.endswith('.npz'):
+            with np.load(p) as f:
+                self.set_weights({k: f[k] for k in f.files})
+            return
+        with open(p, 'rb') as f:
+            magic = f.read(8)
+        if magic != b'\x89HDF\r\n\x1a\n':
+            raise ValueError('%s is neither an .npz nor an HDF5 file' % p)
+        from ..misc_utils.hdf5_lite import read_keras_weights
+        self.set_weights(read_keras_weights(p))
 
     def save_weights(self, path):
         self._sync_trained()
