@@ -295,6 +295,11 @@ typedef struct {
   const float* bn_scale; const float* bn_shift;
   const float* kernel2; const float* bias2;      /* head: loc kernel/bias (kernel/bias = conf) */
   const float* mean; const float* stddev; const int* swap;
+  /* conv followed by BatchNormalization (models/keras_ssd7.py:277-309), raw parameters [cout] each.  Training plans
+   * (ssdk_model_desc.training = 1) run the layer in Keras' training phase: batch statistics over (B,H,W), moving averages
+   * updated with `bn_momentum`; inference plans use the folded bn_scale / bn_shift above. */
+  const float* bn_gamma; const float* bn_beta; const float* bn_mean; const float* bn_var;
+  float bn_eps; float bn_momentum;
 } ssdk_layer_desc;
 
 typedef struct {
@@ -331,18 +336,20 @@ int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms);
 /* ------------------------------------------------------------------------------------------
  * Training step (BASELINE config 3).  Replaces what Keras/TensorFlow do for the reference in model.fit_generator:
  * autodiff of the graph (models/keras_ssd300.py:263-419) and of SSDLoss (keras_ssd_loss.py:98-211), the kernel_regularizer
- * l2(l2_reg) (models/keras_ssd300.py:274) and SGD(lr, momentum) (ssd300_training.ipynb:169).  ReLU / linear graphs only.
+ * l2(l2_reg) (models/keras_ssd300.py:274), SGD(lr, momentum) (ssd300_training.ipynb:169) and Adam (ssd7_training.ipynb:153).
  *   ssdk_train_backward  after ssdk_model_forward on the same images: loss + gradients of every kernel / bias / gamma into one
  *                        flat float32 buffer (so that a single NCCL all-reduce covers it).
  *   ssdk_train_apply     g = grad*grad_scale + 2*l2*w (kernels only); v = momentum*v - lr*g; w += v; re-pack the bf16 planes.
- * Parameter order in the flat buffer: layers in graph order, for each conv [kernel as (cout, kh, kw, cin) | bias], for each
- * head [fused kernel (n_boxes*(C+4), 3, 3, cin) | fused bias], for L2Normalization [gamma].
+ * Parameter order in the flat buffer: layers in graph order, for each conv [kernel as (cout, kh, kw, cin) | bias | BatchNorm
+ * gamma | BatchNorm beta], for each head [fused kernel (n_boxes*(C+4), 3, 3, cin) | fused bias], for L2Normalization [gamma].
+ * ReLU / linear graphs (SSD300 / SSD512) and conv + BatchNormalization + ELU graphs (SSD7).
  * ------------------------------------------------------------------------------------------ */
 typedef struct ssdk_trainer ssdk_trainer;
 int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev /* optional, else allocated */, ssdk_trainer** out);
 int ssdk_trainer_destroy(ssdk_trainer* t);
 int ssdk_trainer_num_params(const ssdk_trainer* t, long long* out_n);
-/* offset (in floats) and element count of a layer's kernel (which=0), bias (1) or gamma (2) inside the flat buffers */
+/* offset (in floats) and element count of a layer's kernel (which=0), bias (1), L2Normalization gamma (2), BatchNormalization
+ * gamma (3) or beta (4) inside the flat buffers */
 int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int which, long long* out_offset, long long* out_count);
 float* ssdk_trainer_grad_buffer(ssdk_trainer* t);
 int ssdk_train_backward(ssdk_trainer* t, const float* y_true_dev, const float* y_pred_dev, int neg_pos_ratio, int n_neg_min,
@@ -360,6 +367,13 @@ int ssdk_train_backward_layers(ssdk_trainer* t, const float* dypred_dev, int hi,
  * multi-GPU global-batch-exact loss, whose phases run between NCCL collectives, see ssdk_ssd_loss_phase). */
 int ssdk_train_backward_dy(ssdk_trainer* t, const float* dypred_dev, void* stream);
 int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float l2_reg, float grad_scale, void* stream);
+/* Adam as Keras applies it (ssd7_training.ipynb:153: Adam(lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-08, decay=0.0)):
+ * g = grad*grad_scale + 2*l2*w (kernels); lr_t = lr*sqrt(1-beta2^t)/(1-beta1^t); m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g^2;
+ * w -= lr_t*m/(sqrt(v)+eps).  `step` = t, counted from 1 by the caller. */
+int ssdk_train_apply_adam(ssdk_trainer* t, float lr, float beta1, float beta2, float eps, float l2_reg, float grad_scale, int step,
+                          void* stream);
+/* Moving mean / variance of a BatchNormalization layer as the training passes left them (float32 [cout] each). */
+int ssdk_trainer_read_bn_stats(ssdk_trainer* t, int layer, float* mean_dev, float* var_dev, void* stream);
 /* Copy the current float32 master parameters (same order / layout as the gradients) to out_dev. */
 int ssdk_trainer_read_params(ssdk_trainer* t, float* out_dev, void* stream);
 

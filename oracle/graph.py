@@ -18,8 +18,10 @@ def make_params(specs, weights, dtype=torch.float32, requires_grad=True):
     return {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=requires_grad) for k, v in weights.items()}
 
 
-def forward(specs, params, x_nhwc, n_classes_total, anchors, variances, dtype=torch.float32):
-    """-> y_pred (B, P, C+12) torch tensor (differentiable w.r.t. ``params``)."""
+def forward(specs, params, x_nhwc, n_classes_total, anchors, variances, dtype=torch.float32, bn_training=False):
+    """-> y_pred (B, P, C+12) torch tensor (differentiable w.r.t. ``params``).  ``bn_training``: BatchNormalization in Keras'
+    training phase (what ``fit_generator`` runs, models/keras_ssd7.py:277-309): batch mean / biased variance over (B,H,W), epsilon
+    1e-3; the batch statistics are returned in ``outs['<bn>/batch_mean' | '/batch_var']`` (biased variance)."""
     outs = {}
     confs, locs = [], []
     for s in specs:
@@ -39,7 +41,12 @@ def forward(specs, params, x_nhwc, n_classes_total, anchors, variances, dtype=to
         if s.op == OP_CONV:
             w = params[s.name + '/kernel'].permute(3, 2, 0, 1)
             y = Fn.conv2d(Fn.pad(xin, (pl, pr, pt, pb)), w, params[s.name + '/bias'], stride=s.stride, dilation=s.dilation)
-            if getattr(s, 'bn', None):          # inference-phase BatchNormalization (Keras epsilon 1e-3) between conv and activation
+            if getattr(s, 'bn', None) and bn_training:
+                g, b = params[s.bn + '/gamma'], params[s.bn + '/beta']
+                mu = y.mean(dim=(0, 2, 3)); var = y.var(dim=(0, 2, 3), unbiased=False)
+                outs[s.bn + '/batch_mean'], outs[s.bn + '/batch_var'] = mu.detach(), var.detach()
+                y = (y - mu.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-3) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+            elif getattr(s, 'bn', None):        # inference-phase BatchNormalization (Keras epsilon 1e-3) between conv and activation
                 g, b = params[s.bn + '/gamma'], params[s.bn + '/beta']
                 mu, var = params[s.bn + '/moving_mean'], params[s.bn + '/moving_variance']
                 y = (y - mu.view(1, -1, 1, 1)) / torch.sqrt(var.view(1, -1, 1, 1) + 1e-3) * g.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
@@ -104,3 +111,22 @@ def sgd_step(params, grads, velocity, lr, momentum, l2_reg):
         new_v[k] = v
         new_p[k] = (w.astype(np.float64) + v).astype(np.float32)
     return new_p, new_v
+
+
+def adam_step(params, grads, m, v, t, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-8, l2_reg=0.0):
+    """Keras Adam (optimizers.py, decay 0): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+    p -= lr_t * m / (sqrt(v) + eps); kernels get the l2 regulariser's gradient 2*l2*w.  ``t`` counts from 1.  numpy dicts."""
+    lr_t = lr * np.sqrt(1.0 - beta_2 ** t) / (1.0 - beta_1 ** t)
+    new_p, new_m, new_v = {}, {}, {}
+    for k, w in params.items():
+        if k not in grads:
+            new_p[k] = w
+            continue
+        g = grads[k].astype(np.float64)
+        if k.endswith('/kernel'):
+            g = g + 2.0 * l2_reg * w.astype(np.float64)
+        mk = beta_1 * m.get(k, 0.0) + (1 - beta_1) * g
+        vk = beta_2 * v.get(k, 0.0) + (1 - beta_2) * g * g
+        new_m[k], new_v[k] = mk, vk
+        new_p[k] = (w.astype(np.float64) - lr_t * mk / (np.sqrt(vk) + epsilon)).astype(np.float32)
+    return new_p, new_m, new_v

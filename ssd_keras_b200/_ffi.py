@@ -64,7 +64,8 @@ class LayerDesc(C.Structure):
                 ('pad_b', C.c_int), ('pad_r', C.c_int), ('act', C.c_int), ('n_boxes', C.c_int),
                 ('kernel', c_float_p), ('bias', c_float_p), ('bn_scale', c_float_p), ('bn_shift', c_float_p),
                 ('kernel2', c_float_p), ('bias2', c_float_p), ('mean', c_float_p), ('stddev', c_float_p),
-                ('swap', c_int_p)]
+                ('swap', c_int_p), ('bn_gamma', c_float_p), ('bn_beta', c_float_p), ('bn_mean', c_float_p), ('bn_var', c_float_p),
+                ('bn_eps', C.c_float), ('bn_momentum', C.c_float)]
 
 
 class ModelDesc(C.Structure):
@@ -148,6 +149,10 @@ def lib():
             L.ssdk_trainer_grad_buffer.argtypes = [vp]
             L.ssdk_trainer_grad_buffer.restype = vp
             L.ssdk_train_backward.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]
+            L.ssdk_train_apply_adam.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp]
+            L.ssdk_train_apply_adam.restype = C.c_int
+            L.ssdk_trainer_read_bn_stats.argtypes = [vp, C.c_int, vp, vp, vp]
+            L.ssdk_trainer_read_bn_stats.restype = C.c_int
             L.ssdk_train_backward_dy.argtypes = [vp, vp, vp]
             L.ssdk_train_backward_dy.restype = C.c_int
             L.ssdk_train_backward_begin.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, vp]

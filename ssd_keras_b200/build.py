@@ -29,6 +29,7 @@ SOURCES = {
     'conv.cu': [],
     'model.cu': [],
     'train.cu': [],
+    'bn.cu': [],
     'wgrad.cu': [],
 }
 

@@ -51,13 +51,27 @@ int build_conv(ssdk_model* m, int li) {
   SSDK_REQUIRE(taps <= kMaxTaps, "conv kernel %dx%d is larger than the supported %d taps", d.kh, d.kw, kMaxTaps);
   SSDK_REQUIRE(head || cout % 8 == 0, "conv output channels must be a multiple of 8 (got %d)", cout);
   L.direct = !head && cin <= 4 && d.stride == 1 && cout % 16 == 0 && (size_t)taps * cin * cout * 4 <= 96 * 1024 && ia.Cs == 8;
+  // conv + BatchNormalization in a training plan: the conv writes its raw output z, batch statistics follow (bn.cu)
+  L.bn_train = m->training && !head && d.bn_gamma && d.bn_beta && d.bn_mean && d.bn_var;
+  if (L.bn_train) {
+    int rc = alloc_act(m, L.z, m->B, L.H, L.W, L.C, 0); if (rc) return rc;
+    rc = upload_f32(m, &L.bn_gamma, d.bn_gamma, cout); if (rc) return rc;
+    rc = upload_f32(m, &L.bn_beta, d.bn_beta, cout); if (rc) return rc;
+    rc = upload_f32(m, &L.bn_mmean, d.bn_mean, cout); if (rc) return rc;
+    rc = upload_f32(m, &L.bn_mvar, d.bn_var, cout); if (rc) return rc;
+    rc = dev_alloc(m, &L.bn_bmean, cout, true); if (rc) return rc;
+    rc = dev_alloc(m, &L.bn_brstd, cout, true); if (rc) return rc;
+    rc = dev_alloc(m, &L.bn_acc, (size_t)2 * cout, true); if (rc) return rc;
+    L.bn_eps = d.bn_eps > 0.f ? d.bn_eps : 1e-3f;
+    L.bn_momentum = (d.bn_momentum > 0.f && d.bn_momentum < 1.f) ? d.bn_momentum : 0.99f;
+  }
   // experiment knob (inference plans only): route the image-facing layer through im2col (K = 27 -> 32) + the tcgen05 GEMM instead
   if (L.direct && !m->training && getenv("SSDK_NO_DIRECT")) L.direct = false;
   if (L.direct) {
     int rc = upload_f32(m, &L.w_f32, d.kernel, (size_t)taps * cin * cout); if (rc) return rc;
     std::vector<float> b0(cout, 0.f);
     rc = upload_f32(m, &L.bias, d.bias ? d.bias : b0.data(), cout); if (rc) return rc;
-    if (d.bn_scale && d.bn_shift) {
+    if (d.bn_scale && d.bn_shift && !L.bn_train) {
       rc = upload_f32(m, &L.bn_scale, d.bn_scale, cout); if (rc) return rc;
       rc = upload_f32(m, &L.bn_shift, d.bn_shift, cout); if (rc) return rc;
     }
@@ -118,19 +132,20 @@ int build_conv(ssdk_model* m, int li) {
   }
   rc = upload_f32(m, &L.bias, bias.data(), bias.size()); if (rc) return rc;
   a.bias = L.bias;
-  if (d.bn_scale && d.bn_shift && !head) {
+  if (d.bn_scale && d.bn_shift && !head && !L.bn_train) {
     rc = upload_f32(m, &L.bn_scale, d.bn_scale, cout); if (rc) return rc;
     rc = upload_f32(m, &L.bn_shift, d.bn_shift, cout); if (rc) return rc;
     a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
   }
-  a.act = d.act;
+  a.act = L.bn_train ? SSDK_ACT_NONE : d.act;
   if (head) {
     a.epi = EPI_F32;
     rc = dev_alloc(m, &L.head_f32, (size_t)m->B * Ho * Wo * cout, true); if (rc) return rc;
     a.out_f32 = L.head_f32;
   } else {
     a.epi = EPI_SPLIT;
-    a.out_hi = L.out.hi; a.out_lo = L.out.lo; a.out_Hp = L.out.Hp(); a.out_Wp = L.out.Wp(); a.out_pad = L.out.pad; a.out_Cs = L.out.Cs;
+    const ActBuf& dst = L.bn_train ? L.z : L.out;
+    a.out_hi = dst.hi; a.out_lo = dst.lo; a.out_Hp = dst.Hp(); a.out_Wp = dst.Wp(); a.out_pad = dst.pad; a.out_Cs = dst.Cs;
   }
   cl.flops_algo = 2.0 * m->B * Ho * Wo * (double)taps * cin * cout;
   m->flops_algo += cl.flops_algo; m->flops_issued += cl.flops_issued;
@@ -403,9 +418,10 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
       case SSDK_OP_HEAD: {
         const LayerPlan& in = m->layers[d.input];
         if (L.direct) {
-          rc = launch_conv_direct(ctx, in.out, L.out, L.w_f32, L.bias, L.bn_scale, L.bn_shift, d.act, d.kh, d.kw, d.dilation, d.pad_t,
-                                  d.pad_l, stream);
+          rc = launch_conv_direct(ctx, in.out, L.bn_train ? L.z : L.out, L.w_f32, L.bias, L.bn_scale, L.bn_shift, L.bn_train ? (int)SSDK_ACT_NONE : d.act,
+                                  d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, stream);
           if (rc) return rc;
+          if (L.bn_train) { rc = launch_bn_forward(ctx, L, d.act, stream); if (rc) return rc; }
           break;
         }
         if (L.im2col) {
@@ -416,6 +432,7 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         rc = launch_conv(ctx, L.launch, stream);
         if (rc) return rc;
         if (m->timing) cudaEventRecord(L.ev1, stream);
+        if (L.bn_train) { rc = launch_bn_forward(ctx, L, d.act, stream); if (rc) return rc; }
         if (d.op == SSDK_OP_HEAD) {
           rc = launch_head_finalize(ctx, L.head_f32, m->B, L.H * L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, m->d_anchors, m->var,
                                     y_pred_dev, stream);

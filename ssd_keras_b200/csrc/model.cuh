@@ -38,6 +38,13 @@ struct LayerPlan {
   float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};
   bool has_mean = false, has_std = false, has_swap = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // BatchNormalization in Keras' training phase (training plans of conv + BN graphs)
+  bool bn_train = false;
+  ActBuf z;                           // conv output before the normalisation (bias added)
+  float *bn_gamma = nullptr, *bn_beta = nullptr, *bn_mmean = nullptr, *bn_mvar = nullptr;   // [C] parameters and moving statistics
+  float *bn_bmean = nullptr, *bn_brstd = nullptr;                                           // [C] batch statistics of the last forward
+  double* bn_acc = nullptr;           // [2*C] reduction scratch
+  float bn_eps = 1e-3f, bn_momentum = 0.99f;
 };
 
 }  // namespace ssdk
@@ -96,6 +103,10 @@ struct ConvGeom {
   int Ho = 0, Wo = 0, B = 0;
   int cout = 0;
 };
+// BatchNormalization (training phase) + activation: z -> out with batch statistics; and its backward on the gradient planes
+int launch_bn_forward(ssdk_ctx* ctx, LayerPlan& L, int act, cudaStream_t s);
+int launch_bn_backward(ssdk_ctx* ctx, LayerPlan& L, int act, const ActBuf& g, float* dgamma, float* dbeta, cudaStream_t s);
+
 int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                    size_t krow, int kblocks, int last_ksteps, int** tile_list_out);
 

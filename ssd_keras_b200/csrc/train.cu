@@ -439,7 +439,9 @@ struct TLayer {
   // parameters (conv / head): master kernel HWIO in L.w_f32, bias in L.bias (shared with the forward plan)
   int cin = 0, cout = 0, taps = 0;
   float *vw = nullptr, *vb = nullptr;       // momentum
-  long long off_w = -1, off_b = -1, off_g = -1;
+  long long off_w = -1, off_b = -1, off_g = -1, off_bng = -1, off_bnb = -1;
+  float *v2w = nullptr, *v2b = nullptr, *v2gamma = nullptr;     // Adam second moments (vw / vb / vgamma hold the first moments)
+  float *m_bng = nullptr, *v_bng = nullptr, *m_bnb = nullptr, *v_bnb = nullptr;   // BatchNormalization gamma / beta optimiser state
   ActBuf g;                                 // gradient of this layer's output (pre-activation); same geometry as the output
   bool has_g = false;
   // data gradient
@@ -518,10 +520,14 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
     TLayer& T = t->tl[i];
     T.li = i; T.op = L.d.op;
     if (is_conv(L.d.op)) {
-      if (L.d.act == SSDK_ACT_ELU || L.bn_scale) { set_error("training supports ReLU / linear graphs without BatchNormalization only (layer %d)", i); return fail(SSDK_ERR_UNSUPPORTED); }
+      if ((L.d.act == SSDK_ACT_ELU || L.bn_scale) && !L.bn_train) {
+        set_error("training: layer %d has an ELU / folded BatchNormalization without the raw BatchNormalization parameters (bn_gamma, ...)", i);
+        return fail(SSDK_ERR_UNSUPPORTED);
+      }
       T.cin = m->layers[L.d.input].C; T.cout = L.C; T.taps = L.d.kh * L.d.kw;
       T.off_w = off; off += (long long)T.cout * T.taps * T.cin;
       T.off_b = off; off += T.cout;
+      if (L.bn_train) { T.off_bng = off; off += T.cout; T.off_bnb = off; off += T.cout; }
     } else if (L.d.op == SSDK_OP_L2NORM) {
       T.off_g = off; off += L.C;
     }
@@ -559,6 +565,12 @@ extern "C" int ssdk_trainer_create(ssdk_model* m, float* flat_grad_dev, ssdk_tra
     if (!is_conv(d.op)) { if (prod_needs_grad) written[pi] = 1; continue; }
     rc = t_alloc(t, &T.vw, (size_t)T.cout * T.taps * T.cin, true); if (rc) return fail(rc);
     rc = t_alloc(t, &T.vb, (size_t)T.cout, true); if (rc) return fail(rc);
+    if (L.bn_train) {
+      rc = t_alloc(t, &T.m_bng, (size_t)T.cout, true); if (rc) return fail(rc);
+      rc = t_alloc(t, &T.v_bng, (size_t)T.cout, true); if (rc) return fail(rc);
+      rc = t_alloc(t, &T.m_bnb, (size_t)T.cout, true); if (rc) return fail(rc);
+      rc = t_alloc(t, &T.v_bnb, (size_t)T.cout, true); if (rc) return fail(rc);
+    }
     // ---- data gradient
     if (prod_needs_grad) {
       if (T.cin % 8 != 0) { set_error("training: input channels must be a multiple of 8 (layer %d)", i); return fail(SSDK_ERR_UNSUPPORTED); }
@@ -709,6 +721,8 @@ extern "C" int ssdk_trainer_param_span(const ssdk_trainer* t, int layer, int whi
   if (which == 0 && T.off_w >= 0) { *out_offset = T.off_w; *out_count = (long long)T.cout * T.taps * T.cin; }
   else if (which == 1 && T.off_b >= 0) { *out_offset = T.off_b; *out_count = T.cout; }
   else if (which == 2 && T.off_g >= 0) { *out_offset = T.off_g; *out_count = t->m->layers[layer].C; }
+  else if (which == 3 && T.off_bng >= 0) { *out_offset = T.off_bng; *out_count = T.cout; }
+  else if (which == 4 && T.off_bnb >= 0) { *out_offset = T.off_bnb; *out_count = T.cout; }
   return SSDK_OK;
 }
 
@@ -815,6 +829,9 @@ int backward_layers(ssdk_trainer* t, const float* dypred, int hi, int lo, cudaSt
       }
       continue;
     }
+    // ---- conv + BatchNormalization + activation: the gradient planes hold d loss / d activation; turn them into the gradient of
+    //      the raw conv output (and produce dgamma / dbeta) before the conv's own gradients are formed
+    if (L.bn_train) { rc = launch_bn_backward(ctx, L, d.act, T.g, t->grad + T.off_bng, t->grad + T.off_bnb, s); if (rc) return rc; }
     // ---- convolution / head: weight + bias gradients
     if (L.direct) {
       const int K = T.taps * T.cin;
@@ -890,6 +907,11 @@ extern "C" int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float
     SSDK_COUNT_LAUNCH(ctx);
     sgd_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bias, T.vb, t->grad + T.off_b, (size_t)T.cout, lr, momentum, grad_scale);
     SSDK_COUNT_LAUNCH(ctx);
+    if (T.off_bng >= 0) {
+      sgd_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bn_gamma, T.m_bng, t->grad + T.off_bng, (size_t)T.cout, lr, momentum, grad_scale);
+      sgd_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bn_beta, T.m_bnb, t->grad + T.off_bnb, (size_t)T.cout, lr, momentum, grad_scale);
+      SSDK_COUNT_LAUNCH(ctx); SSDK_COUNT_LAUNCH(ctx);
+    }
     if (!L.direct) {
       rc = launch_repack(ctx, L.w_f32, T.taps, T.cin, T.cout, L.im2col ? 1 : 0, L.kblocks, L.w_krow, T.cout, L.w_hi, L.w_lo, s); if (rc) return rc;
     }
@@ -900,6 +922,93 @@ extern "C" int ssdk_train_apply(ssdk_trainer* t, float lr, float momentum, float
     }
   }
   SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+namespace {
+
+__global__ void adam_kernel_w(float* __restrict__ w, float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ g, int taps, int cin,
+                              int cout, float lr_t, float b1, float b2, float eps, float l2, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)taps * cin * cout;
+  if (i >= total) return;
+  const int co = (int)(i % cout); const size_t r = i / cout; const int ci = (int)(r % cin); const int t = (int)(r / cin);
+  const float grad = g[((size_t)co * taps + t) * cin + ci] * scale + 2.f * l2 * w[i];
+  const float a = b1 * m1[i] + (1.f - b1) * grad;
+  const float b = b2 * m2[i] + (1.f - b2) * grad * grad;
+  m1[i] = a; m2[i] = b;
+  w[i] -= lr_t * a / (sqrtf(b) + eps);
+}
+__global__ void adam_kernel_flat(float* __restrict__ w, float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ g, size_t n,
+                                 float lr_t, float b1, float b2, float eps, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float grad = g[i] * scale;
+  const float a = b1 * m1[i] + (1.f - b1) * grad;
+  const float b = b2 * m2[i] + (1.f - b2) * grad * grad;
+  m1[i] = a; m2[i] = b;
+  w[i] -= lr_t * a / (sqrtf(b) + eps);
+}
+
+int repack_after_update(ssdk_trainer* t, int i, cudaStream_t s) {
+  ssdk_model* m = t->m;
+  TLayer& T = t->tl[i];
+  LayerPlan& L = m->layers[i];
+  int rc;
+  if (!L.direct) {
+    rc = launch_repack(m->ctx, L.w_f32, T.taps, T.cin, T.cout, L.im2col ? 1 : 0, L.kblocks, L.w_krow, T.cout, L.w_hi, L.w_lo, s); if (rc) return rc;
+  }
+  if (T.has_dgrad) {
+    if (T.dgrad_strided) rc = launch_repack(m->ctx, L.w_f32, T.taps, T.cin, T.cout, 3, T.w2_kblocks, T.w2_krow, T.taps * T.cin, T.w2_hi, T.w2_lo, s);
+    else rc = launch_repack(m->ctx, L.w_f32, T.taps, T.cin, T.cout, 2, T.w2_kblocks, T.w2_krow, T.cin, T.w2_hi, T.w2_lo, s);
+    if (rc) return rc;
+  }
+  return SSDK_OK;
+}
+
+}  // namespace
+
+extern "C" int ssdk_train_apply_adam(ssdk_trainer* t, float lr, float beta1, float beta2, float eps, float l2_reg, float grad_scale, int step,
+                                     void* stream_) {
+  SSDK_REQUIRE(t && step >= 1, "ssdk_train_apply_adam: bad argument");
+  ssdk_model* m = t->m;
+  ssdk_ctx* ctx = m->ctx;
+  cudaStream_t s = (cudaStream_t)stream_;
+  // Keras: lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t)
+  const float lr_t = lr * (float)(std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step)));
+  int rc;
+  for (size_t i = 0; i < t->tl.size(); ++i) {
+    TLayer& T = t->tl[i];
+    LayerPlan& L = m->layers[i];
+    if (T.off_g >= 0) {
+      if (!T.v2gamma) { rc = t_alloc(t, &T.v2gamma, (size_t)L.C, true); if (rc) return rc; }
+      adam_kernel_flat<<<(unsigned)((L.C + 255) / 256), 256, 0, s>>>(L.gamma, T.vgamma, T.v2gamma, t->grad + T.off_g, (size_t)L.C, lr_t, beta1, beta2, eps, grad_scale);
+      SSDK_COUNT_LAUNCH(ctx);
+    }
+    if (T.off_w < 0) continue;
+    const size_t nw = (size_t)T.taps * T.cin * T.cout;
+    if (!T.v2w) { rc = t_alloc(t, &T.v2w, nw, true); if (rc) return rc; rc = t_alloc(t, &T.v2b, (size_t)T.cout, true); if (rc) return rc; }
+    adam_kernel_w<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(L.w_f32, T.vw, T.v2w, t->grad + T.off_w, T.taps, T.cin, T.cout, lr_t, beta1, beta2, eps, l2_reg, grad_scale);
+    SSDK_COUNT_LAUNCH(ctx);
+    adam_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bias, T.vb, T.v2b, t->grad + T.off_b, (size_t)T.cout, lr_t, beta1, beta2, eps, grad_scale);
+    SSDK_COUNT_LAUNCH(ctx);
+    if (T.off_bng >= 0) {
+      adam_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bn_gamma, T.m_bng, T.v_bng, t->grad + T.off_bng, (size_t)T.cout, lr_t, beta1, beta2, eps, grad_scale);
+      adam_kernel_flat<<<(unsigned)((T.cout + 255) / 256), 256, 0, s>>>(L.bn_beta, T.m_bnb, T.v_bnb, t->grad + T.off_bnb, (size_t)T.cout, lr_t, beta1, beta2, eps, grad_scale);
+      SSDK_COUNT_LAUNCH(ctx); SSDK_COUNT_LAUNCH(ctx);
+    }
+    rc = repack_after_update(t, (int)i, s); if (rc) return rc;
+  }
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+extern "C" int ssdk_trainer_read_bn_stats(ssdk_trainer* t, int layer, float* mean_dev, float* var_dev, void* stream_) {
+  SSDK_REQUIRE(t && mean_dev && var_dev && layer >= 0 && layer < (int)t->tl.size(), "ssdk_trainer_read_bn_stats: bad argument");
+  LayerPlan& L = t->m->layers[layer];
+  SSDK_REQUIRE(L.bn_train, "ssdk_trainer_read_bn_stats: layer %d has no BatchNormalization", layer);
+  SSDK_CHECK_CUDA(cudaMemcpyAsync(mean_dev, L.bn_mmean, (size_t)L.C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  SSDK_CHECK_CUDA(cudaMemcpyAsync(var_dev, L.bn_mvar, (size_t)L.C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
   return SSDK_OK;
 }
 
@@ -916,6 +1025,10 @@ extern "C" int ssdk_trainer_read_params(ssdk_trainer* t, float* out_dev, void* s
     hwio_to_ohwi_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(L.w_f32, T.taps, T.cin, T.cout, out_dev + T.off_w);
     SSDK_COUNT_LAUNCH(m->ctx);
     SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev + T.off_b, L.bias, (size_t)T.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (T.off_bng >= 0) {
+      SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev + T.off_bng, L.bn_gamma, (size_t)T.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev + T.off_bnb, L.bn_beta, (size_t)T.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
   }
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;

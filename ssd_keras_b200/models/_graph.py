@@ -261,6 +261,9 @@ class SSDModel:
                     mu, var = self.weights[s.bn + '/moving_mean'], self.weights[s.bn + '/moving_variance']
                     scale = (g.astype(np.float64) / np.sqrt(var.astype(np.float64) + 1e-3))
                     d.bn_scale = fptr(scale); d.bn_shift = fptr(b - mu * scale)
+                    if training:   # Keras' training phase normalises with batch statistics: the plan needs the raw parameters
+                        d.bn_gamma, d.bn_beta, d.bn_mean, d.bn_var = fptr(g), fptr(b), fptr(mu), fptr(var)
+                        d.bn_eps, d.bn_momentum = 1e-3, 0.99
             elif s.op == _ffi.OP_HEAD:
                 d.kernel = fptr(self.weights[s.params['conf_name'] + '/kernel']); d.bias = fptr(self.weights[s.params['conf_name'] + '/bias'])
                 d.kernel2 = fptr(self.weights[s.params['loc_name'] + '/kernel']); d.bias2 = fptr(self.weights[s.params['loc_name'] + '/bias'])

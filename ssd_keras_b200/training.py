@@ -13,13 +13,17 @@ from . import _ffi
 
 class SSDTrainer:
     def __init__(self, model, batch_size, lr=1e-3, momentum=0.9, l2_regularization=None, neg_pos_ratio=3, n_neg_min=0,
-                 alpha=1.0, loss_mode='replica'):
+                 alpha=1.0, loss_mode='replica', optimizer='sgd', beta_1=0.9, beta_2=0.999, epsilon=1e-8):
         """``loss_mode``: 'replica' -- every rank applies the reference loss to its own shard (what Keras data-parallel replicas
         compute); 'global' -- n_positive and the hard-negative top-k run over the whole sharded batch, so that N
         ranks reproduce the single-process reference on the full batch (8e(ii), ``distributed.ssd_loss_global``)."""
         if loss_mode not in ('replica', 'global'):
             raise ValueError("loss_mode must be 'replica' or 'global'")
+        if optimizer not in ('sgd', 'adam'):
+            raise ValueError("optimizer must be 'sgd' (SGD(lr, momentum), ssd300_training.ipynb:169) or 'adam' (ssd7_training.ipynb:153)")
         self.loss_mode = loss_mode
+        self.optimizer, self.beta_1, self.beta_2, self.epsilon = optimizer, float(beta_1), float(beta_2), float(epsilon)
+        self.iterations = 0                      # optimiser steps taken (Adam's bias correction)
         import torch
         self.model = model
         self.batch = int(batch_size)
@@ -114,7 +118,12 @@ class SSDTrainer:
     def apply(self, grad_scale=1.0):
         self._attach()
         self._dirty = True
-        _ffi.check(_ffi.lib().ssdk_train_apply(self.handle, self.lr, self.momentum, self.l2, float(grad_scale), _ffi.stream_ptr()))
+        self.iterations += 1
+        if self.optimizer == 'adam':
+            _ffi.check(_ffi.lib().ssdk_train_apply_adam(self.handle, self.lr, self.beta_1, self.beta_2, self.epsilon, self.l2, float(grad_scale),
+                                                        int(self.iterations), _ffi.stream_ptr()))
+        else:
+            _ffi.check(_ffi.lib().ssdk_train_apply(self.handle, self.lr, self.momentum, self.l2, float(grad_scale), _ffi.stream_ptr()))
 
     def buckets(self, bucket_bytes=None):
         """Layer ranges for the overlapped gradient exchange, top of the graph first: [(hi, lo, offset, count), ...].  The
@@ -159,7 +168,7 @@ class SSDTrainer:
         if self._spans is None:
             out = {}
             for i, s in enumerate(self.model.specs):
-                for which, tag in ((0, 'kernel'), (1, 'bias'), (2, 'gamma')):
+                for which, tag in ((0, 'kernel'), (1, 'bias'), (2, 'gamma'), (3, 'bn_gamma'), (4, 'bn_beta')):
                     o, c = C.c_longlong(), C.c_longlong()
                     _ffi.check(_ffi.lib().ssdk_trainer_param_span(self.handle, i, which, C.byref(o), C.byref(c)))
                     if c.value > 0:
@@ -179,6 +188,11 @@ class SSDTrainer:
                 res[s.name + '/kernel'] = flat[o:o + c].reshape(s.cout, s.kh, s.kw, cin).transpose(1, 2, 3, 0).copy()
                 o, c = self.spans()[(s.name, 'bias')]
                 res[s.name + '/bias'] = flat[o:o + c].copy()
+                if s.bn and (s.name, 'bn_gamma') in self.spans():
+                    o, c = self.spans()[(s.name, 'bn_gamma')]
+                    res[s.bn + '/gamma'] = flat[o:o + c].copy()
+                    o, c = self.spans()[(s.name, 'bn_beta')]
+                    res[s.bn + '/beta'] = flat[o:o + c].copy()
             elif s.op == _ffi.OP_HEAD:
                 cin = m._shapes[m.index[s.inp]][2]
                 nb = s.n_boxes
@@ -203,4 +217,10 @@ class SSDTrainer:
         self._attach()
         out = torch.empty_like(self.grad)
         _ffi.check(_ffi.lib().ssdk_trainer_read_params(self.handle, _ffi.dptr(out), _ffi.stream_ptr()))
-        return self._unflatten(out.cpu().numpy())
+        res = self._unflatten(out.cpu().numpy())
+        for i, s in enumerate(self.model.specs):              # moving statistics of the BatchNormalization layers
+            if s.op == _ffi.OP_CONV and s.bn:
+                mu = torch.empty((s.cout,), dtype=torch.float32, device='cuda'); var = torch.empty_like(mu)
+                _ffi.check(_ffi.lib().ssdk_trainer_read_bn_stats(self.handle, i, _ffi.dptr(mu), _ffi.dptr(var), _ffi.stream_ptr()))
+                res[s.bn + '/moving_mean'], res[s.bn + '/moving_variance'] = mu.cpu().numpy(), var.cpu().numpy()
+        return res

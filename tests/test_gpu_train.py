@@ -190,3 +190,81 @@ def test_trained_weights_belong_to_the_model(tmp_path):
         tr.forward_backward(xd[:1], ytd[:1])
     with pytest.raises(ValueError):
         tr.forward_backward(xd, ytd[:, :100])
+
+
+def test_ssd7_training_step_batchnorm_elu_adam():
+    """SSD7 (conv + BatchNormalization + ELU stages, models/keras_ssd7.py:277-309) trained like ssd7_training.ipynb:153 does:
+    BatchNormalization in its training phase (batch statistics), Adam.  Loss, every gradient incl. the BatchNormalization
+    gamma / beta, the Adam update and the moving statistics against float64 autograd of the same graph."""
+    import torch
+    from oracle import graph as og
+    from oracle import synth
+    from oracle.encoder import OracleEncoder
+    from ssd_keras_b200.models.keras_ssd7 import build_model
+    from ssd_keras_b200.training import SSDTrainer
+    B, H, W, ncls = 4, 96, 128, 5
+    sc = [0.08, 0.16, 0.32, 0.64, 0.96]
+    pre = dict(subtract_mean=127.5, divide_by_stddev=127.5)
+    m = build_model((H, W, 3), ncls, mode='training', l2_regularization=5e-4, scales=sc, normalize_coords=True, weights_seed=4, **pre)
+    w = m.get_weights()
+    rng = np.random.default_rng(3)
+    for k in w:
+        if k.endswith('/bias'):
+            w[k] = (rng.standard_normal(w[k].shape) * 0.05).astype(np.float32)
+        elif k.endswith('/gamma'):
+            w[k] = rng.uniform(0.8, 1.2, w[k].shape).astype(np.float32)
+        elif k.endswith('/beta'):
+            w[k] = (rng.standard_normal(w[k].shape) * 0.1).astype(np.float32)
+    m.set_weights(w)
+    enc = OracleEncoder(H, W, ncls, m.predictor_sizes, scales=sc, aspect_ratios_global=[0.5, 1.0, 2.0], variances=[1.0] * 4,
+                        pos_iou_threshold=0.4, neg_iou_limit=0.3, normalize_coords=True)
+    assert np.array_equal(enc.anchors, m.anchors)
+    x = synth.synth_images(7, B, H, W)
+    y_true = enc(synth.synth_gt(8, B, 3, W, H, ncls)).astype(np.float32)
+    lr = 1e-3
+    tr = SSDTrainer(m, B, lr=lr, l2_regularization=5e-4, optimizer='adam')
+    xd, ytd = torch.from_numpy(x).cuda(), torch.from_numpy(y_true).cuda()
+    loss, _ = tr.forward_backward(xd, ytd)
+    torch.cuda.synchronize()
+    grads = tr.gradients()
+    params = og.make_params(m.specs, w, dtype=torch.float64)
+    yp, outs = og.forward(m.specs, params, x, ncls + 1, m.anchors, [1.0] * 4, dtype=torch.float64, bn_training=True)
+    lvec = og.ssd_loss_torch(y_true, yp)
+    lvec.mean().backward()
+    ref_l = lvec.detach().numpy()
+    assert np.abs(loss.cpu().numpy() - ref_l).max() <= 1e-4 * np.abs(ref_l).max()
+    trainable = [k for k in w if not k.endswith(('/moving_mean', '/moving_variance'))]
+    assert set(grads) == set(trainable)
+    errs = {}
+    for k in trainable:
+        ref = params[k].grad.numpy()
+        errs[k] = float(np.abs(grads[k] - ref).max() / (np.abs(ref).max() + 1e-30))
+    bad = {k: v for k, v in errs.items() if v > 2e-3}
+    assert not bad, bad
+    # one Adam step; moving statistics after one training-phase forward
+    tr.apply(1.0)
+    torch.cuda.synchronize()
+    new_w = tr.get_weights()
+    ref_w, _, _ = og.adam_step({k: w[k] for k in trainable}, {k: params[k].grad.numpy() for k in trainable}, {}, {}, 1, lr=lr, l2_reg=5e-4)
+    for k in trainable:
+        # the very first Adam step moves every weight by lr * sign(g) (m / sqrt(v) = +-1): compare the step, not just the weight
+        step, ref_step = new_w[k] - w[k], ref_w[k] - w[k]
+        big = np.abs(params[k].grad.numpy()) > 1e-3 * np.abs(params[k].grad.numpy()).max()      # where the sign of g is well conditioned
+        np.testing.assert_allclose(step[big], ref_step[big], rtol=2e-3, atol=2e-6)
+    N = B * np.prod([1])
+    for s in m.specs:
+        if getattr(s, 'bn', None):
+            mu, var = outs[s.bn + '/batch_mean'].numpy(), outs[s.bn + '/batch_var'].numpy()
+            n = float(B * m._shapes[m.index[s.name]][0] * m._shapes[m.index[s.name]][1])
+            exp_mean = 0.99 * w[s.bn + '/moving_mean'] + 0.01 * mu
+            exp_var = 0.99 * w[s.bn + '/moving_variance'] + 0.01 * var * n / (n - 1.0)
+            np.testing.assert_allclose(new_w[s.bn + '/moving_mean'], exp_mean, rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(new_w[s.bn + '/moving_variance'], exp_var, rtol=1e-4, atol=1e-5)
+    # the model owns the result: an inference-phase predict uses the updated moving statistics and weights
+    y_after = m.predict(x[:1])
+    assert np.isfinite(y_after).all()
+    # a few more steps: the loss goes down
+    l0 = float(loss.mean().item())
+    for _ in range(8):
+        l = tr.train_on_batch(xd, ytd)
+    assert float(l.mean().item()) < l0
