@@ -57,6 +57,7 @@ struct EncScratch {             // per call, global memory; TG = total number of
   const float* lb;              // [TG] lower bound of each box's row maximum, or NULL (= 0)
   int* counters;                // [B] tickets
   int TG;
+  int dbg;                      // experiment knobs (SSDK_ENC_DEBUG), 0 in production
 };
 
 struct TileSetDev {
@@ -65,6 +66,7 @@ struct TileSetDev {
   const int2* map;              // [n_tiles*kTile] (prior index of a thread or -1, its staging slot)
   const int* runs;              // [n_tiles*kRunRec]: n_runs, then (first prior, length) pairs; staging slots follow run order
   const int* tile_of;           // [P] tile of a prior
+  const unsigned* aligned_mask; // [ceil(n_tiles/32)] bit t: every run of tile t starts and ends on a 16-byte boundary of an image's rows
   const double* bbox;           // [n_tiles*4] corner bounding box of the tile's anchors
 };
 
@@ -624,13 +626,18 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
           if (!(val > 0.0)) val = 0.0;
         }
       }
-      // best exact pair of this warp for the candidate (first prior index on ties)
-      double rvv = 0.0; int rii = INT_MAX;
-      if (__any_sync(0xffffffffu, val > 0.0)) {
-        rvv = val; rii = (val > 0.0) ? a : INT_MAX;
-        warp_argmax(rvv, rii);
+      // best exact pair of this warp for the candidate (lowest prior index on ties): REDUX on the two halves of the (positive)
+      // float64 bit pattern, then on the prior index.  Nothing is stored when no lane evaluated anything: the reduction below
+      // recognises such warps by their U maximum (exact evaluation happens iff some lane's U reaches the threshold gq.z).
+      if (lane == 0) s_wU[warp * Gs + c] = wm;
+      if (__uint_as_float(wm) >= gq.z) {                      // warp-uniform
+        const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a : 0x7fffffffu);
+        if (lane == 0) { s_wV[warp * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + c] = (int)mi; }
       }
-      if (lane == 0) { s_wU[warp * Gs + c] = wm; s_wV[warp * Gs + c] = rvv; s_wI[warp * Gs + c] = rii; }
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -641,12 +648,17 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       float u = 0.f; double bv = 0.0; int bi = INT_MAX;
       if (c >= 0) {
         unsigned m = 0;
+        const float qc = s_cq[c].z;
 #pragma unroll
         for (int w = 0; w < kTile / 32; ++w) {
-          m = max(m, s_wU[w * Gs + c]);
-          const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
-          if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
+          const unsigned wu = s_wU[w * Gs + c];
+          m = max(m, wu);
+          if (__uint_as_float(wu) >= qc) {                    // this warp evaluated pairs of the candidate exactly
+            const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
+            if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
+          }
         }
+        if (!(bv > 0.0)) { bv = 0.0; bi = INT_MAX; }
         u = __fmul_ru(__uint_as_float(m), 1.0f + 4.76837158203125e-7f);     // (1 + 2^-21) covers the reciprocal's 1 ulp
       }
       const size_t o = (size_t)tile * TG + (size_t)(g0 + g);
@@ -667,33 +679,49 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the rows -> visible to the bulk copy engine
     __syncthreads();
     // ---- 5. rows leave: one bulk store per contiguous run of priors ----
-    int nruns = 1;
-    const int* rn = nullptr;
-    if (!ts.linear) { rn = ts.runs + (size_t)tile * kRunRec; nruns = rn[0]; }
-    int slot0 = 0;
+    // (runs whose byte ranges are not 16-byte aligned fall back to coalesced stores by all threads; whether a tile has any is
+    //  known on the host up to the alignment of this image's base address, which is uniform over the CTA)
+    const bool base_ok = ((reinterpret_cast<uintptr_t>(out_y + (size_t)b * p.P * W) & 15) == 0);
+    const int* rn = ts.linear ? nullptr : ts.runs + (size_t)tile * kRunRec;
+    const int lin_len = min(kTile, p.P - tile * kTile);
+    const bool fast = base_ok && (ts.linear ? (((size_t)tile * kTile * W * 4) & 15) == 0 && (((size_t)lin_len * W * 4) & 15) == 0
+                                            : ((ts.aligned_mask[tile >> 5] >> (tile & 31)) & 1u) != 0);
     bool issued = false;
-    for (int r = 0; r < nruns; ++r) {
-      const int start = ts.linear ? tile * kTile : rn[1 + 2 * r];
-      const int len = ts.linear ? min(kTile, p.P - tile * kTile) : rn[2 + 2 * r];
-      float* dst = out_y + ((size_t)b * p.P + start) * W;
-      const float* src = rows + (size_t)slot0 * W;
-      const size_t n_f = (size_t)len * W;
-      const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (((n_f * 4) & 15) == 0) && ((((size_t)slot0 * W * 4) & 15) == 0);
-      if (aligned) {
-        if (tid == 0) {
+    if (fast) {
+      if (tid == 0) {
+        const int nruns = ts.linear ? 1 : rn[0];
+        int slot0 = 0;
+        for (int r = 0; r < nruns; ++r) {
+          const int start = ts.linear ? tile * kTile : rn[1 + 2 * r];
+          const int len = ts.linear ? lin_len : rn[2 + 2 * r];
+          float* dst = out_y + ((size_t)b * p.P + start) * W;
           asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                       ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src)), "r"((uint32_t)(n_f * 4)) : "memory");
+                       ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(rows + (size_t)slot0 * W)), "r"((uint32_t)((size_t)len * W * 4)) : "memory");
+          slot0 += len;
         }
-        issued = true;
-      } else {
-        for (size_t i = tid; i < n_f; i += kTile) dst[i] = src[i];
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      slot0 += len;
+      issued = true;
+    } else {
+      const int nruns = ts.linear ? 1 : rn[0];
+      int slot0 = 0;
+      for (int r = 0; r < nruns; ++r) {
+        const int start = ts.linear ? tile * kTile : rn[1 + 2 * r];
+        const int len = ts.linear ? lin_len : rn[2 + 2 * r];
+        float* dst = out_y + ((size_t)b * p.P + start) * W;
+        const float* src = rows + (size_t)slot0 * W;
+        const size_t n_f = (size_t)len * W;
+        for (size_t i = tid; i < n_f; i += kTile) dst[i] = src[i];
+        slot0 += len;
+      }
     }
-    if (issued && tid == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     store_pending = issued;
   }
   // ---- 6. last CTA of the image: bipartite matching ----
+  if (sc.dbg & 1) {                                             // timing experiments only: no matching stage (wrong results)
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    return;
+  }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (G <= 0) return;
   __syncthreads();                                              // every thread's global writes happen-before thread 0's fence
@@ -798,8 +826,11 @@ void spatial_tiles(TileSetHost& t, int n_layers, const int* fh, const int* fw, c
 
 struct TileSetOwned {
   TileSetDev dev{};
-  int2* d_map = nullptr; int* d_runs = nullptr; int* d_tile_of = nullptr; double* d_bbox = nullptr;
-  void release() { cudaFree(d_map); cudaFree(d_runs); cudaFree(d_tile_of); cudaFree(d_bbox); d_map = nullptr; d_runs = d_tile_of = nullptr; d_bbox = nullptr; dev = TileSetDev{}; }
+  int2* d_map = nullptr; int* d_runs = nullptr; int* d_tile_of = nullptr; double* d_bbox = nullptr; unsigned* d_mask = nullptr;
+  void release() {
+    cudaFree(d_map); cudaFree(d_runs); cudaFree(d_tile_of); cudaFree(d_bbox); cudaFree(d_mask);
+    d_map = nullptr; d_runs = d_tile_of = nullptr; d_bbox = nullptr; d_mask = nullptr; dev = TileSetDev{};
+  }
 };
 
 }  // namespace
@@ -842,7 +873,22 @@ int upload_tiles(ssdk_encoder* e, const TileSetHost* h, int n_linear_tiles, Tile
     SSDK_CHECK_CUDA(cudaMemcpy(o.d_map, m.data(), m.size() * sizeof(int2), cudaMemcpyHostToDevice));
     SSDK_CHECK_CUDA(cudaMemcpy(o.d_runs, h->runs.data(), h->runs.size() * sizeof(int), cudaMemcpyHostToDevice));
     SSDK_CHECK_CUDA(cudaMemcpy(o.d_tile_of, tile_of.data(), tile_of.size() * sizeof(int), cudaMemcpyHostToDevice));
-    o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.tile_of = o.d_tile_of;
+    // a tile's rows can leave by bulk copies iff every run's byte range (relative to the image's first row) is 16-byte aligned
+    const int W = e->p.C + 12;
+    std::vector<unsigned> mask((h->n_tiles + 31) / 32, 0u);
+    for (int t = 0; t < h->n_tiles; ++t) {
+      const int* r = h->runs.data() + (size_t)t * kRunRec;
+      bool ok = ((size_t)e->p.P * W) % 4 == 0;                 // image stride
+      int slot0 = 0;
+      for (int i = 0; i < r[0] && ok; ++i) {
+        ok = (((size_t)r[1 + 2 * i] * W * 4) % 16 == 0) && (((size_t)r[2 + 2 * i] * W * 4) % 16 == 0) && (((size_t)slot0 * W * 4) % 16 == 0);
+        slot0 += r[2 + 2 * i];
+      }
+      if (ok) mask[t >> 5] |= 1u << (t & 31);
+    }
+    SSDK_CHECK_CUDA(cudaMalloc(&o.d_mask, mask.size() * sizeof(unsigned)));
+    SSDK_CHECK_CUDA(cudaMemcpy(o.d_mask, mask.data(), mask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.tile_of = o.d_tile_of; o.dev.aligned_mask = o.d_mask;
   }
   o.dev.bbox = o.d_bbox;
   tile_bbox_kernel<<<n_tiles, kTile>>>(e->p, o.dev, o.d_bbox);
@@ -998,6 +1044,7 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   float* lb = reinterpret_cast<float*>(sc.tI + nt);
   sc.lb = use_lb ? lb : nullptr;
   sc.TG = (int)TG;
+  if (const char* s = getenv("SSDK_ENC_DEBUG")) sc.dbg = atoi(s);
   if (e->counters_n < (size_t)B) {
     SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
     rc = e->counters.ensure((size_t)B * sizeof(int));

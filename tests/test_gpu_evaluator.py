@@ -59,8 +59,8 @@ def test_evaluator_vs_reference(name, use_neutral, bp):
 
 
 def test_evaluator_end_to_end_on_a_model():
-    """Evaluator.__call__ through a model in 'inference' mode: runs, and a model whose detections are the ground truth itself
-    (perfect predictions injected) scores mAP 1."""
+    """Predictions that are the ground truth itself score an 11-point mAP of exactly 1 (precision 1 at every recall level).
+    ('integrate' mode would give 1 - 1/n_gt per class: the reference's integration starts at the first recall value, :869-876.)"""
     from ssd_keras_b200.eval_utils.average_precision_evaluator import Evaluator
     n_classes, ids, labels, neutral, _ = _inputs('a')
     preds = [list() for _ in range(n_classes + 1)]
@@ -73,5 +73,8 @@ def test_evaluator_end_to_end_on_a_model():
     ev.get_num_gt_per_class()
     ev.match_predictions()
     ev.compute_precision_recall()
-    ev.compute_average_precisions(mode='integrate')
+    ev.compute_average_precisions(mode='sample')
     assert abs(ev.compute_mean_average_precision() - 1.0) < 1e-12
+    ng = ev.num_gt_per_class[1:]
+    ev.compute_average_precisions(mode='integrate')
+    np.testing.assert_allclose(ev.average_precisions[1:], 1.0 - 1.0 / ng, rtol=1e-12)
