@@ -14,5 +14,5 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:enc_tiles -c 1 -o gpurun_out/enc_micro_full -f python tools/profile_encode.py 64 > gpurun_out/ncu_enc_micro.log 2>&1
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench3.json 2> gpurun_out/bench3.err
 SSDK_NO_DIRECT=1 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu --no-micro > gpurun_out/bench3_nodirect.json 2> gpurun_out/bench3_nodirect.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_step3.csv python tools/profile_step.py step > gpurun_out/profile_step3.log 2>&1
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_step3.csv python tools/profile_step.py step > gpurun_out/profile_step3.log 2>&1
 tail -6 gpurun_out/pytest3.log; cat gpurun_out/enc_bench3.log | tail -22; cat gpurun_out/loss3.log | tail -3; tail -c 600 gpurun_out/bench3.json; tail -c 300 gpurun_out/bench3_nodirect.json
