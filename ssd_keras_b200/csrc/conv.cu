@@ -414,6 +414,57 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               if (c0 + j < ncols) atomicAdd(dstp + c0 + j, __uint_as_float(vr[j]));
           }
         }
+      } else if (args.epi == EPI_HEAD) {
+        // one thread = one pixel = n_boxes prior rows.  Per box three sweeps over its C+4 accumulator columns (TMEM reads are cheap
+        // and this warp group runs under the MMAs of the next tile): maximum, sum of exponentials, normalised store.
+        const int C = args.head_C, CP4 = C + 4, RW = C + 12;
+        const int pix = y * args.Wo + x;
+        for (int bx = 0; bx < args.head_nb; ++bx) {
+          const int c_lo = bx * CP4, c_hi = c_lo + CP4;
+          const int k_lo = c_lo >> 5, k_hi = (c_hi - 1) >> 5;
+          float mx = -INFINITY;
+          for (int k = k_lo; k <= k_hi; ++k) {
+            uint32_t vr[32];
+            ld_acc32(t_row + (uint32_t)(k * 32), xoff, vr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = k * 32 + j;
+              if (col >= c_lo && col < c_lo + C) mx = fmaxf(mx, __uint_as_float(vr[j]) + s_bias[col]);
+            }
+          }
+          float sum = 0.f;
+          for (int k = k_lo; k <= k_hi; ++k) {
+            uint32_t vr[32];
+            ld_acc32(t_row + (uint32_t)(k * 32), xoff, vr);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = k * 32 + j;
+              if (col >= c_lo && col < c_lo + C) sum += expf(__uint_as_float(vr[j]) + s_bias[col] - mx);
+            }
+          }
+          const int prior = args.head_prior_off + pix * args.head_nb + bx;
+          float* dst = args.out_f32 + ((size_t)n * args.head_P + prior) * RW;
+          for (int k = k_lo; k <= k_hi; ++k) {
+            uint32_t vr[32];
+            ld_acc32(t_row + (uint32_t)(k * 32), xoff, vr);
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int col = k * 32 + j;
+                if (col >= c_lo && col < c_hi) {
+                  const float v = __uint_as_float(vr[j]) + s_bias[col];
+                  const int r = col - c_lo;
+                  dst[r] = r < C ? expf(v - mx) / sum : v;
+                }
+              }
+            }
+          }
+          if (valid) {
+            const float4 an = __ldg(reinterpret_cast<const float4*>(args.head_anchors) + prior);
+            dst[C + 4] = an.x; dst[C + 5] = an.y; dst[C + 6] = an.z; dst[C + 7] = an.w;
+            dst[C + 8] = args.head_var[0]; dst[C + 9] = args.head_var[1]; dst[C + 10] = args.head_var[2]; dst[C + 11] = args.head_var[3];
+          }
+        }
       } else {
         const size_t o = (((size_t)n * args.Ho + y) * args.Wo + x) * (size_t)args.cout + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {

@@ -21,7 +21,7 @@ struct ActBuf {
   size_t elems() const { return rows() * Cs; }
 };
 
-enum { EPI_SPLIT = 0, EPI_F32 = 1, EPI_ATOMIC = 2 };
+enum { EPI_SPLIT = 0, EPI_F32 = 1, EPI_ATOMIC = 2, EPI_HEAD = 3 };
 
 constexpr int kMaxTaps = 25;
 
@@ -62,6 +62,12 @@ struct ConvArgs {
   int out_ld, out_col_off;
   const __nv_bfloat16* mask_hi;   // EPI_SPLIT: zero the result where this plane (same geometry as the output) is <= 0 (ReLU')
   int accumulate;       // EPI_SPLIT: add to the value already stored in the output planes
+  // --- EPI_HEAD: Reshape / softmax / Concat of models/keras_ssd300.py:363-419 in the predictor conv's epilogue.  The tile's columns
+  //     are n_boxes x [C class logits | 4 offsets]; every (pixel, box) becomes one row of y_pred (out_f32):
+  //     [softmax(C) | 4 offsets | 4 anchor coordinates | 4 variances] at prior head_prior_off + pixel * n_boxes + box.
+  int head_nb, head_C, head_P, head_prior_off;
+  const float* head_anchors;      // [P*4]
+  float head_var[4];
 };
 
 struct ConvLaunch {

@@ -139,9 +139,18 @@ int build_conv(ssdk_model* m, int li) {
   }
   a.act = L.bn_train ? SSDK_ACT_NONE : d.act;
   if (head) {
-    a.epi = EPI_F32;
-    rc = dev_alloc(m, &L.head_f32, (size_t)m->B * Ho * Wo * cout, true); if (rc) return rc;
-    a.out_f32 = L.head_f32;
+    // inference plans: softmax / concat / anchors in the epilogue, straight into y_pred (one n-tile holds all boxes of a pixel);
+    // training plans keep the raw logits (the backward pass needs them) and finish with head_finalize_kernel
+    const bool fuse = !m->training && a.n_tiles_n == 1 && !getenv("SSDK_NO_HEAD_FUSION");
+    if (fuse) {
+      a.epi = EPI_HEAD;
+      a.head_nb = d.n_boxes; a.head_C = m->Ctot; a.head_prior_off = 0;          // prior offset, P, anchors: set once they are known
+      L.head_fused = true;
+    } else {
+      a.epi = EPI_F32;
+      rc = dev_alloc(m, &L.head_f32, (size_t)m->B * Ho * Wo * cout, true); if (rc) return rc;
+      a.out_f32 = L.head_f32;
+    }
   } else {
     a.epi = EPI_SPLIT;
     const ActBuf& dst = L.bn_train ? L.z : L.out;
@@ -345,6 +354,12 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
     if (!desc->anchors_f32) { set_error("ssdk_model_create: anchors_f32 is NULL"); return fail(SSDK_ERR_INVALID); }
     rc = upload_f32(m, &m->d_anchors, desc->anchors_f32, (size_t)m->P * 4); if (rc) return fail(rc);
   }
+  for (auto& L : m->layers)
+    if (L.head_fused) {
+      ConvArgs& a = L.launch.args;
+      a.head_P = m->P; a.head_prior_off = L.prior_off; a.head_anchors = m->d_anchors;
+      for (int k = 0; k < 4; ++k) a.head_var[k] = m->var[k];
+    }
   SSDK_CHECK_CUDA(cudaDeviceSynchronize());
   *out = m;
   return SSDK_OK;
@@ -429,11 +444,12 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
           if (rc) return rc;
         }
         if (m->timing) cudaEventRecord(L.ev0, stream);
+        if (L.head_fused) L.launch.args.out_f32 = y_pred_dev;                   // the epilogue writes the prediction rows themselves
         rc = launch_conv(ctx, L.launch, stream);
         if (rc) return rc;
         if (m->timing) cudaEventRecord(L.ev1, stream);
         if (L.bn_train) { rc = launch_bn_forward(ctx, L, d.act, stream); if (rc) return rc; }
-        if (d.op == SSDK_OP_HEAD) {
+        if (d.op == SSDK_OP_HEAD && !L.head_fused) {
           rc = launch_head_finalize(ctx, L.head_f32, m->B, L.H * L.W, d.n_boxes, m->Ctot, m->P, L.prior_off, m->d_anchors, m->var,
                                     y_pred_dev, stream);
           if (rc) return rc;
@@ -460,6 +476,7 @@ extern "C" int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, v
   LayerPlan& L = m->layers[layer];
   cudaStream_t stream = (cudaStream_t)stream_;
   if (L.d.op == SSDK_OP_HEAD) {
+    SSDK_REQUIRE(L.head_f32, "ssdk_model_read_layer: this plan writes the predictor outputs straight into y_pred (no separate head tensor)");
     SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev, L.head_f32, (size_t)m->B * L.H * L.W * L.C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return SSDK_OK;
   }

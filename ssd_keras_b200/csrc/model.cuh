@@ -33,6 +33,7 @@ struct LayerPlan {
   int* tile_list = nullptr;
   ConvLaunch launch{};
   float* head_f32 = nullptr;
+  bool head_fused = false;            // softmax / concat / anchors done in the conv epilogue (inference plans)
   int prior_off = 0;
   int need_pad = 0;                   // border required by the consumers of this layer's output
   float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};
