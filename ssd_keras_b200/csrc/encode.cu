@@ -484,7 +484,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, cf, cq, wU, wV, wI, slot, total;
+  size_t rows, gbox, cf, cq, wU, wV, wI, slot, items, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
@@ -501,7 +501,8 @@ __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-warp maximum of the IoU bound
   s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-warp prior index of the best exact IoU
   s.slot = up16(s.wI + gs * 32);                              // [G] candidate slot of a gt (-1: not a candidate)
-  s.total = up16(s.slot + gs * 4) + 16;
+  s.items = up16(s.slot + gs * 4);                            // [8*G] (slice, candidate) pairs that need exact evaluation, + counter
+  s.total = up16(s.items + gs * 32 + 16) + 16;
   return s;
 }
 
@@ -528,6 +529,8 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
   int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
   int* slot_of = reinterpret_cast<int*>(smem_raw + L.slot);
+  int* s_items = reinterpret_cast<int*>(smem_raw + L.items);
+  int* s_nitems = s_items + (size_t)(kTile / 32) * Gs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const int tile0 = blockIdx.x * tpc;
@@ -615,29 +618,50 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst (thresholds and the stored tile
                                                              // maximum account for it)
       const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
-      double val = 0.0;
-      if (live && U >= gq.z) {                                // rare: the pair may decide something -> the reference's float64 IoU
+      if (lane == 0) s_wU[warp * Gs + c] = wm;
+      if (live && U >= p.thr_adj) {                           // rare: the pair may matter for the anchor's own row -> exact float64 IoU
         const int g = __float_as_int(gq.y);
         Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
         const double inter64 = inter_area(gb, ab);
         if (inter64 > 0.0) {
-          val = iou_value(gb, ab, inter64);
+          const double val = iou_value(gb, ab, inter64);
           if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
-          if (!(val > 0.0)) val = 0.0;
         }
       }
-      // best exact pair of this warp for the candidate (lowest prior index on ties): REDUX on the two halves of the (positive)
-      // float64 bit pattern, then on the prior index.  Nothing is stored when no lane evaluated anything: the reduction below
-      // recognises such warps by their U maximum (exact evaluation happens iff some lane's U reaches the threshold gq.z).
-      if (lane == 0) s_wU[warp * Gs + c] = wm;
-      if (__uint_as_float(wm) >= gq.z) {                      // warp-uniform
-        const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
-        const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a : 0x7fffffffu);
-        if (lane == 0) { s_wV[warp * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + c] = (int)mi; }
+    }
+    // ---- 3b. exact per-(box, tile) bests, spread evenly over the warps ----
+    // A (warp slice w, candidate c) pair needs the reference's float64 IoU for its 32 anchors iff the slice's U maximum reaches
+    // the candidate's threshold gq.z (min of the row threshold and the box's row-maximum lower bound).  With the box-shape-major
+    // thread order these pairs concentrate in the slices of the best-fitting shape; listing them and dealing them out round-robin
+    // keeps all eight warps busy instead of leaving six of them waiting at the barrier for two.
+    if (tid == 0) *s_nitems = 0;
+    __syncthreads();
+    for (int idx = tid; idx < (kTile / 32) * ncand; idx += kTile) {
+      const int w = idx / ncand, c = idx - w * ncand;
+      if (__uint_as_float(s_wU[w * Gs + c]) >= s_cq[c].z) s_items[atomicAdd(s_nitems, 1)] = (w << 16) | c;
+    }
+    __syncthreads();
+    const int n_items = *s_nitems;
+    for (int it = warp; it < n_items; it += kTile / 32) {
+      const int w = s_items[it] >> 16, c = s_items[it] & 0xffff;
+      int pos2;
+      const int a2 = tile_anchor(ts, tile, w * 32 + lane, p.P, pos2);
+      double val = 0.0;
+      if (a2 >= 0) {
+        const int g = __float_as_int(s_cq[c].y);
+        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
+        const Box ab2 = load_anchor(p, a2);
+        const double inter64 = inter_area(gb, ab2);
+        if (inter64 > 0.0) { val = iou_value(gb, ab2, inter64); if (!(val > 0.0)) val = 0.0; }
       }
+      // best pair of the slice (lowest prior index on ties): REDUX on the two halves of the (positive) float64 bit pattern, then
+      // on the prior index
+      const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
+      const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a2 : 0x7fffffffu);
+      if (lane == 0) { s_wV[w * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[w * Gs + c] = (int)mi; }
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

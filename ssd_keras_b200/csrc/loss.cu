@@ -58,6 +58,7 @@ struct LossArgs {
   int* ties_local;                     // multi-GPU: out, boxes equal to T on this rank
   // outputs
   float* out_loss; int* out_stats; const float* upstream; float* out_grad;
+  unsigned long long* dbg_times;       // optional [8]: globaltimer of CTA 0 at the phase boundaries (SSDK_LOSS_TIMES)
   int stages;                          // shared-memory stages of phase A / D tile loads (1 or 2)
   int bulk_ok;                         // rows of a tile start 16-byte aligned: cp.async.bulk is usable
 };
@@ -111,38 +112,56 @@ __device__ __forceinline__ T block_sum(T v, T* s_red) {       // fixed-order blo
 // Returns the fine bin; `want` becomes the rank inside it, `in_bin` its population.  All threads get the same answer.
 __device__ void select_bin(const unsigned* hist, int zero_fine, long long n_zero, long long& want, long long& in_bin, int& bin,
                            long long* s_scan) {
-  // coarse: 2048 bins / 128 threads = 16 each, scanned from the top
+  // Every global load below is issued by many threads at once (a serial scan by one thread would pay the L2 latency per bin).
   const int t = threadIdx.x;
-  long long mine = 0;
+  __shared__ long long s_misc[4];
+  // coarse: 2048 bins / 128 threads = 16 each, thread t owns bins c_hi .. c_hi - 15 (scanned from the top)
   const int c_hi = kCoarse - 1 - t * 16;
-  for (int i = 0; i < 16; ++i) {
-    const int c = c_hi - i;
-    mine += __ldcg(hist + c) + ((zero_fine >= 0 && (zero_fine >> 5) == c) ? n_zero : 0);
-  }
+  unsigned cv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) cv[i] = __ldcg(hist + c_hi - i);
+  long long mine = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) mine += (long long)cv[i] + ((zero_fine >= 0 && (zero_fine >> 5) == c_hi - i) ? n_zero : 0);
   __syncthreads();
   s_scan[t] = mine;
   __syncthreads();
   if (t == 0) {
     long long acc = 0; int owner = kRows - 1;
     for (int i = 0; i < kRows; ++i) { if (acc + s_scan[i] >= want) { owner = i; break; } acc += s_scan[i]; }
-    // inside the owner's 16 coarse bins
-    int c = kCoarse - 1 - owner * 16, csel = c - 15;
-    for (int i = 0; i < 16; ++i, --c) {
-      const long long v = __ldcg(hist + c) + ((zero_fine >= 0 && (zero_fine >> 5) == c) ? n_zero : 0);
-      if (acc + v >= want) { csel = c; break; }
-      acc += v;
-    }
-    // inside the coarse bin: 32 fine bins from the top
-    int f = csel * 32 + 31, fsel = csel * 32; long long pop = 0;
-    for (int i = 0; i < 32; ++i, --f) {
-      const long long v = __ldcg(hist + kCoarse + f) + ((f == zero_fine) ? n_zero : 0);
-      if (acc + v >= want) { fsel = f; pop = v; break; }
-      acc += v;
-    }
-    s_scan[0] = fsel; s_scan[1] = want - acc; s_scan[2] = pop;
+    s_misc[0] = owner; s_misc[1] = acc;
   }
   __syncthreads();
-  bin = (int)s_scan[0]; want = s_scan[1]; in_bin = s_scan[2];
+  if (t == (int)s_misc[0]) {                           // the owner scans its 16 bins (already in registers)
+    long long acc = s_misc[1];
+    int csel = c_hi - 15;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const long long v = (long long)cv[i] + ((zero_fine >= 0 && (zero_fine >> 5) == c_hi - i) ? n_zero : 0);
+      if (acc + v >= want) { csel = c_hi - i; break; }
+      acc += v;
+    }
+    s_misc[2] = csel; s_misc[3] = acc;
+  }
+  __syncthreads();
+  const int csel = (int)s_misc[2];
+  if (t < 32) {                                         // the 32 fine bins of that coarse bin, one per lane, top first
+    const int f = csel * 32 + 31 - t;
+    s_scan[t] = (long long)__ldcg(hist + kCoarse + f) + ((f == zero_fine) ? n_zero : 0);
+  }
+  __syncthreads();
+  if (t == 0) {
+    long long acc = s_misc[3];
+    int fsel = csel * 32; long long pop = 0;
+    for (int i = 0; i < 32; ++i) {
+      const long long v = s_scan[i];
+      if (acc + v >= want) { fsel = csel * 32 + 31 - i; pop = v; break; }
+      acc += v;
+    }
+    s_misc[0] = fsel; s_misc[1] = want - acc; s_misc[2] = pop;
+  }
+  __syncthreads();
+  bin = (int)s_misc[0]; want = s_misc[1]; in_bin = s_misc[2];
   __syncthreads();
 }
 
@@ -416,14 +435,18 @@ __device__ void phase_d(const LossArgs& a, const Sel& s, bool ordered_ties, long
   }
   __syncthreads();
   if (!s_is_last) return;
-  for (int b = tid; b < a.B; b += kRows) {
+  for (int b = warp; b < a.B; b += kRows / 32) {               // one warp per image: lanes stride over the tiles, fixed-order tree
     double pc = 0, loc = 0, ng = 0;
-    for (int i = 0; i < a.tiles_per_img; ++i) {
+    for (int i = lane; i < a.tiles_per_img; i += 32) {
       const size_t t = (size_t)b * a.tiles_per_img + i;
       pc += __ldcg(a.part + t * 2); loc += __ldcg(a.part + t * 2 + 1); ng += __ldcg(a.negpart + t);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pc += __shfl_xor_sync(0xffffffffu, pc, o); loc += __shfl_xor_sync(0xffffffffu, loc, o); ng += __shfl_xor_sync(0xffffffffu, ng, o);
+    }
     const double total = (pc + ng + (double)a.alpha * loc) * (double)s.inv_norm;    // :204
-    a.out_loss[b] = (float)(total * (double)a.global_B);                            // :209
+    if (lane == 0) a.out_loss[b] = (float)(total * (double)a.global_B);             // :209
   }
   if (tid == 0 && a.out_stats) {
     a.out_stats[0] = s.n_pos; a.out_stats[1] = s.nnz; a.out_stats[2] = s.none ? 0 : s.k; a.out_stats[3] = s.none ? 0 : (int)s.want;
@@ -454,16 +477,25 @@ __global__ void __launch_bounds__(kRows) ssd_loss_kernel(const __grid_constant__
   __shared__ uint64_t s_bars[3];
   __shared__ long long s_scan[kRows];
   cg::grid_group grid = cg::this_grid();
+  auto stamp = [&](int i) {
+    if (a.dbg_times && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg_times[i] = t; }
+  };
   const uint32_t bar0 = setup_barriers(s_bars);
+  stamp(0);
   phase_a(a, smem, bar0);
+  stamp(1);
   grid.sync();
+  stamp(2);
   Sel s;
   read_counts(a, s);
   int b1 = 0; long long want1 = 0;
   if (!s.none) level1(a, s, b1, want1, s_scan);
+  stamp(3);
   phase_b(a, s, b1);
   grid.sync();
+  stamp(4);
   finish_select(a, s, b1, want1, s_scan);
+  stamp(5);
   const bool ordered = !s.none && s.want < s.ties_total;                 // uniform over the grid
   if (ordered) {
     phase_ties(a, s);
@@ -474,6 +506,7 @@ __global__ void __launch_bounds__(kRows) ssd_loss_kernel(const __grid_constant__
     s.want = s.ties_total;                                               // every box equal to T is kept: no order needed
   }
   phase_d(a, s, ordered, 0, smem, bar0 + 16);
+  stamp(6);
 }
 
 // The same phases as separate launches (multi-GPU, global-batch-exact): 0 = A, 1 = B, 2 = threshold + local ties, 3 = scan, 4 = D
@@ -614,7 +647,21 @@ int loss_run(ssdk_ctx* ctx, const float* y_true, const float* y_pred, int B, int
   rc = fill_args(ctx, a, y_true, y_pred, B, P, C, ratio, n_neg_min, alpha, ws, parity, out_grad != nullptr, plan, true);
   if (rc) return rc;
   a.out_loss = out_loss; a.out_stats = out_stats; a.upstream = upstream; a.out_grad = out_grad;
-  return launch_fused(ctx, a, plan, stream);
+  static unsigned long long* d_times = nullptr;
+  if (getenv("SSDK_LOSS_TIMES")) {                                     // experiment: phase boundaries of CTA 0
+    if (!d_times) SSDK_CHECK_CUDA(cudaMalloc(&d_times, 64));
+    a.dbg_times = d_times;
+  }
+  rc = launch_fused(ctx, a, plan, stream);
+  if (rc == SSDK_OK && a.dbg_times) {
+    unsigned long long h[8] = {0};
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
+    SSDK_CHECK_CUDA(cudaMemcpy(h, d_times, 56, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "ssd_loss phases (CTA 0, us): A %.1f | sync %.1f | level1 %.1f | B+sync %.1f | select2 %.1f | D %.1f | total %.1f (grid %d, smem %zu)\n",
+            (h[1] - h[0]) / 1e3, (h[2] - h[1]) / 1e3, (h[3] - h[2]) / 1e3, (h[4] - h[3]) / 1e3, (h[5] - h[4]) / 1e3, (h[6] - h[5]) / 1e3,
+            (h[6] - h[0]) / 1e3, plan.grid, plan.smem);
+  }
+  return rc;
 }
 
 }  // namespace

@@ -236,8 +236,15 @@ def test_ssd7_training_step_batchnorm_elu_adam():
     trainable = [k for k in w if not k.endswith(('/moving_mean', '/moving_variance'))]
     assert set(grads) == set(trainable)
     errs = {}
+    bn_convs = {s.name for s in m.specs if getattr(s, 'bn', None)}
     for k in trainable:
         ref = params[k].grad.numpy()
+        if k.endswith('/bias') and k.split('/')[0] in bn_convs:
+            # a bias in front of a BatchNormalization has an exactly zero gradient (the batch mean removes it): the float64
+            # reference is rounding noise, ours must be small against the layer's beta gradient (same sum, not cancelled)
+            scale = np.abs(params[[s.bn for s in m.specs if s.name == k.split('/')[0]][0] + '/beta'].grad.numpy()).max()
+            errs[k] = float(np.abs(grads[k]).max() / scale) / 10.0
+            continue
         errs[k] = float(np.abs(grads[k] - ref).max() / (np.abs(ref).max() + 1e-30))
     bad = {k: v for k, v in errs.items() if v > 2e-3}
     assert not bad, bad
@@ -249,9 +256,10 @@ def test_ssd7_training_step_batchnorm_elu_adam():
     for k in trainable:
         # the very first Adam step moves every weight by lr * sign(g) (m / sqrt(v) = +-1): compare the step, not just the weight
         step, ref_step = new_w[k] - w[k], ref_w[k] - w[k]
+        if k.endswith('/bias') and k.split('/')[0] in bn_convs:
+            continue                                            # zero gradient: the step is lr * sign(noise)
         big = np.abs(params[k].grad.numpy()) > 1e-3 * np.abs(params[k].grad.numpy()).max()      # where the sign of g is well conditioned
         np.testing.assert_allclose(step[big], ref_step[big], rtol=2e-3, atol=2e-6)
-    N = B * np.prod([1])
     for s in m.specs:
         if getattr(s, 'bn', None):
             mu, var = outs[s.bn + '/batch_mean'].numpy(), outs[s.bn + '/batch_var'].numpy()
