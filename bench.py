@@ -238,7 +238,7 @@ def micro_benchmarks(peaks):
     bytes_ = 32 * (8732 * 16 + 8 * 20 + 8732 * 4 * 33)
     out['encode_ssd300_b32'] = {'ms': ms, 'images_per_s': 32e3 / ms, 'algorithmic_GB': bytes_ / 1e9, 'GBps': bytes_ / ms / 1e6,
                                 'frac_hbm': bytes_ / ms / 1e6 / hbm, 'launches_per_call': 1,
-                                'timing': '50 back-to-back calls between two CUDA events, median of 10'}
+                                'kernels': 'enc_tiles_kernel (G <= 16: no lower-bound pre-pass)', 'timing': '50 back-to-back calls between two CUDA events, median of 10'}
     del ybuf
     y_true = enc.encode_device(gdev, offs)
     y_pred = torch.from_numpy(synth.synth_y_pred(3, 32, enc.anchors, 21, sharp=2.0)).cuda()
@@ -258,7 +258,7 @@ def micro_benchmarks(peaks):
     bytes_ = Bm * (100000 * 16 + 128 * 20 + 100000 * 4 * 33)
     out['encode_micro_p1e5_g128'] = {'batch': Bm, 'ms': ms, 'priors_per_s': Bm * 1e5 / ms * 1e3, 'iou_pairs_per_s': Bm * 1.28e7 / ms * 1e3,
                                      'algorithmic_GB': bytes_ / 1e9, 'GBps': bytes_ / ms / 1e6, 'frac_hbm': bytes_ / ms / 1e6 / hbm,
-                                     'launches_per_call': 1}
+                                     'launches_per_call': 2, 'kernels': 'enc_lb_kernel (row-maximum lower bounds, ~1% of the time) + enc_tiles_kernel'}
     del ybuf
     anc = torch.from_numpy(encm.anchors_f32.copy()).cuda()
     boxes = torch.stack([anc[:, 0] - anc[:, 2] / 2, anc[:, 1] - anc[:, 3] / 2, anc[:, 0] + anc[:, 2] / 2, anc[:, 1] + anc[:, 3] / 2], 1)
@@ -532,11 +532,15 @@ def run_ours(args):
     fl_algo, fl_issued = model.flops(BATCH)
     peak = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')          # from one ncu --set full capture of this workload
-    if os.path.exists(tp):
-        with open(tp) as f:
-            tj = json.load(f)
-        traffic, traffic_src = tj.get('dram_bytes_per_step'), 'profiles/r01_conv_traffic.json (dram read+write bytes of the %d conv launches of one step, ncu --set full)' % tj.get('launches_per_step', 0)
+    for name in ('r02_conv_traffic.json', 'r01_conv_traffic.json'):       # newest ncu --set full capture of this workload first
+        tp = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj.get('dram_bytes_per_step')
+            traffic_src = 'profiles/%s (dram read+write bytes of the %d conv launches of one step, ncu --set full; %s)' % (
+                name, tj.get('launches_per_step', 0), tj.get('source', ''))
+            break
     roofline = {'bound': 'tensor', 'kernel': 'conv_tcgen05_kernel (all conv launches of one step)',
                 'achieved': fl_algo / conv_ms / 1e9, 'peak': peak, 'unit': 'TFLOP/s', 'frac': fl_algo / conv_ms / 1e9 / peak,
                 'peak_source': peaks_src + ', bf16_tflops_sustained', 'traffic': traffic, 'traffic_unit': 'bytes per step',
