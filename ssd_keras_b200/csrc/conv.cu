@@ -21,6 +21,9 @@
 #include <cudaTypedefs.h>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
 
 namespace ssdk {
 
@@ -144,6 +147,49 @@ __device__ __forceinline__ void ld_acc32(uint32_t taddr, uint32_t xoff, uint32_t
     tmem_ld32(taddr + xoff, w);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+  }
+}
+
+// Predictor-head epilogue for a compile-time row width CP4 = n_classes + 4 (25: Pascal VOC, the benchmark configuration): one thread =
+// one pixel = n_boxes prior rows.  With CP4 known the accumulator columns of a box are compile-time register indices, so each box
+// costs one sweep: <= 2 TMEM loads, C bias adds, C exponentials (kept in registers), one reciprocal, C+12 stores.
+template <int CP4>
+__device__ __forceinline__ void epi_head_fixed(const ConvArgs& args, uint32_t t_row, uint32_t xoff, bool valid, int n, int pix,
+                                               const float* s_bias) {
+  constexpr int C = CP4 - 4, RW = C + 12;
+#pragma unroll
+  for (int bx = 0; bx < 8; ++bx) {
+    if (bx >= args.head_nb) break;                               // uniform
+    constexpr int kMaxCol = 256;
+    const int c_lo = bx * CP4;                                   // compile-time after unrolling
+    const int k_lo = c_lo >> 5, k_hi = (c_lo + CP4 - 1) >> 5;
+    if (c_lo + CP4 > kMaxCol) break;
+    uint32_t v0[32], v1[32];
+    ld_acc32(t_row + (uint32_t)(k_lo * 32), xoff, v0);
+    if (k_hi != k_lo) ld_acc32(t_row + (uint32_t)(k_hi * 32), xoff, v1);
+    if (!valid) continue;
+    float e[CP4];
+#pragma unroll
+    for (int r = 0; r < CP4; ++r) {
+      const int col = c_lo + r;
+      e[r] = __uint_as_float(((col >> 5) == k_lo) ? v0[col & 31] : v1[col & 31]) + s_bias[col];
+    }
+    float mx = e[0];
+#pragma unroll
+    for (int r = 1; r < C; ++r) mx = fmaxf(mx, e[r]);
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < C; ++r) { e[r] = expf(e[r] - mx); sum += e[r]; }
+    const float inv = 1.0f / sum;
+    const int prior = args.head_prior_off + pix * args.head_nb + bx;
+    float* dst = args.out_f32 + ((size_t)n * args.head_P + prior) * RW;
+    const float4 an = __ldg(reinterpret_cast<const float4*>(args.head_anchors) + prior);
+#pragma unroll
+    for (int r = 0; r < C; ++r) dst[r] = e[r] * inv;
+#pragma unroll
+    for (int r = C; r < CP4; ++r) dst[r] = e[r];
+    dst[C + 4] = an.x; dst[C + 5] = an.y; dst[C + 6] = an.z; dst[C + 7] = an.w;
+    dst[C + 8] = args.head_var[0]; dst[C + 9] = args.head_var[1]; dst[C + 10] = args.head_var[2]; dst[C + 11] = args.head_var[3];
   }
 }
 
@@ -419,6 +465,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         // and this warp group runs under the MMAs of the next tile): maximum, sum of exponentials, normalised store.
         const int C = args.head_C, CP4 = C + 4, RW = C + 12;
         const int pix = y * args.Wo + x;
+        if (CP4 == 25 && args.head_nb <= 8) { epi_head_fixed<25>(args, t_row, xoff, valid, n, pix, s_bias); continue; }
         for (int bx = 0; bx < args.head_nb; ++bx) {
           const int c_lo = bx * CP4, c_hi = c_lo + CP4;
           const int k_lo = c_lo >> 5, k_hi = (c_hi - 1) >> 5;
@@ -695,6 +742,240 @@ int launch_conv_direct(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const
   const unsigned blocks = (unsigned)((total + 255) / 256);
   // (a fully unrolled <3, 3> instantiation was measured slower on B200: 771 vs 683 us for conv1_1 at batch 32)
   conv_direct_kernel<0, 0><<<blocks, 256, smem, stream>>>(in, out, w, bias, bn_scale, bn_shift, act, kh, kw, dil, pad_t, pad_l);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_first_kernel: the image-facing layer (Cin <= 4: conv1_1 3x3x3 of models/keras_ssd300.py:263, conv1 5x5x3 of
+// models/keras_ssd7.py:277) on the tensor cores.  K = taps * 4 (channels padded to 4) is far too thin for the TMA ring of
+// conv_tcgen05_kernel -- an explicit im2col would write and re-read ten times the layer's input -- so the A tile is GATHERED:
+//   warps  0- 7  epilogue, two groups of four (TMEM lane quarter = warp % 4), group g drains accumulator g
+//   warps  8-15  gather, two groups of 128 threads; thread = one output pixel: reads the taps' 8-byte (4-channel) hi / lo words
+//                from the zero-bordered input planes (L1/L2 hits: every word is used by taps of neighbouring pixels) and writes
+//                them K-major into the 128B-swizzled A stage; group g fills the stages of tiles g, g+2, ...
+//   warp   16    TMEM allocation, tcgen05.mma issue (<= 8 k-steps x 3 products per tile), commits
+// The weights (K-major, swizzled image prepared on the host) stay in shared memory for the whole launch.  The layer is bound by
+// writing its output (B*H*W*Cout*4 bytes of hi+lo planes); the epilogue is the one of the other activation-producing launches.
+// ------------------------------------------------------------------------------------------------
+struct FirstArgs {
+  ActBuf in;
+  const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;   // [kblocks][BN][64] swizzled images
+  int KH, KW, dil, pad_t, pad_l;
+  int kblocks, ksteps;        // 64-wide blocks / 16-wide MMA steps that cover taps * 4
+  int BN, stages, split;
+  long long M;                // B * Ho * Wo output pixels
+  int n_tiles, Ho, Wo;
+  ConvArgs epi;               // bias / bn / act / output planes as the shared epilogue expects them
+};
+constexpr int kFirstThreads = 17 * 32;
+
+__global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __grid_constant__ FirstArgs fa) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SA = fa.stages, BN = fa.BN, split = fa.split, KB = fa.kblocks;
+  const uint32_t a_plane = (uint32_t)KB * kATile;                      // one stage plane (hi or lo)
+  const uint32_t a_stage = a_plane * (split ? 2 : 1);
+  const uint32_t b_block = (uint32_t)BN * 128u;                        // one k-block of the weight tile
+  const uint32_t b_plane = b_block * KB;
+  const uint32_t ring_b = smem_base + a_stage * SA;
+  const uint32_t bar_base = ring_b + b_plane * (split ? 2 : 1);
+  auto fullA = [&](int i) { return bar_base + 8u * i; };
+  auto emptyA = [&](int i) { return bar_base + 8u * (SA + i); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * SA + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_al + (tmem_slot - smem_base));
+  float* s_bias = reinterpret_cast<float*>(smem_al + (bar_base + 256u - smem_base));
+  float* s_scale = s_bias + fa.epi.cout;
+  float* s_shift = s_scale + fa.epi.cout;
+  for (int i = threadIdx.x; i < fa.epi.cout; i += blockDim.x) {
+    s_bias[i] = fa.epi.bias ? fa.epi.bias[i] : 0.f;
+    if (fa.epi.bn_scale) { s_scale[i] = fa.epi.bn_scale[i]; s_shift[i] = fa.epi.bn_shift[i]; }
+  }
+  {   // resident weights: straight copy of the swizzled images
+    const uint4* src_h = reinterpret_cast<const uint4*>(fa.w_hi);
+    const uint4* src_l = reinterpret_cast<const uint4*>(fa.w_lo);
+    uint4* dst = reinterpret_cast<uint4*>(smem_al + (ring_b - smem_base));
+    const int n16 = (int)(b_plane >> 4);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) { dst[i] = src_h[i]; if (split) dst[n16 + i] = src_l[i]; }
+  }
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * BN) tmem_cols <<= 1;
+  if (warp == 16) {
+    if (lane == 0) {
+      for (int i = 0; i < SA; ++i) { mbar_init(fullA(i), 128); mbar_init(emptyA(i), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // the weight copy above is read by the MMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int taps = fa.KH * fa.KW;
+
+  if (warp == 16) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(BN);
+    int it = 0;
+    for (int t = blockIdx.x; t < fa.n_tiles; t += gridDim.x, ++it) {
+      const int st = it % SA;
+      const int acc = it & 1;
+      mbar_wait(fullA(st), (uint32_t)(it / SA) & 1u);
+      mbar_wait(tempty_bar(acc), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t a0 = smem_base + a_stage * st;
+        for (int ks = 0; ks < fa.ksteps; ++ks) {
+          const int kb = ks >> 2, k = ks & 3;
+          const uint32_t ah = (a0 + (uint32_t)kb * kATile) >> 4, bh = (ring_b + (uint32_t)kb * b_block) >> 4;
+          const uint64_t da = kDescHi | (uint64_t)(ah + 2 * k), db = kDescHi | (uint64_t)(bh + 2 * k);
+          tc_mma(d, da, db, idesc, ks ? 1u : 0u);
+          if (split) {
+            tc_mma(d, da, kDescHi | (uint64_t)(bh + (b_plane >> 4) + 2 * k), idesc, 1u);
+            tc_mma(d, kDescHi | (uint64_t)(ah + (a_plane >> 4) + 2 * k), db, idesc, 1u);
+          }
+        }
+        tc_commit(emptyA(st));
+        tc_commit(tfull_bar(acc));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // ===================== gather =====================
+    const int grp = (warp - 8) >> 2;
+    const int r = ((warp - 8) & 3) * 32 + lane;                        // row of the tile
+    const int slots = fa.ksteps * 4;                                   // 8-byte (4-channel) K slots; slots >= taps hold zeros
+    int it = 0;
+    for (int t = blockIdx.x; t < fa.n_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int st = it % SA;
+      const long long v = (long long)t * kBM + r;
+      const bool valid = v < fa.M;
+      int n = 0, y = 0, x = 0;
+      if (valid) {
+        n = (int)(v / ((long long)fa.Ho * fa.Wo));
+        const int rem = (int)(v - (long long)n * fa.Ho * fa.Wo);
+        y = rem / fa.Wo; x = rem - y * fa.Wo;
+      }
+      mbar_wait(emptyA(st), ((uint32_t)(it / SA) & 1u) ^ 1u);
+      unsigned char* stage = smem_al + (a_stage * st);
+      for (int s0 = 0; s0 < slots; s0 += 4) {                          // four taps in flight per round
+        uint2 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int tap = s0 + j;
+          h[j] = make_uint2(0, 0); l[j] = make_uint2(0, 0);
+          if (valid && tap < taps) {
+            const int kh = tap / fa.KW, kw = tap - kh * fa.KW;
+            const int iy = y + kh * fa.dil - fa.pad_t, ix = x + kw * fa.dil - fa.pad_l;
+            if (iy >= 0 && iy < fa.in.H && ix >= 0 && ix < fa.in.W) {
+              const size_t src = act_index(fa.in, n, iy, ix);
+              h[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.hi + src));
+              if (split) l[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.lo + src));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int tap = s0 + j;
+          const uint32_t off = (uint32_t)(tap >> 4) * kATile + (uint32_t)r * 128u + ((uint32_t)(((tap >> 1) & 7) ^ (r & 7)) << 4) + (uint32_t)(tap & 1) * 8u;
+          *reinterpret_cast<uint2*>(stage + off) = h[j];
+          if (split) *reinterpret_cast<uint2*>(stage + a_plane + off) = l[j];
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA's async proxy
+      mbar_arrive(fullA(st));
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int grp = warp >> 2, q = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < fa.n_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int acc = it & 1;
+      mbar_wait(tfull_bar(acc), (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const long long v = (long long)t * kBM + q * 32 + lane;
+      const bool valid = v < fa.M;
+      size_t o = 0;
+      if (valid) {
+        const int n = (int)(v / ((long long)fa.Ho * fa.Wo));
+        const int rem = (int)(v - (long long)n * fa.Ho * fa.Wo);
+        const int y = rem / fa.Wo, x = rem - y * fa.Wo;
+        o = (((size_t)n * fa.epi.out_Hp + (y + fa.epi.out_pad)) * fa.epi.out_Wp + (x + fa.epi.out_pad)) * fa.epi.out_Cs;
+      }
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      epi_split<false>(fa.epi, t_row, 0u, fa.epi.cout, 0, o, valid, s_bias, s_scale, s_shift);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// K-major, 128B-swizzled shared-memory image of the image-facing layer's weights: row = output channel (padded to BN), element
+// k = tap * 4 + c.  HWIO kernel in.
+void first_weight_image(const float* hwio, int taps, int cin, int cout, int BN, int kblocks, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+  hi.assign((size_t)kblocks * BN * 64, 0); lo.assign((size_t)kblocks * BN * 64, 0);
+  auto f2bf = [](float f) { uint32_t u; memcpy(&u, &f, 4); if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+                            u += 0x7fffu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); };
+  auto bf2f = [](uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; };
+  for (int o = 0; o < cout; ++o)
+    for (int t = 0; t < taps; ++t)
+      for (int c = 0; c < cin; ++c) {
+        const int k = t * 4 + c, kb = k >> 6, kk = k & 63;
+        const size_t byte = (size_t)kb * BN * 128 + (size_t)o * 128 + ((size_t)((kk >> 3) ^ (o & 7)) << 4) + (size_t)(kk & 7) * 2;
+        const float w = hwio[((size_t)t * cin + c) * cout + o];
+        const uint16_t h = f2bf(w);
+        hi[byte / 2] = h; lo[byte / 2] = f2bf(w - bf2f(h));
+      }
+}
+
+int first_tc_supported(int taps, int cin, int cout) { return cin <= 4 && taps * 4 <= 128 && cout % 8 == 0 && cout <= 128; }
+
+int launch_conv_first(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                      const float* bias, const float* bn_scale, const float* bn_shift, int act, int kh, int kw, int dil, int pad_t,
+                      int pad_l, cudaStream_t stream) {
+  FirstArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.in = in; fa.w_hi = w_hi; fa.w_lo = w_lo;
+  fa.KH = kh; fa.KW = kw; fa.dil = dil; fa.pad_t = pad_t; fa.pad_l = pad_l;
+  const int K = kh * kw * 4;
+  fa.ksteps = (K + 15) / 16; fa.kblocks = (K + 63) / 64;
+  fa.BN = (out.C + 15) / 16 * 16;
+  fa.split = (in.lo && w_lo) ? 1 : 0;
+  fa.M = (long long)out.B * out.H * out.W; fa.Ho = out.H; fa.Wo = out.W;
+  fa.n_tiles = (int)((fa.M + kBM - 1) / kBM);
+  const size_t a_stage = (size_t)fa.kblocks * kATile * (fa.split ? 2 : 1);
+  const size_t b_bytes = (size_t)fa.kblocks * fa.BN * 128 * (fa.split ? 2 : 1);
+  const size_t fixed = 1024 + b_bytes + 256 + ((size_t)out.C * 3 * sizeof(float) + 127) / 128 * 128 + 128;
+  fa.stages = (int)std::min<size_t>(4, (200 * 1024 - fixed) / a_stage);
+  SSDK_REQUIRE(fa.stages >= 2, "image-facing convolution: the gathered A tile does not fit in shared memory twice");
+  fa.epi.cout = out.C; fa.epi.bias = bias; fa.epi.bn_scale = bn_scale; fa.epi.bn_shift = bn_shift; fa.epi.act = act;
+  fa.epi.out_hi = out.hi; fa.epi.out_lo = out.lo; fa.epi.out_Hp = out.Hp(); fa.epi.out_Wp = out.Wp(); fa.epi.out_pad = out.pad; fa.epi.out_Cs = out.Cs;
+  const size_t smem = fixed + a_stage * fa.stages;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSDK_CHECK_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = std::min(fa.n_tiles, ctx->sm_count);
+  conv_first_kernel<<<grid, kFirstThreads, smem, stream>>>(fa);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;

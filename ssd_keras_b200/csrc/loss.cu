@@ -29,6 +29,7 @@ namespace {
 constexpr int kRows = 128;             // rows per tile == threads per CTA
 constexpr int kCoarse = 2048;          // coarse bins: key >> 21 (level 1), (key >> 5) & 2047 (level 2)
 constexpr int kFine = 65536;           // fine bins:   key >> 16 (level 1), key & 65535 (level 2)
+constexpr int kCache = 2048;           // per-CTA direct-mapped cache of level-1 fine bins (slot = bin & 2047, tag = bin >> 11)
 constexpr unsigned kZeroKey = 0x80000000u;
 
 __device__ __forceinline__ unsigned okey(float f) {       // order-preserving key: larger float -> larger unsigned
@@ -197,9 +198,15 @@ __device__ void phase_a(const LossArgs& a, unsigned char* smem, uint32_t bar0) {
   const size_t stage_floats = (size_t)kRows * W;
   float* s_buf = reinterpret_cast<float*>(smem);                        // [stages][2][kRows*W]
   unsigned* s_coarse = reinterpret_cast<unsigned*>(smem + (size_t)a.stages * 2 * stage_floats * 4);   // [kCoarse]
+  // The negative losses of one batch crowd into a few hundred fine bins (same exponent, neighbouring mantissas): one global
+  // atomic per box serialises on those addresses in L2.  Each CTA counts in a direct-mapped shared-memory cache instead and adds
+  // its totals once at the end; a box whose slot is held by another bin falls back to the global atomic.
+  int* s_ftag = reinterpret_cast<int*>(s_coarse + kCoarse);             // [kCache] bin >> 11 of the slot's owner, -1 = free
+  unsigned* s_fcnt = reinterpret_cast<unsigned*>(s_ftag + kCache);      // [kCache]
   __shared__ double s_red[4];
   __shared__ unsigned long long s_redu[4];
   for (int i = tid; i < kCoarse; i += kRows) s_coarse[i] = 0;
+  for (int i = tid; i < kCache; i += kRows) { s_ftag[i] = -1; s_fcnt[i] = 0; }
   if (a.hist_next)                                                       // clear the other parity's histograms for the next call
     for (size_t i = (size_t)blockIdx.x * kRows + tid; i < 2ull * (kCoarse + kFine); i += (size_t)gridDim.x * kRows) a.hist_next[i] = 0;
   __syncthreads();
@@ -249,7 +256,10 @@ __device__ void phase_a(const LossArgs& a, unsigned char* smem, uint32_t bar0) {
       if (nl != 0.f) {
         nz = 1;
         const unsigned key = okey(nl);
-        atomicAdd(a.hist1 + kCoarse + (key >> 16), 1u);
+        const int fine = (int)(key >> 16), slot = fine & (kCache - 1), tag = fine >> 11;
+        int cur = *reinterpret_cast<volatile int*>(s_ftag + slot);
+        if (cur < 0) { const int old = atomicCAS(s_ftag + slot, -1, tag); cur = old < 0 ? tag : old; }
+        if (cur == tag) atomicAdd(s_fcnt + slot, 1u); else atomicAdd(a.hist1 + kCoarse + fine, 1u);
         atomicAdd(s_coarse + (key >> 21), 1u);
       }
     }
@@ -284,6 +294,7 @@ __device__ void phase_a(const LossArgs& a, unsigned char* smem, uint32_t bar0) {
   }
   __syncthreads();
   for (int i = tid; i < kCoarse; i += kRows) { const unsigned v = s_coarse[i]; if (v) atomicAdd(a.hist1 + i, v); }
+  for (int i = tid; i < kCache; i += kRows) { const unsigned v = s_fcnt[i]; if (v) atomicAdd(a.hist1 + kCoarse + ((s_ftag[i] << 11) | i), v); }
 }
 
 // ---- phase B: histogram of the low key bits inside the level-1 bin ---------------------------------------------------
@@ -456,7 +467,7 @@ __device__ void phase_d(const LossArgs& a, const Sel& s, bool ordered_ties, long
 // shared-memory layout (dynamic): phase A: stages * 2 tiles | coarse histogram;  phase D: y_true tile | y_pred tile | grad tile
 __host__ __device__ inline size_t loss_smem_bytes(int W, int stages, bool grad) {
   const size_t tile = (size_t)kRows * W * 4;
-  const size_t pa = (size_t)stages * 2 * tile + kCoarse * 4;
+  const size_t pa = (size_t)stages * 2 * tile + kCoarse * 4 + kCache * 8;
   const size_t pd = grad ? 3 * tile : 0;
   return (pa > pd ? pa : pd) + 128;
 }

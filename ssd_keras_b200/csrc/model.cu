@@ -76,7 +76,21 @@ int build_conv(ssdk_model* m, int li) {
       rc = upload_f32(m, &L.bn_shift, d.bn_shift, cout); if (rc) return rc;
     }
     const double fl = 2.0 * m->B * L.H * L.W * (double)taps * cin * cout;
-    m->flops_algo += fl;                 // not tensor-core work: counted as algorithmic FLOPs only
+    m->flops_algo += fl;                 // counted as algorithmic FLOPs only (the timed conv launches exclude this layer)
+    // inference plans: the layer runs on the tensor cores with a gathered A tile (conv_first_kernel); training plans keep the fp32
+    // direct kernel, whose weights are the optimizer's master copy
+    if (!m->training && first_tc_supported(taps, cin, cout) && d.dilation >= 1 && !getenv("SSDK_NO_FIRST_TC")) {
+      std::vector<uint16_t> whi, wlo;
+      const int K = taps * 4, BN = (cout + 15) / 16 * 16;
+      first_weight_image(d.kernel, taps, cin, cout, BN, (K + 63) / 64, whi, wlo);
+      rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
+      SSDK_CHECK_CUDA(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
+      if (m->split) {
+        rc = dev_alloc(m, &L.w_lo, wlo.size(), false); if (rc) return rc;
+        SSDK_CHECK_CUDA(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+      }
+      L.first_tc = true;
+    }
     return SSDK_OK;
   }
   L.im2col = (d.stride != 1) || (cin < 8);
@@ -433,6 +447,10 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
       case SSDK_OP_HEAD: {
         const LayerPlan& in = m->layers[d.input];
         if (L.direct) {
+          if (L.first_tc)
+            rc = launch_conv_first(ctx, in.out, L.out, L.w_hi, L.w_lo, L.bias, L.bn_scale, L.bn_shift, d.act, d.kh, d.kw, d.dilation, d.pad_t,
+                                   d.pad_l, stream);
+          else
           rc = launch_conv_direct(ctx, in.out, L.bn_train ? L.z : L.out, L.w_f32, L.bias, L.bn_scale, L.bn_shift, L.bn_train ? (int)SSDK_ACT_NONE : d.act,
                                   d.kh, d.kw, d.dilation, d.pad_t, d.pad_l, stream);
           if (rc) return rc;

@@ -23,6 +23,7 @@ struct LayerPlan {
   ActBuf out;                         // INPUT / CONV / MAXPOOL / L2NORM
   bool im2col = false;
   bool direct = false;                // fp32 SIMT path for the image-facing conv (Cin < 8)
+  bool first_tc = false;           // direct layer of an inference plan on the tensor cores (conv_first_kernel)
   float* w_f32 = nullptr;
   int Kpad = 0;
   __nv_bfloat16* col_hi = nullptr; __nv_bfloat16* col_lo = nullptr;
