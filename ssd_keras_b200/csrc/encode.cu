@@ -68,6 +68,8 @@ struct TileSetDev {
   const int* tile_of;           // [P] tile of a prior
   const unsigned* aligned_mask; // [ceil(n_tiles/32)] bit t: every run of tile t starts and ends on a 16-byte boundary of an image's rows
   const double* bbox;           // [n_tiles*4] corner bounding box of the tile's anchors
+  const float4* cls;            // [n_tiles*8*2] per 32-thread slice of a tile: (min x0, min y0, max x1, max y1) rounded outwards |
+                                //               (max width, max height) rounded up, min area rounded down, -
 };
 
 struct OffsArg { int v[kInlineB + 1]; };
@@ -408,62 +410,102 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     for (int g = tid; g < G; g += kTile) matches[g] = ra[g];
     __syncthreads();
     if (tid == 0 && s_flag[1]) matches[0] = 0;
-  } else if (warp == 0) {
-    // the reference's G sequential rounds (one warp)
-    for (int g = lane; g < G; g += 32) matches[g] = 0;
-    __syncwarp();
-    int n_removed = 0;
-    for (int round = 0; round < G; ++round) {
-      double v = -1.0; int gi = INT_MAX;
-      for (int g = lane; g < G; g += 32)
-        if (rv[g] > v) { v = rv[g]; gi = g; }                   // ascending g per lane: first index kept
-      warp_argmax(v, gi);
-      const int a_star = ra[gi];
-      __syncwarp();
-      if (lane == 0) { matches[gi] = a_star; rv[gi] = 0.0; ra[gi] = 0; removed[n_removed] = a_star; }
-      ++n_removed;
-      __syncwarp();
-      if (!(v > 0.0)) continue;                                  // nothing left to match: no row can point at a_star
-      for (int base = 0; base < G; base += 32) {
-        const int g = base + lane;
-        unsigned need = __ballot_sync(0xffffffffu, g < G && rv[g] > 0.0 && ra[g] == a_star);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          const int gg = base + src;
-          const size_t col = (size_t)(g0 + gg);
-          const Box gb = gbox(gg);
-          // the row lost its best anchor: re-evaluate that anchor's tile without the taken priors, reduce the row again;
-          // repeat while the new best is itself a taken prior recorded by another tile
-          int stale = a_star;
-          double nv; int ni;
-          for (;;) {
-            const int st = tile_of_prior(ts, stale);
-            double tv; int ti;
-            warp_tile_best(p, ts, gb, st, removed, n_removed, tv, ti);
-            if (lane == 0) { sc.tV[(size_t)st * TG + col] = tv; sc.tI[(size_t)st * TG + col] = ti; }
-            __syncwarp();
-            nv = 0.0; ni = INT_MAX;
-            for (int t = lane; t < ts.n_tiles; t += 32) {
-              const double v2 = (t == st) ? tv : __ldcg(sc.tV + (size_t)t * TG + col);
-              if (v2 > 0.0) {
-                const int i2 = (t == st) ? ti : __ldcg(sc.tI + (size_t)t * TG + col);
-                if (v2 > nv || (v2 == nv && i2 < ni)) { nv = v2; ni = i2; }
-              }
-            }
-            warp_argmax(nv, ni);
-            if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
-            stale = ni;
-          }
-          // pairs below the row's lower bound were never evaluated: if the best that is left fell below it, search all tiles
-          const float lbg = sc.lb ? __ldg(sc.lb + col) : 0.f;
-          if (nv < (double)lbg) warp_row_best(p, ts, gb, sc.tU + col, TG, removed, n_removed, nv, ni);
-          if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
-          __syncwarp();
+  } else {
+    // Some boxes want the same prior.  The reference's G rounds take the rows in descending (row maximum, then ascending box
+    // index) order; a round only interferes with later ones by removing the prior a LATER row points at.  So instead of G
+    // sequential rounds: find the first row (in that order) that has such a later duplicate, settle every row before it at once
+    // (none of them can lose its prior), settle that row, let the duplicates recompute their maximum without the taken priors (one
+    // warp each; their value can only drop, so they stay behind the settled rows), and repeat.  One iteration per conflict.
+    __shared__ double s_cv[kTile / 32];
+    __shared__ int s_ci[kTile / 32];
+    __shared__ int s_first, s_nrem, s_nvict;
+    int* victims = matches + G;                               // [G] rows that lost their prior in this iteration
+    for (int g = tid; g < G; g += kTile) matches[g] = 0;
+    if (tid == 0) s_nrem = 0;
+    __syncthreads();
+    for (;;) {
+      // A. the first row with a later duplicate
+      double cv = -1.0; int ci = INT_MAX;
+      for (int g = tid; g < G; g += kTile) {
+        const double v = rv[g];
+        if (!(v > 0.0)) continue;
+        const int a = ra[g];
+        bool has = false;
+        for (int g2 = 0; g2 < G; ++g2) {
+          const double v2 = rv[g2];
+          has |= (g2 != g) && (v2 > 0.0) && (ra[g2] == a) && (v2 < v || (v2 == v && g2 > g));
+        }
+        if (has && (v > cv || (v == cv && g < ci))) { cv = v; ci = g; }
+      }
+      warp_argmax(cv, ci);
+      if (lane == 0) { s_cv[warp] = cv; s_ci[warp] = ci; }
+      __syncthreads();
+      if (tid == 0) {
+        double bv = -1.0; int bi = INT_MAX;
+        for (int w = 0; w < kTile / 32; ++w)
+          if (s_cv[w] > bv || (s_cv[w] == bv && s_ci[w] < bi)) { bv = s_cv[w]; bi = s_ci[w]; }
+        s_first = (bv > 0.0) ? bi : -1;
+      }
+      __syncthreads();
+      const int f = s_first;
+      const double fv = f >= 0 ? rv[f] : 0.0;
+      const int a_star = f >= 0 ? ra[f] : -1;
+      __syncthreads();                                           // everyone has read row f before it is settled
+      // B. settle every positive row ahead of f (all of them when there is no conflict left), and f itself
+      for (int g = tid; g < G; g += kTile) {
+        const double v = rv[g];
+        if (!(v > 0.0)) continue;
+        if (f < 0 || g == f || v > fv || (v == fv && g < f)) {
+          const int a = ra[g];
+          matches[g] = a;
+          removed[atomicAdd(&s_nrem, 1)] = a;
+          rv[g] = 0.0; ra[g] = 0;
         }
       }
-      __syncwarp();
+      __syncthreads();
+      if (f < 0) break;
+      // C. the rows that pointed at f's prior recompute their maximum (one warp per row)
+      const int n_removed = s_nrem;
+      if (tid == 0) s_nvict = 0;
+      __syncthreads();
+      for (int g = tid; g < G; g += kTile)
+        if (rv[g] > 0.0 && ra[g] == a_star) victims[atomicAdd(&s_nvict, 1)] = g;
+      __syncthreads();
+      const int n_vict = s_nvict;
+      for (int vi = warp; vi < n_vict; vi += kTile / 32) {
+        const int gg = victims[vi];
+        const size_t col = (size_t)(g0 + gg);
+        const Box gb = gbox(gg);
+        // re-evaluate the tile of the lost prior without the taken priors, reduce the row again; repeat while the new best is itself
+        // a taken prior recorded by another tile
+        int stale = a_star;
+        double nv; int ni;
+        for (;;) {
+          const int st = tile_of_prior(ts, stale);
+          double tv; int ti;
+          warp_tile_best(p, ts, gb, st, removed, n_removed, tv, ti);
+          if (lane == 0) { sc.tV[(size_t)st * TG + col] = tv; sc.tI[(size_t)st * TG + col] = ti; }
+          __syncwarp();
+          nv = 0.0; ni = INT_MAX;
+          for (int t = lane; t < ts.n_tiles; t += 32) {
+            const double v2 = (t == st) ? tv : __ldcg(sc.tV + (size_t)t * TG + col);
+            if (v2 > 0.0) {
+              const int i2 = (t == st) ? ti : __ldcg(sc.tI + (size_t)t * TG + col);
+              if (v2 > nv || (v2 == nv && i2 < ni)) { nv = v2; ni = i2; }
+            }
+          }
+          warp_argmax(nv, ni);
+          if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
+          stale = ni;
+        }
+        // pairs below the row's lower bound were never evaluated: if the best that is left fell below it, search all tiles
+        const float lbg = sc.lb ? __ldg(sc.lb + col) : 0.f;
+        if (nv < (double)lbg) warp_row_best(p, ts, gb, sc.tU + col, TG, removed, n_removed, nv, ni);
+        if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
+      }
+      __syncthreads();
     }
+    if (tid == 0 && s_nrem < G) matches[0] = 0;                  // rounds with nothing left to match select (box 0, prior 0)
   }
   __syncthreads();
   // y_encoded[i, bipartite_matches, :-8] = labels_one_hot (:363): last writer wins; the matched column is all zero afterwards
@@ -484,25 +526,26 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, cf, cq, wU, wV, wI, slot, items, total;
+  size_t rows, gbox, gf, gq, wU, wV, wI, slot, cand, wl, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
   const size_t gs = (size_t)(G > 0 ? G : 1);
   size_t rows_bytes = ((size_t)kTile * W * sizeof(float) + 15) & ~(size_t)15;
-  const size_t fin = (gs * 20 + 15) & ~(size_t)15;            // finish_image scratch lives in the row staging area
+  const size_t fin = (gs * 24 + 15) & ~(size_t)15;            // finish_image scratch lives in the row staging area
   if (fin > rows_bytes) rows_bytes = fin;
   auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   s.rows = 0;
   s.gbox = rows_bytes;                                        // [G*5] f64 corner boxes of the ground truth
-  s.cf = up16(s.gbox + gs * 40);                              // [G] float4: outward-rounded corners of a candidate
-  s.cq = up16(s.cf + gs * 16);                                // [G] float4: (area rounded down, gt index, exact-evaluation threshold, -)
-  s.wV = up16(s.cq + gs * 16);                                // [8*G] f64: per-warp best exact IoU
-  s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-warp maximum of the IoU bound
-  s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-warp prior index of the best exact IoU
-  s.slot = up16(s.wI + gs * 32);                              // [G] candidate slot of a gt (-1: not a candidate)
-  s.items = up16(s.slot + gs * 4);                            // [8*G] (slice, candidate) pairs that need exact evaluation, + counter
-  s.total = up16(s.items + gs * 32 + 16) + 16;
+  s.gf = up16(s.gbox + gs * 40);                              // [G] float4: outward-rounded corners of a box
+  s.gq = up16(s.gf + gs * 16);                                // [G] float4: (area rounded down, row-maximum threshold, candidate threshold, -)
+  s.wV = up16(s.gq + gs * 16);                                // [8*G] f64: per-slice best exact IoU of a candidate
+  s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-slice bound of the IoU of a candidate
+  s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-slice prior index of the best exact IoU
+  s.slot = up16(s.wI + gs * 32);                              // [G] candidate slot of a gt (-1: not a candidate of this tile)
+  s.cand = up16(s.slot + gs * 4);                             // [G] gt index of a candidate slot (ascending)
+  s.wl = up16(s.cand + gs * 4);                               // [8*G] u16: per-slice list of candidate slots that pass the slice's bound
+  s.total = up16(s.wl + gs * 16) + 16;
   return s;
 }
 
@@ -523,14 +566,14 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   const EncSmem L = enc_smem_layout(W, G);
   float* rows = reinterpret_cast<float*>(smem_raw + L.rows);
   double* s_gbox = reinterpret_cast<double*>(smem_raw + L.gbox);
-  float4* s_cf = reinterpret_cast<float4*>(smem_raw + L.cf);
-  float4* s_cq = reinterpret_cast<float4*>(smem_raw + L.cq);
+  float4* s_gf = reinterpret_cast<float4*>(smem_raw + L.gf);
+  float4* s_gq = reinterpret_cast<float4*>(smem_raw + L.gq);
   double* s_wV = reinterpret_cast<double*>(smem_raw + L.wV);
   unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
   int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
   int* slot_of = reinterpret_cast<int*>(smem_raw + L.slot);
-  int* s_items = reinterpret_cast<int*>(smem_raw + L.items);
-  int* s_nitems = s_items + (size_t)(kTile / 32) * Gs;
+  int* s_cand = reinterpret_cast<int*>(smem_raw + L.cand);
+  unsigned short* s_wl = reinterpret_cast<unsigned short*>(smem_raw + L.wl);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const int tile0 = blockIdx.x * tpc;
@@ -549,6 +592,16 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     bad |= !gt_template(r, p, t, cls);
     const Box gb = corners_from_template(t, p.coords, p.d);
     s_gbox[g * 5] = gb.x0; s_gbox[g * 5 + 1] = gb.y0; s_gbox[g * 5 + 2] = gb.x1; s_gbox[g * 5 + 3] = gb.y1; s_gbox[g * 5 + 4] = gb.area;
+    // outward-rounded float32 corners, area rounded down: ingredients of IoU bounds that can only err upwards
+    s_gf[g] = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
+    // a pair needs the exact float64 IoU for the box's row maximum from q_row (the lower bound of that maximum, lowered by more
+    // than the bound's own slack; "any overlap at all" when there is none), for the anchor's own row from thr_adj
+    float q_row = 1.401298464e-45f;
+    if (sc.lb) {
+      const float lbg = __ldg(sc.lb + g0 + g);
+      if (lbg > 0.f) q_row = fmaxf(q_row, nextafterf(lbg * 0.99999905f, 0.f));
+    }
+    s_gq[g] = make_float4(__double2float_rd(gb.area), q_row, fminf(q_row, p.thr_adj), 0.f);
   }
   const int any_bad = __syncthreads_or(bad ? 1 : 0);          // also publishes s_gbox
   if (blockIdx.x == 0 && tid == 0 && any_bad && status) atomicMax(status, b + 1);
@@ -559,14 +612,14 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       a = tile_anchor(ts, tile, tid, p.P, pos);
       if (a >= 0) load_anchor_t(p, a, at);
     }
-    // ---- 2. ordered candidate list (ascending gt index) ----
+    // ---- 2. ordered candidate list (ascending gt index): boxes that touch the tile's bounding box ----
     const double bb[4] = {ts.bbox[tile * 4], ts.bbox[tile * 4 + 1], ts.bbox[tile * 4 + 2], ts.bbox[tile * 4 + 3]};
     int ncand = 0;
     for (int gbase = 0; gbase < G; gbase += kTile) {
       const int g = gbase + tid;
-      bool hit = false; Box gb{};
+      bool hit = false;
       if (g < G) {
-        gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
+        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3];
         hit = bbox_hits(bb, gb);
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -577,25 +630,42 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       for (int w = 0; w < kTile / 32; ++w) { const int c = s_wcnt[w]; if (w < warp) wbase += c; total += c; }
       if (hit) {
         const int cpos = wbase + __popc(m & ((1u << lane) - 1));
-        // outward-rounded float32 corners, area rounded down: ingredients of an IoU bound that can only err upwards
-        s_cf[cpos] = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
-        // exact evaluation is needed from the smaller of: the threshold an anchor's own row depends on, and the lower bound of
-        // this box's row maximum (both lowered by more than the bound's own slack; never below "any overlap at all")
-        float q = 1.401298464e-45f;
-        if (sc.lb) {
-          const float lbg = __ldg(sc.lb + g0 + g);
-          if (lbg > 0.f) q = fmaxf(q, nextafterf(lbg * 0.99999905f, 0.f));
-        }
-        q = fminf(q, p.thr_adj);
-        s_cq[cpos] = make_float4(__double2float_rd(gb.area), __int_as_float(g), q, 0.f);
-        slot_of[g] = cpos;
+        s_cand[cpos] = g; slot_of[g] = cpos;
       } else if (g < G) {
         slot_of[g] = -1;
       }
       ncand += total;
       __syncthreads();
     }
-    // ---- 3. this thread's anchor against the candidates ----
+    // ---- 2b. per 32-anchor slice: which candidates can reach their threshold with ANY anchor of the slice ----
+    // Bound of the IoU of a whole slice against a box: the overlap along x is at most min(widest anchor, box width, rightmost anchor
+    // edge - box left, box right - leftmost anchor edge), likewise along y; the union is at least smallest anchor area + box area -
+    // that intersection.  With the box-shape-major thread order a slice holds one shape at neighbouring positions, so the bound is
+    // tight and only the few boxes near the slice survive: the per-anchor loop below runs over ~1 candidate instead of ~20.
+    const float4 k0 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2);
+    const float4 k1 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2 + 1);
+    int nlist = 0;
+    for (int cb = 0; cb < ncand; cb += 32) {
+      const int c = cb + lane;
+      bool keep = false;
+      if (c < ncand) {
+        const int g = s_cand[c];
+        const float4 gf = s_gf[g];
+        const float4 gq = s_gq[g];
+        const float ox = fmaxf(fminf(fminf(k1.x, __fsub_ru(gf.z, gf.x)), fminf(__fsub_ru(k0.z, gf.x), __fsub_ru(gf.z, k0.x))), 0.f);
+        const float oy = fmaxf(fminf(fminf(k1.y, __fsub_ru(gf.w, gf.y)), fminf(__fsub_ru(k0.w, gf.y), __fsub_ru(gf.w, k0.y))), 0.f);
+        const float inter = __fmul_ru(ox, oy);
+        const float un = fmaxf(__fsub_rd(__fadd_rd(k1.z, gq.x), inter), 1e-30f);
+        const float um = __fmul_ru(__fmul_ru(inter, rcp_approx(un)), 1.0f + 4.76837158203125e-7f);   // (1 + 2^-21): the reciprocal's ulp
+        keep = um >= gq.z;
+        s_wU[warp * Gs + c] = __float_as_uint(um);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) s_wl[warp * Gs + nlist + __popc(m & ((1u << lane) - 1))] = (unsigned short)c;
+      nlist += __popc(m);
+    }
+    __syncwarp();
+    // ---- 3. this thread's anchor against the slice's candidates ----
     const bool live = a >= 0;
     float fx0 = 0.f, fy0 = 0.f, fx1 = -INFINITY, fy1 = -INFINITY, fa = 0.f;
     Box ab{};
@@ -606,10 +676,11 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       fa = __double2float_rd(ab.area);
     }
     double best = 0.0; int best_g = -1;
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 gf = s_cf[c];
-      const float4 gq = s_cq[c];
+    for (int k = 0; k < nlist; ++k) {
+      const int c = s_wl[warp * Gs + k];
+      const int g = s_cand[c];
+      const float4 gf = s_gf[g];
+      const float4 gq = s_gq[g];
       // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
       const float iw = fmaxf(__fsub_ru(fminf(fx1, gf.z), fmaxf(fx0, gf.x)), 0.f);
       const float ih = fmaxf(__fsub_ru(fminf(fy1, gf.w), fmaxf(fy0, gf.y)), 0.f);
@@ -618,50 +689,28 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst (thresholds and the stored tile
                                                              // maximum account for it)
       const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
-      if (lane == 0) s_wU[warp * Gs + c] = wm;
-      if (live && U >= p.thr_adj) {                           // rare: the pair may matter for the anchor's own row -> exact float64 IoU
-        const int g = __float_as_int(gq.y);
+      const float wmi = __fmul_ru(__uint_as_float(wm), 1.0f + 4.76837158203125e-7f);   // (1 + 2^-21): the reciprocal's ulp
+      const bool row_need = wmi >= gq.y;                     // the slice may hold the box's row maximum (warp-uniform)
+      const bool own_need = live && U >= p.thr_adj;          // the pair may matter for the anchor's own row
+      double val = 0.0;
+      if ((row_need && live) || own_need) {
         Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
         const double inter64 = inter_area(gb, ab);
-        if (inter64 > 0.0) {
-          const double val = iou_value(gb, ab, inter64);
-          if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
-        }
+        if (inter64 > 0.0) { val = iou_value(gb, ab, inter64); if (!(val > 0.0)) val = 0.0; }
+        if (own_need && val > best) { best = val; best_g = g; }    // strict '>' keeps the first gt on ties (np.argmax)
       }
-    }
-    // ---- 3b. exact per-(box, tile) bests, spread evenly over the warps ----
-    // A (warp slice w, candidate c) pair needs the reference's float64 IoU for its 32 anchors iff the slice's U maximum reaches
-    // the candidate's threshold gq.z (min of the row threshold and the box's row-maximum lower bound).  With the box-shape-major
-    // thread order these pairs concentrate in the slices of the best-fitting shape; listing them and dealing them out round-robin
-    // keeps all eight warps busy instead of leaving six of them waiting at the barrier for two.
-    if (tid == 0) *s_nitems = 0;
-    __syncthreads();
-    for (int idx = tid; idx < (kTile / 32) * ncand; idx += kTile) {
-      const int w = idx / ncand, c = idx - w * ncand;
-      if (__uint_as_float(s_wU[w * Gs + c]) >= s_cq[c].z) s_items[atomicAdd(s_nitems, 1)] = (w << 16) | c;
-    }
-    __syncthreads();
-    const int n_items = *s_nitems;
-    for (int it = warp; it < n_items; it += kTile / 32) {
-      const int w = s_items[it] >> 16, c = s_items[it] & 0xffff;
-      int pos2;
-      const int a2 = tile_anchor(ts, tile, w * 32 + lane, p.P, pos2);
-      double val = 0.0;
-      if (a2 >= 0) {
-        const int g = __float_as_int(s_cq[c].y);
-        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
-        const Box ab2 = load_anchor(p, a2);
-        const double inter64 = inter_area(gb, ab2);
-        if (inter64 > 0.0) { val = iou_value(gb, ab2, inter64); if (!(val > 0.0)) val = 0.0; }
+      if (row_need) {
+        // best pair of the slice (lowest prior index on ties): REDUX on the two halves of the (non-negative) float64 bit pattern,
+        // then on the prior index
+        const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
+        const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a : 0x7fffffffu);
+        if (lane == 0) { s_wV[warp * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + c] = (int)mi; }
       }
-      // best pair of the slice (lowest prior index on ties): REDUX on the two halves of the (positive) float64 bit pattern, then
-      // on the prior index
-      const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
-      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-      const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
-      const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a2 : 0x7fffffffu);
-      if (lane == 0) { s_wV[w * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[w * Gs + c] = (int)mi; }
+      // the slice's entry becomes the maximum of the per-pair bounds: ">= q_row" below then means "evaluated exactly"
+      if (lane == 0) s_wU[warp * Gs + c] = __float_as_uint(wmi);
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -672,18 +721,18 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       float u = 0.f; double bv = 0.0; int bi = INT_MAX;
       if (c >= 0) {
         unsigned m = 0;
-        const float qc = s_cq[c].z;
+        const float q_row = s_gq[g].y;
 #pragma unroll
         for (int w = 0; w < kTile / 32; ++w) {
           const unsigned wu = s_wU[w * Gs + c];
           m = max(m, wu);
-          if (__uint_as_float(wu) >= qc) {                    // this warp evaluated pairs of the candidate exactly
+          if (__uint_as_float(wu) >= q_row) {                 // slice w evaluated its pairs with the box exactly ...
             const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
             if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
           }
         }
         if (!(bv > 0.0)) { bv = 0.0; bi = INT_MAX; }
-        u = __fmul_ru(__uint_as_float(m), 1.0f + 4.76837158203125e-7f);     // (1 + 2^-21) covers the reciprocal's 1 ulp
+        u = __uint_as_float(m);
       }
       const size_t o = (size_t)tile * TG + (size_t)(g0 + g);
       sc.tU[o] = u; sc.tV[o] = bv; sc.tI[o] = bi;
@@ -762,7 +811,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   finish_image(p, ts, sc, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, out_y, out_match);
 }
 
-__global__ void tile_bbox_kernel(EncParams p, TileSetDev ts, double* __restrict__ bbox) {
+__global__ void tile_bbox_kernel(EncParams p, TileSetDev ts, double* __restrict__ bbox, float4* __restrict__ cls) {
   __shared__ double s[4][kTile / 32];
   const int tile = blockIdx.x;
   int pos;
@@ -776,6 +825,25 @@ __global__ void tile_bbox_kernel(EncParams p, TileSetDev ts, double* __restrict_
   }
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) { s[0][w] = x0; s[1][w] = y0; s[2][w] = x1; s[3][w] = y1; }
+  {   // bounds of this 32-thread slice for the IoU bound of a whole slice against a box (enc_tiles_kernel, step 2b)
+    double bw = -1e300, bh = -1e300, ar = 1e300;
+    if (a >= 0) { Box ab = load_anchor(p, a); bw = __dsub_rn(ab.x1, ab.x0); bh = __dsub_rn(ab.y1, ab.y0); ar = ab.area; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bw = fmax(bw, __shfl_xor_sync(0xffffffffu, bw, o)); bh = fmax(bh, __shfl_xor_sync(0xffffffffu, bh, o));
+      ar = fmin(ar, __shfl_xor_sync(0xffffffffu, ar, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      float4 c0, c1;
+      if (x0 > x1) {                                            // no anchor in the slice: can never be a candidate
+        c0 = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY); c1 = make_float4(0.f, 0.f, 1.f, 0.f);
+      } else {
+        c0 = make_float4(__double2float_rd(x0), __double2float_rd(y0), __double2float_ru(x1), __double2float_ru(y1));
+        c1 = make_float4(__double2float_ru(bw), __double2float_ru(bh), __double2float_rd(ar), 0.f);
+      }
+      cls[((size_t)tile * (kTile / 32) + w) * 2] = c0; cls[((size_t)tile * (kTile / 32) + w) * 2 + 1] = c1;
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < kTile / 32; ++i) { x0 = fmin(x0, s[0][i]); y0 = fmin(y0, s[1][i]); x1 = fmax(x1, s[2][i]); y1 = fmax(y1, s[3][i]); }
@@ -850,9 +918,9 @@ void spatial_tiles(TileSetHost& t, int n_layers, const int* fh, const int* fw, c
 
 struct TileSetOwned {
   TileSetDev dev{};
-  int2* d_map = nullptr; int* d_runs = nullptr; int* d_tile_of = nullptr; double* d_bbox = nullptr; unsigned* d_mask = nullptr;
+  int2* d_map = nullptr; int* d_runs = nullptr; int* d_tile_of = nullptr; double* d_bbox = nullptr; unsigned* d_mask = nullptr; float4* d_cls = nullptr;
   void release() {
-    cudaFree(d_map); cudaFree(d_runs); cudaFree(d_tile_of); cudaFree(d_bbox); cudaFree(d_mask);
+    cudaFree(d_map); cudaFree(d_runs); cudaFree(d_tile_of); cudaFree(d_bbox); cudaFree(d_mask); cudaFree(d_cls); d_cls = nullptr;
     d_map = nullptr; d_runs = d_tile_of = nullptr; d_bbox = nullptr; d_mask = nullptr; dev = TileSetDev{};
   }
 };
@@ -883,6 +951,7 @@ namespace {
 int upload_tiles(ssdk_encoder* e, const TileSetHost* h, int n_linear_tiles, TileSetOwned& o) {
   const int n_tiles = h ? h->n_tiles : n_linear_tiles;
   SSDK_CHECK_CUDA(cudaMalloc(&o.d_bbox, (size_t)n_tiles * 4 * sizeof(double)));
+  SSDK_CHECK_CUDA(cudaMalloc(&o.d_cls, (size_t)n_tiles * (kTile / 32) * 2 * sizeof(float4)));
   o.dev.n_tiles = n_tiles; o.dev.linear = h ? 0 : 1;
   if (h) {
     std::vector<int2> m(h->map.size());
@@ -915,7 +984,8 @@ int upload_tiles(ssdk_encoder* e, const TileSetHost* h, int n_linear_tiles, Tile
     o.dev.map = o.d_map; o.dev.runs = o.d_runs; o.dev.tile_of = o.d_tile_of; o.dev.aligned_mask = o.d_mask;
   }
   o.dev.bbox = o.d_bbox;
-  tile_bbox_kernel<<<n_tiles, kTile>>>(e->p, o.dev, o.d_bbox);
+  o.dev.cls = o.d_cls;
+  tile_bbox_kernel<<<n_tiles, kTile>>>(e->p, o.dev, o.d_bbox, o.d_cls);
   SSDK_COUNT_LAUNCH(e->ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;
