@@ -51,7 +51,6 @@ struct EncParams {
 };
 
 struct EncScratch {             // per call, global memory; TG = total number of ground-truth boxes in the batch
-  float* tU;                    // [n_tiles*TG] upper bound of the best IoU between a box and the anchors of a tile
   double* tV;                   // [n_tiles*TG] best EXACT IoU among the evaluated pairs (0: none)
   int* tI;                      // [n_tiles*TG] its prior index (lowest on ties)
   const float* lb;              // [TG] lower bound of each box's row maximum, or NULL (= 0)
@@ -296,33 +295,53 @@ __device__ void warp_tile_best(const EncParams& p, const TileSetDev& ts, const B
   out_v = bv; out_i = bi;
 }
 
-// One warp: the exact best anchor of `gb` over ALL tiles, ignoring `removed`, from the per-tile upper bounds alone: tiles are
-// visited in descending-bound order until the next bound is below the best exact value found.  General and exact, but slow
-// when many tiles tie at the maximum -- only used when a row drops below its lower bound during the sequential rounds.
-__device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const float* ucol, int stride, const int* removed,
-                              int n_removed, double& out_v, int& out_i) {
+// Upper bound (can only err upwards) of the float64 IoU between ANY anchor of a 32-thread slice (bounds k0, k1 of
+// TileSetDev::cls) and a box given by outward-rounded float32 corners gf and its area rounded down.
+__device__ __forceinline__ float slice_iou_bound(const float4 k0, const float4 k1, const float4 gf, float g_area) {
+  const float ox = fmaxf(fminf(fminf(k1.x, __fsub_ru(gf.z, gf.x)), fminf(__fsub_ru(k0.z, gf.x), __fsub_ru(gf.z, k0.x))), 0.f);
+  const float oy = fmaxf(fminf(fminf(k1.y, __fsub_ru(gf.w, gf.y)), fminf(__fsub_ru(k0.w, gf.y), __fsub_ru(gf.w, k0.y))), 0.f);
+  const float inter = __fmul_ru(ox, oy);
+  const float un = fmaxf(__fsub_rd(__fadd_rd(k1.z, g_area), inter), 1e-30f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(un));
+  return __fmul_ru(__fmul_ru(inter, r), 1.0f + 4.76837158203125e-7f);          // (1 + 2^-21): the reciprocal's ulp
+}
+
+// One warp: the exact best anchor of `gb` over ALL slices of all tiles, ignoring `removed`, starting from a known candidate
+// (out_v, out_i) (0 / INT_MAX for none).  Lanes test 32 slice bounds at a time; a slice is evaluated exactly (one anchor per
+// lane) only while its bound reaches the best value found so far.  Used when a row falls below its lower bound after losing
+// its prior: pairs under that bound were never evaluated by the tile pass.
+__device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const int* removed, int n_removed,
+                              double& out_v, int& out_i) {
   const int lane = threadIdx.x & 31;
-  double best = 0.0; int bidx = INT_MAX;
-  float cur_u = 0.f; int cur_t = -1; bool first = true;
-  for (;;) {
-    float nu = 0.f; int nt = INT_MAX;                    // next tile after the cursor in (bound desc, tile asc) order
-    for (int t = lane; t < ts.n_tiles; t += 32) {
-      const float u = __ldcg(ucol + (size_t)t * stride);
-      const bool after = first || (u < cur_u) || (u == cur_u && t > cur_t);
-      if (after && u > 0.f && (u > nu || (u == nu && t < nt))) { nu = u; nt = t; }
+  const float4 gf = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
+  const float g_area = __double2float_rd(gb.area);
+  double best = out_v; int bidx = out_i;
+  const int n_slices = ts.n_tiles * (kTile / 32);
+  for (int base = 0; base < n_slices; base += 32) {
+    const int sidx = base + lane;
+    float bound = -1.f;
+    if (sidx < n_slices) bound = slice_iou_bound(__ldg(ts.cls + (size_t)sidx * 2), __ldg(ts.cls + (size_t)sidx * 2 + 1), gf, g_area);
+    unsigned m = __ballot_sync(0xffffffffu, bound > 0.f && (double)bound >= best);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int sl = base + src;
+      int pos;
+      const int a = tile_anchor(ts, sl / (kTile / 32), (sl % (kTile / 32)) * 32 + lane, p.P, pos);
+      double v = 0.0; int vi = INT_MAX;
+      if (a >= 0) {
+        const Box ab = load_anchor(p, a);
+        const double inter = inter_area(gb, ab);
+        if (inter > 0.0) {
+          const double iv = iou_value(gb, ab, inter);
+          if (iv > 0.0 && !is_removed(removed, n_removed, a)) { v = iv; vi = a; }
+        }
+      }
+      warp_argmax(v, vi);
+      if (v > best || (v == best && v > 0.0 && vi < bidx)) { best = v; bidx = vi; }
+      m &= __ballot_sync(0xffffffffu, (double)bound >= best);     // the rest of this batch against the improved best
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ou = __shfl_xor_sync(0xffffffffu, nu, o);
-      const int ot = __shfl_xor_sync(0xffffffffu, nt, o);
-      if (ou > nu || (ou == nu && ot < nt)) { nu = ou; nt = ot; }
-    }
-    if (nt == INT_MAX) break;
-    if ((double)nu < best) break;                        // no anchor of the remaining tiles can reach (or tie) the best
-    double bv; int bi;
-    warp_tile_best(p, ts, gb, nt, removed, n_removed, bv, bi);
-    if (bv > best || (bv == best && bv > 0.0 && bi < bidx)) { best = bv; bidx = bi; }
-    cur_u = nu; cur_t = nt; first = false;
   }
   out_v = best; out_i = bidx;
 }
@@ -369,7 +388,8 @@ __global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ E
 // match_bipartite_greedy (matching_utils.py:63-77), run by the last CTA of an image
 // ------------------------------------------------------------------------------------------
 __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
-                             int b, const double* s_gbox, unsigned char* scratch, float* __restrict__ out_y, int* __restrict__ out_match) {
+                             int b, const double* s_gbox, unsigned char* scratch, double* pv, int* pi, float* __restrict__ out_y,
+                             int* __restrict__ out_match) {
   __shared__ int s_flag[2];
   double* rv = reinterpret_cast<double*>(scratch);           // [G] current row maximum
   int* ra = reinterpret_cast<int*>(rv + G);                   // [G] its (first) prior index
@@ -381,19 +401,33 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     Box q; q.x0 = s_gbox[g * 5]; q.y0 = s_gbox[g * 5 + 1]; q.x1 = s_gbox[g * 5 + 2]; q.y1 = s_gbox[g * 5 + 3]; q.area = s_gbox[g * 5 + 4];
     return q;
   };
-  // exact row maxima: one thread per box over the tile bests (coalesced: consecutive threads read consecutive boxes)
-  for (int g = tid; g < G; g += kTile) {
-    double bv = 0.0; int bi = INT_MAX;
-    const size_t col = (size_t)(g0 + g);
-#pragma unroll 4
-    for (int t = 0; t < ts.n_tiles; ++t) {
-      const double v = __ldcg(sc.tV + (size_t)t * TG + col);
-      if (v > 0.0) {
-        const int i = __ldcg(sc.tI + (size_t)t * TG + col);
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  // exact row maxima over the tile bests: kTile / G threads per box (each scans every nparts-th tile, eight loads in flight),
+  // combined through shared memory; consecutive threads read consecutive boxes
+  {
+    const int nparts = G < kTile ? (kTile / G < kTile / 32 ? kTile / G : kTile / 32) : 1;       // <= 8: pv / pi hold 8 * G entries
+    for (int gbase = 0; gbase < G; gbase += kTile) {
+      const int g = gbase + (nparts > 1 ? tid % G : tid), part = nparts > 1 ? tid / G : 0;
+      double bv = 0.0; int bi = INT_MAX;
+      if (g < G && part < nparts) {
+        const size_t col = (size_t)(g0 + g);
+#pragma unroll 8
+        for (int t = part; t < ts.n_tiles; t += nparts) {
+          const double v = __ldcg(sc.tV + (size_t)t * TG + col);
+          const int i = __ldcg(sc.tI + (size_t)t * TG + col);
+          if (v > 0.0 && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+        }
+        pv[part * G + g] = bv; pi[part * G + g] = bi;
       }
+      __syncthreads();
+      if (g < G && part == 0) {
+        for (int q = 1; q < nparts; ++q) {
+          const double v = pv[q * G + g]; const int i = pi[q * G + g];
+          if (v > 0.0 && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+        }
+        rv[g] = bv; ra[g] = (bv > 0.0) ? bi : 0;                  // argmax of an all-zero row is 0
+      }
+      __syncthreads();
     }
-    rv[g] = bv; ra[g] = (bv > 0.0) ? bi : 0;                    // argmax of an all-zero row is 0
   }
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
   __syncthreads();
@@ -500,7 +534,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         }
         // pairs below the row's lower bound were never evaluated: if the best that is left fell below it, search all tiles
         const float lbg = sc.lb ? __ldg(sc.lb + col) : 0.f;
-        if (nv < (double)lbg) warp_row_best(p, ts, gb, sc.tU + col, TG, removed, n_removed, nv, ni);
+        if (nv < (double)lbg) { if (!(nv > 0.0)) { nv = 0.0; ni = INT_MAX; } warp_row_best(p, ts, gb, removed, n_removed, nv, ni); }
         if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
       }
       __syncthreads();
@@ -607,6 +641,8 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   if (blockIdx.x == 0 && tid == 0 && any_bad && status) atomicMax(status, b + 1);
 
   bool store_pending = false;
+  int prev_one = -1;                                            // staging-row entry this thread set to 1 in the previous tile
+  for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barrier below)
   for (int tile = tile0; tile < tile1; ++tile) {
     if (tile != tile0) {
       a = tile_anchor(ts, tile, tid, p.P, pos);
@@ -652,11 +688,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
         const int g = s_cand[c];
         const float4 gf = s_gf[g];
         const float4 gq = s_gq[g];
-        const float ox = fmaxf(fminf(fminf(k1.x, __fsub_ru(gf.z, gf.x)), fminf(__fsub_ru(k0.z, gf.x), __fsub_ru(gf.z, k0.x))), 0.f);
-        const float oy = fmaxf(fminf(fminf(k1.y, __fsub_ru(gf.w, gf.y)), fminf(__fsub_ru(k0.w, gf.y), __fsub_ru(gf.w, k0.y))), 0.f);
-        const float inter = __fmul_ru(ox, oy);
-        const float un = fmaxf(__fsub_rd(__fadd_rd(k1.z, gq.x), inter), 1e-30f);
-        const float um = __fmul_ru(__fmul_ru(inter, rcp_approx(un)), 1.0f + 4.76837158203125e-7f);   // (1 + 2^-21): the reciprocal's ulp
+        const float um = slice_iou_bound(k0, k1, gf, gq.x);
         keep = um >= gq.z;
         s_wU[warp * Gs + c] = __float_as_uint(um);
       }
@@ -718,26 +750,23 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     // ---- per (gt, tile) results -> global (consecutive threads write consecutive boxes) ----
     for (int g = tid; g < G; g += kTile) {
       const int c = slot_of[g];
-      float u = 0.f; double bv = 0.0; int bi = INT_MAX;
+      double bv = 0.0; int bi = INT_MAX;
       if (c >= 0) {
-        unsigned m = 0;
         const float q_row = s_gq[g].y;
 #pragma unroll
         for (int w = 0; w < kTile / 32; ++w) {
-          const unsigned wu = s_wU[w * Gs + c];
-          m = max(m, wu);
-          if (__uint_as_float(wu) >= q_row) {                 // slice w evaluated its pairs with the box exactly ...
+          if (__uint_as_float(s_wU[w * Gs + c]) >= q_row) {     // slice w evaluated its pairs with the box exactly ...
             const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
             if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
           }
         }
         if (!(bv > 0.0)) { bv = 0.0; bi = INT_MAX; }
-        u = __uint_as_float(m);
       }
       const size_t o = (size_t)tile * TG + (size_t)(g0 + g);
-      sc.tU[o] = u; sc.tV[o] = bv; sc.tI[o] = bi;
+      sc.tV[o] = bv; sc.tI[o] = bi;
     }
     // ---- 4. this anchor's row ----
+    if (prev_one >= 0) { rows[prev_one] = 0.f; prev_one = -1; }   // (the previous tile's bulk store has finished reading: barrier above)
     if (live) {
       RowDecision dec{-1, false};
       double val = best;
@@ -746,7 +775,16 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
         if (p.multi && val >= p.pos_thr) { dec.match_g = arg; val = 0.0; }   // column zeroed after matching (:381)
         if (val >= p.neg_lim) dec.neutral = true;                            // :388-390
       }
-      emit_row(p, gt, gt_f64, g0, at, dec, rows + (size_t)pos * W);
+      // the class part of the staging rows is kept all-zero between tiles: set this row's single 1, remember where it went
+      const RowCompact r = make_row(p, gt, gt_f64, g0, at, dec);
+      float* dst = rows + (size_t)pos * W;
+      if (r.one >= 0) { dst[r.one] = 1.f; prev_one = pos * W + r.one; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dst[p.C + k] = r.o4[k];
+        dst[p.C + 4 + k] = (float)at[k];
+        dst[p.C + 8 + k] = (float)p.var[k];
+      }
       if (out_match) out_match[(size_t)b * p.P + a] = (dec.match_g >= 0) ? dec.match_g : (dec.neutral ? -2 : -1);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the rows -> visible to the bulk copy engine
@@ -808,7 +846,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   }
   __syncthreads();
   if (!s_last) return;
-  finish_image(p, ts, sc, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, out_y, out_match);
+  finish_image(p, ts, sc, gt, gt_f64, g0, G, b, s_gbox, smem_raw + L.rows, s_wV, s_wI, out_y, out_match);
 }
 
 __global__ void tile_bbox_kernel(EncParams p, TileSetDev ts, double* __restrict__ bbox, float4* __restrict__ cls) {
@@ -1126,15 +1164,14 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   int tpc = max_g <= 16 ? 1 : (max_g <= 48 ? 2 : 4);
   if (const char* s = getenv("SSDK_ENC_TPC")) tpc = std::max(1, atoi(s));
   while (tpc > 1 && (long long)ceil_div(ts.n_tiles, tpc) * B < 8ll * e->ctx->sm_count) tpc >>= 1;
-  // scratch: tV (f64) | tU (f32) | tI (i32) each [n_tiles * TG], lb [TG]
+  // scratch: tV (f64) | tI (i32) each [n_tiles * TG], lb [TG]
   const size_t TG = (size_t)(total_g > 0 ? total_g : 1);
   const size_t nt = TG * (size_t)ts.n_tiles;
-  int rc = e->tiles.ensure(nt * 16 + TG * 4 + 64);
+  int rc = e->tiles.ensure(nt * 12 + TG * 4 + 64);
   if (rc) return rc;
   EncScratch sc{};
   sc.tV = reinterpret_cast<double*>(e->tiles.ptr);
-  sc.tU = reinterpret_cast<float*>(sc.tV + nt);
-  sc.tI = reinterpret_cast<int*>(sc.tU + nt);
+  sc.tI = reinterpret_cast<int*>(sc.tV + nt);
   float* lb = reinterpret_cast<float*>(sc.tI + nt);
   sc.lb = use_lb ? lb : nullptr;
   sc.TG = (int)TG;
