@@ -793,6 +793,8 @@ struct FirstArgs {
   ActBuf in;
   const __nv_bfloat16* w_hi; const __nv_bfloat16* w_lo;   // [kblocks][BN][64] swizzled images
   int KH, KW, dil, pad_t, pad_l;
+  int tap_off[32];            // element offset of tap t's 4-channel word relative to the output pixel's own word in the input planes
+                              // (the planes' zero border covers every tap: checked on the host)
   int kblocks, ksteps;        // 64-wide blocks / 16-wide MMA steps that cover taps * 4
   int BN, stages, split;
   long long M;                // B * Ho * Wo output pixels
@@ -897,30 +899,31 @@ __global__ void __launch_bounds__(kFirstThreads, 1) conv_first_kernel(const __gr
         const int rem = (int)(v - (long long)n * fa.Ho * fa.Wo);
         y = rem / fa.Wo; x = rem - y * fa.Wo;
       }
-      mbar_wait(emptyA(st), ((uint32_t)(it / SA) & 1u) ^ 1u);
-      unsigned char* stage = smem_al + (a_stage * st);
-      for (int s0 = 0; s0 < slots; s0 += 4) {                          // four taps in flight per round
-        uint2 h[4], l[4];
+      const size_t src0 = valid ? act_index(fa.in, n, y, x) : 0;
+      // all loads of a round are issued before the first store (twelve taps = the whole 3x3 kernel in one round trip)
+      constexpr int kRound = 12;
+      uint2 h[kRound], l[kRound];
+      for (int s0 = 0; s0 < slots; s0 += kRound) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kRound; ++j) {
           const int tap = s0 + j;
           h[j] = make_uint2(0, 0); l[j] = make_uint2(0, 0);
           if (valid && tap < taps) {
-            const int kh = tap / fa.KW, kw = tap - kh * fa.KW;
-            const int iy = y + kh * fa.dil - fa.pad_t, ix = x + kw * fa.dil - fa.pad_l;
-            if (iy >= 0 && iy < fa.in.H && ix >= 0 && ix < fa.in.W) {
-              const size_t src = act_index(fa.in, n, iy, ix);
-              h[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.hi + src));
-              if (split) l[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.lo + src));
-            }
+            const long long src = (long long)src0 + fa.tap_off[tap];
+            h[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.hi + src));
+            if (split) l[j] = __ldg(reinterpret_cast<const uint2*>(fa.in.lo + src));
           }
         }
+        if (s0 == 0) mbar_wait(emptyA(st), ((uint32_t)(it / SA) & 1u) ^ 1u);   // (the loads above do not touch the stage)
+        unsigned char* stage = smem_al + (a_stage * st);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kRound; ++j) {
           const int tap = s0 + j;
-          const uint32_t off = (uint32_t)(tap >> 4) * kATile + (uint32_t)r * 128u + ((uint32_t)(((tap >> 1) & 7) ^ (r & 7)) << 4) + (uint32_t)(tap & 1) * 8u;
-          *reinterpret_cast<uint2*>(stage + off) = h[j];
-          if (split) *reinterpret_cast<uint2*>(stage + a_plane + off) = l[j];
+          if (tap < slots) {
+            const uint32_t off = (uint32_t)(tap >> 4) * kATile + (uint32_t)r * 128u + ((uint32_t)(((tap >> 1) & 7) ^ (r & 7)) << 4) + (uint32_t)(tap & 1) * 8u;
+            *reinterpret_cast<uint2*>(stage + off) = h[j];
+            if (split) *reinterpret_cast<uint2*>(stage + a_plane + off) = l[j];
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMA's async proxy
@@ -976,6 +979,9 @@ void first_weight_image(const float* hwio, int taps, int cin, int cout, int BN, 
       }
 }
 
+bool first_border_ok(const ActBuf& in, int kh, int kw, int dil, int pad_t, int pad_l) {
+  return in.pad >= pad_t && in.pad >= pad_l && in.pad >= (kh - 1) * dil - pad_t && in.pad >= (kw - 1) * dil - pad_l;
+}
 int first_tc_supported(int taps, int cin, int cout) { return cin <= 4 && taps * 4 <= 128 && cout % 8 == 0 && cout <= 128; }
 
 int launch_conv_first(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
@@ -985,6 +991,11 @@ int launch_conv_first(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const 
   memset(&fa, 0, sizeof(fa));
   fa.in = in; fa.w_hi = w_hi; fa.w_lo = w_lo;
   fa.KH = kh; fa.KW = kw; fa.dil = dil; fa.pad_t = pad_t; fa.pad_l = pad_l;
+  SSDK_REQUIRE(first_border_ok(in, kh, kw, dil, pad_t, pad_l), "image-facing convolution: the input planes' zero border is too small");
+  for (int t = 0; t < kh * kw; ++t) {
+    const int dy = (t / kw) * dil - pad_t, dx = (t % kw) * dil - pad_l;
+    fa.tap_off[t] = (dy * in.Wp() + dx) * in.Cs;
+  }
   const int K = kh * kw * 4;
   fa.ksteps = (K + 15) / 16; fa.kblocks = (K + 63) / 64;
   fa.BN = (out.C + 15) / 16 * 16;

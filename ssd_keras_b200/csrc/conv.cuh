@@ -98,6 +98,7 @@ int launch_conv_direct(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const
                        const float* bn_shift, int act, int kh, int kw, int dil, int pad_t, int pad_l, cudaStream_t stream);
 // image-facing layer on the tensor cores (gathered A tile, weights resident in shared memory as a swizzled image)
 int first_tc_supported(int taps, int cin, int cout);
+bool first_border_ok(const ActBuf& in, int kh, int kw, int dil, int pad_t, int pad_l);
 void first_weight_image(const float* hwio, int taps, int cin, int cout, int BN, int kblocks, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
 int launch_conv_first(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                       const float* bias, const float* bn_scale, const float* bn_shift, int act, int kh, int kw, int dil, int pad_t,

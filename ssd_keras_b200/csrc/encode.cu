@@ -151,9 +151,6 @@ __device__ __forceinline__ Box load_anchor(const EncParams& p, int a) {
   return corners_from_template(t, p.coords, p.d);
 }
 
-__device__ __forceinline__ bool bbox_hits(const double* bb, const Box& g) {
-  return (bb[2] > g.x0) && (bb[0] < g.x1) && (bb[3] > g.y0) && (bb[1] < g.y1);
-}
 
 // ------------------------------------------------------------------------------------------
 // IoU matrix (tests / microbench): out[g*P + a], bit-exact float64.
@@ -312,35 +309,45 @@ __device__ __forceinline__ float slice_iou_bound(const float4 k0, const float4 k
 // lane) only while its bound reaches the best value found so far.  Used when a row falls below its lower bound after losing
 // its prior: pairs under that bound were never evaluated by the tile pass.
 __device__ void warp_row_best(const EncParams& p, const TileSetDev& ts, const Box& gb, const int* removed, int n_removed,
-                              double& out_v, int& out_i) {
+                              double& out_v, int& out_i, int part, int nparts) {
+  // (this warp takes every nparts-th batch of 32 slices; four batches of bounds are computed before any is acted on, so their
+  //  loads overlap)
   const int lane = threadIdx.x & 31;
   const float4 gf = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
   const float g_area = __double2float_rd(gb.area);
   double best = out_v; int bidx = out_i;
   const int n_slices = ts.n_tiles * (kTile / 32);
-  for (int base = 0; base < n_slices; base += 32) {
-    const int sidx = base + lane;
-    float bound = -1.f;
-    if (sidx < n_slices) bound = slice_iou_bound(__ldg(ts.cls + (size_t)sidx * 2), __ldg(ts.cls + (size_t)sidx * 2 + 1), gf, g_area);
-    unsigned m = __ballot_sync(0xffffffffu, bound > 0.f && (double)bound >= best);
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      const int sl = base + src;
-      int pos;
-      const int a = tile_anchor(ts, sl / (kTile / 32), (sl % (kTile / 32)) * 32 + lane, p.P, pos);
-      double v = 0.0; int vi = INT_MAX;
-      if (a >= 0) {
-        const Box ab = load_anchor(p, a);
-        const double inter = inter_area(gb, ab);
-        if (inter > 0.0) {
-          const double iv = iou_value(gb, ab, inter);
-          if (iv > 0.0 && !is_removed(removed, n_removed, a)) { v = iv; vi = a; }
+  for (int base0 = part * 32; base0 < n_slices; base0 += nparts * 32 * 4) {
+    float bound[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int sidx = base0 + u * nparts * 32 + lane;
+      bound[u] = -1.f;
+      if (sidx < n_slices) bound[u] = slice_iou_bound(__ldg(ts.cls + (size_t)sidx * 2), __ldg(ts.cls + (size_t)sidx * 2 + 1), gf, g_area);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int base = base0 + u * nparts * 32;
+      unsigned m = __ballot_sync(0xffffffffu, bound[u] > 0.f && (double)bound[u] >= best);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int sl = base + src;
+        int pos;
+        const int a = tile_anchor(ts, sl / (kTile / 32), (sl % (kTile / 32)) * 32 + lane, p.P, pos);
+        double v = 0.0; int vi = INT_MAX;
+        if (a >= 0) {
+          const Box ab = load_anchor(p, a);
+          const double inter = inter_area(gb, ab);
+          if (inter > 0.0) {
+            const double iv = iou_value(gb, ab, inter);
+            if (iv > 0.0 && !is_removed(removed, n_removed, a)) { v = iv; vi = a; }
+          }
         }
+        warp_argmax(v, vi);
+        if (v > best || (v == best && v > 0.0 && vi < bidx)) { best = v; bidx = vi; }
+        m &= __ballot_sync(0xffffffffu, (double)bound[u] >= best);   // the rest of this batch against the improved best
       }
-      warp_argmax(v, vi);
-      if (v > best || (v == best && v > 0.0 && vi < bidx)) { best = v; bidx = vi; }
-      m &= __ballot_sync(0xffffffffu, (double)bound >= best);     // the rest of this batch against the improved best
     }
   }
   out_v = best; out_i = bidx;
@@ -506,12 +513,12 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         if (rv[g] > 0.0 && ra[g] == a_star) victims[atomicAdd(&s_nvict, 1)] = g;
       __syncthreads();
       const int n_vict = s_nvict;
+      // C1. per row (one warp each): re-evaluate the tile of the lost prior without the taken priors, reduce the row again;
+      // repeat while the new best is itself a taken prior recorded by another tile
       for (int vi = warp; vi < n_vict; vi += kTile / 32) {
         const int gg = victims[vi];
         const size_t col = (size_t)(g0 + gg);
         const Box gb = gbox(gg);
-        // re-evaluate the tile of the lost prior without the taken priors, reduce the row again; repeat while the new best is itself
-        // a taken prior recorded by another tile
         int stale = a_star;
         double nv; int ni;
         for (;;) {
@@ -532,10 +539,31 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
           if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
           stale = ni;
         }
-        // pairs below the row's lower bound were never evaluated: if the best that is left fell below it, search all tiles
-        const float lbg = sc.lb ? __ldg(sc.lb + col) : 0.f;
-        if (nv < (double)lbg) { if (!(nv > 0.0)) { nv = 0.0; ni = INT_MAX; } warp_row_best(p, ts, gb, removed, n_removed, nv, ni); }
-        if (lane == 0) { rv[gg] = nv; ra[gg] = (nv > 0.0) ? ni : 0; }
+        if (lane == 0) { pv[vi] = (nv > 0.0) ? nv : 0.0; pi[vi] = (nv > 0.0) ? ni : INT_MAX; }
+      }
+      __syncthreads();
+      // C2. pairs below a row's lower bound were never evaluated by the tile pass: a row whose best that is left fell below it is
+      // searched over all slices, by all warps together
+      for (int vi = 0; vi < n_vict; ++vi) {
+        const int gg = victims[vi];
+        const float lbg = sc.lb ? __ldg(sc.lb + g0 + gg) : 0.f;
+        double nv = pv[vi]; int ni = pi[vi];
+        if (!(nv < (double)lbg)) continue;                       // uniform over the CTA
+        warp_row_best(p, ts, gbox(gg), removed, n_removed, nv, ni, warp, kTile / 32);
+        if (lane == 0) { s_cv[warp] = nv; s_ci[warp] = ni; }
+        __syncthreads();
+        if (tid == 0) {
+          double bv = 0.0; int bi = INT_MAX;
+          for (int w = 0; w < kTile / 32; ++w)
+            if (s_cv[w] > bv || (s_cv[w] == bv && s_cv[w] > 0.0 && s_ci[w] < bi)) { bv = s_cv[w]; bi = s_ci[w]; }
+          pv[vi] = bv; pi[vi] = bi;
+        }
+        __syncthreads();
+      }
+      for (int vi = tid; vi < n_vict; vi += kTile) {
+        const int gg = victims[vi];
+        const double nv = pv[vi];
+        rv[gg] = nv; ra[gg] = (nv > 0.0) ? pi[vi] : 0;
       }
       __syncthreads();
     }
@@ -560,7 +588,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, gf, gq, wU, wV, wI, slot, cand, wl, total;
+  size_t rows, gbox, gf, gq, wU, wV, wI, wl, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
@@ -576,9 +604,7 @@ __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   s.wV = up16(s.gq + gs * 16);                                // [8*G] f64: per-slice best exact IoU of a candidate
   s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-slice bound of the IoU of a candidate
   s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-slice prior index of the best exact IoU
-  s.slot = up16(s.wI + gs * 32);                              // [G] candidate slot of a gt (-1: not a candidate of this tile)
-  s.cand = up16(s.slot + gs * 4);                             // [G] gt index of a candidate slot (ascending)
-  s.wl = up16(s.cand + gs * 4);                               // [8*G] u16: per-slice list of candidate slots that pass the slice's bound
+  s.wl = up16(s.wI + gs * 32);                                // [8*G] u16: per-slice list of the boxes that pass the slice's bound
   s.total = up16(s.wl + gs * 16) + 16;
   return s;
 }
@@ -590,7 +616,6 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
                                                              const __grid_constant__ EncScratch sc, float* __restrict__ out_y,
                                                              int* __restrict__ out_match, int* __restrict__ status) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ int s_wcnt[kTile / 32];
   __shared__ int s_last;
   const int b = blockIdx.y;
   const int g0 = INLINE_OFFS ? offs_arg.v[b] : offs_dev[b];
@@ -605,8 +630,6 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   double* s_wV = reinterpret_cast<double*>(smem_raw + L.wV);
   unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
   int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
-  int* slot_of = reinterpret_cast<int*>(smem_raw + L.slot);
-  int* s_cand = reinterpret_cast<int*>(smem_raw + L.cand);
   unsigned short* s_wl = reinterpret_cast<unsigned short*>(smem_raw + L.wl);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -648,52 +671,27 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       a = tile_anchor(ts, tile, tid, p.P, pos);
       if (a >= 0) load_anchor_t(p, a, at);
     }
-    // ---- 2. ordered candidate list (ascending gt index): boxes that touch the tile's bounding box ----
-    const double bb[4] = {ts.bbox[tile * 4], ts.bbox[tile * 4 + 1], ts.bbox[tile * 4 + 2], ts.bbox[tile * 4 + 3]};
-    int ncand = 0;
-    for (int gbase = 0; gbase < G; gbase += kTile) {
-      const int g = gbase + tid;
-      bool hit = false;
-      if (g < G) {
-        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3];
-        hit = bbox_hits(bb, gb);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0) s_wcnt[warp] = __popc(m);
-      __syncthreads();
-      int wbase = ncand, total = 0;
-#pragma unroll
-      for (int w = 0; w < kTile / 32; ++w) { const int c = s_wcnt[w]; if (w < warp) wbase += c; total += c; }
-      if (hit) {
-        const int cpos = wbase + __popc(m & ((1u << lane) - 1));
-        s_cand[cpos] = g; slot_of[g] = cpos;
-      } else if (g < G) {
-        slot_of[g] = -1;
-      }
-      ncand += total;
-      __syncthreads();
-    }
-    // ---- 2b. per 32-anchor slice: which candidates can reach their threshold with ANY anchor of the slice ----
+    // ---- 2. per 32-anchor slice: which boxes can reach their threshold with ANY anchor of the slice ----
     // Bound of the IoU of a whole slice against a box: the overlap along x is at most min(widest anchor, box width, rightmost anchor
     // edge - box left, box right - leftmost anchor edge), likewise along y; the union is at least smallest anchor area + box area -
     // that intersection.  With the box-shape-major thread order a slice holds one shape at neighbouring positions, so the bound is
-    // tight and only the few boxes near the slice survive: the per-anchor loop below runs over ~1 candidate instead of ~20.
+    // tight and only the few boxes near the slice survive: the per-anchor loop below runs over ~1 box instead of all that touch the
+    // tile.  Every warp works on its own list (ascending box index): no CTA-wide barrier before the results are combined.
     const float4 k0 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2);
     const float4 k1 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2 + 1);
     int nlist = 0;
-    for (int cb = 0; cb < ncand; cb += 32) {
-      const int c = cb + lane;
+    for (int gb0 = 0; gb0 < G; gb0 += 32) {
+      const int g = gb0 + lane;
       bool keep = false;
-      if (c < ncand) {
-        const int g = s_cand[c];
+      if (g < G) {
         const float4 gf = s_gf[g];
         const float4 gq = s_gq[g];
         const float um = slice_iou_bound(k0, k1, gf, gq.x);
         keep = um >= gq.z;
-        s_wU[warp * Gs + c] = __float_as_uint(um);
+        s_wU[warp * Gs + g] = __float_as_uint(um);
       }
       const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) s_wl[warp * Gs + nlist + __popc(m & ((1u << lane) - 1))] = (unsigned short)c;
+      if (keep) s_wl[warp * Gs + nlist + __popc(m & ((1u << lane) - 1))] = (unsigned short)g;
       nlist += __popc(m);
     }
     __syncwarp();
@@ -709,8 +707,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     }
     double best = 0.0; int best_g = -1;
     for (int k = 0; k < nlist; ++k) {
-      const int c = s_wl[warp * Gs + k];
-      const int g = s_cand[c];
+      const int g = s_wl[warp * Gs + k];
       const float4 gf = s_gf[g];
       const float4 gq = s_gq[g];
       // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
@@ -739,29 +736,26 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
         const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
         const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
         const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a : 0x7fffffffu);
-        if (lane == 0) { s_wV[warp * Gs + c] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + c] = (int)mi; }
+        if (lane == 0) { s_wV[warp * Gs + g] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + g] = (int)mi; }
       }
       // the slice's entry becomes the maximum of the per-pair bounds: ">= q_row" below then means "evaluated exactly"
-      if (lane == 0) s_wU[warp * Gs + c] = __float_as_uint(wmi);
+      if (lane == 0) s_wU[warp * Gs + g] = __float_as_uint(wmi);
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
     // ---- per (gt, tile) results -> global (consecutive threads write consecutive boxes) ----
     for (int g = tid; g < G; g += kTile) {
-      const int c = slot_of[g];
       double bv = 0.0; int bi = INT_MAX;
-      if (c >= 0) {
-        const float q_row = s_gq[g].y;
+      const float q_row = s_gq[g].y;
 #pragma unroll
-        for (int w = 0; w < kTile / 32; ++w) {
-          if (__uint_as_float(s_wU[w * Gs + c]) >= q_row) {     // slice w evaluated its pairs with the box exactly ...
-            const double v = s_wV[w * Gs + c]; const int i = s_wI[w * Gs + c];
-            if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
-          }
+      for (int w = 0; w < kTile / 32; ++w) {
+        if (__uint_as_float(s_wU[w * Gs + g]) >= q_row) {       // slice w evaluated its pairs with the box exactly ...
+          const double v = s_wV[w * Gs + g]; const int i = s_wI[w * Gs + g];
+          if (v > bv || (v == bv && v > 0.0 && i < bi)) { bv = v; bi = i; }
         }
-        if (!(bv > 0.0)) { bv = 0.0; bi = INT_MAX; }
       }
+      if (!(bv > 0.0)) { bv = 0.0; bi = INT_MAX; }
       const size_t o = (size_t)tile * TG + (size_t)(g0 + g);
       sc.tV[o] = bv; sc.tI[o] = bi;
     }

@@ -79,7 +79,8 @@ int build_conv(ssdk_model* m, int li) {
     m->flops_algo += fl;                 // counted as algorithmic FLOPs only (the timed conv launches exclude this layer)
     // inference plans: the layer runs on the tensor cores with a gathered A tile (conv_first_kernel); training plans keep the fp32
     // direct kernel, whose weights are the optimizer's master copy
-    if (!m->training && first_tc_supported(taps, cin, cout) && d.dilation >= 1 && !getenv("SSDK_NO_FIRST_TC")) {
+    if (!m->training && first_tc_supported(taps, cin, cout) && d.dilation >= 1 && first_border_ok(ia, d.kh, d.kw, d.dilation, d.pad_t, d.pad_l) &&
+        !getenv("SSDK_NO_FIRST_TC")) {
       std::vector<uint16_t> whi, wlo;
       const int K = taps * 4, BN = (cout + 15) / 16 * 16;
       first_weight_image(d.kernel, taps, cin, cout, BN, (K + 63) / 64, whi, wlo);
