@@ -57,6 +57,7 @@ struct EncScratch {             // per call, global memory; TG = total number of
   int* counters;                // [B] tickets
   int TG;
   int dbg;                      // experiment knobs (SSDK_ENC_DEBUG), 0 in production
+  unsigned long long* prof;     // SSDK_ENC_DEBUG=2: [16] nanoseconds / event counts of the matching stage, summed over images
 };
 
 struct TileSetDev {
@@ -404,6 +405,16 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
   int* matches = removed + G;                                 // [G]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = p.C + 12, TG = sc.TG;
+  unsigned long long t_prev = 0;
+  auto lap = [&](int slot) {                                  // SSDK_ENC_DEBUG=2: time since the previous lap -> prof[slot]
+    if (sc.prof && tid == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (slot >= 0) atomicAdd(sc.prof + slot, t - t_prev);
+      t_prev = t;
+    }
+  };
+  auto count = [&](int slot, int n) { if (sc.prof && tid == 0 && n) atomicAdd(sc.prof + slot, (unsigned long long)n); };
+  lap(-1);
   auto gbox = [&](int g) {
     Box q; q.x0 = s_gbox[g * 5]; q.y0 = s_gbox[g * 5 + 1]; q.x1 = s_gbox[g * 5 + 2]; q.y1 = s_gbox[g * 5 + 3]; q.area = s_gbox[g * 5 + 4];
     return q;
@@ -436,6 +447,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
       __syncthreads();
     }
   }
+  lap(0);
   if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
   __syncthreads();
   for (int g = tid; g < G; g += kTile) {
@@ -464,7 +476,9 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     for (int g = tid; g < G; g += kTile) matches[g] = 0;
     if (tid == 0) s_nrem = 0;
     __syncthreads();
+    lap(1);
     for (;;) {
+      count(8, 1);
       // A. the first row with a later duplicate
       double cv = -1.0; int ci = INT_MAX;
       for (int g = tid; g < G; g += kTile) {
@@ -504,6 +518,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         }
       }
       __syncthreads();
+      lap(2);
       if (f < 0) break;
       // C. the rows that pointed at f's prior recompute their maximum (one warp per row)
       const int n_removed = s_nrem;
@@ -513,6 +528,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         if (rv[g] > 0.0 && ra[g] == a_star) victims[atomicAdd(&s_nvict, 1)] = g;
       __syncthreads();
       const int n_vict = s_nvict;
+      count(9, n_vict);
       // C1. per row (one warp each): re-evaluate the tile of the lost prior without the taken priors, reduce the row again;
       // repeat while the new best is itself a taken prior recorded by another tile
       for (int vi = warp; vi < n_vict; vi += kTile / 32) {
@@ -542,6 +558,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         if (lane == 0) { pv[vi] = (nv > 0.0) ? nv : 0.0; pi[vi] = (nv > 0.0) ? ni : INT_MAX; }
       }
       __syncthreads();
+      lap(3);
       // C2. pairs below a row's lower bound were never evaluated by the tile pass: a row whose best that is left fell below it is
       // searched over all slices, by all warps together
       for (int vi = 0; vi < n_vict; ++vi) {
@@ -549,6 +566,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         const float lbg = sc.lb ? __ldg(sc.lb + g0 + gg) : 0.f;
         double nv = pv[vi]; int ni = pi[vi];
         if (!(nv < (double)lbg)) continue;                       // uniform over the CTA
+        count(10, 1);
         warp_row_best(p, ts, gbox(gg), removed, n_removed, nv, ni, warp, kTile / 32);
         if (lane == 0) { s_cv[warp] = nv; s_ci[warp] = ni; }
         __syncthreads();
@@ -566,6 +584,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
         rv[gg] = nv; ra[gg] = (nv > 0.0) ? pi[vi] : 0;
       }
       __syncthreads();
+      lap(4);
     }
     if (tid == 0 && s_nrem < G) matches[0] = 0;                  // rounds with nothing left to match select (box 0, prior 0)
   }
@@ -582,6 +601,9 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     emit_row(p, gt, gt_f64, g0, at, dec, out_y + ((size_t)b * p.P + a) * W);
     if (out_match) out_match[(size_t)b * p.P + a] = g;
   }
+  __syncthreads();
+  lap(5);
+  count(11, 1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1170,6 +1192,12 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   sc.lb = use_lb ? lb : nullptr;
   sc.TG = (int)TG;
   if (const char* s = getenv("SSDK_ENC_DEBUG")) sc.dbg = atoi(s);
+  static unsigned long long* d_prof = nullptr;
+  if (sc.dbg & 2) {
+    if (!d_prof) SSDK_CHECK_CUDA(cudaMalloc(&d_prof, 16 * sizeof(unsigned long long)));
+    SSDK_CHECK_CUDA(cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream));
+    sc.prof = d_prof;
+  }
   if (e->counters_n < (size_t)B) {
     SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
     rc = e->counters.ensure((size_t)B * sizeof(int));
@@ -1228,6 +1256,15 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   }
   SSDK_COUNT_LAUNCH(e->ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
+  if (sc.prof) {                                                // experiments only: synchronises
+    unsigned long long h[16];
+    SSDK_CHECK_CUDA(cudaStreamSynchronize(stream));
+    SSDK_CHECK_CUDA(cudaMemcpy(h, sc.prof, sizeof(h), cudaMemcpyDeviceToHost));
+    const double n = h[11] ? (double)h[11] : 1.0;
+    fprintf(stderr, "enc matching stage, per image (us): row maxima %.1f | duplicates? %.1f | A+B %.1f | C1 %.1f | C2+write %.1f | tail %.1f"
+                    " || iterations %.1f victims %.1f below-bound searches %.1f (images %llu)\n",
+            h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3, h[5] / n / 1e3, h[8] / n, h[9] / n, h[10] / n, h[11]);
+  }
   return SSDK_OK;
 }
 

@@ -335,6 +335,10 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
     LayerPlan& in = m->layers[d.input];
     const bool im2col = (d.stride != 1) || (in.C < 8);
     if (!im2col) in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)));
+    // the image-facing layer's gathered A tile (conv_first_kernel) reads its taps from the input planes' zero border
+    if (!desc->training && in.C < 8 && d.stride == 1)
+      in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_l),
+                                                   std::max((d.kh - 1) * d.dilation - d.pad_t, (d.kw - 1) * d.dilation - d.pad_l)));
     // training: the image-facing weight-gradient kernel reads its 3x3 window without bounds checks
     if (desc->training && in.C < 8 && d.stride == 1)
       in.need_pad = std::max(in.need_pad, d.dilation * std::max(d.kh - 1, d.kw - 1));
