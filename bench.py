@@ -335,12 +335,11 @@ def dist_extras(world, rank, peaks, model_inf_weights):
     ybuf = torch.empty((Bt, 8732, 33), dtype=torch.float32, device='cuda')
     tr = SSDTrainer(mt, Bt, lr=1e-4, momentum=0.9)
 
-    def step():
-        tr.train_on_batch(xt, enc.encode_device(gdev, offs, out=ybuf))
-    ms_overlap = timed(step)
-    tr.bucket_bytes = 1 << 40                                   # one bucket: the exchange starts when the backward pass is over
-    ms_serial = timed(step)
-    tr.bucket_bytes = 24 << 20
+    def step(overlap):
+        tr.train_on_batch(xt, enc.encode_device(gdev, offs, out=ybuf), overlap=overlap)
+    ms_overlap = timed(lambda: step(True))                      # gradient buckets on a side stream under the backward pass
+    ms_serial = timed(lambda: step(False))                      # one all-reduce when the backward pass is over
+    ms_default = ms_overlap if world > 2 else ms_serial         # what train_on_batch(overlap=None) runs at this world size
 
     def step_local():                                           # the same step without any exchange (what a single GPU does)
         loss, _, dy = tr._loss_and_dy(xt, enc.encode_device(gdev, offs, out=ybuf))
@@ -350,7 +349,8 @@ def dist_extras(world, rank, peaks, model_inf_weights):
     nbytes = tr.n_params * 4
     out['train_step_ssd300_b32_per_gpu'] = {
         'ms_overlapped_buckets': ms_overlap, 'ms_single_allreduce_after_backward': ms_serial, 'ms_no_exchange': ms_local,
-        'images_per_s': world * Bt * 1e3 / ms_overlap, 'allreduce_MB': nbytes / 1e6, 'buckets': len(tr.buckets()),
+        'ms_default': ms_default, 'default': 'bucketed from 4 ranks on, single exchange below (SSDTrainer.train_on_batch)',
+        'images_per_s': world * Bt * 1e3 / ms_default, 'allreduce_MB': nbytes / 1e6, 'buckets': len(tr.buckets()),
         'exposed_exchange_ms': ms_overlap - ms_local, 'unoverlapped_exchange_ms': ms_serial - ms_local,
         'allreduce_busbw_GBps_if_serial': (2.0 * (world - 1) / world * nbytes / 1e9) / max((ms_serial - ms_local) * 1e-3, 1e-9),
         'scaling': 'weak', 'loss_mode': 'replica'}

@@ -277,12 +277,23 @@ __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
 __device__ void warp_tile_best(const EncParams& p, const TileSetDev& ts, const Box& gb, int tile, const int* removed, int n_removed,
                                double& out_v, int& out_i) {
   const int lane = threadIdx.x & 31;
+  // the eight anchors of a lane: all index loads, then all anchor loads, then the arithmetic (one memory round trip each instead
+  // of eight dependent pairs)
+  int an[kTile / 32];
+  double at[kTile / 32][4];
+#pragma unroll
+  for (int k = 0; k < kTile / 32; ++k) { int pos; an[k] = tile_anchor(ts, tile, k * 32 + lane, p.P, pos); }
+#pragma unroll
+  for (int k = 0; k < kTile / 32; ++k) {
+    at[k][0] = at[k][1] = at[k][2] = at[k][3] = 0.0;
+    if (an[k] >= 0) load_anchor_t(p, an[k], at[k]);
+  }
   double bv = 0.0; int bi = INT_MAX;
-  for (int s = lane; s < kTile; s += 32) {
-    int pos;
-    const int a = tile_anchor(ts, tile, s, p.P, pos);
+#pragma unroll
+  for (int k = 0; k < kTile / 32; ++k) {
+    const int a = an[k];
     if (a < 0) continue;
-    const Box ab = load_anchor(p, a);
+    const Box ab = corners_from_template(at[k], p.coords, p.d);
     const double inter = inter_area(gb, ab);
     if (inter > 0.0) {
       const double v = iou_value(gb, ab, inter);
@@ -610,7 +621,7 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, gf, gq, wU, wV, wI, wl, total;
+  size_t rows, gbox, gf, gq, wU, wV, wI, wl, items, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
@@ -627,7 +638,8 @@ __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-slice bound of the IoU of a candidate
   s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-slice prior index of the best exact IoU
   s.wl = up16(s.wI + gs * 32);                                // [8*G] u16: per-slice list of the boxes that pass the slice's bound
-  s.total = up16(s.wl + gs * 16) + 16;
+  s.items = up16(s.wl + gs * 16);                             // [8*G] (slice << 16 | box) pairs whose exact per-slice best is needed, + counter
+  s.total = up16(s.items + gs * 32 + 16) + 16;
   return s;
 }
 
@@ -653,6 +665,8 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
   int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
   unsigned short* s_wl = reinterpret_cast<unsigned short*>(smem_raw + L.wl);
+  int* s_items = reinterpret_cast<int*>(smem_raw + L.items);
+  int* s_nitems = s_items + (size_t)(kTile / 32) * Gs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   const int tile0 = blockIdx.x * tpc;
@@ -688,6 +702,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   bool store_pending = false;
   int prev_one = -1;                                            // staging-row entry this thread set to 1 in the previous tile
   for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barrier below)
+  if (tid == 0) *s_nitems = 0;
   for (int tile = tile0; tile < tile1; ++tile) {
     if (tile != tile0) {
       a = tile_anchor(ts, tile, tid, p.P, pos);
@@ -741,31 +756,51 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
                                                              // maximum account for it)
       const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
       const float wmi = __fmul_ru(__uint_as_float(wm), 1.0f + 4.76837158203125e-7f);   // (1 + 2^-21): the reciprocal's ulp
-      const bool row_need = wmi >= gq.y;                     // the slice may hold the box's row maximum (warp-uniform)
-      const bool own_need = live && U >= p.thr_adj;          // the pair may matter for the anchor's own row
-      double val = 0.0;
-      if ((row_need && live) || own_need) {
+      const bool own_need = live && U >= p.thr_adj;          // the pair may matter for the anchor's own row -> exact float64 IoU
+      if (own_need) {
         Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
         const double inter64 = inter_area(gb, ab);
-        if (inter64 > 0.0) { val = iou_value(gb, ab, inter64); if (!(val > 0.0)) val = 0.0; }
-        if (own_need && val > best) { best = val; best_g = g; }    // strict '>' keeps the first gt on ties (np.argmax)
+        if (inter64 > 0.0) {
+          const double val = iou_value(gb, ab, inter64);
+          if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
+        }
       }
-      if (row_need) {
-        // best pair of the slice (lowest prior index on ties): REDUX on the two halves of the (non-negative) float64 bit pattern,
-        // then on the prior index
-        const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
-        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-        const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
-        const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a : 0x7fffffffu);
-        if (lane == 0) { s_wV[warp * Gs + g] = __hiloint2double((int)mh, (int)ml); s_wI[warp * Gs + g] = (int)mi; }
+      // the slice's entry becomes the maximum of the per-pair bounds; when it reaches the box's row threshold the slice may hold the
+      // box's row maximum: queued for exact evaluation (below), and ">= q_row" later means "evaluated exactly"
+      if (lane == 0) {
+        s_wU[warp * Gs + g] = __float_as_uint(wmi);
+        if (wmi >= gq.y) s_items[atomicAdd(s_nitems, 1)] = (warp << 16) | g;
       }
-      // the slice's entry becomes the maximum of the per-pair bounds: ">= q_row" below then means "evaluated exactly"
-      if (lane == 0) s_wU[warp * Gs + g] = __float_as_uint(wmi);
+    }
+    // ---- 3b. exact per-(box, slice) bests, dealt out over all warps ----
+    // These evaluations pile up in the slices of the best-fitting anchor shape (every anchor inside a large box ties its row
+    // maximum up to rounding): left to their own warps, two of eight would do all of it while six wait at the barrier.
+    __syncthreads();
+    const int n_items = *s_nitems;
+    for (int it = warp; it < n_items; it += kTile / 32) {
+      const int w = s_items[it] >> 16, g = s_items[it] & 0xffff;
+      int pos2;
+      const int a2 = tile_anchor(ts, tile, w * 32 + lane, p.P, pos2);
+      double val = 0.0;
+      if (a2 >= 0) {
+        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
+        const Box ab2 = load_anchor(p, a2);
+        const double inter64 = inter_area(gb, ab2);
+        if (inter64 > 0.0) { val = iou_value(gb, ab2, inter64); if (!(val > 0.0)) val = 0.0; }
+      }
+      // best pair of the slice (lowest prior index on ties): REDUX on the two halves of the (non-negative) float64 bit pattern,
+      // then on the prior index
+      const unsigned hi = (unsigned)__double2hiint(val), lo = (unsigned)__double2loint(val);
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      const bool top = (hi == mh) && (lo == ml) && (val > 0.0);
+      const unsigned mi = __reduce_min_sync(0xffffffffu, top ? (unsigned)a2 : 0x7fffffffu);
+      if (lane == 0) { s_wV[w * Gs + g] = __hiloint2double((int)mh, (int)ml); s_wI[w * Gs + g] = (int)mi; }
     }
     // the previous tile's bulk store must have finished reading the staging rows before they are rewritten
     if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
+    if (tid == 0) *s_nitems = 0;                                  // (next appended after the barrier that follows the row stores)
     // ---- per (gt, tile) results -> global (consecutive threads write consecutive boxes) ----
     for (int g = tid; g < G; g += kTile) {
       double bv = 0.0; int bi = INT_MAX;

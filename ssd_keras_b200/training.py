@@ -145,11 +145,14 @@ class SSDTrainer:
         self._buckets = (bucket_bytes, out)
         return out
 
-    def train_on_batch(self, images, y_true, group=None):
+    def train_on_batch(self, images, y_true, group=None, overlap=None):
         """forward + loss + backward + gradient exchange + SGD update.  Returns the per-image loss tensor (B,).
-        With several ranks the flat gradient buffer is all-reduced in buckets, from the top of the network down, each as soon
-        as its layers have been differentiated: NCCL runs on its own stream and overlaps the weight / data gradient kernels of
-        the lower layers."""
+        With several ranks the flat gradient buffer is all-reduced either in buckets, from the top of the network down, each as
+        soon as its layers have been differentiated (NCCL on its own stream under the weight / data gradient kernels of the lower
+        layers), or in one call after the backward pass.  ``overlap=None`` picks: measured on B200 at 2 ranks the whole 105 MB
+        exchange costs 0.5 ms alone while NCCL's kernels delay the persistent 148-CTA conv launches by more than that when they
+        run side by side, so the bucketed exchange is used from 4 ranks on (SSDK_OVERLAP=0/1 overrides)."""
+        import os
         import torch.distributed as dist
         on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         loss, _, dy = self._loss_and_dy(images, y_true)
@@ -157,8 +160,15 @@ class SSDTrainer:
             self._backward_layers(dy, len(self.model.specs) - 1, 0)
             self.apply(1.0)
             return loss
+        if overlap is None:
+            env = os.environ.get('SSDK_OVERLAP')
+            overlap = (env == '1') if env in ('0', '1') else dist.get_world_size(group) > 2
         from .distributed import all_reduce_buckets_
-        all_reduce_buckets_(self.grad, self.buckets(), lambda hi, lo: self._backward_layers(dy, hi, lo), group=group)
+        if overlap:
+            all_reduce_buckets_(self.grad, self.buckets(), lambda hi, lo: self._backward_layers(dy, hi, lo), group=group)
+        else:
+            self._backward_layers(dy, len(self.model.specs) - 1, 0)
+            dist.all_reduce(self.grad, group=group)
         # 'replica': the mean of the replicas' gradients; 'global': the shards' gradients of the GLOBAL batch mean add up
         self.apply(1.0 if self.loss_mode == 'global' else 1.0 / dist.get_world_size(group))
         return loss
