@@ -1063,9 +1063,60 @@ __global__ void maxpool_kernel(ActBuf in, ActBuf out, int KH, int KW, int stride
   if (out.lo) *reinterpret_cast<uint4*>(out.lo + o) = ol;
 }
 
+// 2x2 / stride 2 without top-left padding (every pool of the VGG trunk but pool5): the four taps are loaded up front (eight
+// independent 16-byte loads per thread); a tap that falls off the bottom / right edge ('same' pooling of an odd extent) is
+// clamped onto its in-range neighbour, which cannot change a first-maximum scan.
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(ActBuf in, ActBuf out) {
+  const int groups = in.Cs / 8;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)out.B * out.H * out.W * groups;
+  if (i >= total) return;
+  const int g = (int)(i % groups);
+  const size_t pix = i / groups;
+  const int xo = (int)(pix % out.W); const int yo = (int)((pix / out.W) % out.H); const int n = (int)(pix / ((size_t)out.W * out.H));
+  const int y0 = 2 * yo, x0 = 2 * xo, y1 = min(y0 + 1, in.H - 1), x1 = min(x0 + 1, in.W - 1);
+  const size_t s00 = act_index(in, n, y0, x0) + (size_t)g * 8, s01 = act_index(in, n, y0, x1) + (size_t)g * 8;
+  const size_t s10 = act_index(in, n, y1, x0) + (size_t)g * 8, s11 = act_index(in, n, y1, x1) + (size_t)g * 8;
+  uint4 h[4], l[4];
+  h[0] = __ldcs(reinterpret_cast<const uint4*>(in.hi + s00)); h[1] = __ldcs(reinterpret_cast<const uint4*>(in.hi + s01));
+  h[2] = __ldcs(reinterpret_cast<const uint4*>(in.hi + s10)); h[3] = __ldcs(reinterpret_cast<const uint4*>(in.hi + s11));
+  if (in.lo) {
+    l[0] = __ldcs(reinterpret_cast<const uint4*>(in.lo + s00)); l[1] = __ldcs(reinterpret_cast<const uint4*>(in.lo + s01));
+    l[2] = __ldcs(reinterpret_cast<const uint4*>(in.lo + s10)); l[3] = __ldcs(reinterpret_cast<const uint4*>(in.lo + s11));
+  } else {
+    l[0] = l[1] = l[2] = l[3] = make_uint4(0, 0, 0, 0);
+  }
+  float best[8];
+  uint32_t bh[8], bl[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bh[e] = 0; bl[e] = 0; }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const uint32_t hw[4] = {h[t].x, h[t].y, h[t].z, h[t].w}, lw[4] = {l[t].x, l[t].y, l[t].z, l[t].w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t hb = (hw[e >> 1] >> ((e & 1) * 16)) & 0xffffu, lb = (lw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+      const float v = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+      if (v > best[e]) { best[e] = v; bh[e] = hb; bl[e] = lb; }
+    }
+  }
+  const size_t o = act_index(out, n, yo, xo) + (size_t)g * 8;
+  uint4 oh, ol;
+  oh.x = bh[0] | (bh[1] << 16); oh.y = bh[2] | (bh[3] << 16); oh.z = bh[4] | (bh[5] << 16); oh.w = bh[6] | (bh[7] << 16);
+  ol.x = bl[0] | (bl[1] << 16); ol.y = bl[2] | (bl[3] << 16); ol.z = bl[4] | (bl[5] << 16); ol.w = bl[6] | (bl[7] << 16);
+  *reinterpret_cast<uint4*>(out.hi + o) = oh;
+  if (out.lo) *reinterpret_cast<uint4*>(out.lo + o) = ol;
+}
+
 int launch_maxpool(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, int kh, int kw, int stride, int pad_t, int pad_l,
                    cudaStream_t stream) {
   const size_t total = (size_t)out.B * out.H * out.W * (in.Cs / 8);
+  if (kh == 2 && kw == 2 && stride == 2 && pad_t == 0 && pad_l == 0 && 2 * (out.H - 1) < in.H && 2 * (out.W - 1) < in.W) {
+    maxpool2x2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+    SSDK_COUNT_LAUNCH(ctx);
+    SSDK_CHECK_CUDA(cudaGetLastError());
+    return SSDK_OK;
+  }
   maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out, kh, kw, stride, pad_t, pad_l);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());

@@ -86,61 +86,85 @@ template <int NT>
 __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* keys, int* s_hist, int* s_misc,
                            int* s_w, bool& more) {
   const int tid = threadIdx.x;
-  int cnt = 0;
-  for (int i = tid; i < s.n; i += NT) {
-    uint32_t k;
-    if (remaining(s, st, i, s.scores[i], k)) ++cnt;
-  }
-  const int R = block_sum_int<NT>(cnt, s_w);
-  if (R == 0) { more = false; return 0; }
-  const bool take_all = (R <= cap);
-  uint32_t T = 0;
-  int m_ties = 0;
-  if (!take_all) {
-    uint32_t prefix = 0, mask = 0;
-    int want = cap;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      for (int i = tid; i < 256; i += NT) s_hist[i] = 0;
-      __syncthreads();
-      for (int i = tid; i < s.n; i += NT) {
+  // Radix select over the order-preserving keys, 8 bits per pass.  The first pass doubles as the count of remaining candidates
+  // (its histogram total); four scores are loaded before any is used so that their latencies overlap.
+  uint32_t prefix = 0, mask = 0;
+  int want = cap, R = 0, ties_total = 0;
+  bool take_all = false;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += NT) s_hist[i] = 0;
+    __syncthreads();
+    for (int i0 = tid; i0 < s.n; i0 += 4 * NT) {
+      float sc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; sc[u] = i < s.n ? s.scores[i] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT;
         uint32_t k;
-        if (remaining(s, st, i, s.scores[i], k) && ((k & mask) == prefix)) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
+        if (i < s.n && remaining(s, st, i, sc[u], k) && ((k & mask) == prefix)) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
       }
-      __syncthreads();
-      if (tid < 32) {                      // warp 0: suffix scan over the 256 bins, 8 bins per lane
-        int loc[8], sum = 0;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { loc[e] = s_hist[255 - (tid * 8 + e)]; sum += loc[e]; }
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
-        int acc = incl - sum;              // candidates in bins above this lane's 8 bins
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (acc < want && acc + loc[e] >= want) { s_misc[0] = 255 - (tid * 8 + e); s_misc[1] = want - acc; }
-          acc += loc[e];
-        }
-      }
-      __syncthreads();
-      prefix |= ((uint32_t)s_misc[0]) << shift;
-      mask |= 0xFFu << shift;
-      want = s_misc[1];
-      __syncthreads();
     }
-    T = prefix; m_ties = want;
+    __syncthreads();
+    if (tid < 32) {                      // warp 0: suffix scan over the 256 bins, 8 bins per lane
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { loc[e] = s_hist[255 - (tid * 8 + e)]; sum += loc[e]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+      if (tid == 31) s_misc[4] = incl;   // candidates that match the prefix so far (first pass: all remaining ones)
+      int acc = incl - sum;              // candidates in bins above this lane's 8 bins
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (acc < want && acc + loc[e] >= want) { s_misc[0] = 255 - (tid * 8 + e); s_misc[1] = want - acc; s_misc[5] = loc[e]; }
+        acc += loc[e];
+      }
+    }
+    __syncthreads();
+    if (shift == 24) {
+      R = s_misc[4];
+      if (R == 0) { __syncthreads(); more = false; return 0; }
+      if (R <= cap) { take_all = true; __syncthreads(); break; }
+    }
+    prefix |= ((uint32_t)s_misc[0]) << shift;
+    mask |= 0xFFu << shift;
+    want = s_misc[1];
+    ties_total = s_misc[5];
+    __syncthreads();
   }
+  const uint32_t T = prefix;
+  const int m_ties = want;
+  // every candidate equal to the boundary key is kept: their order does not matter, no ranking needed
+  const bool all_ties = take_all || (m_ties >= ties_total);
   if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
-  for (int base = 0; base < s.n; base += NT) {
-    const int i = base + tid;
-    bool take = false, tie = false;
-    uint32_t k = 0;
-    if (i < s.n && remaining(s, st, i, s.scores[i], k)) {
-      if (take_all || k > T) take = true;
-      else if (k == T) tie = true;
+  if (all_ties) {
+    for (int i0 = tid; i0 < s.n; i0 += 4 * NT) {
+      float sc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; sc[u] = i < s.n ? s.scores[i] : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT;
+        uint32_t k = 0;
+        if (i < s.n && remaining(s, st, i, sc[u], k) && (take_all || k >= T)) {
+          const int slot = atomicAdd(&s_misc[2], 1);
+          keys[slot] = ((u64)(~k) << 32) | (uint32_t)i;
+        }
+      }
     }
-    if (!take_all) {                       // ties at the boundary are taken in ascending index order
+  } else {
+    for (int base = 0; base < s.n; base += NT) {
+      const int i = base + tid;
+      bool take = false, tie = false;
+      uint32_t k = 0;
+      if (i < s.n && remaining(s, st, i, s.scores[i], k)) {
+        if (k > T) take = true;
+        else if (k == T) tie = true;
+      }
+      // ties at the boundary are taken in ascending index order
       unsigned bal = __ballot_sync(0xffffffffu, tie);
       int wrank = __popc(bal & ((1u << lane) - 1));
       if (lane == 0) s_w[warp] = __popc(bal);
@@ -151,10 +175,10 @@ __device__ int band_select(const SegView& s, const BandState& st, int cap, u64* 
       if (tie && tie_rank < m_ties) take = true;
       __syncthreads();
       if (tid == 0) s_misc[3] += total;
-    }
-    if (take) {
-      int slot = atomicAdd(&s_misc[2], 1);
-      keys[slot] = ((u64)(~k) << 32) | (uint32_t)i;
+      if (take) {
+        int slot = atomicAdd(&s_misc[2], 1);
+        keys[slot] = ((u64)(~k) << 32) | (uint32_t)i;
+      }
     }
   }
   __syncthreads();

@@ -277,27 +277,29 @@ __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
 __device__ void warp_tile_best(const EncParams& p, const TileSetDev& ts, const Box& gb, int tile, const int* removed, int n_removed,
                                double& out_v, int& out_i) {
   const int lane = threadIdx.x & 31;
-  // the eight anchors of a lane: all index loads, then all anchor loads, then the arithmetic (one memory round trip each instead
-  // of eight dependent pairs)
-  int an[kTile / 32];
-  double at[kTile / 32][4];
-#pragma unroll
-  for (int k = 0; k < kTile / 32; ++k) { int pos; an[k] = tile_anchor(ts, tile, k * 32 + lane, p.P, pos); }
-#pragma unroll
-  for (int k = 0; k < kTile / 32; ++k) {
-    at[k][0] = at[k][1] = at[k][2] = at[k][3] = 0.0;
-    if (an[k] >= 0) load_anchor_t(p, an[k], at[k]);
-  }
+  // the eight anchors of a lane in two batches of four: index loads, then anchor loads, then the arithmetic (one memory round trip
+  // per batch and stage instead of eight dependent pairs; four at a time keeps the register count of the tile kernel)
   double bv = 0.0; int bi = INT_MAX;
+  for (int k0 = 0; k0 < kTile / 32; k0 += 4) {
+    int an[4];
+    double at[4][4];
 #pragma unroll
-  for (int k = 0; k < kTile / 32; ++k) {
-    const int a = an[k];
-    if (a < 0) continue;
-    const Box ab = corners_from_template(at[k], p.coords, p.d);
-    const double inter = inter_area(gb, ab);
-    if (inter > 0.0) {
-      const double v = iou_value(gb, ab, inter);
-      if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
+    for (int k = 0; k < 4; ++k) { int pos; an[k] = tile_anchor(ts, tile, (k0 + k) * 32 + lane, p.P, pos); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      at[k][0] = at[k][1] = at[k][2] = at[k][3] = 0.0;
+      if (an[k] >= 0) load_anchor_t(p, an[k], at[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int a = an[k];
+      if (a < 0) continue;
+      const Box ab = corners_from_template(at[k], p.coords, p.d);
+      const double inter = inter_area(gb, ab);
+      if (inter > 0.0) {
+        const double v = iou_value(gb, ab, inter);
+        if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
+      }
     }
   }
   warp_argmax(bv, bi);
@@ -555,12 +557,18 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
           if (lane == 0) { sc.tV[(size_t)st * TG + col] = tv; sc.tI[(size_t)st * TG + col] = ti; }
           __syncwarp();
           nv = 0.0; ni = INT_MAX;
-          for (int t = lane; t < ts.n_tiles; t += 32) {
-            const double v2 = (t == st) ? tv : __ldcg(sc.tV + (size_t)t * TG + col);
-            if (v2 > 0.0) {
-              const int i2 = (t == st) ? ti : __ldcg(sc.tI + (size_t)t * TG + col);
-              if (v2 > nv || (v2 == nv && i2 < ni)) { nv = v2; ni = i2; }
+          for (int t0 = lane; t0 < ts.n_tiles; t0 += 128) {         // four tiles per lane in flight
+            double v4[4]; int i4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int t = t0 + u * 32;
+              v4[u] = 0.0; i4[u] = INT_MAX;
+              if (t < ts.n_tiles && t != st) { v4[u] = __ldcg(sc.tV + (size_t)t * TG + col); i4[u] = __ldcg(sc.tI + (size_t)t * TG + col); }
+              else if (t == st) { v4[u] = tv; i4[u] = ti; }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (v4[u] > 0.0 && (v4[u] > nv || (v4[u] == nv && i4[u] < ni))) { nv = v4[u]; ni = i4[u]; }
           }
           warp_argmax(nv, ni);
           if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
