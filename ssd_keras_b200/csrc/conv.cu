@@ -659,8 +659,41 @@ __global__ void im2col_kernel(ActBuf in, __nv_bfloat16* __restrict__ out_hi, __n
   if (out_lo) out_lo[i] = l;
 }
 
+// The same with eight channels (one 16-byte word of a plane) per thread: whenever the input has a multiple of 8 channels, eight
+// consecutive K indices are eight consecutive channels of one tap.
+__global__ void im2col8_kernel(ActBuf in, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int Ho, int Wo,
+                               int KH, int KW, int stride, int dil, int pad_t, int pad_l, int Kpad) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int K8 = Kpad / 8;
+  const size_t total = (size_t)in.B * Ho * Wo * K8;
+  if (i >= total) return;
+  const int k = (int)(i % K8) * 8;
+  const size_t row = i / K8;
+  const int xo = (int)(row % Wo); const int yo = (int)((row / Wo) % Ho); const int n = (int)(row / ((size_t)Wo * Ho));
+  uint4 h = make_uint4(0, 0, 0, 0), l = h;
+  if (k < KH * KW * in.C) {
+    const int c = k % in.C; const int tap = k / in.C; const int kw = tap % KW; const int kh = tap / KW;
+    const int y = yo * stride + kh * dil - pad_t, x = xo * stride + kw * dil - pad_l;
+    if (y >= 0 && y < in.H && x >= 0 && x < in.W) {
+      const size_t s = act_index(in, n, y, x) + c;
+      h = *reinterpret_cast<const uint4*>(in.hi + s);
+      if (in.lo) l = *reinterpret_cast<const uint4*>(in.lo + s);
+    }
+  }
+  *reinterpret_cast<uint4*>(out_hi + row * Kpad + k) = h;
+  if (out_lo) *reinterpret_cast<uint4*>(out_lo + row * Kpad + k) = l;
+}
+
 int launch_im2col(ssdk_ctx* ctx, const ActBuf& in, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int Ho, int Wo, int kh, int kw,
                   int stride, int dil, int pad_t, int pad_l, int Kpad, cudaStream_t stream) {
+  if (in.C % 8 == 0 && in.Cs == in.C && Kpad % 8 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 &&
+      (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0)) {
+    const size_t total8 = (size_t)in.B * Ho * Wo * (Kpad / 8);
+    im2col8_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, stream>>>(in, out_hi, out_lo, Ho, Wo, kh, kw, stride, dil, pad_t, pad_l, Kpad);
+    SSDK_COUNT_LAUNCH(ctx);
+    SSDK_CHECK_CUDA(cudaGetLastError());
+    return SSDK_OK;
+  }
   const size_t total = (size_t)in.B * Ho * Wo * Kpad;
   im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out_hi, out_lo, Ho, Wo, kh, kw, stride, dil, pad_t, pad_l, Kpad);
   SSDK_COUNT_LAUNCH(ctx);

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ E
 // ------------------------------------------------------------------------------------------
 // match_bipartite_greedy (matching_utils.py:63-77), run by the last CTA of an image
 // ------------------------------------------------------------------------------------------
-__device__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
+__device__ __noinline__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
                              int b, const double* s_gbox, unsigned char* scratch, double* pv, int* pi, float* __restrict__ out_y,
                              int* __restrict__ out_match) {
   __shared__ int s_flag[2];
@@ -492,19 +492,26 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     lap(1);
     for (;;) {
       count(8, 1);
-      // A. the first row with a later duplicate
-      double cv = -1.0; int ci = INT_MAX;
-      for (int g = tid; g < G; g += kTile) {
+      // A. the first row with a later duplicate (kTile / G threads share a row's scan over the other rows)
+      const int np_a = G < kTile ? kTile / G : 1;
+      for (int g = tid; g < G; g += kTile) victims[g] = 0;
+      __syncthreads();
+      for (int idx = tid; idx < G * np_a; idx += kTile) {
+        const int g = idx % G, part = idx / G;
         const double v = rv[g];
         if (!(v > 0.0)) continue;
         const int a = ra[g];
         bool has = false;
-        for (int g2 = 0; g2 < G; ++g2) {
+        for (int g2 = part; g2 < G; g2 += np_a) {
           const double v2 = rv[g2];
           has |= (g2 != g) && (v2 > 0.0) && (ra[g2] == a) && (v2 < v || (v2 == v && g2 > g));
         }
-        if (has && (v > cv || (v == cv && g < ci))) { cv = v; ci = g; }
+        if (has) victims[g] = 1;
       }
+      __syncthreads();
+      double cv = -1.0; int ci = INT_MAX;
+      for (int g = tid; g < G; g += kTile)
+        if (victims[g]) { const double v = rv[g]; if (v > cv || (v == cv && g < ci)) { cv = v; ci = g; } }
       warp_argmax(cv, ci);
       if (lane == 0) { s_cv[warp] = cv; s_ci[warp] = ci; }
       __syncthreads();
@@ -711,10 +718,12 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   int prev_one = -1;                                            // staging-row entry this thread set to 1 in the previous tile
   for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barrier below)
   if (tid == 0) *s_nitems = 0;
+  int a_n = -1, pos_n = 0;
+  double at_n[4] = {0, 0, 0, 0};
   for (int tile = tile0; tile < tile1; ++tile) {
-    if (tile != tile0) {
-      a = tile_anchor(ts, tile, tid, p.P, pos);
-      if (a >= 0) load_anchor_t(p, a, at);
+    if (tile != tile0) {                                          // prefetched during the previous tile
+      a = a_n; pos = pos_n;
+      at[0] = at_n[0]; at[1] = at_n[1]; at[2] = at_n[2]; at[3] = at_n[3];
     }
     // ---- 2. per 32-anchor slice: which boxes can reach their threshold with ANY anchor of the slice ----
     // Bound of the IoU of a whole slice against a box: the overlap along x is at most min(widest anchor, box width, rightmost anchor
@@ -784,6 +793,11 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     // These evaluations pile up in the slices of the best-fitting anchor shape (every anchor inside a large box ties its row
     // maximum up to rounding): left to their own warps, two of eight would do all of it while six wait at the barrier.
     __syncthreads();
+    // the next tile's anchor: issued here so that its two dependent loads complete behind the rest of this tile
+    if (tile + 1 < tile1) {
+      a_n = tile_anchor(ts, tile + 1, tid, p.P, pos_n);
+      if (a_n >= 0) load_anchor_t(p, a_n, at_n);
+    }
     const int n_items = *s_nitems;
     for (int it = warp; it < n_items; it += kTile / 32) {
       const int w = s_items[it] >> 16, g = s_items[it] & 0xffff;
