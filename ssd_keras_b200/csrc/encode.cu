@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ E
 // ------------------------------------------------------------------------------------------
 // match_bipartite_greedy (matching_utils.py:63-77), run by the last CTA of an image
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
+__device__ void finish_image(const EncParams& p, const TileSetDev& ts, const EncScratch& sc, const void* gt, int gt_f64, int g0, int G,
                              int b, const double* s_gbox, unsigned char* scratch, double* pv, int* pi, float* __restrict__ out_y,
                              int* __restrict__ out_match) {
   __shared__ int s_flag[2];
@@ -492,26 +492,19 @@ __device__ __noinline__ void finish_image(const EncParams& p, const TileSetDev& 
     lap(1);
     for (;;) {
       count(8, 1);
-      // A. the first row with a later duplicate (kTile / G threads share a row's scan over the other rows)
-      const int np_a = G < kTile ? kTile / G : 1;
-      for (int g = tid; g < G; g += kTile) victims[g] = 0;
-      __syncthreads();
-      for (int idx = tid; idx < G * np_a; idx += kTile) {
-        const int g = idx % G, part = idx / G;
+      // A. the first row with a later duplicate
+      double cv = -1.0; int ci = INT_MAX;
+      for (int g = tid; g < G; g += kTile) {
         const double v = rv[g];
         if (!(v > 0.0)) continue;
         const int a = ra[g];
         bool has = false;
-        for (int g2 = part; g2 < G; g2 += np_a) {
+        for (int g2 = 0; g2 < G; ++g2) {
           const double v2 = rv[g2];
           has |= (g2 != g) && (v2 > 0.0) && (ra[g2] == a) && (v2 < v || (v2 == v && g2 > g));
         }
-        if (has) victims[g] = 1;
+        if (has && (v > cv || (v == cv && g < ci))) { cv = v; ci = g; }
       }
-      __syncthreads();
-      double cv = -1.0; int ci = INT_MAX;
-      for (int g = tid; g < G; g += kTile)
-        if (victims[g]) { const double v = rv[g]; if (v > cv || (v == cv && g < ci)) { cv = v; ci = g; } }
       warp_argmax(cv, ci);
       if (lane == 0) { s_cv[warp] = cv; s_ci[warp] = ci; }
       __syncthreads();
@@ -636,7 +629,7 @@ __device__ __noinline__ void finish_image(const EncParams& p, const TileSetDev& 
 // enc_tiles_kernel
 // ------------------------------------------------------------------------------------------
 struct EncSmem {            // byte offsets inside the dynamic shared memory
-  size_t rows, gbox, gf, gq, wU, wV, wI, wl, items, total;
+  size_t rows, gbox, gf, gq, wU, wV, wI, items, total;
 };
 __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   EncSmem s;
@@ -652,8 +645,7 @@ __host__ __device__ inline EncSmem enc_smem_layout(int W, int G) {
   s.wV = up16(s.gq + gs * 16);                                // [8*G] f64: per-slice best exact IoU of a candidate
   s.wU = up16(s.wV + gs * 64);                                // [8*G] u32: per-slice bound of the IoU of a candidate
   s.wI = up16(s.wU + gs * 32);                                // [8*G] i32: per-slice prior index of the best exact IoU
-  s.wl = up16(s.wI + gs * 32);                                // [8*G] u16: per-slice list of the boxes that pass the slice's bound
-  s.items = up16(s.wl + gs * 16);                             // [8*G] (slice << 16 | box) pairs whose exact per-slice best is needed, + counter
+  s.items = up16(s.wI + gs * 32);                             // [8*G] (slice << 16 | box) pairs whose exact per-slice best is needed, + counter
   s.total = up16(s.items + gs * 32 + 16) + 16;
   return s;
 }
@@ -679,7 +671,6 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   double* s_wV = reinterpret_cast<double*>(smem_raw + L.wV);
   unsigned* s_wU = reinterpret_cast<unsigned*>(smem_raw + L.wU);
   int* s_wI = reinterpret_cast<int*>(smem_raw + L.wI);
-  unsigned short* s_wl = reinterpret_cast<unsigned short*>(smem_raw + L.wl);
   int* s_items = reinterpret_cast<int*>(smem_raw + L.items);
   int* s_nitems = s_items + (size_t)(kTile / 32) * Gs;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -718,38 +709,19 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
   int prev_one = -1;                                            // staging-row entry this thread set to 1 in the previous tile
   for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barrier below)
   if (tid == 0) *s_nitems = 0;
-  int a_n = -1, pos_n = 0;
-  double at_n[4] = {0, 0, 0, 0};
   for (int tile = tile0; tile < tile1; ++tile) {
-    if (tile != tile0) {                                          // prefetched during the previous tile
-      a = a_n; pos = pos_n;
-      at[0] = at_n[0]; at[1] = at_n[1]; at[2] = at_n[2]; at[3] = at_n[3];
+    if (tile != tile0) {
+      a = tile_anchor(ts, tile, tid, p.P, pos);
+      if (a >= 0) load_anchor_t(p, a, at);
     }
     // ---- 2. per 32-anchor slice: which boxes can reach their threshold with ANY anchor of the slice ----
     // Bound of the IoU of a whole slice against a box: the overlap along x is at most min(widest anchor, box width, rightmost anchor
     // edge - box left, box right - leftmost anchor edge), likewise along y; the union is at least smallest anchor area + box area -
     // that intersection.  With the box-shape-major thread order a slice holds one shape at neighbouring positions, so the bound is
     // tight and only the few boxes near the slice survive: the per-anchor loop below runs over ~1 box instead of all that touch the
-    // tile.  Every warp works on its own list (ascending box index): no CTA-wide barrier before the results are combined.
+    // tile, and every warp does the same amount of work here.
     const float4 k0 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2);
     const float4 k1 = __ldg(ts.cls + ((size_t)tile * (kTile / 32) + warp) * 2 + 1);
-    int nlist = 0;
-    for (int gb0 = 0; gb0 < G; gb0 += 32) {
-      const int g = gb0 + lane;
-      bool keep = false;
-      if (g < G) {
-        const float4 gf = s_gf[g];
-        const float4 gq = s_gq[g];
-        const float um = slice_iou_bound(k0, k1, gf, gq.x);
-        keep = um >= gq.z;
-        s_wU[warp * Gs + g] = __float_as_uint(um);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (keep) s_wl[warp * Gs + nlist + __popc(m & ((1u << lane) - 1))] = (unsigned short)g;
-      nlist += __popc(m);
-    }
-    __syncwarp();
-    // ---- 3. this thread's anchor against the slice's candidates ----
     const bool live = a >= 0;
     float fx0 = 0.f, fy0 = 0.f, fx1 = -INFINITY, fy1 = -INFINITY, fa = 0.f;
     Box ab{};
@@ -760,44 +732,46 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
       fa = __double2float_rd(ab.area);
     }
     double best = 0.0; int best_g = -1;
-    for (int k = 0; k < nlist; ++k) {
-      const int g = s_wl[warp * Gs + k];
-      const float4 gf = s_gf[g];
-      const float4 gq = s_gq[g];
-      // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
-      const float iw = fmaxf(__fsub_ru(fminf(fx1, gf.z), fmaxf(fx0, gf.x)), 0.f);
-      const float ih = fmaxf(__fsub_ru(fminf(fy1, gf.w), fmaxf(fy0, gf.y)), 0.f);
-      const float inter = __fmul_ru(iw, ih);
-      const float un = fmaxf(__fsub_rd(__fadd_rd(fa, gq.x), inter), 1e-30f);
-      const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst (thresholds and the stored tile
-                                                             // maximum account for it)
-      const unsigned wm = __reduce_max_sync(0xffffffffu, __float_as_uint(U));
-      const float wmi = __fmul_ru(__uint_as_float(wm), 1.0f + 4.76837158203125e-7f);   // (1 + 2^-21): the reciprocal's ulp
-      const bool own_need = live && U >= p.thr_adj;          // the pair may matter for the anchor's own row -> exact float64 IoU
-      if (own_need) {
-        Box gb; gb.x0 = s_gbox[g * 5]; gb.y0 = s_gbox[g * 5 + 1]; gb.x1 = s_gbox[g * 5 + 2]; gb.y1 = s_gbox[g * 5 + 3]; gb.area = s_gbox[g * 5 + 4];
-        const double inter64 = inter_area(gb, ab);
-        if (inter64 > 0.0) {
-          const double val = iou_value(gb, ab, inter64);
-          if (val > best) { best = val; best_g = g; }         // strict '>' keeps the first gt on ties (np.argmax)
-        }
+    for (int gb0 = 0; gb0 < G; gb0 += 32) {
+      const int g = gb0 + lane;
+      bool own_f = false;
+      if (g < G) {
+        const float4 gf = s_gf[g];
+        const float4 gq = s_gq[g];
+        const float um = slice_iou_bound(k0, k1, gf, gq.x);
+        s_wU[warp * Gs + g] = __float_as_uint(um);
+        // the slice may hold the box's row maximum: queued for exact evaluation by whichever warp is free (3b); "um >= q_row" is
+        // also how the reduction below knows that the slice was evaluated
+        if (um >= gq.y) s_items[atomicAdd(s_nitems, 1)] = (warp << 16) | g;
+        own_f = um >= p.thr_adj;                                // some anchor of the slice may reach its own-row threshold
       }
-      // the slice's entry becomes the maximum of the per-pair bounds; when it reaches the box's row threshold the slice may hold the
-      // box's row maximum: queued for exact evaluation (below), and ">= q_row" later means "evaluated exactly"
-      if (lane == 0) {
-        s_wU[warp * Gs + g] = __float_as_uint(wmi);
-        if (wmi >= gq.y) s_items[atomicAdd(s_nitems, 1)] = (warp << 16) | g;
+      // ---- 3. own rows: rare (a box whose IoU with this slice can reach min(pos_iou_threshold, neg_iou_limit)) ----
+      unsigned mo = __ballot_sync(0xffffffffu, own_f);
+      while (mo) {                                              // ascending box index: np.argmax keeps the first maximum
+        const int g2 = gb0 + __ffs(mo) - 1;
+        mo &= mo - 1;
+        const float4 gf = s_gf[g2];
+        const float ga = s_gq[g2].x;
+        // U >= fl64(inter / union): widths and intersection rounded up, union rounded down (directed rounding is monotone)
+        const float iw = fmaxf(__fsub_ru(fminf(fx1, gf.z), fmaxf(fx0, gf.x)), 0.f);
+        const float ih = fmaxf(__fsub_ru(fminf(fy1, gf.w), fmaxf(fy0, gf.y)), 0.f);
+        const float inter = __fmul_ru(iw, ih);
+        const float un = fmaxf(__fsub_rd(__fadd_rd(fa, ga), inter), 1e-30f);
+        const float U = __fmul_ru(inter, rcp_approx(un));      // within 2^-23 below the bound at worst (thr_adj accounts for it)
+        if (live && U >= p.thr_adj) {                           // exact float64 IoU
+          Box gb; gb.x0 = s_gbox[g2 * 5]; gb.y0 = s_gbox[g2 * 5 + 1]; gb.x1 = s_gbox[g2 * 5 + 2]; gb.y1 = s_gbox[g2 * 5 + 3]; gb.area = s_gbox[g2 * 5 + 4];
+          const double inter64 = inter_area(gb, ab);
+          if (inter64 > 0.0) {
+            const double val = iou_value(gb, ab, inter64);
+            if (val > best) { best = val; best_g = g2; }        // strict '>' keeps the first gt on ties (np.argmax)
+          }
+        }
       }
     }
     // ---- 3b. exact per-(box, slice) bests, dealt out over all warps ----
     // These evaluations pile up in the slices of the best-fitting anchor shape (every anchor inside a large box ties its row
     // maximum up to rounding): left to their own warps, two of eight would do all of it while six wait at the barrier.
     __syncthreads();
-    // the next tile's anchor: issued here so that its two dependent loads complete behind the rest of this tile
-    if (tile + 1 < tile1) {
-      a_n = tile_anchor(ts, tile + 1, tid, p.P, pos_n);
-      if (a_n >= 0) load_anchor_t(p, a_n, at_n);
-    }
     const int n_items = *s_nitems;
     for (int it = warp; it < n_items; it += kTile / 32) {
       const int w = s_items[it] >> 16, g = s_items[it] & 0xffff;
