@@ -702,13 +702,13 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     }
     s_gq[g] = make_float4(__double2float_rd(gb.area), q_row, fminf(q_row, p.thr_adj), 0.f);
   }
+  if (tid == 0) *s_nitems = 0;                                  // (warps append right after the barrier below)
   const int any_bad = __syncthreads_or(bad ? 1 : 0);          // also publishes s_gbox
   if (blockIdx.x == 0 && tid == 0 && any_bad && status) atomicMax(status, b + 1);
 
   bool store_pending = false;
   int prev_one = -1;                                            // staging-row entry this thread set to 1 in the previous tile
-  for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barrier below)
-  if (tid == 0) *s_nitems = 0;
+  for (int i = tid; i < kTile * W; i += kTile) rows[i] = 0.f;   // (published by the barriers of the first tile)
   for (int tile = tile0; tile < tile1; ++tile) {
     if (tile != tile0) {
       a = tile_anchor(ts, tile, tid, p.P, pos);
