@@ -200,29 +200,50 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
                                           const float* s_bias, const float* s_scale, const float* s_shift) {
   if (!BWD && !args.bn_scale && args.act == SSDK_ACT_RELU && args.out_lo) {
     // the common forward case (bias + ReLU, hi/lo planes) without per-element branches: packed conversions (two values per
-    // cvt.rn.bf16x2.f32), biases fetched four at a time.  Bit-identical to the generic path below.
+    // cvt.rn.bf16x2.f32), biases fetched four at a time, and 32-byte stores (one full sector per lane and instruction: a thread's
+    // row is 2*Cout bytes of its own, so 16-byte stores leave every sector half written per instruction).  Bit-identical to the
+    // generic path below.
+    const bool wide = (args.out_Cs % 16 == 0) && ((n0 & 15) == 0);
     for (int c0 = 0; c0 < ncols; c0 += 32) {
       uint32_t vr[32];
       ld_acc32(t_row + (uint32_t)c0, xoff, vr);
       if (!valid) continue;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (c0 + g * 8 < ncols) {
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + g * 8 + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint32_t ph[4], pl[4];
+      for (int g2 = 0; g2 < 2; ++g2) {
+        uint32_t ph[8], pl[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float f0 = fmaxf(__uint_as_float(vr[g * 8 + j * 2]) + bb[j * 2], 0.f);
-            const float f1 = fmaxf(__uint_as_float(vr[g * 8 + j * 2 + 1]) + bb[j * 2 + 1], 0.f);
-            const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-            const uint32_t hp = *reinterpret_cast<const uint32_t*>(&h);
-            const __nv_bfloat162 l = __floats2bfloat162_rn(f0 - __uint_as_float(hp << 16), f1 - __uint_as_float(hp & 0xffff0000u));
-            ph[j] = hp; pl[j] = *reinterpret_cast<const uint32_t*>(&l);
+        for (int h = 0; h < 2; ++h) {
+          const int g = g2 * 2 + h;
+          if (c0 + g * 8 < ncols) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + g * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float f0 = fmaxf(__uint_as_float(vr[g * 8 + j * 2]) + bb[j * 2], 0.f);
+              const float f1 = fmaxf(__uint_as_float(vr[g * 8 + j * 2 + 1]) + bb[j * 2 + 1], 0.f);
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+              const uint32_t hp = *reinterpret_cast<const uint32_t*>(&hh);
+              const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - __uint_as_float(hp << 16), f1 - __uint_as_float(hp & 0xffff0000u));
+              ph[h * 4 + j] = hp; pl[h * 4 + j] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
           }
-          *reinterpret_cast<uint4*>(args.out_hi + o + c0 + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(args.out_lo + o + c0 + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        const int cA = c0 + g2 * 16;
+        if (wide && cA + 16 <= ncols) {
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(args.out_hi + o + cA), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]),
+                       "r"(ph[3]), "r"(ph[4]), "r"(ph[5]), "r"(ph[6]), "r"(ph[7]) : "memory");
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(args.out_lo + o + cA), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]),
+                       "r"(pl[3]), "r"(pl[4]), "r"(pl[5]), "r"(pl[6]), "r"(pl[7]) : "memory");
+        } else {
+          if (cA < ncols) {
+            *reinterpret_cast<uint4*>(args.out_hi + o + cA) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(args.out_lo + o + cA) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+          if (cA + 8 < ncols) {
+            *reinterpret_cast<uint4*>(args.out_hi + o + cA + 8) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            *reinterpret_cast<uint4*>(args.out_lo + o + cA + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+          }
         }
       }
     }
