@@ -640,6 +640,19 @@ __global__ void preprocess_kernel(const float* __restrict__ img, int B, int H, i
   }
   const int sw[3] = {swap.x, swap.y, swap.z};
   const size_t o = act_index(out, n, y, x);
+  if (out.Cs == 8 && Cimg == 3) {               // one 16-byte word per plane and pixel (channels 3..7 are zero)
+    const float w0 = v[sw[0]], w1 = v[sw[1]], w2 = v[sw[2]];
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(w0, w1);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(w2);
+    const uint32_t hp = *reinterpret_cast<const uint32_t*>(&h01);
+    *reinterpret_cast<uint4*>(out.hi + o) = make_uint4(hp, (uint32_t)__bfloat16_as_ushort(h2), 0u, 0u);
+    if (out.lo) {
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(w0 - __uint_as_float(hp << 16), w1 - __uint_as_float(hp & 0xffff0000u));
+      const __nv_bfloat16 l2 = __float2bfloat16_rn(w2 - __bfloat162float(h2));
+      *reinterpret_cast<uint4*>(out.lo + o) = make_uint4(*reinterpret_cast<const uint32_t*>(&l01), (uint32_t)__bfloat16_as_ushort(l2), 0u, 0u);
+    }
+    return;
+  }
   for (int c = 0; c < Cimg && c < 3; ++c) split_store(out, o + c, v[sw[c]]);
 }
 
@@ -1192,8 +1205,66 @@ __global__ void l2norm_kernel(ActBuf in, ActBuf out, const float* __restrict__ g
   for (int c = lane; c < in.C; c += 32) split_store(out, o + c, split_load(in, s + c) * inv * __ldg(gamma + c));
 }
 
+// The same with eight channels (16 bytes of each plane) per lane and step: up to 512 channels stay in registers between the two
+// passes.  The sum of squares is formed in a different order than above (per-lane partial sums of 8, then the warp tree).
+__global__ void __launch_bounds__(256) l2norm8_kernel(ActBuf in, ActBuf out, const float* __restrict__ gamma) {
+  const size_t pix = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)in.B * in.H * in.W;
+  if (pix >= total) return;
+  const int x = (int)(pix % in.W); const int y = (int)((pix / in.W) % in.H); const int n = (int)(pix / ((size_t)in.W * in.H));
+  const size_t s = act_index(in, n, y, x), o = act_index(out, n, y, x);
+  float v[2][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c = (k * 32 + lane) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[k][e] = 0.f;
+    if (c < in.C) {
+      const uint4 h4 = *reinterpret_cast<const uint4*>(in.hi + s + c);
+      uint4 l4 = make_uint4(0, 0, 0, 0);
+      if (in.lo) l4 = *reinterpret_cast<const uint4*>(in.lo + s + c);
+      const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t hb = (hw[e >> 1] >> ((e & 1) * 16)) & 0xffffu, lb = (lw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        v[k][e] = __uint_as_float(hb << 16) + __uint_as_float(lb << 16);
+        ss += v[k][e] * v[k][e];
+      }
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c = (k * 32 + lane) * 8;
+    if (c < in.C) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float f0 = v[k][j * 2] * inv * gm[j * 2], f1 = v[k][j * 2 + 1] * inv * gm[j * 2 + 1];
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+        const uint32_t hp = *reinterpret_cast<const uint32_t*>(&hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - __uint_as_float(hp << 16), f1 - __uint_as_float(hp & 0xffff0000u));
+        ph[j] = hp; pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(out.hi + o + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (out.lo) *reinterpret_cast<uint4*>(out.lo + o + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+}
+
 int launch_l2norm(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const float* gamma, cudaStream_t stream) {
   const size_t total = (size_t)in.B * in.H * in.W;
+  if (in.C % 8 == 0 && in.C <= 512 && in.Cs == in.C && out.Cs == out.C && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0) {
+    l2norm8_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(in, out, gamma);
+    SSDK_COUNT_LAUNCH(ctx);
+    SSDK_CHECK_CUDA(cudaGetLastError());
+    return SSDK_OK;
+  }
   l2norm_kernel<<<(unsigned)((total + 7) / 8), 256, 0, stream>>>(in, out, gamma);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());

@@ -211,9 +211,34 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   a.Ho = g.Ho; a.Wo = g.Wo; a.B = g.B;
   a.cout = g.cout;
   a.BN = g.cout <= 64 ? 64 : (g.cout <= 128 ? 128 : 256);
-  a.n_tiles_n = (g.cout + a.BN - 1) / a.BN;
   a.split = m->split;
   a.k_split = 1;
+  if (a.BN == 256 && g.cout % 128 == 0) {                       // (not the predictor heads: their epilogue needs all boxes in one tile)
+    // 256-wide tiles on few m-tiles leave the last wave of the persistent grid mostly empty (conv5_x: 220 units on 148 SMs), and
+    // with the cross-term accumulator they run single-buffered in TMEM; 128-wide tiles double the units and keep two accumulator
+    // sets, at the price of fetching every A slab once more.  Pick by the number of full-width waves (SSDK_BN_MAX forces).
+    long long n_valid = 0;
+    for (long long t = 0; t < (a.M_total + 127) / 128; ++t) {
+      bool any = false;
+      for (int r = 0; r < 128 && !any; ++r) {
+        const long long v = t * 128 + r;
+        if (v >= a.M_total) break;
+        const int rr = (int)(v % a.rows_per_img);
+        any = (rr / a.in_Wp < g.Ho) && (rr % a.in_Wp < g.Wo);
+      }
+      n_valid += any;
+    }
+    const int sms = m->ctx->sm_count;
+    const long long u256 = n_valid * ((g.cout + 255) / 256), u128 = n_valid * ((g.cout + 127) / 128);
+    const bool deep = a.split && a.KH * a.KW * kblocks >= 32;
+    const double t256 = (double)((u256 + sms - 1) / sms) * 256.0 * (deep ? 1.04 : 1.0);
+    const double t128 = (double)((u128 + sms - 1) / sms) * 128.0 * 1.03;
+    bool use128 = t128 < 0.95 * t256;
+    if (const char* e = getenv("SSDK_BN_AUTO")) { if (!atoi(e)) use128 = false; }
+    if (const char* e = getenv("SSDK_BN_MAX")) use128 = atoi(e) <= 128;
+    if (use128) a.BN = 128;
+  }
+  a.n_tiles_n = (g.cout + a.BN - 1) / a.BN;
   // two m-tiles per work unit when the accumulators fit (2 buffers x 2 tiles x BN <= 512 TMEM columns): the 64/128-channel
   // layers are bound by re-fetching the weight tiles from L2 for every m-tile, pairing halves that traffic
   const int n_m = (a.M_total + 127) / 128;
