@@ -385,6 +385,8 @@ __global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ E
   gt_template(r, p, t, cls);
   const Box gb = corners_from_template(t, p.coords, p.d);
   const double cx = 0.5 * (gb.x0 + gb.x1), cy = 0.5 * (gb.y0 + gb.y1);
+  const float4 gf = make_float4(__double2float_rd(gb.x0), __double2float_rd(gb.y0), __double2float_ru(gb.x1), __double2float_ru(gb.y1));
+  const float g_area = __double2float_rd(gb.area);
   double best = 0.0;
   for (int base = 0; base < ts.n_tiles; base += 32) {
     const int tile = base + lane;
@@ -397,9 +399,29 @@ __global__ void __launch_bounds__(kTile) enc_lb_kernel(const __grid_constant__ E
     while (m) {
       const int src = __ffs(m) - 1;
       m &= m - 1;
-      double v; int i;
-      warp_tile_best(p, ts, gb, base + src, nullptr, 0, v, i);
-      best = fmax(best, v);
+      // only the slices of that tile whose bound still reaches the best value found so far (lanes 0..7 test one slice each);
+      // any evaluated anchor gives a valid lower bound, so skipping slices can only loosen it
+      const int t = base + src;
+      float bound = -1.f;
+      if (lane < kTile / 32)
+        bound = slice_iou_bound(__ldg(ts.cls + ((size_t)t * (kTile / 32) + lane) * 2), __ldg(ts.cls + ((size_t)t * (kTile / 32) + lane) * 2 + 1), gf, g_area);
+      unsigned ms = __ballot_sync(0xffffffffu, bound > 0.f && (double)bound >= best);
+      while (ms) {
+        const int w = __ffs(ms) - 1;
+        ms &= ms - 1;
+        int pos;
+        const int a = tile_anchor(ts, t, w * 32 + lane, p.P, pos);
+        double v = 0.0;
+        if (a >= 0) {
+          const Box ab = load_anchor(p, a);
+          const double inter = inter_area(gb, ab);
+          if (inter > 0.0) { v = iou_value(gb, ab, inter); if (!(v > 0.0)) v = 0.0; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        best = fmax(best, v);
+        ms &= __ballot_sync(0xffffffffu, (double)bound >= best);
+      }
     }
   }
   if (lane == 0) lb[g0 + g] = __double2float_rd(best);

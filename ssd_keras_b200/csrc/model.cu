@@ -214,9 +214,8 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   a.split = m->split;
   a.k_split = 1;
   if (a.BN == 256 && g.cout % 128 == 0) {                       // (not the predictor heads: their epilogue needs all boxes in one tile)
-    // 256-wide tiles on few m-tiles leave the last wave of the persistent grid mostly empty (conv5_x: 220 units on 148 SMs), and
-    // with the cross-term accumulator they run single-buffered in TMEM; 128-wide tiles double the units and keep two accumulator
-    // sets, at the price of fetching every A slab once more.  Pick by the number of full-width waves (SSDK_BN_MAX forces).
+    // 256-wide tiles on few m-tiles leave the last wave of the persistent grid mostly empty (conv5_x: 220 units on 148 SMs);
+    // 128-wide tiles double the units.  Pick by the number of full-width waves (SSDK_BN_MAX forces, SSDK_BN_AUTO=0 disables).
     long long n_valid = 0;
     for (long long t = 0; t < (a.M_total + 127) / 128; ++t) {
       bool any = false;
@@ -230,9 +229,12 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
     }
     const int sms = m->ctx->sm_count;
     const long long u256 = n_valid * ((g.cout + 255) / 256), u128 = n_valid * ((g.cout + 127) / 128);
-    const bool deep = a.split && a.KH * a.KW * kblocks >= 32;
-    const double t256 = (double)((u256 + sms - 1) / sms) * 256.0 * (deep ? 1.04 : 1.0);
-    const double t128 = (double)((u128 + sms - 1) / sms) * 128.0 * 1.03;
+    // measured on B200 (same-box A/B, SSDK_BN_MAX=128): a 128-wide tile costs 15-18 % more per FLOP than a 256-wide one (its MMAs
+    // sit at the shared-memory operand bandwidth: conv3_x 460 -> 542 us, conv4_x 513 -> 588 us), so it only pays where the
+    // 256-wide grid wastes more than that: conv5_x (220 units on 148 SMs) 178 -> 168 us, conv6_2 / conv7_2 / conv8_2 54 -> 39,
+    // 34 -> 25, 32 -> 24 us
+    const double t256 = (double)((u256 + sms - 1) / sms) * 256.0;
+    const double t128 = (double)((u128 + sms - 1) / sms) * 128.0 * 1.18;
     bool use128 = t128 < 0.95 * t256;
     if (const char* e = getenv("SSDK_BN_AUTO")) { if (!atoi(e)) use128 = false; }
     if (const char* e = getenv("SSDK_BN_MAX")) use128 = atoi(e) <= 128;
