@@ -32,6 +32,7 @@ namespace {
 constexpr int kNmsThreads = 128;  // NMS: small CTAs, many segments resident per SM (the scan is latency bound)
 constexpr int kNmsCap = 2048;     // NMS band capacity (64-bit keys in shared memory)
 constexpr int kKeptSm = 512;      // kept (prepared) boxes cached in shared memory
+constexpr int kMaskN = 256;       // first-band candidates resolved through a pairwise suppression bit matrix
 constexpr int kTopThreads = 512;  // top-k stage
 constexpr int kTopCap = 16384;    // largest supported top_k
 
@@ -323,6 +324,64 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams prm) {
     const int cnt = band_select<NT>(sv, st, prm.band_cap, keys, s_hist, s_misc, s_w, more);
     if (cnt == 0) break;
     bitonic_sort<NT>(keys, cnt);
+    if (st.first && cnt <= kMaskN && prm.cap >= 1) {
+      // First band, at most 256 candidates (stage 1 of the two-stage scheme): the greedy scan without its serial chain.  All
+      // pairwise suppression bits (candidate j against every earlier candidate i) are computed in parallel, then one warp walks
+      // the candidates 32 at a time: a candidate survives iff none of the survivors so far suppresses it -- bit operations only.
+      PBox<T>* cb = reinterpret_cast<PBox<T>*>(kbox);          // candidate boxes (kept boxes are compacted into the same array)
+      uint32_t* msk = reinterpret_cast<uint32_t*>(keys + kMaskN);   // [kMaskN][kMaskN / 32], behind the sorted keys
+      for (int j = threadIdx.x; j < cnt; j += NT)
+        cb[j] = prepare_box<T, LAYER>(boxes + (size_t)(uint32_t)(keys[j] & 0xffffffffull) * 4, dd);
+      __syncthreads();
+      for (int r = 0; r < 2; ++r) {                            // rows t and 255 - t: the same number of tests for every thread
+        const int j = r == 0 ? (int)threadIdx.x : kMaskN - 1 - (int)threadIdx.x;
+        if (j >= cnt || (r == 1 && j < NT)) continue;
+        const PBox<T> c = cb[j];
+        for (int w = 0; w <= (j >> 5); ++w) {
+          uint32_t bits = 0;
+          const int i1 = min(j, w * 32 + 32);
+          for (int i = w * 32; i < i1; ++i) bits |= (suppressed<T, LAYER>(c, cb[i], thr) ? 1u : 0u) << (i & 31);
+          msk[j * (kMaskN / 32) + w] = bits;
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t kw = 0;                                        // lane w (< 8): survivors among candidates 32 w .. 32 w + 31
+        int count = 0;
+        const int n_chunks = (cnt + 31) >> 5;
+        for (int c = 0; c < n_chunks && count < prm.cap; ++c) {
+          const int j = c * 32 + lane;
+          const bool valid = j < cnt;
+          uint32_t early = 0;
+          for (int w = 0; w < c; ++w) {
+            const uint32_t k_w = __shfl_sync(0xffffffffu, kw, w);
+            if (valid) early |= msk[j * (kMaskN / 32) + w] & k_w;
+          }
+          const uint32_t intra = valid ? msk[j * (kMaskN / 32) + c] : 0u;
+          const uint32_t alive = __ballot_sync(0xffffffffu, valid && early == 0u);
+          uint32_t kc = 0;
+          for (int b = 0; b < 32; ++b) {                        // (uniform: every lane runs the same 32 steps)
+            const uint32_t ib = __shfl_sync(0xffffffffu, intra, b);
+            if (((alive >> b) & 1u) && !(ib & kc) && count < prm.cap) { kc |= 1u << b; ++count; }
+          }
+          if (lane == c) kw = kc;
+          // survivors of this chunk -> kept list and kept boxes, in order
+          const bool mine = (kc >> lane) & 1u;
+          const int pos = (count - __popc(kc)) + __popc(kc & ((1u << lane) - 1));
+          PBox<T> bx{};
+          if (mine) bx = cb[j];
+          __syncwarp();
+          if (mine) {
+            kept[pos] = (int)(uint32_t)(keys[j] & 0xffffffffull);
+            if (pos < kKeptSm) { kbox[pos * 5] = bx.x0; kbox[pos * 5 + 1] = bx.y0; kbox[pos * 5 + 2] = bx.x1; kbox[pos * 5 + 3] = bx.y1; kbox[pos * 5 + 4] = bx.a; }
+          }
+          __syncwarp();
+        }
+        if (lane == 0) s_K = count;
+      }
+      __syncthreads();
+      if (s_K >= prm.cap) done = true;
+    } else
     for (int c0 = 0; c0 < cnt && !done; c0 += NT) {
       const int j = c0 + threadIdx.x;
       bool alive = j < cnt;

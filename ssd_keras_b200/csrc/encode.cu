@@ -1230,7 +1230,7 @@ int encode_launch(ssdk_encoder* e, const void* gt_dev, int gt_f64, const int* of
   const bool use_spatial = e->spatial.dev.n_tiles > 0 && max_g >= spatial_min;
   const TileSetDev& ts = use_spatial ? e->spatial.dev : e->linear.dev;
   const bool use_lb = max_g >= lb_min && total_g > 0;
-  int tpc = max_g <= 16 ? 1 : (max_g <= 48 ? 2 : 4);
+  int tpc = max_g <= 16 ? 1 : (max_g <= 48 ? 2 : (max_g < 96 ? 4 : 8));   // tiles per CTA: amortises the per-CTA box set-up (measured)
   if (const char* s = getenv("SSDK_ENC_TPC")) tpc = std::max(1, atoi(s));
   while (tpc > 1 && (long long)ceil_div(ts.n_tiles, tpc) * B < 8ll * e->ctx->sm_count) tpc >>= 1;
   // scratch: tV (f64) | tI (i32) each [n_tiles * TG], lb [TG]
