@@ -273,39 +273,6 @@ __device__ __forceinline__ bool is_removed(const int* removed, int n, int a) {
   return r;
 }
 
-// One warp: best exact IoU (> 0, lowest prior index on ties) of box `gb` among the anchors of `tile` not in `removed`.
-__device__ void warp_tile_best(const EncParams& p, const TileSetDev& ts, const Box& gb, int tile, const int* removed, int n_removed,
-                               double& out_v, int& out_i) {
-  const int lane = threadIdx.x & 31;
-  // the eight anchors of a lane in two batches of four: index loads, then anchor loads, then the arithmetic (one memory round trip
-  // per batch and stage instead of eight dependent pairs; four at a time keeps the register count of the tile kernel)
-  double bv = 0.0; int bi = INT_MAX;
-  for (int k0 = 0; k0 < kTile / 32; k0 += 4) {
-    int an[4];
-    double at[4][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { int pos; an[k] = tile_anchor(ts, tile, (k0 + k) * 32 + lane, p.P, pos); }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      at[k][0] = at[k][1] = at[k][2] = at[k][3] = 0.0;
-      if (an[k] >= 0) load_anchor_t(p, an[k], at[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int a = an[k];
-      if (a < 0) continue;
-      const Box ab = corners_from_template(at[k], p.coords, p.d);
-      const double inter = inter_area(gb, ab);
-      if (inter > 0.0) {
-        const double v = iou_value(gb, ab, inter);
-        if (v > 0.0 && (v > bv || (v == bv && a < bi)) && !is_removed(removed, n_removed, a)) { bv = v; bi = a; }
-      }
-    }
-  }
-  warp_argmax(bv, bi);
-  out_v = bv; out_i = bi;
-}
-
 // Upper bound (can only err upwards) of the float64 IoU between ANY anchor of a 32-thread slice (bounds k0, k1 of
 // TileSetDev::cls) and a box given by outward-rounded float32 corners gf and its area rounded down.
 __device__ __forceinline__ float slice_iou_bound(const float4 k0, const float4 k1, const float4 gf, float g_area) {
@@ -504,8 +471,8 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
     // sequential rounds: find the first row (in that order) that has such a later duplicate, settle every row before it at once
     // (none of them can lose its prior), settle that row, let the duplicates recompute their maximum without the taken priors (one
     // warp each; their value can only drop, so they stay behind the settled rows), and repeat.  One iteration per conflict.
-    __shared__ double s_cv[kTile / 32];
-    __shared__ int s_ci[kTile / 32];
+    __shared__ double s_cv[kTile / 32], s_sv[kTile / 32];
+    __shared__ int s_ci[kTile / 32], s_si[kTile / 32];
     __shared__ int s_first, s_nrem, s_nvict;
     int* victims = matches + G;                               // [G] rows that lost their prior in this iteration
     for (int g = tid; g < G; g += kTile) matches[g] = 0;
@@ -564,39 +531,62 @@ __device__ void finish_image(const EncParams& p, const TileSetDev& ts, const Enc
       __syncthreads();
       const int n_vict = s_nvict;
       count(9, n_vict);
-      // C1. per row (one warp each): re-evaluate the tile of the lost prior without the taken priors, reduce the row again;
-      // repeat while the new best is itself a taken prior recorded by another tile
-      for (int vi = warp; vi < n_vict; vi += kTile / 32) {
+      // C1. per row, all eight warps together: re-evaluate the tile of the lost prior without the taken priors (one 32-anchor
+      // slice per warp) while every thread looks at one or two of the other tiles' recorded bests; repeat while the new best is
+      // itself a taken prior recorded by another tile
+      for (int vi = 0; vi < n_vict; ++vi) {
         const int gg = victims[vi];
         const size_t col = (size_t)(g0 + gg);
         const Box gb = gbox(gg);
         int stale = a_star;
-        double nv; int ni;
-        for (;;) {
+        for (;;) {                                              // (uniform over the CTA)
           const int st = tile_of_prior(ts, stale);
-          double tv; int ti;
-          warp_tile_best(p, ts, gb, st, removed, n_removed, tv, ti);
-          if (lane == 0) { sc.tV[(size_t)st * TG + col] = tv; sc.tI[(size_t)st * TG + col] = ti; }
-          __syncwarp();
-          nv = 0.0; ni = INT_MAX;
-          for (int t0 = lane; t0 < ts.n_tiles; t0 += 128) {         // four tiles per lane in flight
-            double v4[4]; int i4[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int t = t0 + u * 32;
-              v4[u] = 0.0; i4[u] = INT_MAX;
-              if (t < ts.n_tiles && t != st) { v4[u] = __ldcg(sc.tV + (size_t)t * TG + col); i4[u] = __ldcg(sc.tI + (size_t)t * TG + col); }
-              else if (t == st) { v4[u] = tv; i4[u] = ti; }
+          // this warp's slice of tile st
+          double tv = 0.0; int ti = INT_MAX;
+          {
+            int pos;
+            const int a = tile_anchor(ts, st, warp * 32 + lane, p.P, pos);
+            if (a >= 0) {
+              const Box ab = load_anchor(p, a);
+              const double inter = inter_area(gb, ab);
+              if (inter > 0.0) {
+                const double v = iou_value(gb, ab, inter);
+                if (v > 0.0 && !is_removed(removed, n_removed, a)) { tv = v; ti = a; }
+              }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (v4[u] > 0.0 && (v4[u] > nv || (v4[u] == nv && i4[u] < ni))) { nv = v4[u]; ni = i4[u]; }
           }
+          // this thread's share of the other tiles
+          double nv = 0.0; int ni = INT_MAX;
+          for (int t = tid; t < ts.n_tiles; t += kTile) {
+            if (t == st) continue;
+            const double v2 = __ldcg(sc.tV + (size_t)t * TG + col);
+            const int i2 = __ldcg(sc.tI + (size_t)t * TG + col);
+            if (v2 > 0.0 && (v2 > nv || (v2 == nv && i2 < ni))) { nv = v2; ni = i2; }
+          }
+          warp_argmax(tv, ti);
           warp_argmax(nv, ni);
-          if (!(nv > 0.0) || !is_removed(removed, n_removed, ni)) break;   // warp-uniform
-          stale = ni;
+          if (lane == 0) { s_cv[warp] = tv; s_ci[warp] = ti; s_sv[warp] = nv; s_si[warp] = ni; }
+          __syncthreads();
+          if (tid == 0) {
+            double bt = 0.0; int it = INT_MAX, io = INT_MAX; double bo = 0.0;
+            for (int w = 0; w < kTile / 32; ++w) {
+              if (s_cv[w] > bt || (s_cv[w] == bt && s_cv[w] > 0.0 && s_ci[w] < it)) { bt = s_cv[w]; it = s_ci[w]; }
+              if (s_sv[w] > bo || (s_sv[w] == bo && s_sv[w] > 0.0 && s_si[w] < io)) { bo = s_sv[w]; io = s_si[w]; }
+            }
+            if (!(bt > 0.0)) { bt = 0.0; it = INT_MAX; }
+            sc.tV[(size_t)st * TG + col] = bt; sc.tI[(size_t)st * TG + col] = it;
+            double nb = bt; int nib = it;
+            if (bo > nb || (bo == nb && bo > 0.0 && io < nib)) { nb = bo; nib = io; }
+            const bool again = (nb > 0.0) && is_removed(removed, n_removed, nib);
+            s_first = again ? nib : -1;                          // (s_first is free in this part of the iteration)
+            if (!again) { pv[vi] = (nb > 0.0) ? nb : 0.0; pi[vi] = (nb > 0.0) ? nib : INT_MAX; }
+          }
+          __syncthreads();
+          const int nxt = s_first;
+          __syncthreads();                                       // everyone has read the verdict before the next round overwrites it
+          if (nxt < 0) break;
+          stale = nxt;
         }
-        if (lane == 0) { pv[vi] = (nv > 0.0) ? nv : 0.0; pi[vi] = (nv > 0.0) ? ni : INT_MAX; }
       }
       __syncthreads();
       lap(3);
@@ -909,8 +899,7 @@ __global__ void __launch_bounds__(kTile, 3) enc_tiles_kernel(const __grid_consta
     __threadfence();
     const int old = atomicAdd(sc.counters + b, 1);
     const int last = (old == (int)gridDim.x - 1);
-    if (last) sc.counters[b] = 0;                               // ready for the next launch
-    __threadfence();
+    if (last) { sc.counters[b] = 0; __threadfence(); }          // ready for the next launch; acquire side of the ticket
     s_last = last;
   }
   __syncthreads();
