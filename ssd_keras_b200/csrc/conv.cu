@@ -593,13 +593,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   }
 }
 
-int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream) {
+int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream, int grid_cap) {
   static bool attr_set = false;
   if (!attr_set) {
     SSDK_CHECK_CUDA(cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tcgen05_kernel<<<L.grid, 256, L.smem, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, L.args);
+  // the kernel is persistent with a static stride over its work units: any grid size computes the same result
+  const int grid = grid_cap > 0 ? std::max(1, std::min(L.grid, grid_cap)) : L.grid;
+  conv_tcgen05_kernel<<<grid, 256, L.smem, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, L.args);
   SSDK_COUNT_LAUNCH(ctx);
   SSDK_CHECK_CUDA(cudaGetLastError());
   return SSDK_OK;

@@ -87,7 +87,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ro
 int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint32_t box[4]);
 size_t conv_smem_bytes(const ConvArgs& a);
 void conv_pick_stages(ConvArgs& a);
-int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream);
+int launch_conv(ssdk_ctx* ctx, const ConvLaunch& L, cudaStream_t stream, int grid_cap = 0);   // grid_cap > 0: at most that many CTAs
 
 // elementwise / data movement kernels
 int launch_preprocess(ssdk_ctx* ctx, const float* images, int B, int H, int W, int Cimg, const float* mean, const float* stddev,

@@ -176,6 +176,53 @@ int build_conv(ssdk_model* m, int li) {
   return SSDK_OK;
 }
 
+
+// Two-stream schedule for inference plans.  The tail of an SSD trunk (conv7_1 ... conv9_2 at batch 32) and the predictor heads on
+// the small feature maps are launches of 3 ... 36 CTAs that each wait out their own TMA / MMA latency chain while >100 SMs idle;
+// the predictor heads on the large maps are wide but independent of that tail.  From the first trunk convolution after which every
+// trunk convolution is narrow (grid <= R), narrow launches go to a second stream and the wide ones stay on the caller's stream with
+// their persistent grid capped at sm_count - (widest narrow grid), so both sets always find free SMs (every conv CTA owns an SM:
+// ~200 KB of shared memory).  Cross-stream dependencies are events recorded at issue time; the streams join before the call returns.
+// SSDK_OVERLAP=0 disables, SSDK_OVERLAP_R sets R (default sm_count / 4).
+int plan_overlap(ssdk_model* m) {
+  const int n = (int)m->layers.size();
+  m->on_side.assign(n, 0);
+  m->overlap_from = -1; m->grid_cap = 0;
+  if (m->training) return SSDK_OK;
+  if (const char* e = getenv("SSDK_OVERLAP")) { if (!atoi(e)) return SSDK_OK; }
+  int R = m->ctx->sm_count / 4;
+  if (const char* e = getenv("SSDK_OVERLAP_R")) R = atoi(e);
+  auto is_gemm = [&](const LayerPlan& L) { return (L.d.op == SSDK_OP_CONV || L.d.op == SSDK_OP_HEAD) && !L.direct; };
+  // first trunk convolution from which on all trunk convolutions are narrow
+  int from = -1;
+  for (int i = n - 1; i >= 0; --i) {
+    const LayerPlan& L = m->layers[i];
+    if (L.d.op != SSDK_OP_CONV) continue;
+    if (L.direct || L.launch.grid > R) break;
+    from = i;
+  }
+  if (from < 0) return SSDK_OK;
+  int widest = 0, wide_after = 0;
+  for (int i = from; i < n; ++i) {
+    const LayerPlan& L = m->layers[i];
+    if (is_gemm(L)) {
+      if (L.launch.grid <= R) { m->on_side[i] = 1; widest = std::max(widest, L.launch.grid); }
+      else ++wide_after;
+    } else if (L.d.op != SSDK_OP_INPUT && L.d.input >= 0 && m->on_side[L.d.input]) {
+      m->on_side[i] = 1;                       // element-wise consumer of a narrow producer: stays on its producer's stream
+    }
+  }
+  if (!wide_after || !widest) { m->on_side.assign(n, 0); return SSDK_OK; }      // nothing to run next to the narrow launches
+  m->overlap_from = from;
+  m->grid_cap = std::max(1, m->ctx->sm_count - widest);
+  int lo = 0, hi = 0;
+  SSDK_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  SSDK_CHECK_CUDA(cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, hi));
+  m->dep_ev.resize(n + 1, nullptr);
+  for (auto& e : m->dep_ev) SSDK_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return SSDK_OK;
+}
+
 }  // namespace
 
 namespace ssdk {
@@ -406,6 +453,7 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
       a.head_P = m->P; a.head_prior_off = L.prior_off; a.head_anchors = m->d_anchors;
       for (int k = 0; k < 4; ++k) a.head_var[k] = m->var[k];
     }
+  rc = plan_overlap(m); if (rc) return fail(rc);
   SSDK_CHECK_CUDA(cudaDeviceSynchronize());
   *out = m;
   return SSDK_OK;
@@ -414,6 +462,8 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
 extern "C" int ssdk_model_destroy(ssdk_model* m) {
   if (!m) return SSDK_OK;
   for (auto& L : m->layers) { if (L.ev0) cudaEventDestroy(L.ev0); if (L.ev1) cudaEventDestroy(L.ev1); }
+  for (auto& e : m->dep_ev) if (e) cudaEventDestroy(e);
+  if (m->side) { cudaStreamSynchronize(m->side); cudaStreamDestroy(m->side); }
   for (void* p : m->allocs) cudaFree(p);
   delete m;
   return SSDK_OK;
@@ -463,12 +513,37 @@ extern "C" int ssdk_model_last_conv_ms(ssdk_model* m, float* out_ms) {
 extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float* y_pred_dev, void* stream_) {
   SSDK_REQUIRE(m && images_dev, "ssdk_model_forward: NULL argument");
   SSDK_REQUIRE(m->P == 0 || y_pred_dev, "ssdk_model_forward: y_pred_dev is NULL");
-  cudaStream_t stream = (cudaStream_t)stream_;
+  cudaStream_t main_stream = (cudaStream_t)stream_;
   ssdk_ctx* ctx = m->ctx;
   int rc;
+  // two-stream schedule (plan_overlap); instrumented passes (per-launch events) stay on one stream
+  const bool overlap = m->overlap_from >= 0 && !m->timing;
+  // issue counters per stream (0: caller's, 1: side) and, per consumer stream, how much of the OTHER stream it has already waited for
+  int issued[2] = {0, 0}, seen[2] = {0, 0}, side_used = 0;
+  std::vector<int>& pos = m->issue_pos;
+  pos.assign(m->layers.size(), 0);
   for (size_t i = 0; i < m->layers.size(); ++i) {
     LayerPlan& L = m->layers[i];
     const ssdk_layer_desc& d = L.d;
+    const int sx = overlap && m->on_side[i] ? 1 : 0;
+    cudaStream_t stream = sx ? m->side : main_stream;
+    int cap = 0;
+    if (overlap) {
+      if (d.op != SSDK_OP_INPUT && d.input >= 0) {
+        const int sy = m->on_side[d.input] ? 1 : 0;
+        // the first launch on the side stream also orders it behind everything the caller's stream holds (previous calls included)
+        const bool first_side = sx == 1 && !side_used;
+        if ((sy != sx && pos[d.input] > seen[sx]) || first_side) {
+          cudaStream_t other = sx ? main_stream : m->side;
+          SSDK_CHECK_CUDA(cudaEventRecord(m->dep_ev[i], other));
+          SSDK_CHECK_CUDA(cudaStreamWaitEvent(stream, m->dep_ev[i], 0));
+          seen[sx] = issued[sx ^ 1];
+        }
+      }
+      if (sx) side_used = 1;
+      pos[i] = ++issued[sx];
+      if (!sx && side_used) cap = m->grid_cap;
+    }
     switch (d.op) {
       case SSDK_OP_INPUT:
         rc = launch_preprocess(ctx, images_dev, m->B, m->H, m->W, m->Cimg, L.has_mean ? L.mean : nullptr,
@@ -495,7 +570,7 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         }
         if (m->timing) cudaEventRecord(L.ev0, stream);
         if (L.head_fused) L.launch.args.out_f32 = y_pred_dev;                   // the epilogue writes the prediction rows themselves
-        rc = launch_conv(ctx, L.launch, stream);
+        rc = launch_conv(ctx, L.launch, stream, cap);
         if (rc) return rc;
         if (m->timing) cudaEventRecord(L.ev1, stream);
         if (L.bn_train) { rc = launch_bn_forward(ctx, L, d.act, stream); if (rc) return rc; }
@@ -517,6 +592,10 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
       default:
         break;
     }
+  }
+  if (side_used) {                             // join: whatever the caller enqueues next sees the finished prediction tensor
+    SSDK_CHECK_CUDA(cudaEventRecord(m->dep_ev.back(), m->side));
+    SSDK_CHECK_CUDA(cudaStreamWaitEvent(main_stream, m->dep_ev.back(), 0));
   }
   return SSDK_OK;
 }

@@ -61,6 +61,14 @@ struct ssdk_model {
   double flops_algo = 0, flops_issued = 0;
   int timing = 0;
   std::vector<void*> allocs;
+  // two-stream schedule of inference plans (model.cu, plan_overlap): the narrow tail of the trunk and the narrow predictor
+  // heads run on `side` while the wide predictor heads run on the caller's stream with a capped grid
+  cudaStream_t side = nullptr;
+  std::vector<uint8_t> on_side;       // per layer: 1 = issued on `side`
+  std::vector<cudaEvent_t> dep_ev;    // cross-stream dependencies (one per layer is enough) + join
+  int grid_cap = 0;                   // grid limit of the conv launches that stay on the caller's stream while `side` is busy
+  int overlap_from = -1;              // first layer issued on `side` (-1: single-stream plan)
+  std::vector<int> issue_pos;         // scratch of ssdk_model_forward: issue position of every layer on its stream
 };
 
 namespace ssdk {

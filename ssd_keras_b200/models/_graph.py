@@ -295,15 +295,87 @@ class SSDModel:
         y = self.forward_device(images)
         return y if self.decoder is None else self.decoder(y)
 
+    def predict_stream(self, batches, post=None):
+        """Generator over HOST batches -> HOST results, in order, software-pipelined: while the kernels of batch i run, batch
+        i+1 is already on its way to the device (copy stream) and the host is still reading the result of batch i-1; the host
+        only ever waits for the device->host copy of the PREVIOUS batch, so the GPU does not idle between batches (what Keras'
+        ``predict_generator`` does with its queue of prefetched batches; the reference drives its models that way in
+        eval_utils/average_precision_evaluator.py:373-380).
+
+        batches: iterable of float32 (B,H,W,3) pinned CPU tensors (used as they are) or ndarrays (pinned here, one host copy).
+        post:    optional function applied to the device result of each batch before it is downloaded (e.g. an all-gather).
+        Yields pinned CPU tensors; a yielded tensor is overwritten when the generator is advanced twice more."""
+        import torch
+        main = torch.cuda.current_stream()
+        if getattr(self, '_up_stream', None) is None:
+            self._up_stream = torch.cuda.Stream()
+        up = self._up_stream
+        slots = [None, None, None]                      # pinned result buffers, rotated
+
+        def upload(hb):
+            if not torch.is_tensor(hb):
+                hb = torch.from_numpy(np.ascontiguousarray(hb, dtype=np.float32))
+            if not hb.is_pinned():
+                hb = hb.pin_memory()
+            with torch.cuda.stream(up):
+                x = hb.cuda(non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up)
+            return x, ev, hb                            # hb is kept alive until its copy has been consumed
+
+        it = iter(batches)
+        nxt = None
+        for hb in it:
+            nxt = upload(hb)
+            break
+        pending = None                                  # (pinned buffer, event) of the batch whose result is still in flight
+        i = 0
+        while nxt is not None:
+            x, ev, _keep = nxt
+            nxt = None
+            for hb in it:                               # issue the NEXT upload before this batch's kernels
+                nxt = upload(hb)
+                break
+            main.wait_event(ev)
+            x.record_stream(main)
+            out = self.predict_device(x)
+            if post is not None:
+                out = post(out)
+            buf = slots[i % 3]
+            if buf is None or buf.shape != out.shape or buf.dtype != out.dtype:
+                buf = slots[i % 3] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            buf.copy_(out, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0]
+            pending = (buf, done)
+            i += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0]
+
+    def predict_generator(self, generator, steps=None):
+        """Keras' ``Model.predict_generator``: pulls ``steps`` batches (all of them if None) from ``generator`` -- each an image
+        batch or a tuple whose first element is one -- and returns the concatenated predictions as one ndarray.  The batches are
+        pipelined through :meth:`predict_stream`."""
+        import itertools
+
+        def images():
+            src = generator if steps is None else itertools.islice(generator, int(steps))
+            for item in src:
+                yield item[0] if isinstance(item, (tuple, list)) else item
+        outs = [r.numpy().copy() for r in self.predict_stream(images())]
+        if not outs:
+            raise ValueError('predict_generator: the generator yielded no batch')
+        return np.concatenate(outs, axis=0)
+
     def predict(self, x, batch_size=None):
         """Keras-style: ndarray (N,H,W,3) -> ndarray ((N,P,C+12) in 'training' mode, (N,top_k,6) otherwise)."""
-        import torch
         x = np.asarray(x, dtype=np.float32)
         bs = batch_size or x.shape[0]
-        outs = []
-        for i in range(0, x.shape[0], bs):
-            xb = torch.from_numpy(np.ascontiguousarray(x[i:i + bs])).pin_memory().cuda(non_blocking=True)
-            outs.append(self.predict_device(xb).cpu().numpy())
+        outs = [r.numpy().copy() for r in self.predict_stream(x[i:i + bs] for i in range(0, x.shape[0], bs))]
         return np.concatenate(outs, axis=0)
 
     def read_layer(self, name, batch):
