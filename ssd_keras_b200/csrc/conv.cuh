@@ -17,8 +17,13 @@ struct ActBuf {
   int B = 0, H = 0, W = 0, C = 0;   // logical shape
   int Cs = 0;                        // stored channels (multiple of 8)
   int pad = 0;
+  // shared = 1 (inference plans): the row pitch is W + pad, not W + 2*pad -- the right border of a row IS the left border of the
+  // next one (the same zeros).  Every index stays ((n*Hp + y + pad)*Wp + x + pad)*Cs; a tap that runs off the right edge lands
+  // in the next row's left border.  The implicit GEMM computes every position of the stored grid, so this cuts its padding rows:
+  // fc6 (19 wide, border 6) goes from 61 % to 76 % valid rows, the 19-wide conv5_x from 90 % to 95 %.
+  int shared = 0;
   __host__ __device__ int Hp() const { return H + 2 * pad; }
-  __host__ __device__ int Wp() const { return W + 2 * pad; }
+  __host__ __device__ int Wp() const { return W + (shared ? pad : 2 * pad); }
   size_t rows() const { return (size_t)B * Hp() * Wp(); }
   size_t elems() const { return rows() * Cs; }
 };
@@ -40,6 +45,7 @@ struct ConvArgs {
   int slab_rows;        // rows per A slab = round_up8(128 + (KW-1)*kw_rows) <= 256
   int stages_a, stages_b;
   int acc_split;        // 1: the two cross terms (hi*lo, lo*hi) accumulate in their own TMEM columns and are added in the epilogue
+  int fuse_b;           // 1 (needs acc_split): A_hi * [B_hi ; B_lo] as ONE MMA of N = BN + n into [main | cross], then A_lo * B_hi into cross
   int acc_bufs;         // accumulator sets in TMEM (2: the epilogue of tile i overlaps the MMAs of tile i+1; 1 when columns run out)
   int resident_b;       // 1: all KH*KW*kblocks weight tiles of the (single) n-tile stay in shared memory for the whole launch
   int mt;               // m-tiles per work unit (1 or 2): with 2, every weight tile feeds two 128-row MMAs (halves the weight traffic)
@@ -68,6 +74,12 @@ struct ConvArgs {
   //     are n_boxes x [C class logits | 4 offsets]; every (pixel, box) becomes one row of y_pred (out_f32):
   //     [softmax(C) | 4 offsets | 4 anchor coordinates | 4 variances] at prior head_prior_off + pixel * n_boxes + box.
   int head_nb, head_C, head_P, head_prior_off;
+  // --- L2Normalization folded into its producer and its consumers (inference plans, models/keras_ssd300.py:316 ->
+  //     keras_layer_L2Normalization.py:61-63).  Producer (EPI_SPLIT): every epilogue thread also stores the sum of squares of the
+  //     channels it wrote, one partial per n-tile: ssq_out[n_tile * ssq_stride + output row].  Consumer (predictor head, gamma folded
+  //     into its kernel): each accumulator row is multiplied by rsqrt(max(sum of the partials, 1e-12)) before the bias is added.
+  float* ssq_out; long long ssq_stride;
+  const float* row_scale; int row_scale_tiles, row_scale_shift;       // partials of row (virtual row + shift)
   const float* head_anchors;      // [P*4]
   float head_var[4];
 };

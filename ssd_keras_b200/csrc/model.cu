@@ -11,7 +11,7 @@ namespace {
 // Pack an HWIO float32 kernel (optionally two kernels fused per box: conf + loc) into K-major bf16 hi/lo planes
 // [cout][taps][kblocks*64] (virtual path) or [cout][kblocks*64] with k = (kh*KW+kw)*cin + c (im2col path).
 void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, bool im2col, int Ctot,
-                  std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, std::vector<float>& bias) {
+                  std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, std::vector<float>& bias, const float* in_scale = nullptr) {
   const ssdk_layer_desc& d = L.d;
   const size_t Krow = im2col ? (size_t)kblocks * 64 : (size_t)taps * kblocks * 64;
   hi.assign((size_t)cout * Krow, 0); lo.assign((size_t)cout * Krow, 0);
@@ -30,7 +30,8 @@ void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, 
     }
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < cin; ++c) {
-        const float w = ker[((size_t)t * cin + c) * ocn + oc];       // HWIO: ((kh*KW+kw)*cin + c)*cout + o
+        float w = ker[((size_t)t * cin + c) * ocn + oc];             // HWIO: ((kh*KW+kw)*cin + c)*cout + o
+        if (in_scale) w *= in_scale[c];                              // folded L2Normalization: gamma of the input channel
         const size_t k = im2col ? (size_t)t * cin + c : (size_t)t * kblocks * 64 + c;
         const uint16_t h = f2bf(w);
         hi[(size_t)o * Krow + k] = h;
@@ -42,7 +43,7 @@ void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, 
 int build_conv(ssdk_model* m, int li) {
   LayerPlan& L = m->layers[li];
   const ssdk_layer_desc& d = L.d;
-  const LayerPlan& in = m->layers[d.input];
+  const LayerPlan& in = m->layers[L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.input : d.input];   // folded L2Normalization: read its input
   const ActBuf& ia = in.out;
   const int cin = in.C;
   const bool head = d.op == SSDK_OP_HEAD;
@@ -118,7 +119,7 @@ int build_conv(ssdk_model* m, int li) {
   L.kblocks = kblocks;
   // weights
   std::vector<uint16_t> whi, wlo; std::vector<float> bias;
-  pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias);
+  pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias, L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.kernel : nullptr);
   const size_t Krow = whi.size() / cout;
   L.w_krow = Krow;
   int rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
@@ -153,6 +154,14 @@ int build_conv(ssdk_model* m, int li) {
     a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
   }
   a.act = L.bn_train ? SSDK_ACT_NONE : d.act;
+  if (L.fold_l2n >= 0) {               // rows of this head are scaled by the producer's per-pixel 1/norm (partials per producer n-tile)
+    a.row_scale = in.ssq; a.row_scale_tiles = in.launch.args.n_tiles_n; a.ssq_stride = (long long)ia.rows();
+    a.row_scale_shift = ia.pad * ia.Wp() + ia.pad;      // output (y, x) of a 'same' convolution <-> stored input row of pixel (y, x)
+  }
+  if (L.wants_ssq) {
+    int rc2 = dev_alloc(m, &L.ssq, (size_t)a.n_tiles_n * L.out.rows(), true); if (rc2) return rc2;
+    a.ssq_out = L.ssq; a.ssq_stride = (long long)L.out.rows();
+  }
   if (head) {
     // inference plans: softmax / concat / anchors in the epilogue, straight into y_pred (one n-tile holds all boxes of a pixel);
     // training plans keep the raw logits (the backward pass needs them) and finish with head_finalize_kernel
@@ -313,6 +322,18 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
       if (2 * 2 * a.mt * a.BN > 512) a.acc_bufs = 1;
       if (a.acc_bufs * 2 * a.mt * a.BN > 512) { a.acc_split = 0; a.acc_bufs = 2; }
     } }
+  // The hi and lo planes of a weight tile lie back to back in a ring slot and the cross-term accumulator follows the main one in
+  // TMEM, so for BN <= 128 the products A_hi*B_hi and A_hi*B_lo are ONE MMA of N = 2*BN (operand [B_hi ; B_lo], result
+  // [main | cross]); A_lo*B_hi follows into the cross columns.  Two issues instead of three per k-step, and the A_hi tile is read
+  // from shared memory once instead of twice: N = 64 MMAs are bound by the operand bandwidth (4 KB of A + 2 KB of B per 32 clocks),
+  // the combined one moves 8 KB per 64 clocks.  Tiles without a cross-term accumulator get one when the columns are there
+  // (64-wide tiles with paired m-tiles: 2 sets x 2 tiles x 2 x 64 = 512).  SSDK_FUSE_B=0 restores three MMAs.
+  a.fuse_b = 0;
+  { const char* e = getenv("SSDK_FUSE_B"); const int want = e ? atoi(e) : 1;
+    if (want && a.split && a.BN <= 128) {
+      if (!a.acc_split && 2 * 2 * a.mt * a.BN <= 512) { a.acc_split = 1; a.acc_bufs = 2; }
+      if (a.acc_split) a.fuse_b = 1;
+    } }
   conv_pick_stages(a);
   { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
   // m-tiles that hold at least one valid output row
@@ -349,9 +370,11 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
   double issued = 0;
   for (int nt = 0; nt < a.n_tiles_n; ++nt) {
     int ne = std::min(a.BN, ((g.cout - nt * a.BN) + 15) / 16 * 16);
-    issued += 2.0 * a.n_tiles_m * a.mt * 128.0 * ne * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
+    // MMA columns per product: 3 x ne, or (BN + ne) + ne with the fused weight operand
+    const double cols = !m->split ? ne : (a.fuse_b ? (double)(a.BN + 2 * ne) : 3.0 * ne);
+    issued += 2.0 * a.n_tiles_m * a.mt * 128.0 * cols * (double)(a.KH * a.KW) * ((kblocks - 1) * 64 + a.last_ksteps * 16);
   }
-  cl.flops_issued = issued * (m->split ? 3.0 : 1.0);
+  cl.flops_issued = issued;
   return SSDK_OK;
 }
 
@@ -402,11 +425,30 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
       L.H = in.H; L.W = in.W; L.C = in.C;
     } else { set_error("layer %d: unknown op %d", i, d.op); return fail(SSDK_ERR_INVALID); }
   }
+  // pass 1b (inference plans): L2Normalization layers that only feed 3x3 / 1x1 'same' predictor heads and follow a tensor-core
+  // convolution are folded away (SSDK_FOLD_L2N=0 keeps the separate kernel)
+  { const char* e = getenv("SSDK_FOLD_L2N"); const bool want = e ? atoi(e) != 0 : true;
+    for (int i = 0; i < n && want && !desc->training; ++i) {
+      LayerPlan& N = m->layers[i];
+      if (N.d.op != SSDK_OP_L2NORM || !N.d.kernel) continue;
+      LayerPlan& P = m->layers[N.d.input];
+      const bool prod_ok = P.d.op == SSDK_OP_CONV && P.C >= 8 && P.C % 8 == 0 && P.in_C >= 8 && !(P.d.bn_gamma && desc->training);
+      int users = 0; bool ok = prod_ok;
+      for (int k = i + 1; k < n && ok; ++k) {
+        const ssdk_layer_desc& u = m->layers[k].d;
+        if (u.op == SSDK_OP_INPUT || u.input != i) continue;
+        ++users;
+        ok = u.op == SSDK_OP_HEAD && u.stride == 1 && m->layers[k].H == N.H && m->layers[k].W == N.W;
+      }
+      if (!ok || !users) continue;
+      N.folded = true; P.wants_ssq = true;
+      for (int k = i + 1; k < n; ++k) if (m->layers[k].d.op != SSDK_OP_INPUT && m->layers[k].d.input == i) m->layers[k].fold_l2n = i;
+    } }
   // pass 2: border each producer must provide (max over its virtual-path conv consumers)
   for (int i = 0; i < n; ++i) {
     const ssdk_layer_desc& d = m->layers[i].d;
     if (d.op != SSDK_OP_CONV && d.op != SSDK_OP_HEAD) continue;
-    LayerPlan& in = m->layers[d.input];
+    LayerPlan& in = m->layers[m->layers[i].fold_l2n >= 0 ? m->layers[m->layers[i].fold_l2n].d.input : d.input];
     const bool im2col = (d.stride != 1) || (in.C < 8);
     if (!im2col) in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)));
     // the image-facing layer's gathered A tile (conv_first_kernel) reads its taps from the input planes' zero border
@@ -552,7 +594,7 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         break;
       case SSDK_OP_CONV:
       case SSDK_OP_HEAD: {
-        const LayerPlan& in = m->layers[d.input];
+        const LayerPlan& in = m->layers[L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.input : d.input];
         if (L.direct) {
           if (L.first_tc)
             rc = launch_conv_first(ctx, in.out, L.out, L.w_hi, L.w_lo, L.bias, L.bn_scale, L.bn_shift, d.act, d.kh, d.kw, d.dilation, d.pad_t,
@@ -586,6 +628,7 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         if (rc) return rc;
         break;
       case SSDK_OP_L2NORM:
+        if (L.folded) break;                     // done by its producer's and its consumers' epilogues
         rc = launch_l2norm(ctx, m->layers[d.input].out, L.out, L.gamma, stream);
         if (rc) return rc;
         break;
@@ -608,6 +651,10 @@ extern "C" int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, v
     SSDK_REQUIRE(L.head_f32, "ssdk_model_read_layer: this plan writes the predictor outputs straight into y_pred (no separate head tensor)");
     SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev, L.head_f32, (size_t)m->B * L.H * L.W * L.C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return SSDK_OK;
+  }
+  if (L.folded) {                                // the forward pass never materialises this tensor: form it now from its input
+    int rc = launch_l2norm(m->ctx, m->layers[L.d.input].out, L.out, L.gamma, stream);
+    if (rc) return rc;
   }
   return launch_unpack(m->ctx, L.out, out_dev, stream);
 }

@@ -35,6 +35,13 @@ struct LayerPlan {
   ConvLaunch launch{};
   float* head_f32 = nullptr;
   bool head_fused = false;            // softmax / concat / anchors done in the conv epilogue (inference plans)
+  // L2Normalization fold (inference plans): the L2NORM layer itself is not launched (`folded`); its producer writes per-pixel
+  // sums of squares (`ssq`), its consumers (`fold_l2n` = index of the L2NORM layer) read the producer's tensor with gamma folded
+  // into their kernels and scale their accumulator rows
+  bool folded = false;
+  int fold_l2n = -1;
+  bool wants_ssq = false;
+  float* ssq = nullptr;
   int prior_off = 0;
   int need_pad = 0;                   // border required by the consumers of this layer's output
   float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};
@@ -95,7 +102,10 @@ inline int upload_f32(ssdk_model* m, float** out, const float* host, size_t n) {
 
 inline int alloc_act(ssdk_model* m, ActBuf& a, int B, int H, int W, int C, int pad) {
   a.B = B; a.H = H; a.W = W; a.C = C; a.Cs = (C + 7) / 8 * 8; a.pad = pad;
-  size_t n = a.elems() + 64 * 8;         // slack: TMA boxes may start on the last rows
+  a.shared = 0;
+  if (!m->training && pad > 0) { const char* e = getenv("SSDK_SHARED_BORDER"); a.shared = e ? (atoi(e) ? 1 : 0) : 1; }
+  // slack: TMA boxes may start on the last rows; with a shared border the last row's right border lies behind the last image
+  size_t n = a.elems() + std::max<size_t>(64 * 8, (size_t)(pad + 1) * a.Cs);
   int rc = dev_alloc(m, &a.hi, n, true);
   if (rc) return rc;
   if (m->split) { rc = dev_alloc(m, &a.lo, n, true); if (rc) return rc; }
