@@ -155,7 +155,7 @@ __device__ __forceinline__ void ld_acc32(uint32_t taddr, uint32_t xoff, uint32_t
 // costs one sweep: <= 2 TMEM loads, C bias adds, C exponentials (kept in registers), one reciprocal, C+12 stores.
 template <int CP4>
 __device__ __forceinline__ void epi_head_fixed(const ConvArgs& args, uint32_t t_row, uint32_t xoff, bool valid, int n, int pix,
-                                               const float* s_bias, float rs) {
+                                               const float* s_bias) {
   constexpr int C = CP4 - 4, RW = C + 12;
 #pragma unroll
   for (int bx = 0; bx < 8; ++bx) {
@@ -172,7 +172,7 @@ __device__ __forceinline__ void epi_head_fixed(const ConvArgs& args, uint32_t t_
 #pragma unroll
     for (int r = 0; r < CP4; ++r) {
       const int col = c_lo + r;
-      e[r] = fmaf(__uint_as_float(((col >> 5) == k_lo) ? v0[col & 31] : v1[col & 31]), rs, s_bias[col]);
+      e[r] = __uint_as_float(((col >> 5) == k_lo) ? v0[col & 31] : v1[col & 31]) + s_bias[col];
     }
     float mx = e[0];
 #pragma unroll
@@ -197,8 +197,7 @@ __device__ __forceinline__ void epi_head_fixed(const ConvArgs& args, uint32_t t_
 // 16-byte store.  BWD adds what the data-gradient launches need: ReLU'(forward value) mask and accumulation into the output.
 template <bool BWD>
 __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, uint32_t xoff, int ncols, int n0, size_t o, bool valid,
-                                          const float* s_bias, const float* s_scale, const float* s_shift, float* ssq_dst = nullptr) {
-  float ssq = 0.f;                 // folded L2Normalization: sum of squares of the (float32) activations this thread writes
+                                          const float* s_bias, const float* s_scale, const float* s_shift) {
   if (!BWD && !args.bn_scale && args.act == SSDK_ACT_RELU && args.out_lo) {
     // the common forward case (bias + ReLU, hi/lo planes) without per-element branches: packed conversions (two values per
     // cvt.rn.bf16x2.f32), biases fetched four at a time, and 32-byte stores (one full sector per lane and instruction: a thread's
@@ -223,7 +222,6 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
             for (int j = 0; j < 4; ++j) {
               const float f0 = fmaxf(__uint_as_float(vr[g * 8 + j * 2]) + bb[j * 2], 0.f);
               const float f1 = fmaxf(__uint_as_float(vr[g * 8 + j * 2 + 1]) + bb[j * 2 + 1], 0.f);
-              ssq = fmaf(f0, f0, ssq); ssq = fmaf(f1, f1, ssq);
               const __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
               const uint32_t hp = *reinterpret_cast<const uint32_t*>(&hh);
               const __nv_bfloat162 ll = __floats2bfloat162_rn(f0 - __uint_as_float(hp << 16), f1 - __uint_as_float(hp & 0xffff0000u));
@@ -249,7 +247,6 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
         }
       }
     }
-    if (ssq_dst && valid) *ssq_dst = ssq;
     return;
   }
   for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -283,7 +280,6 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
               xv += __uint_as_float(((ohw[j] >> (e * 16)) & 0xffffu) << 16) + __uint_as_float(((olw[j] >> (e * 16)) & 0xffffu) << 16);
             }
             f[e] = xv;
-            if (!BWD) ssq = fmaf(xv, xv, ssq);
           }
           __nv_bfloat16 h0 = __float2bfloat16_rn(f[0]), h1 = __float2bfloat16_rn(f[1]);
           __nv_bfloat16 l0 = __float2bfloat16_rn(f[0] - __bfloat162float(h0));
@@ -296,7 +292,6 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
       }
     }
   }
-  if (!BWD && ssq_dst && valid) *ssq_dst = ssq;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,11 +504,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       const uint32_t t_row = tmem_base + (uint32_t)((acc * MT + mt) * XS * BN) + ((uint32_t)(q * 32) << 16);
       const uint32_t xoff = (uint32_t)((XS - 1) * BN);
       if (args.epi == EPI_SPLIT) {
-        const size_t orow = ((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad);
-        const size_t o = orow * args.out_Cs + n0;
-        float* ssq_dst = args.ssq_out ? args.ssq_out + (size_t)(n0 / BN) * (size_t)args.ssq_stride + orow : nullptr;
+        const size_t o = (((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad)) * args.out_Cs + n0;
         if (args.mask_hi || args.accumulate) epi_split<true>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
-        else epi_split<false>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift, ssq_dst);
+        else epi_split<false>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
       } else if (args.epi == EPI_ATOMIC) {
         float* dstp = args.out_f32 + (size_t)v * args.out_ld + args.out_col_off + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -526,17 +519,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
       } else if (args.epi == EPI_HEAD) {
-        float rs = 1.f;                                        // folded L2Normalization: 1 / norm of this pixel's input channels
-        if (args.row_scale && valid) {
-          float ss = 0.f;
-          for (int p = 0; p < args.row_scale_tiles; ++p) ss += __ldg(args.row_scale + (size_t)p * (size_t)args.ssq_stride + (size_t)(v + args.row_scale_shift));
-          rs = rsqrtf(fmaxf(ss, 1e-12f));
-        }
         // one thread = one pixel = n_boxes prior rows.  Per box three sweeps over its C+4 accumulator columns (TMEM reads are cheap
         // and this warp group runs under the MMAs of the next tile): maximum, sum of exponentials, normalised store.
         const int C = args.head_C, CP4 = C + 4, RW = C + 12;
         const int pix = y * args.Wo + x;
-        if (CP4 == 25 && args.head_nb <= 8) { epi_head_fixed<25>(args, t_row, xoff, valid, n, pix, s_bias, rs); continue; }
+        if (CP4 == 25 && args.head_nb <= 8) { epi_head_fixed<25>(args, t_row, xoff, valid, n, pix, s_bias); continue; }
         for (int bx = 0; bx < args.head_nb; ++bx) {
           const int c_lo = bx * CP4, c_hi = c_lo + CP4;
           const int k_lo = c_lo >> 5, k_hi = (c_hi - 1) >> 5;
@@ -547,7 +534,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int col = k * 32 + j;
-              if (col >= c_lo && col < c_lo + C) mx = fmaxf(mx, fmaf(__uint_as_float(vr[j]), rs, s_bias[col]));
+              if (col >= c_lo && col < c_lo + C) mx = fmaxf(mx, __uint_as_float(vr[j]) + s_bias[col]);
             }
           }
           float sum = 0.f;
@@ -557,7 +544,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int col = k * 32 + j;
-              if (col >= c_lo && col < c_lo + C) sum += expf(fmaf(__uint_as_float(vr[j]), rs, s_bias[col]) - mx);
+              if (col >= c_lo && col < c_lo + C) sum += expf(__uint_as_float(vr[j]) + s_bias[col] - mx);
             }
           }
           const int prior = args.head_prior_off + pix * args.head_nb + bx;
@@ -570,7 +557,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               for (int j = 0; j < 32; ++j) {
                 const int col = k * 32 + j;
                 if (col >= c_lo && col < c_hi) {
-                  const float v = fmaf(__uint_as_float(vr[j]), rs, s_bias[col]);
+                  const float v = __uint_as_float(vr[j]) + s_bias[col];
                   const int r = col - c_lo;
                   dst[r] = r < C ? expf(v - mx) / sum : v;
                 }
@@ -584,12 +571,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           }
         }
       } else {
-        float rs = 1.f;
-        if (args.row_scale && valid) {
-          float ss = 0.f;
-          for (int p = 0; p < args.row_scale_tiles; ++p) ss += __ldg(args.row_scale + (size_t)p * (size_t)args.ssq_stride + (size_t)(v + args.row_scale_shift));
-          rs = rsqrtf(fmaxf(ss, 1e-12f));
-        }
         const size_t o = (((size_t)n * args.Ho + y) * args.Wo + x) * (size_t)args.cout + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t vr[32];
@@ -599,7 +580,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             for (int j = 0; j < 32; ++j) {
               if (c0 + j < ncols) {
                 const int col = n0 + c0 + j;
-                float xv = fmaf(__uint_as_float(vr[j]), rs, s_bias[col]);
+                float xv = __uint_as_float(vr[j]) + s_bias[col];
                 args.out_f32[o + c0 + j] = apply_act(xv, args.act);
               }
             }

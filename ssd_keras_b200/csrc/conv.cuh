@@ -74,12 +74,6 @@ struct ConvArgs {
   //     are n_boxes x [C class logits | 4 offsets]; every (pixel, box) becomes one row of y_pred (out_f32):
   //     [softmax(C) | 4 offsets | 4 anchor coordinates | 4 variances] at prior head_prior_off + pixel * n_boxes + box.
   int head_nb, head_C, head_P, head_prior_off;
-  // --- L2Normalization folded into its producer and its consumers (inference plans, models/keras_ssd300.py:316 ->
-  //     keras_layer_L2Normalization.py:61-63).  Producer (EPI_SPLIT): every epilogue thread also stores the sum of squares of the
-  //     channels it wrote, one partial per n-tile: ssq_out[n_tile * ssq_stride + output row].  Consumer (predictor head, gamma folded
-  //     into its kernel): each accumulator row is multiplied by rsqrt(max(sum of the partials, 1e-12)) before the bias is added.
-  float* ssq_out; long long ssq_stride;
-  const float* row_scale; int row_scale_tiles, row_scale_shift;       // partials of row (virtual row + shift)
   const float* head_anchors;      // [P*4]
   float head_var[4];
 };

@@ -11,7 +11,7 @@ namespace {
 // Pack an HWIO float32 kernel (optionally two kernels fused per box: conf + loc) into K-major bf16 hi/lo planes
 // [cout][taps][kblocks*64] (virtual path) or [cout][kblocks*64] with k = (kh*KW+kw)*cin + c (im2col path).
 void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, bool im2col, int Ctot,
-                  std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, std::vector<float>& bias, const float* in_scale = nullptr) {
+                  std::vector<uint16_t>& hi, std::vector<uint16_t>& lo, std::vector<float>& bias) {
   const ssdk_layer_desc& d = L.d;
   const size_t Krow = im2col ? (size_t)kblocks * 64 : (size_t)taps * kblocks * 64;
   hi.assign((size_t)cout * Krow, 0); lo.assign((size_t)cout * Krow, 0);
@@ -30,8 +30,7 @@ void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, 
     }
     for (int t = 0; t < taps; ++t)
       for (int c = 0; c < cin; ++c) {
-        float w = ker[((size_t)t * cin + c) * ocn + oc];             // HWIO: ((kh*KW+kw)*cin + c)*cout + o
-        if (in_scale) w *= in_scale[c];                              // folded L2Normalization: gamma of the input channel
+        const float w = ker[((size_t)t * cin + c) * ocn + oc];       // HWIO: ((kh*KW+kw)*cin + c)*cout + o
         const size_t k = im2col ? (size_t)t * cin + c : (size_t)t * kblocks * 64 + c;
         const uint16_t h = f2bf(w);
         hi[(size_t)o * Krow + k] = h;
@@ -43,7 +42,7 @@ void pack_weights(const LayerPlan& L, int cin, int cout, int taps, int kblocks, 
 int build_conv(ssdk_model* m, int li) {
   LayerPlan& L = m->layers[li];
   const ssdk_layer_desc& d = L.d;
-  const LayerPlan& in = m->layers[L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.input : d.input];   // folded L2Normalization: read its input
+  const LayerPlan& in = m->layers[d.input];
   const ActBuf& ia = in.out;
   const int cin = in.C;
   const bool head = d.op == SSDK_OP_HEAD;
@@ -119,7 +118,7 @@ int build_conv(ssdk_model* m, int li) {
   L.kblocks = kblocks;
   // weights
   std::vector<uint16_t> whi, wlo; std::vector<float> bias;
-  pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias, L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.kernel : nullptr);
+  pack_weights(L, cin, cout, taps, kblocks, L.im2col, m->Ctot, whi, wlo, bias);
   const size_t Krow = whi.size() / cout;
   L.w_krow = Krow;
   int rc = dev_alloc(m, &L.w_hi, whi.size(), false); if (rc) return rc;
@@ -154,14 +153,6 @@ int build_conv(ssdk_model* m, int li) {
     a.bn_scale = L.bn_scale; a.bn_shift = L.bn_shift;
   }
   a.act = L.bn_train ? SSDK_ACT_NONE : d.act;
-  if (L.fold_l2n >= 0) {               // rows of this head are scaled by the producer's per-pixel 1/norm (partials per producer n-tile)
-    a.row_scale = in.ssq; a.row_scale_tiles = in.launch.args.n_tiles_n; a.ssq_stride = (long long)ia.rows();
-    a.row_scale_shift = ia.pad * ia.Wp() + ia.pad;      // output (y, x) of a 'same' convolution <-> stored input row of pixel (y, x)
-  }
-  if (L.wants_ssq) {
-    int rc2 = dev_alloc(m, &L.ssq, (size_t)a.n_tiles_n * L.out.rows(), true); if (rc2) return rc2;
-    a.ssq_out = L.ssq; a.ssq_stride = (long long)L.out.rows();
-  }
   if (head) {
     // inference plans: softmax / concat / anchors in the epilogue, straight into y_pred (one n-tile holds all boxes of a pixel);
     // training plans keep the raw logits (the backward pass needs them) and finish with head_finalize_kernel
@@ -290,7 +281,9 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
     // 256-wide grid wastes more than that: conv5_x (220 units on 148 SMs) 178 -> 168 us, conv6_2 / conv7_2 / conv8_2 54 -> 39,
     // 34 -> 25, 32 -> 24 us
     const double t256 = (double)((u256 + sms - 1) / sms) * 256.0;
-    const double t128 = (double)((u128 + sms - 1) / sms) * 128.0 * 1.18;
+    double pen = 1.18;                                  // SSDK_BN128_PENALTY: experiment knob for this factor
+    if (const char* e = getenv("SSDK_BN128_PENALTY")) pen = atof(e);
+    const double t128 = (double)((u128 + sms - 1) / sms) * 128.0 * pen;
     bool use128 = t128 < 0.95 * t256;
     if (const char* e = getenv("SSDK_BN_AUTO")) { if (!atoi(e)) use128 = false; }
     if (const char* e = getenv("SSDK_BN_MAX")) use128 = atoi(e) <= 128;
@@ -425,30 +418,11 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
       L.H = in.H; L.W = in.W; L.C = in.C;
     } else { set_error("layer %d: unknown op %d", i, d.op); return fail(SSDK_ERR_INVALID); }
   }
-  // pass 1b (inference plans): L2Normalization layers that only feed 3x3 / 1x1 'same' predictor heads and follow a tensor-core
-  // convolution are folded away (SSDK_FOLD_L2N=0 keeps the separate kernel)
-  { const char* e = getenv("SSDK_FOLD_L2N"); const bool want = e ? atoi(e) != 0 : true;
-    for (int i = 0; i < n && want && !desc->training; ++i) {
-      LayerPlan& N = m->layers[i];
-      if (N.d.op != SSDK_OP_L2NORM || !N.d.kernel) continue;
-      LayerPlan& P = m->layers[N.d.input];
-      const bool prod_ok = P.d.op == SSDK_OP_CONV && P.C >= 8 && P.C % 8 == 0 && P.in_C >= 8 && !(P.d.bn_gamma && desc->training);
-      int users = 0; bool ok = prod_ok;
-      for (int k = i + 1; k < n && ok; ++k) {
-        const ssdk_layer_desc& u = m->layers[k].d;
-        if (u.op == SSDK_OP_INPUT || u.input != i) continue;
-        ++users;
-        ok = u.op == SSDK_OP_HEAD && u.stride == 1 && m->layers[k].H == N.H && m->layers[k].W == N.W;
-      }
-      if (!ok || !users) continue;
-      N.folded = true; P.wants_ssq = true;
-      for (int k = i + 1; k < n; ++k) if (m->layers[k].d.op != SSDK_OP_INPUT && m->layers[k].d.input == i) m->layers[k].fold_l2n = i;
-    } }
   // pass 2: border each producer must provide (max over its virtual-path conv consumers)
   for (int i = 0; i < n; ++i) {
     const ssdk_layer_desc& d = m->layers[i].d;
     if (d.op != SSDK_OP_CONV && d.op != SSDK_OP_HEAD) continue;
-    LayerPlan& in = m->layers[m->layers[i].fold_l2n >= 0 ? m->layers[m->layers[i].fold_l2n].d.input : d.input];
+    LayerPlan& in = m->layers[d.input];
     const bool im2col = (d.stride != 1) || (in.C < 8);
     if (!im2col) in.need_pad = std::max(in.need_pad, std::max(std::max(d.pad_t, d.pad_b), std::max(d.pad_l, d.pad_r)));
     // the image-facing layer's gathered A tile (conv_first_kernel) reads its taps from the input planes' zero border
@@ -594,7 +568,7 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         break;
       case SSDK_OP_CONV:
       case SSDK_OP_HEAD: {
-        const LayerPlan& in = m->layers[L.fold_l2n >= 0 ? m->layers[L.fold_l2n].d.input : d.input];
+        const LayerPlan& in = m->layers[d.input];
         if (L.direct) {
           if (L.first_tc)
             rc = launch_conv_first(ctx, in.out, L.out, L.w_hi, L.w_lo, L.bias, L.bn_scale, L.bn_shift, d.act, d.kh, d.kw, d.dilation, d.pad_t,
@@ -628,7 +602,6 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
         if (rc) return rc;
         break;
       case SSDK_OP_L2NORM:
-        if (L.folded) break;                     // done by its producer's and its consumers' epilogues
         rc = launch_l2norm(ctx, m->layers[d.input].out, L.out, L.gamma, stream);
         if (rc) return rc;
         break;
@@ -651,10 +624,6 @@ extern "C" int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, v
     SSDK_REQUIRE(L.head_f32, "ssdk_model_read_layer: this plan writes the predictor outputs straight into y_pred (no separate head tensor)");
     SSDK_CHECK_CUDA(cudaMemcpyAsync(out_dev, L.head_f32, (size_t)m->B * L.H * L.W * L.C * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     return SSDK_OK;
-  }
-  if (L.folded) {                                // the forward pass never materialises this tensor: form it now from its input
-    int rc = launch_l2norm(m->ctx, m->layers[L.d.input].out, L.out, L.gamma, stream);
-    if (rc) return rc;
   }
   return launch_unpack(m->ctx, L.out, out_dev, stream);
 }

@@ -35,13 +35,6 @@ struct LayerPlan {
   ConvLaunch launch{};
   float* head_f32 = nullptr;
   bool head_fused = false;            // softmax / concat / anchors done in the conv epilogue (inference plans)
-  // L2Normalization fold (inference plans): the L2NORM layer itself is not launched (`folded`); its producer writes per-pixel
-  // sums of squares (`ssq`), its consumers (`fold_l2n` = index of the L2NORM layer) read the producer's tensor with gamma folded
-  // into their kernels and scale their accumulator rows
-  bool folded = false;
-  int fold_l2n = -1;
-  bool wants_ssq = false;
-  float* ssq = nullptr;
   int prior_off = 0;
   int need_pad = 0;                   // border required by the consumers of this layer's output
   float mean[3] = {0, 0, 0}, stddev[3] = {1, 1, 1}; int swap[3] = {0, 1, 2};

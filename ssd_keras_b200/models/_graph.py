@@ -304,13 +304,16 @@ class SSDModel:
 
         batches: iterable of float32 (B,H,W,3) pinned CPU tensors (used as they are) or ndarrays (pinned here, one host copy).
         post:    optional function applied to the device result of each batch before it is downloaded (e.g. an all-gather).
-        Yields pinned CPU tensors; a yielded tensor is overwritten when the generator is advanced twice more."""
+        Yields pinned CPU tensors out of three rotating buffers owned by the model (allocating pinned memory costs milliseconds,
+        so it happens once per result shape): a yielded tensor is overwritten when two more batches have gone through this model."""
         import torch
         main = torch.cuda.current_stream()
         if getattr(self, '_up_stream', None) is None:
             self._up_stream = torch.cuda.Stream()
+            self._pin_slots = [None, None, None]
+            self._pin_next = 0
         up = self._up_stream
-        slots = [None, None, None]                      # pinned result buffers, rotated
+        slots = self._pin_slots                         # pinned result buffers, rotated
 
         def upload(hb):
             if not torch.is_tensor(hb):
@@ -341,9 +344,11 @@ class SSDModel:
             out = self.predict_device(x)
             if post is not None:
                 out = post(out)
-            buf = slots[i % 3]
+            k = self._pin_next
+            self._pin_next = (k + 1) % 3
+            buf = slots[k]
             if buf is None or buf.shape != out.shape or buf.dtype != out.dtype:
-                buf = slots[i % 3] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                buf = slots[k] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
             buf.copy_(out, non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
