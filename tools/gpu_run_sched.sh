@@ -1,22 +1,16 @@
 #!/bin/bash
-# new plan features (two-stream schedule, fused weight operand, shared border, folded L2Normalization): parity tests, a knock-out
-# pass if they fail, then same-box A/B of the knobs (short bench runs)
+# plan features of this round (two-stream schedule, fused weight operand, shared border): parity tests, the training check with and
+# without the fused operand, then same-box A/B of the knobs (short bench runs)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 rm -f gpurun_out/bench_sched.log gpurun_out/bench_sched.err
-timeout 300 python tools/e2e_diag.py > gpurun_out/e2e_diag.log 2>&1
+for f in 1 0; do
+  SSDK_FUSE_B=$f timeout 200 python tools/train_check.py --case 3 > gpurun_out/train_case3_fuse$f.log 2>&1
+done
 T="tests/test_gpu_schedule.py tests/test_gpu_model.py tests/test_gpu_reference_goldens.py tests/test_gpu_train.py"
 timeout 1200 python -m pytest $T -m gpu -q -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/pytest_sched.log
-rc=${PIPESTATUS[0]}
-echo "exit $rc" >> gpurun_out/pytest_sched.log
-if [ "$rc" != "0" ]; then
-  for k in SSDK_FUSE_B SSDK_SHARED_BORDER SSDK_FOLD_L2N; do
-    env $k=0 timeout 600 python -m pytest tests/test_gpu_model.py tests/test_gpu_reference_goldens.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -12 > gpurun_out/pytest_sched_$k.log
-    echo "== $k=0: exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_sched.log
-  done
-fi
-OFF="SSDK_FUSE_B=0 SSDK_SHARED_BORDER=0 SSDK_FOLD_L2N=0"
-for cfg in "$OFF" "SSDK_SHARED_BORDER=0 SSDK_FOLD_L2N=0" "SSDK_FUSE_B=0 SSDK_FOLD_L2N=0" "SSDK_FUSE_B=0 SSDK_SHARED_BORDER=0" "SSDK_OVERLAP_R=37" "SSDK_OVERLAP_R=50" "$OFF" "SSDK_OVERLAP_R=37"; do
+echo "exit ${PIPESTATUS[0]}" >> gpurun_out/pytest_sched.log
+for cfg in "SSDK_X=0" "SSDK_BN128_PENALTY=1.03" "SSDK_BN128_PENALTY=1.10" "SSDK_OVERLAP_R=37" "SSDK_X=0" "SSDK_BN128_PENALTY=1.03"; do
   echo "== $cfg" >> gpurun_out/bench_sched.log
   env $cfg timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-micro 2>> gpurun_out/bench_sched.err | python -c "
 import sys, json
@@ -26,4 +20,4 @@ for l in sys.stdin:
     print(json.dumps({k: j[k] for k in ('value', 'ms_per_step', 'gpu_launches')} | {'e2e': j['e2e']['value'], 'e2e_ms': j['e2e']['ms_per_step'], 'conv_ms': j['roofline']['conv_ms_per_step'], 'frac': j['roofline']['frac'], 'clk': j['clocks']['sm_mhz'], 'why': j['clocks']['reasons']}))
 " >> gpurun_out/bench_sched.log
 done
-cat gpurun_out/e2e_diag.log; tail -12 gpurun_out/pytest_sched.log; cat gpurun_out/bench_sched.log; tail -5 gpurun_out/bench_sched.err
+grep -n "BAD\|CASE\|weights after\|loss" gpurun_out/train_case3_fuse1.log | head -20; grep -n "BAD\|CASE" gpurun_out/train_case3_fuse0.log | head; tail -12 gpurun_out/pytest_sched.log; cat gpurun_out/bench_sched.log; tail -5 gpurun_out/bench_sched.err
