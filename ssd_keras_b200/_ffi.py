@@ -131,6 +131,10 @@ def lib():
         L.ssdk_assemble_batch.restype = C.c_int
         L.ssdk_l2_normalize.argtypes = [vp, vp, C.c_longlong, C.c_int, vp, vp, vp]
         L.ssdk_l2_normalize.restype = C.c_int
+        L.ssdk_conv2d_fwd.argtypes = [vp, vp] + [C.c_int] * 4 + [vp, vp] + [C.c_int] * 11 + [vp, vp]
+        L.ssdk_conv2d_fwd.restype = C.c_int
+        L.ssdk_maxpool.argtypes = [vp, vp] + [C.c_int] * 11 + [vp, vp]
+        L.ssdk_maxpool.restype = C.c_int
         if hasattr(L, 'ssdk_model_create'):
             L.ssdk_model_create.argtypes = [vp, C.POINTER(ModelDesc), C.POINTER(vp)]
             L.ssdk_model_destroy.argtypes = [vp]

@@ -1339,6 +1339,24 @@ __global__ void unpack_kernel(ActBuf in, float* __restrict__ out) {
   out[i] = split_load(in, act_index(in, n, y, x) + c);
 }
 
+// float32 NHWC tensor -> split bf16 planes of an activation buffer (SSDK_OP_TENSOR); channels beyond C stay zero
+__global__ void pack_kernel(const float* __restrict__ in, ActBuf out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)out.B * out.H * out.W * out.C;
+  if (i >= total) return;
+  const int c = (int)(i % out.C); const size_t pix = i / out.C;
+  const int x = (int)(pix % out.W); const int y = (int)((pix / out.W) % out.H); const int n = (int)(pix / ((size_t)out.W * out.H));
+  split_store(out, act_index(out, n, y, x) + c, in[i]);
+}
+
+int launch_pack(ssdk_ctx* ctx, const float* in, const ActBuf& out, cudaStream_t stream) {
+  const size_t total = (size_t)out.B * out.H * out.W * out.C;
+  pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);
+  SSDK_COUNT_LAUNCH(ctx);
+  SSDK_CHECK_CUDA(cudaGetLastError());
+  return SSDK_OK;
+}
+
 int launch_unpack(ssdk_ctx* ctx, const ActBuf& in, float* out, cudaStream_t stream) {
   const size_t total = (size_t)in.B * in.H * in.W * in.C;
   unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, out);

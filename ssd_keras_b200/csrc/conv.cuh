@@ -115,5 +115,6 @@ int launch_l2norm(ssdk_ctx* ctx, const ActBuf& in, const ActBuf& out, const floa
 int launch_head_finalize(ssdk_ctx* ctx, const float* head, int B, int HW, int n_boxes, int C, int P, int prior_off,
                          const float* anchors, const float* variances, float* y_pred, cudaStream_t stream);
 int launch_unpack(ssdk_ctx* ctx, const ActBuf& in, float* out, cudaStream_t stream);
+int launch_pack(ssdk_ctx* ctx, const float* in, const ActBuf& out, cudaStream_t stream);      // float32 NHWC -> hi/lo planes (interior only)
 
 }  // namespace ssdk

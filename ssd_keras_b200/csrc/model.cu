@@ -393,6 +393,7 @@ extern "C" int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssd
     LayerPlan& L = m->layers[i];
     L.d = desc->layers[i];
     const ssdk_layer_desc& d = L.d;
+    if (d.op == SSDK_OP_TENSOR) { L.H = m->H; L.W = m->W; L.C = m->Cimg; continue; }
     if (d.op == SSDK_OP_INPUT) {
       L.H = m->H; L.W = m->W; L.C = m->Cimg;
       if (d.mean) { L.has_mean = true; for (int c = 0; c < 3; ++c) L.mean[c] = d.mean[c]; }
@@ -561,6 +562,10 @@ extern "C" int ssdk_model_forward(ssdk_model* m, const float* images_dev, float*
       if (!sx && side_used) cap = m->grid_cap;
     }
     switch (d.op) {
+      case SSDK_OP_TENSOR:
+        rc = launch_pack(ctx, images_dev, L.out, stream);
+        if (rc) return rc;
+        break;
       case SSDK_OP_INPUT:
         rc = launch_preprocess(ctx, images_dev, m->B, m->H, m->W, m->Cimg, L.has_mean ? L.mean : nullptr,
                                L.has_std ? L.stddev : nullptr, L.has_swap ? L.swap : nullptr, L.out, stream);
@@ -626,4 +631,60 @@ extern "C" int ssdk_model_read_layer(ssdk_model* m, int layer, float* out_dev, v
     return SSDK_OK;
   }
   return launch_unpack(m->ctx, L.out, out_dev, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stand-alone layer calls (ssdk_conv2d_fwd, ssdk_maxpool): a one-layer graph through the same plan builder
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int run_single_layer(ssdk_ctx* ctx, const float* x_dev, int B, int H, int W, int C, const ssdk_layer_desc& layer, int precision,
+                     float* y_dev, void* stream) {
+  ssdk_layer_desc layers[2];
+  memset(layers, 0, sizeof(layers));
+  layers[0].op = SSDK_OP_TENSOR; layers[0].input = -1;
+  layers[1] = layer; layers[1].input = 0;
+  ssdk_model_desc md;
+  memset(&md, 0, sizeof(md));
+  md.batch = B; md.img_height = H; md.img_width = W; md.img_channels = C; md.n_classes_total = 0;
+  md.n_layers = 2; md.layers = layers; md.precision = precision; md.anchors_f32 = nullptr; md.training = 0;
+  ssdk_model* m = nullptr;
+  int rc = ssdk_model_create(ctx, &md, &m);
+  if (rc) return rc;
+  rc = ssdk_model_forward(m, x_dev, nullptr, stream);
+  if (!rc) rc = ssdk_model_read_layer(m, 1, y_dev, stream);
+  const cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);     // the plan's buffers are freed below
+  ssdk_model_destroy(m);
+  if (!rc && e != cudaSuccess) { set_error("ssdk single-layer call failed: %s", cudaGetErrorString(e)); return SSDK_ERR_CUDA; }
+  return rc;
+}
+}  // namespace
+
+extern "C" int ssdk_conv2d_fwd(ssdk_ctx* ctx, const float* x_dev, int B, int H, int W, int Cin, const float* kernel_hwio_host,
+                               const float* bias_host, int Cout, int kh, int kw, int stride, int dilation, int pad_t, int pad_l,
+                               int pad_b, int pad_r, int act, int precision, float* y_dev, void* stream) {
+  SSDK_REQUIRE(ctx && x_dev && kernel_hwio_host && y_dev, "ssdk_conv2d_fwd: NULL argument");
+  SSDK_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "ssdk_conv2d_fwd: bad tensor shape");
+  SSDK_REQUIRE(Cout % 8 == 0, "ssdk_conv2d_fwd: output channels must be a multiple of 8 (got %d)", Cout);
+  SSDK_REQUIRE(Cin >= 8 || (stride == 1 && Cin <= 4), "ssdk_conv2d_fwd: 5..7 input channels are not supported (pad the tensor to 8)");
+  SSDK_REQUIRE(pad_t >= 0 && pad_l >= 0 && pad_b >= 0 && pad_r >= 0, "ssdk_conv2d_fwd: negative padding");
+  ssdk_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  std::vector<float> zero_bias;
+  if (!bias_host) { zero_bias.assign(Cout, 0.f); bias_host = zero_bias.data(); }
+  d.op = SSDK_OP_CONV; d.cout = Cout; d.kh = kh; d.kw = kw; d.stride = stride; d.dilation = dilation;
+  d.pad_t = pad_t; d.pad_l = pad_l; d.pad_b = pad_b; d.pad_r = pad_r; d.act = act;
+  d.kernel = kernel_hwio_host; d.bias = bias_host;
+  return run_single_layer(ctx, x_dev, B, H, W, Cin, d, precision, y_dev, stream);
+}
+
+extern "C" int ssdk_maxpool(ssdk_ctx* ctx, const float* x_dev, int B, int H, int W, int C, int kh, int kw, int stride, int pad_t,
+                            int pad_l, int pad_b, int pad_r, float* y_dev, void* stream) {
+  SSDK_REQUIRE(ctx && x_dev && y_dev, "ssdk_maxpool: NULL argument");
+  SSDK_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0, "ssdk_maxpool: bad argument");
+  SSDK_REQUIRE(pad_t >= 0 && pad_l >= 0 && pad_b >= 0 && pad_r >= 0 && pad_t < kh && pad_l < kw, "ssdk_maxpool: bad padding");
+  ssdk_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  d.op = SSDK_OP_MAXPOOL; d.kh = kh; d.kw = kw; d.stride = stride; d.dilation = 1;
+  d.pad_t = pad_t; d.pad_l = pad_l; d.pad_b = pad_b; d.pad_r = pad_r;
+  return run_single_layer(ctx, x_dev, B, H, W, C, d, 0, y_dev, stream);
 }
