@@ -141,10 +141,12 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // Accumulator read: 32 columns of this thread's TMEM lane; with a separate cross-term accumulator (`xoff` columns further)
 // the two partial sums are added here in fp32 round-to-nearest.
 __device__ __forceinline__ void ld_acc32(uint32_t taddr, uint32_t xoff, uint32_t (&v)[32]) {
-  tmem_ld32(taddr, v);
-  if (xoff) {
+  if (!xoff) { tmem_ld32(taddr, v); return; }
+  {
     uint32_t w[32];
-    tmem_ld32(taddr + xoff, w);
+    tmem_ld32_nowait(taddr, v);            // both loads in flight, one wait (SSDK: the epilogue of 256-wide tiles with a cross-term
+    tmem_ld32_nowait(taddr + xoff, w);     // accumulator does not overlap the next tile's MMAs, so its latency is on the critical path)
+    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
   }
@@ -195,7 +197,7 @@ __device__ __forceinline__ void epi_head_fixed(const ConvArgs& args, uint32_t t_
 
 // Epilogue of the activation-producing launches: bias / folded BatchNorm / activation -> bf16 hi+lo planes, 8 channels per
 // 16-byte store.  BWD adds what the data-gradient launches need: ReLU'(forward value) mask and accumulation into the output.
-template <bool BWD>
+template <bool BWD, bool PIPE = false>
 __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, uint32_t xoff, int ncols, int n0, size_t o, bool valid,
                                           const float* s_bias, const float* s_scale, const float* s_shift) {
   if (!BWD && !args.bn_scale && args.act == SSDK_ACT_RELU && args.out_lo) {
@@ -204,10 +206,8 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
     // row is 2*Cout bytes of its own, so 16-byte stores leave every sector half written per instruction).  Bit-identical to the
     // generic path below.
     const bool wide = (args.out_Cs % 16 == 0) && ((n0 & 15) == 0);
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
-      uint32_t vr[32];
-      ld_acc32(t_row + (uint32_t)c0, xoff, vr);
-      if (!valid) continue;
+    // one chunk of 32 accumulator columns: bias + ReLU, hi/lo split, stores
+    auto process = [&](const uint32_t (&vr)[32], int c0) {
 #pragma unroll
       for (int g2 = 0; g2 < 2; ++g2) {
         uint32_t ph[8], pl[8];
@@ -245,6 +245,42 @@ __device__ __forceinline__ void epi_split(const ConvArgs& args, uint32_t t_row, 
             *reinterpret_cast<uint4*>(args.out_lo + o + cA + 8) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
           }
         }
+      }
+    
+    };
+    if constexpr (PIPE) {
+      // software-pipelined accumulator reads (conv_tcgen05_kernel): the TMEM loads of chunk c+1 are issued before chunk c is converted
+      // and stored, so their latency hides behind that work (tcgen05.wait::ld waits for every load this thread has issued).  It
+      // matters for the 256-wide tiles with a cross-term accumulator: they have ONE accumulator set, so their epilogue does not run
+      // under the next tile's MMAs.  args.epi_pipe (SSDK_EPI_PIPE): 2 = as described (default), 1 = both loads of a chunk in flight
+      // but no prefetch, 0 = one load at a time.
+      const int pipe = args.epi_pipe;
+      uint32_t va[32], vb[32];
+      if (pipe == 2) {
+        tmem_ld32_nowait(t_row, va);
+        if (xoff) tmem_ld32_nowait(t_row + xoff, vb);
+      }
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t vr[32];
+        if (pipe != 2) {
+          tmem_ld32_nowait(t_row + (uint32_t)c0, va);
+          if (pipe == 0) tmem_ld_wait();
+          if (xoff) tmem_ld32_nowait(t_row + (uint32_t)c0 + xoff, vb);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vr[j] = xoff ? __float_as_uint(__uint_as_float(va[j]) + __uint_as_float(vb[j])) : va[j];
+        if (pipe == 2 && c0 + 32 < ncols) {
+          tmem_ld32_nowait(t_row + (uint32_t)(c0 + 32), va);
+          if (xoff) tmem_ld32_nowait(t_row + (uint32_t)(c0 + 32) + xoff, vb);
+        }
+        if (valid) process(vr, c0);
+      }
+    } else {
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t vr[32];
+        ld_acc32(t_row + (uint32_t)c0, xoff, vr);
+        if (valid) process(vr, c0);
       }
     }
     return;
@@ -506,7 +542,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       if (args.epi == EPI_SPLIT) {
         const size_t o = (((size_t)n * args.out_Hp + (y + args.out_pad)) * args.out_Wp + (x + args.out_pad)) * args.out_Cs + n0;
         if (args.mask_hi || args.accumulate) epi_split<true>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
-        else epi_split<false>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
+        else epi_split<false, true>(args, t_row, xoff, ncols, n0, o, valid, s_bias, s_scale, s_shift);
       } else if (args.epi == EPI_ATOMIC) {
         float* dstp = args.out_f32 + (size_t)v * args.out_ld + args.out_col_off + n0;
         for (int c0 = 0; c0 < ncols; c0 += 32) {

@@ -50,6 +50,7 @@ struct ConvArgs {
   int resident_b;       // 1: all KH*KW*kblocks weight tiles of the (single) n-tile stay in shared memory for the whole launch
   int mt;               // m-tiles per work unit (1 or 2): with 2, every weight tile feeds two 128-row MMAs (halves the weight traffic)
   int bo_mode;          // how the UMMA descriptor's base-offset field is filled for row-shifted A tiles (debug knob)
+  int epi_pipe;         // forward epilogue: 2 = TMEM loads of the next 32 columns issued before the current ones are converted / stored, 1 / 0 = experiment knobs
   int n_tiles_m;        // number of entries in tile_list
   int n_tiles_n;
   const int* tile_list; // m-tile indices that contain at least one valid row

@@ -329,6 +329,7 @@ int plan_conv_gemm(ssdk_model* m, ConvLaunch& cl, const ConvGeom& g, const __nv_
     } }
   conv_pick_stages(a);
   { const char* e = getenv("SSDK_BO_MODE"); a.bo_mode = e ? atoi(e) : 0; }
+  { const char* e = getenv("SSDK_EPI_PIPE"); a.epi_pipe = e ? atoi(e) : 2; }
   // m-tiles that hold at least one valid output row
   std::vector<int> tiles;
   for (int t = 0; t < n_m; t += a.mt) {
