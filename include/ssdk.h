@@ -332,6 +332,14 @@ int ssdk_conv2d_fwd(ssdk_ctx* ctx, const float* x_dev, int B, int H, int W, int 
 int ssdk_maxpool(ssdk_ctx* ctx, const float* x_dev, int B, int H, int W, int C, int kh, int kw, int stride,
                  int pad_t, int pad_l, int pad_b, int pad_r, float* y_dev, void* stream);
 
+/* The two-stream schedule ssdk_model_create gives an inference plan, as a host-only function on plain arrays (no
+ * device needed): kind[i] 0 = not a tensor-core GEMM launch (pool, L2Norm, input), 1 = trunk convolution, 2 = predictor head;
+ * grid[i] = CTAs of that launch; input[i] = producing layer or -1; R <= 0 selects the default (sm_count / 3 + 1).
+ * out_on_side[i] = 1: issued on the second stream; *out_from = first such layer (-1: single stream); *out_grid_cap = grid limit of
+ * the GEMM launches that stay on the caller's stream meanwhile.  The reference has no counterpart (Keras/TF schedule their graph). */
+int ssdk_schedule_preview(int n_layers, const int* kind, const int* grid, const int* input, int R, int sm_count,
+                          unsigned char* out_on_side, int* out_from, int* out_grid_cap);
+
 int ssdk_model_create(ssdk_ctx* ctx, const ssdk_model_desc* desc, ssdk_model** out);
 int ssdk_model_destroy(ssdk_model* m);
 int ssdk_model_num_priors(const ssdk_model* m, int* out_P);

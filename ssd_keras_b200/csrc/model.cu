@@ -184,6 +184,38 @@ int build_conv(ssdk_model* m, int li) {
 // their persistent grid capped at sm_count - (widest narrow grid), so both sets always find free SMs (every conv CTA owns an SM:
 // ~200 KB of shared memory).  Cross-stream dependencies are events recorded at issue time; the streams join before the call returns.
 // SSDK_OVERLAP=0 disables, SSDK_OVERLAP_R sets R (default sm_count / 3 + 1).
+// The decision itself, on plain arrays (also behind ssdk_schedule_preview, so that it is testable without a device).
+// kind[i]: 0 = not a tensor-core GEMM launch (pool, L2Norm, input, image-facing conv), 1 = trunk convolution, 2 = predictor head;
+// grid[i]: CTAs of the launch (kind > 0); input[i]: producing layer or -1.  Returns the first side-stream layer (-1: one stream).
+int overlap_assign(int n, const int* kind, const int* grid, const int* input, int R, int sm_count, uint8_t* on_side, int* grid_cap) {
+  for (int i = 0; i < n; ++i) on_side[i] = 0;
+  *grid_cap = 0;
+  // first trunk convolution from which on all trunk convolutions are narrow
+  int from = -1;
+  for (int i = n - 1; i >= 0; --i) {
+    if (kind[i] == 2) continue;                 // heads do not decide where the trunk turns narrow
+    if (kind[i] == 0) continue;
+    if (grid[i] > R) break;
+    from = i;
+  }
+  if (from < 0) return -1;
+  int widest = 0, wide_after = 0;
+  for (int i = from; i < n; ++i) {
+    if (kind[i] > 0) {
+      if (grid[i] <= R) { on_side[i] = 1; widest = std::max(widest, grid[i]); }
+      else ++wide_after;
+    } else if (input[i] >= 0 && on_side[input[i]]) {
+      on_side[i] = 1;                           // element-wise consumer of a narrow producer: stays on its producer's stream
+    }
+  }
+  if (!wide_after || !widest) {                 // nothing to run next to the narrow launches
+    for (int i = 0; i < n; ++i) on_side[i] = 0;
+    return -1;
+  }
+  *grid_cap = std::max(1, sm_count - widest);
+  return from;
+}
+
 int plan_overlap(ssdk_model* m) {
   const int n = (int)m->layers.size();
   m->on_side.assign(n, 0);
@@ -192,29 +224,17 @@ int plan_overlap(ssdk_model* m) {
   if (const char* e = getenv("SSDK_OVERLAP")) { if (!atoi(e)) return SSDK_OK; }
   int R = m->ctx->sm_count / 3 + 1;      // 50 of 148: measured on B200 against sm_count / 4 (5.76 / 5.91 ms vs 5.84 / 5.95 ms per step)
   if (const char* e = getenv("SSDK_OVERLAP_R")) R = atoi(e);
-  auto is_gemm = [&](const LayerPlan& L) { return (L.d.op == SSDK_OP_CONV || L.d.op == SSDK_OP_HEAD) && !L.direct; };
-  // first trunk convolution from which on all trunk convolutions are narrow
-  int from = -1;
-  for (int i = n - 1; i >= 0; --i) {
+  std::vector<int> kind(n, 0), grid(n, 0), input(n, -1);
+  for (int i = 0; i < n; ++i) {
     const LayerPlan& L = m->layers[i];
-    if (L.d.op != SSDK_OP_CONV) continue;
-    if (L.direct || L.launch.grid > R) break;
-    from = i;
+    const bool gemm = (L.d.op == SSDK_OP_CONV || L.d.op == SSDK_OP_HEAD) && !L.direct;
+    // an image-facing (direct) convolution in the trunk ends the narrow suffix like a wide one: give it a grid no R admits
+    if (L.d.op == SSDK_OP_CONV && L.direct) { kind[i] = 1; grid[i] = 1 << 30; }
+    else if (gemm) { kind[i] = L.d.op == SSDK_OP_HEAD ? 2 : 1; grid[i] = L.launch.grid; }
+    input[i] = (L.d.op == SSDK_OP_INPUT || L.d.op == SSDK_OP_TENSOR) ? -1 : L.d.input;
   }
-  if (from < 0) return SSDK_OK;
-  int widest = 0, wide_after = 0;
-  for (int i = from; i < n; ++i) {
-    const LayerPlan& L = m->layers[i];
-    if (is_gemm(L)) {
-      if (L.launch.grid <= R) { m->on_side[i] = 1; widest = std::max(widest, L.launch.grid); }
-      else ++wide_after;
-    } else if (L.d.op != SSDK_OP_INPUT && L.d.input >= 0 && m->on_side[L.d.input]) {
-      m->on_side[i] = 1;                       // element-wise consumer of a narrow producer: stays on its producer's stream
-    }
-  }
-  if (!wide_after || !widest) { m->on_side.assign(n, 0); return SSDK_OK; }      // nothing to run next to the narrow launches
-  m->overlap_from = from;
-  m->grid_cap = std::max(1, m->ctx->sm_count - widest);
+  m->overlap_from = overlap_assign(n, kind.data(), grid.data(), input.data(), R, m->ctx->sm_count, m->on_side.data(), &m->grid_cap);
+  if (m->overlap_from < 0) return SSDK_OK;
   int lo = 0, hi = 0;
   SSDK_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   SSDK_CHECK_CUDA(cudaStreamCreateWithPriority(&m->side, cudaStreamNonBlocking, hi));
@@ -688,4 +708,13 @@ extern "C" int ssdk_maxpool(ssdk_ctx* ctx, const float* x_dev, int B, int H, int
   d.op = SSDK_OP_MAXPOOL; d.kh = kh; d.kw = kw; d.stride = stride; d.dilation = 1;
   d.pad_t = pad_t; d.pad_l = pad_l; d.pad_b = pad_b; d.pad_r = pad_r;
   return run_single_layer(ctx, x_dev, B, H, W, C, d, 0, y_dev, stream);
+}
+
+extern "C" int ssdk_schedule_preview(int n_layers, const int* kind, const int* grid, const int* input, int R, int sm_count,
+                                     unsigned char* out_on_side, int* out_from, int* out_grid_cap) {
+  SSDK_REQUIRE(n_layers > 0 && kind && grid && input && out_on_side && out_from && out_grid_cap, "ssdk_schedule_preview: bad argument");
+  for (int i = 0; i < n_layers; ++i)
+    SSDK_REQUIRE(input[i] < i && kind[i] >= 0 && kind[i] <= 2, "ssdk_schedule_preview: layer %d: input must refer to an earlier layer, kind must be 0..2", i);
+  *out_from = overlap_assign(n_layers, kind, grid, input, R > 0 ? R : sm_count / 3 + 1, sm_count, out_on_side, out_grid_cap);
+  return SSDK_OK;
 }
