@@ -151,7 +151,7 @@ class SSDTrainer:
         soon as its layers have been differentiated (NCCL on its own stream under the weight / data gradient kernels of the lower
         layers), or in one call after the backward pass.  ``overlap=None`` picks: measured on B200 at 2 ranks the whole 105 MB
         exchange costs 0.5 ms alone while NCCL's kernels delay the persistent 148-CTA conv launches by more than that when they
-        run side by side, so the bucketed exchange is used from 4 ranks on (SSDK_OVERLAP=0/1 overrides)."""
+        run side by side, so the bucketed exchange is used from 4 ranks on (SSDK_GRAD_OVERLAP=0/1 overrides; SSDK_OVERLAP is the two-stream schedule of inference plans)."""
         import os
         import torch.distributed as dist
         on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -161,7 +161,7 @@ class SSDTrainer:
             self.apply(1.0)
             return loss
         if overlap is None:
-            env = os.environ.get('SSDK_OVERLAP')
+            env = os.environ.get('SSDK_GRAD_OVERLAP')
             overlap = (env == '1') if env in ('0', '1') else dist.get_world_size(group) > 2
         from .distributed import all_reduce_buckets_
         if overlap:
