@@ -12,6 +12,7 @@ import numpy as np
 from .. import _ffi
 from ..keras_layers.keras_layer_DecodeDetections import DecodeDetections
 from ..keras_layers.keras_layer_DecodeDetectionsFast import DecodeDetectionsFast
+from ._keras_api import KerasTrainingMixin
 
 
 class _LayerInfo:
@@ -44,7 +45,7 @@ def tf_same_pool_pad(size, k, s):
     return total // 2, total - total // 2
 
 
-class SSDModel:
+class SSDModel(KerasTrainingMixin):
     def __init__(self, specs, img_height, img_width, img_channels, n_classes_total, anchor_cfg, variances, mode,
                  decode_cfg, l2_reg=0.0, precision='bf16x3', seed=0):
         self.specs = specs
