@@ -225,6 +225,24 @@ def tf_nms_fast(boxes, scores, max_output_size, iou_threshold):
     return selected
 
 
+def tf_nms_c(boxes, scores, max_output_size, iou_threshold):
+    """``tf_nms`` through the C restatement oracle/tf_nms.c (compiled by oracle/cbuild.py); falls back to ``tf_nms_fast`` where no
+    compiler exists.  Bit-identical to both (tests/test_oracle_c_nms_cpu.py); what bench.py's CPU arm times."""
+    import ctypes as C
+    from .cbuild import tf_nms_lib
+    lib = tf_nms_lib()
+    if lib is None:
+        return tf_nms_fast(boxes, scores, max_output_size, iou_threshold)
+    b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
+    sc = np.ascontiguousarray(scores, dtype=np.float32).reshape(-1)
+    out = np.empty(max(int(max_output_size), 1), np.int32)
+    k = lib.tf_nms_f32(b.ctypes.data_as(C.POINTER(C.c_float)), sc.ctypes.data_as(C.POINTER(C.c_float)), int(sc.shape[0]),
+                       int(max_output_size), C.c_float(np.float32(iou_threshold)), out.ctypes.data_as(C.POINTER(C.c_int)))
+    if k < 0:
+        raise MemoryError('tf_nms_f32')
+    return [int(v) for v in out[:k]]
+
+
 def _layer_boxes(y_pred, normalize_coords, img_height, img_width):
     """keras_layer_DecodeDetections.py:124-146 in float32."""
     f = np.float32
@@ -251,7 +269,7 @@ def _topk_pad(rows, top_k):
 
 
 def decode_layer(y_pred, confidence_thresh=0.01, iou_threshold=0.45, top_k=200, nms_max_output_size=400,
-                 normalize_coords=True, img_height=None, img_width=None, return_indices=False):
+                 normalize_coords=True, img_height=None, img_width=None, return_indices=False, nms=None):
     """DecodeDetections.call, keras_layer_DecodeDetections.py:109-265 -> (B, top_k, 6) float32.
 
     ``return_indices`` also returns, per image, the prior index of every output row (-1 for padding)."""
@@ -270,7 +288,7 @@ def decode_layer(y_pred, confidence_thresh=0.01, iou_threshold=0.45, top_k=200, 
             blk = np.zeros((nms_max_output_size, 6), f)                        # :211-214 pad to 400 rows
             bidx = np.full(nms_max_output_size, -1, np.int64)
             if m.size:
-                sel = tf_nms_fast(boxes[b, m], conf[m], nms_max_output_size, iou_threshold)
+                sel = (nms or tf_nms_fast)(boxes[b, m], conf[m], nms_max_output_size, iou_threshold)
                 k = len(sel)
                 blk[:k, 0] = c
                 blk[:k, 1] = conf[m][sel]
