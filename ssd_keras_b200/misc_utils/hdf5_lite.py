@@ -496,11 +496,12 @@ class _Writer:
             f.write(bytes(b))
 
 
-def write_keras_weights(path, weights, full_model=False, chunked=()):
+def write_keras_weights(path, weights, full_model=False, chunked=(), root_attrs=None):
     """``weights``: ``{'conv1_1/kernel': array, 'conv1_1/bias': array, ...}`` -> an HDF5 file with the layout of
     ``model.save_weights`` (``/<layer>/<layer>/kernel:0`` datasets, ``layer_names`` / ``weight_names`` attributes); with
     ``full_model`` everything sits below ``/model_weights`` like in ``model.save``; the weights named in ``chunked`` are stored
-    chunked with shuffle + gzip filters."""
+    chunked with shuffle + gzip filters; ``root_attrs`` (name -> bytes / array) become attributes of the root group, where
+    ``model.save`` keeps ``model_config``."""
     w = _Writer()
     layers = {}
     for k, v in weights.items():
@@ -517,7 +518,10 @@ def write_keras_weights(path, weights, full_model=False, chunked=()):
     attrs = {'layer_names': np.array([l.encode() for l in layers]), 'backend': np.array(b'tensorflow'), 'keras_version': np.array(b'2.1.4')}
     if full_model:
         mw, _, _ = w.group(top, attrs=attrs)
-        root, bt, heap = w.group([('model_weights', mw)])
+        ra = {k: (np.array(v) if isinstance(v, (bytes, str)) else np.asarray(v)) for k, v in (root_attrs or {}).items()}
+        root, bt, heap = w.group([('model_weights', mw)], attrs=ra or None)
     else:
+        if root_attrs:
+            attrs.update({k: (np.array(v) if isinstance(v, (bytes, str)) else np.asarray(v)) for k, v in root_attrs.items()})
         root, bt, heap = w.group(top, attrs=attrs)
     w.finish(root, bt, heap, path)

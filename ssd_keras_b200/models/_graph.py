@@ -45,6 +45,35 @@ def tf_same_pool_pad(size, k, s):
     return total // 2, total - total // 2
 
 
+def records_config(name):
+    """Decorator of the three builders: remembers the (JSON-able) arguments of the call on the model it returns, for ``save``."""
+    import functools
+    import inspect
+
+    def plain(v):
+        if isinstance(v, np.ndarray):
+            return v.tolist()
+        if isinstance(v, (np.floating, np.integer)):
+            return v.item()
+        if isinstance(v, (list, tuple)):
+            return [plain(q) for q in v]
+        return v
+
+    def deco(fn):
+        sig = inspect.signature(fn)
+
+        @functools.wraps(fn)
+        def wrapper(*a, **kw):
+            out = fn(*a, **kw)
+            b = sig.bind(*a, **kw)
+            b.apply_defaults()
+            args = {k: plain(v) for k, v in b.arguments.items() if k != 'return_predictor_sizes'}
+            (out[0] if isinstance(out, tuple) else out)._build_config = (name, args)
+            return out
+        return wrapper
+    return deco
+
+
 class SSDModel(KerasTrainingMixin):
     def __init__(self, specs, img_height, img_width, img_channels, n_classes_total, anchor_cfg, variances, mode,
                  decode_cfg, l2_reg=0.0, precision='bf16x3', seed=0):
@@ -202,8 +231,30 @@ class SSDModel(KerasTrainingMixin):
         self.set_weights(read_keras_weights(p))
 
     def save_weights(self, path):
+        """``model.save_weights(path)``: a Keras-layout HDF5 weights file for ``*.h5`` / ``*.hdf5`` (what ``load_weights`` of this
+        package AND of Keras read), an ``.npz`` with the same names otherwise."""
         self._sync_trained()
-        np.savez(path, **self.weights)
+        p = str(path)
+        if p.endswith(('.h5', '.hdf5')):
+            from ..misc_utils.hdf5_lite import write_keras_weights
+            write_keras_weights(p, self.weights)
+        else:
+            np.savez(p, **self.weights)
+
+    def save(self, filepath):
+        """``model.save(filepath)`` (reference ``ssd300_training.ipynb:409-413`` via ``ModelCheckpoint``): one HDF5 file with the
+        weights below ``/model_weights`` (Keras' layout: ``load_weights(filepath, by_name=True)`` of either library reads it) and,
+        as the root attribute ``model_config``, the builder call that made this model -- what ``models.load_model`` rebuilds it
+        from.  Optimizer state is not stored."""
+        import json
+        self._sync_trained()
+        if getattr(self, '_build_config', None) is None:
+            raise ValueError('this model was not made by ssd_300 / ssd_512 / build_model: save_weights() it instead')
+        name, kwargs = self._build_config
+        cfg = json.dumps({'class_name': 'SSDModel', 'config': {'builder': name, 'kwargs': kwargs}}).encode()
+        from ..misc_utils.hdf5_lite import write_keras_weights
+        write_keras_weights(str(filepath), self.weights, full_model=True,
+                            root_attrs={'model_config': cfg, 'keras_version': b'2.1.4', 'backend': b'ssd_keras_b200'})
 
     # -- execution ---------------------------------------------------------------------------
     def _release(self):

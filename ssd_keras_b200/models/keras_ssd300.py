@@ -4,7 +4,7 @@ Returns an ``SSDModel`` (see ``_graph.py``) instead of a Keras ``Model``: VGG-16
 layers + L2Normalization + six fused conf/loc predictor heads, executed as tcgen05 implicit-GEMM kernels."""
 
 from .. import _ffi
-from ._graph import SSDModel, Spec, resolve_box_args, same_pad, tf_same_pool_pad
+from ._graph import SSDModel, Spec, records_config, resolve_box_args, same_pad, tf_same_pool_pad
 
 RELU = _ffi.ACT_RELU
 
@@ -51,6 +51,7 @@ def _finish(specs, sources, n_boxes):
                           params={'conf_name': src + '_mbox_conf', 'loc_name': src + '_mbox_loc'}))
 
 
+@records_config('ssd_300')
 def ssd_300(image_size, n_classes, mode='training', l2_regularization=0.0005, min_scale=None, max_scale=None, scales=None,
             aspect_ratios_global=None,
             aspect_ratios_per_layer=[[1.0, 2.0, 0.5], [1.0, 2.0, 0.5, 3.0, 1.0 / 3.0], [1.0, 2.0, 0.5, 3.0, 1.0 / 3.0],

@@ -1,9 +1,10 @@
 """``ssd_512`` on B200 -- same signature as the reference builder (``models/keras_ssd512.py:31-60``):
 the SSD300 graph with seven predictor layers (extra stride-2 stages and the 4x4 'valid' conv10_2, :312-321)."""
-from ._graph import SSDModel, resolve_box_args
+from ._graph import SSDModel, records_config, resolve_box_args
 from .keras_ssd300 import _extra, _finish, _input_spec, _vgg_base
 
 
+@records_config('ssd_512')
 def ssd_512(image_size, n_classes, mode='training', l2_regularization=0.0005, min_scale=None, max_scale=None, scales=None,
             aspect_ratios_global=None,
             aspect_ratios_per_layer=[[1.0, 2.0, 0.5], [1.0, 2.0, 0.5, 3.0, 1.0 / 3.0], [1.0, 2.0, 0.5, 3.0, 1.0 / 3.0],

@@ -2,9 +2,10 @@
 ``ssd_7`` is an alias.  Seven conv + BatchNormalization(eps 1e-3, folded) + ELU stages with 'valid' 2x2 pools and
 four predictor heads on conv4..conv7 (:277-331)."""
 from .. import _ffi
-from ._graph import SSDModel, Spec, resolve_box_args, same_pad
+from ._graph import SSDModel, Spec, records_config, resolve_box_args, same_pad
 
 
+@records_config('build_model')
 def build_model(image_size, n_classes, mode='training', l2_regularization=0.0, min_scale=0.1, max_scale=0.9, scales=None,
                 aspect_ratios_global=[0.5, 1.0, 2.0], aspect_ratios_per_layer=None, two_boxes_for_ar1=True, steps=None,
                 offsets=None, clip_boxes=False, variances=[1.0, 1.0, 1.0, 1.0], coords='centroids', normalize_coords=False,
