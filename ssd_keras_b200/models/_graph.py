@@ -138,6 +138,50 @@ class SSDModel(KerasTrainingMixin):
     def layers(self):
         return [self.get_layer(s.name) for s in self.specs]
 
+    @property
+    def input_shape(self):
+        return (None, self.img_height, self.img_width, self.img_channels)
+
+    @property
+    def output_shape(self):
+        """(None, P, C+12) in 'training' mode, (None, top_k, 6) with a decoder layer at the end (keras_ssd300.py:421-446)."""
+        if self.decoder is None:
+            return (None, self.n_boxes_total, self.n_classes + 12)
+        return (None, int(self.decode_cfg['top_k']), 6)
+
+    def count_params(self):
+        """Keras' ``model.count_params()``: trainable + non-trainable (BatchNormalization moving statistics) parameters."""
+        return int(sum(int(np.prod(s)) for s in self.weight_shapes().values()))
+
+    def summary(self, line_length=100, print_fn=print):
+        """A ``model.summary()`` in Keras' spirit: one row per layer of the plan (the fused predictor heads show up under both of
+        their Keras names), then the parameter totals."""
+        shapes = self.weight_shapes()
+        rows = []
+        for s in self.specs:
+            h, w, c = self._shapes[self.index[s.name]]
+            if s.op == _ffi.OP_HEAD:
+                for nm in (s.params['conf_name'], s.params['loc_name']):
+                    n_par = sum(int(np.prod(v)) for k, v in shapes.items() if k.startswith(nm + '/'))
+                    rows.append((nm + ' (Conv2D)', str(self.get_layer(nm).output_shape), n_par, s.inp))
+                continue
+            kind = {_ffi.OP_INPUT: 'InputLayer', _ffi.OP_CONV: 'Conv2D', _ffi.OP_MAXPOOL: 'MaxPooling2D', _ffi.OP_L2NORM: 'L2Normalization'}.get(s.op, '?')
+            n_par = sum(int(np.prod(v)) for k, v in shapes.items() if k.split('/')[0] in (s.name, s.bn))
+            rows.append(('%s (%s)' % (s.name, kind), str((None, h, w, c)), n_par, s.inp or ''))
+        print_fn('_' * line_length)
+        print_fn('%-38s%-26s%-12s%s' % ('Layer (type)', 'Output Shape', 'Param #', 'Connected to'))
+        print_fn('=' * line_length)
+        for r in rows:
+            print_fn('%-38s%-26s%-12d%s' % r)
+        print_fn('=' * line_length)
+        total = self.count_params()
+        non_tr = sum(int(np.prod(v)) for k, v in shapes.items() if k.endswith(('/moving_mean', '/moving_variance')))
+        print_fn('Output: %s   (mode=%r)' % (self.output_shape, self.mode))
+        print_fn('Total params: {:,}'.format(total))
+        print_fn('Trainable params: {:,}'.format(total - non_tr))
+        print_fn('Non-trainable params: {:,}'.format(non_tr))
+        print_fn('_' * line_length)
+
     # -- weights -----------------------------------------------------------------------------
     def weight_shapes(self):
         out = {}

@@ -70,3 +70,20 @@ def test_builders_keep_their_signatures():
     # the config-recording wrapper must not hide the reference's parameter list (tests/test_signature_parity_cpu.py reads it)
     assert list(inspect.signature(ssd_300).parameters)[:3] == ['image_size', 'n_classes', 'mode']
     assert 'return_predictor_sizes' in inspect.signature(build_model).parameters
+
+
+def test_count_params_summary_and_shapes():
+    m = ssd_300((300, 300, 3), 20, mode='training', scales=[0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05])
+    assert m.count_params() == 26285486                      # SSD300 / Pascal VOC, the figure of the reference's model.summary()
+    assert m.input_shape == (None, 300, 300, 3) and m.output_shape == (None, 8732, 33)
+    mi = ssd_300((300, 300, 3), 20, mode='inference', scales=[0.1, 0.2, 0.37, 0.54, 0.71, 0.88, 1.05], top_k=150)
+    assert mi.output_shape == (None, 150, 6)
+    lines = []
+    m.summary(print_fn=lines.append)
+    text = '\n'.join(lines)
+    assert 'conv4_3_norm (L2Normalization)' in text and 'conv4_3_norm_mbox_conf (Conv2D)' in text and 'fc7_mbox_loc (Conv2D)' in text
+    assert 'Total params: 26,285,486' in text and 'Non-trainable params: 0' in text
+    m7 = build_model((300, 480, 3), 5, mode='training', scales=[0.08, 0.16, 0.32, 0.64, 0.96])
+    lines = []
+    m7.summary(print_fn=lines.append)
+    assert any(l.startswith('Non-trainable params:') and not l.endswith(' 0') for l in lines)     # BatchNormalization statistics
