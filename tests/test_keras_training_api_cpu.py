@@ -102,3 +102,59 @@ def test_fit_generator_loop_with_stubbed_device_step(monkeypatch):
             self.model.stop_training = True
     h = m.fit_generator(gen, steps_per_epoch=5, epochs=3, callbacks=[StopAfterFirst()])
     assert h.epoch == [0] and len(h.history['loss']) == 1
+
+
+def test_reference_notebook_callbacks_with_stubbed_device_step(monkeypatch, tmp_path):
+    """ModelCheckpoint / LearningRateScheduler / TerminateOnNaN / CSVLogger as ssd300_training.ipynb:404-425 sets them up, plus
+    EarlyStopping / ReduceLROnPlateau of ssd7_training.ipynb:300-325."""
+    from ssd_keras_b200 import callbacks as cb
+    from ssd_keras_b200.misc_utils.hdf5_lite import read_datasets
+    from ssd_keras_b200.models import load_model
+    m = _model()
+    m.compile(optimizer=optimizers.SGD(lr=1e-3, momentum=0.9), loss=SSDLoss().compute_loss)
+    train = iter([5.0, 5.0, 4.0, 4.0, 3.5, 3.5, 3.6, 3.6, 3.7, 3.7, 3.8, 3.8, 9.0, 9.0])
+    val = iter([4.0, 3.0, 3.2, 3.3, 3.4, 3.5, 3.6])
+    monkeypatch.setattr(m, 'train_on_batch', lambda x, y: next(train))
+    monkeypatch.setattr(m, 'evaluate_generator', lambda g, steps: next(val))
+    gen = ((np.zeros((2, 96, 96, 3), np.float32), np.zeros((2, 10, 18), np.float32)) for _ in itertools.count())
+
+    def lr_schedule(epoch):
+        return 0.001 if epoch < 2 else 0.0001
+    ckpt = cb.ModelCheckpoint(filepath=str(tmp_path / 'ssd_epoch-{epoch:02d}_loss-{loss:.4f}_val_loss-{val_loss:.4f}.h5'), monitor='val_loss',
+                              verbose=0, save_best_only=True, save_weights_only=False, mode='auto', period=1)
+    log = cb.CSVLogger(filename=str(tmp_path / 'log.csv'), separator=',', append=True)
+    stop = cb.EarlyStopping(monitor='val_loss', min_delta=0.0, patience=3, verbose=0)
+    h = m.fit_generator(gen, steps_per_epoch=2, epochs=7, callbacks=[ckpt, log, cb.LearningRateScheduler(schedule=lr_schedule, verbose=0),
+                                                                      cb.TerminateOnNaN(), stop], validation_data=gen, validation_steps=1)
+    # val_loss: 4.0, 3.0 (best), 3.2, 3.3, 3.4 -> three epochs without improvement: stop after epoch index 4
+    assert h.epoch == [0, 1, 2, 3, 4] and stop.stopped_epoch == 4
+    saved = sorted(p.name for p in tmp_path.glob('*.h5'))
+    assert saved == ['ssd_epoch-01_loss-5.0000_val_loss-4.0000.h5', 'ssd_epoch-02_loss-4.0000_val_loss-3.0000.h5']     # only improvements
+    assert '/model_weights/conv1/conv1/kernel:0' in read_datasets(str(tmp_path / saved[1]))
+    assert load_model(str(tmp_path / saved[1])).n_classes == m.n_classes
+    assert m.optimizer.lr == 0.0001
+    rows = (tmp_path / 'log.csv').read_text().strip().split('\n')
+    assert rows[0] == 'epoch,loss,val_loss' and rows[2].startswith('1,4.0,3.0') and len(rows) == 6
+    # ReduceLROnPlateau: factor 0.5 after 2 epochs without an improvement of more than epsilon
+    m.optimizer.lr = 0.01
+    r = cb.ReduceLROnPlateau(monitor='val_loss', factor=0.5, patience=2, verbose=0, epsilon=0.001, cooldown=0, min_lr=0.004)
+    r.set_model(m)
+    for e, v in enumerate([1.0, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9, 0.9]):
+        r.on_epoch_end(e, {'val_loss': v})
+    assert m.optimizer.lr == 0.004                          # 0.01 -> 0.005 -> max(0.0025, min_lr)
+    # TerminateOnNaN
+    t = cb.TerminateOnNaN(); t.set_model(m); m.stop_training = False
+    t.on_batch_end(0, {'loss': float('nan')})
+    assert m.stop_training
+    with pytest.raises(ValueError):
+        cb.ModelCheckpoint('x.h5', mode='sideways')
+    with pytest.raises(ValueError):
+        cb.ReduceLROnPlateau(factor=1.0)
+    # weights-only checkpoints every second epoch
+    m.stop_training = False
+    c2 = cb.ModelCheckpoint(str(tmp_path / 'w-{epoch:02d}.h5'), save_weights_only=True, period=2)
+    c2.set_model(m)
+    for e in range(4):
+        c2.on_epoch_end(e, {'loss': 1.0})
+    assert sorted(p.name for p in tmp_path.glob('w-*.h5')) == ['w-02.h5', 'w-04.h5']
+    assert '/conv1/conv1/kernel:0' in read_datasets(str(tmp_path / 'w-02.h5'))
