@@ -230,7 +230,10 @@ def tf_nms_c(boxes, scores, max_output_size, iou_threshold):
     compiler exists.  Bit-identical to both (tests/test_oracle_c_nms_cpu.py); what bench.py's CPU arm times."""
     import ctypes as C
     from .cbuild import tf_nms_lib
-    lib = tf_nms_lib()
+    try:
+        lib = tf_nms_lib()
+    except (OSError, RuntimeError):
+        lib = None
     if lib is None:
         return tf_nms_fast(boxes, scores, max_output_size, iou_threshold)
     b = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 4)
